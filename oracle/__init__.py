@@ -1,0 +1,324 @@
+"""ctypes front-end of the CPU ORACLE (oracle/hydra_oracle.c).
+
+TEST INFRASTRUCTURE ONLY.  Importers allowed: tests/, __graft_entry__.smoke(),
+bench.py's cpu_baseline / --impl reference legs.  The product package
+(hydra_b200/) must never import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBS: dict[str, C.CDLL] = {}
+
+c_sz = C.c_size_t
+P = C.POINTER
+
+
+def build(fast: bool = False, force: bool = False) -> str:
+    name = "libhydra_oracle_fast.so" if fast else "libhydra_oracle.so"
+    path = os.path.join(_HERE, name)
+    if force or not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(
+        os.path.join(_HERE, "hydra_oracle.c")
+    ):
+        args = ["make", "-C", _HERE, name] + (["-B"] if force else [])
+        subprocess.run(args, check=True, capture_output=True)
+    return path
+
+
+def lib(fast: bool = False, rebuild: bool = False) -> C.CDLL:
+    key = "fast" if fast else "strict"
+    if key not in _LIBS or rebuild:
+        L = C.CDLL(build(fast, force=rebuild))
+        L.ho_sparse_dotprod.restype = C.c_double
+        L.ho_lut_dotprod.restype = C.c_double
+        L.ho_mt_res53.restype = C.c_double
+        L.ho_mt_normal.restype = C.c_double
+        L.ho_mt_gamma.restype = C.c_double
+        L.ho_mt_gamma.argtypes = [C.c_void_p, C.c_double]
+        L.ho_mt_u32.restype = C.c_uint32
+        _LIBS[key] = L
+    return _LIBS[key]
+
+
+def _p(a, t=None):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+# --------------------------------------------------------------------------- LUT
+def lut_build():
+    a = np.empty(1024, np.float64)
+    b = np.empty(1024, np.float64)
+    lib().ho_lut_build(_p(a), _p(b))
+    return a, b
+
+
+# --------------------------------------------------------------------------- staging
+@dataclass
+class SparseLists:
+    """Reference sparse representation (src/data.cpp:1224-1290)."""
+
+    I1: np.ndarray
+    N1S: np.ndarray
+    N1L: np.ndarray
+    I2: np.ndarray
+    N2S: np.ndarray
+    N2L: np.ndarray
+    IM: np.ndarray
+    NMS: np.ndarray
+    NML: np.ndarray
+
+
+def snp_len_byt(n: int) -> int:
+    return (n + 3) // 4
+
+
+def sparse_fill_indices(bed: np.ndarray, nind: int) -> SparseLists:
+    """bed: (M, NB) uint8 column-major PLINK bytes (header stripped)."""
+    bed = _c(bed, np.uint8)
+    M, NB = bed.shape
+    n1 = c_sz()
+    n2 = c_sz()
+    nm = c_sz()
+    L = lib()
+    L.ho_sparse_get_sizes_from_raw(_p(bed), C.c_uint(M), C.c_uint(NB), C.c_uint(nind), C.byref(n1), C.byref(n2), C.byref(nm))
+    I1 = np.empty(max(n1.value, 1), np.uint32)
+    I2 = np.empty(max(n2.value, 1), np.uint32)
+    IM = np.empty(max(nm.value, 1), np.uint32)
+    S = [np.zeros(M, np.uint64) for _ in range(6)]
+    L.ho_sparse_fill_indices(_p(bed), C.c_uint(M), C.c_uint(NB), C.c_uint(nind),
+                             _p(S[0]), _p(S[1]), _p(I1), _p(S[2]), _p(S[3]), _p(I2), _p(S[4]), _p(S[5]), _p(IM))
+    return SparseLists(I1[: n1.value], S[0], S[1], I2[: n2.value], S[2], S[3], IM[: nm.value], S[4], S[5])
+
+
+def correct_for_missing_phenotype(sp: SparseLists, na_inds: np.ndarray, usebed=None) -> None:
+    na = _c(na_inds, np.uint32)
+    M = len(sp.N1S)
+    ub = None if usebed is None else _c(usebed, np.uint8)
+    L = lib()
+    for (S, Ln, I) in ((sp.N1S, sp.N1L, sp.I1), (sp.N2S, sp.N2L, sp.I2), (sp.NMS, sp.NML, sp.IM)):
+        L.ho_sparse_correct_for_missing_phenotype(_p(S), _p(Ln), _p(I), C.c_int(M), _p(ub), _p(na), C.c_int(len(na)))
+
+
+def bed_marker_from_sparse(nbytes: int, i1, i2, im) -> np.ndarray:
+    out = np.empty(nbytes, np.uint8)
+    i1 = _c(i1, np.uint32)
+    i2 = _c(i2, np.uint32)
+    im = _c(im, np.uint32)
+    lib().ho_bed_marker_from_sparse(_p(out), c_sz(nbytes), _p(i1), c_sz(len(i1)), _p(i2), c_sz(len(i2)), _p(im), c_sz(len(im)))
+    return out
+
+
+def marker_stats_brr(N: int, n1l, n2l, nml):
+    n1l = _c(n1l, np.uint64)
+    n2l = _c(n2l, np.uint64)
+    nml = _c(nml, np.uint64)
+    M = len(n1l)
+    mave = np.empty(M)
+    mstd = np.empty(M)
+    lib().ho_marker_stats_brr(C.c_int(M), C.c_uint(N), _p(n1l), _p(n2l), _p(nml), _p(mave), _p(mstd))
+    return mave, mstd
+
+
+def center_and_scale(y):
+    y = np.array(y, dtype=np.float64, copy=True)
+    lib().ho_center_and_scale(_p(y), C.c_int(len(y)))
+    return y
+
+
+# --------------------------------------------------------------------------- kernels
+def sparse_dotprod(eps, sp: SparseLists, m: int, mave: float, mstd: float, fast=False) -> float:
+    eps = _c(eps, np.float64)
+    return lib(fast).ho_sparse_dotprod(
+        _p(eps), _p(sp.I1), c_sz(int(sp.N1S[m])), c_sz(int(sp.N1L[m])), _p(sp.I2), c_sz(int(sp.N2S[m])), c_sz(int(sp.N2L[m])),
+        _p(sp.IM), c_sz(int(sp.NMS[m])), c_sz(int(sp.NML[m])), C.c_double(mave), C.c_double(mstd), C.c_int(len(eps)))
+
+
+def lut_dotprod(raw, eps, mave: float, mstd: float) -> float:
+    raw = _c(raw, np.uint8)
+    eps = _c(eps, np.float64)
+    return lib().ho_lut_dotprod(_p(raw), _p(eps), C.c_int(len(eps)), C.c_double(mave), C.c_double(mstd))
+
+
+def sparse_scaadd(N: int, dmult: float, sp: SparseLists, m: int, mave: float, mstd: float):
+    out = np.empty(N)
+    lib().ho_sparse_scaadd(
+        _p(out), C.c_double(dmult), _p(sp.I1), c_sz(int(sp.N1S[m])), c_sz(int(sp.N1L[m])), _p(sp.I2), c_sz(int(sp.N2S[m])),
+        c_sz(int(sp.N2L[m])), _p(sp.IM), c_sz(int(sp.NMS[m])), c_sz(int(sp.NML[m])), C.c_double(mave), C.c_double(mstd), C.c_int(N))
+    return out
+
+
+def lut_scaadd(N: int, raw, dbeta: float, mave: float, mstd: float):
+    raw = _c(raw, np.uint8)
+    out = np.empty(N)
+    lib().ho_lut_scaadd(_p(out), _p(raw), C.c_double(dbeta), C.c_double(mave), C.c_double(mstd), C.c_int(N))
+    return out
+
+
+def define_blocks(Mtot: int, T: int):
+    s = np.zeros(T, np.int32)
+    l = np.zeros(T, np.int32)
+    lib().ho_define_blocks_of_markers(C.c_int(Mtot), _p(s), _p(l), C.c_uint(T))
+    return s, l
+
+
+# --------------------------------------------------------------------------- RNG spec v1
+class MT:
+    def __init__(self, seed: int):
+        self.buf = C.create_string_buffer(lib().ho_sizeof_mt())
+        lib().ho_mt_seed(self.buf, C.c_uint32(seed & 0xFFFFFFFF))
+
+    def u32(self):
+        return lib().ho_mt_u32(self.buf)
+
+    def res53(self):
+        return lib().ho_mt_res53(self.buf)
+
+    def normal(self):
+        return lib().ho_mt_normal(self.buf)
+
+    def gamma(self, a):
+        return lib().ho_mt_gamma(self.buf, C.c_double(a))
+
+
+def philox4x32(ctr, key):
+    c = (C.c_uint32 * 4)(*ctr)
+    k = (C.c_uint32 * 2)(*key)
+    o = (C.c_uint32 * 4)()
+    lib().ho_philox4x32(c, k, o)
+    return list(o)
+
+
+def marker_draws(seed, task, iteration, j):
+    u = C.c_double()
+    z = C.c_double()
+    lib().ho_marker_draws(C.c_uint32(seed), C.c_uint32(task), C.c_uint32(iteration), C.c_uint32(j), C.byref(u), C.byref(z))
+    return u.value, z.value
+
+
+class TapeMaker:
+    """Positional draw tape of RNG spec v1."""
+
+    def __init__(self, seed: int, T: int, Mtot: int, shuffle: bool = True):
+        self.seed, self.T, self.Mtot, self.shuffle = seed, T, Mtot, shuffle
+        sz = lib().ho_sizeof_mt()
+        self.streams = C.create_string_buffer(sz * T)
+        for r in range(T):
+            lib().ho_mt_seed(C.byref(self.streams, sz * r), C.c_uint32((seed + 1000 * r) & 0xFFFFFFFF))
+        s, l = define_blocks(Mtot, T)
+        self.perm_state = np.concatenate([np.arange(n, dtype=np.int32) for n in l]) if Mtot else np.zeros(0, np.int32)
+        self.it = 0
+
+    def next(self):
+        T, M = self.T, self.Mtot
+        zmu = np.empty(T)
+        perm = np.empty(M, np.int32)
+        u = np.empty(M)
+        z = np.empty(M)
+        lib().ho_tape_iteration(self.streams, C.c_uint32(self.seed), C.c_int(T), C.c_int(M), C.c_uint32(self.it),
+                                _p(self.perm_state), _p(zmu), _p(perm), _p(u), _p(z), C.c_int(1 if self.shuffle else 0))
+        self.it += 1
+        return zmu, perm, u, z
+
+    def make(self, n_iter: int):
+        zs, ps, us, zz = [], [], [], []
+        for _ in range(n_iter):
+            a, b, c, d = self.next()
+            zs.append(a), ps.append(b), us.append(c), zz.append(d)
+        return dict(zmu=np.array(zs), perm=np.array(ps, dtype=np.int32), u=np.array(us), z=np.array(zz))
+
+
+# --------------------------------------------------------------------------- synthetic data
+def synth_thresholds(p: float, pmiss: float = 0.001):
+    t = (C.c_uint32 * 3)()
+    lib().ho_synth_thresholds(C.c_double(p), C.c_double(pmiss), t)
+    return np.array(list(t), dtype=np.uint32)
+
+
+def synth_bed(seed: int, N: int, thresholds: np.ndarray, attempts=None, j0: int = 0, fast=False) -> np.ndarray:
+    """thresholds: (M,3) uint32 -> (M, ceil(N/4)) uint8 BED columns."""
+    thresholds = _c(thresholds, np.uint32)
+    M = thresholds.shape[0]
+    out = np.empty((M, snp_len_byt(N)), np.uint8)
+    L = lib(fast)
+    for j in range(M):
+        att = 0 if attempts is None else int(attempts[j])
+        L.ho_synth_bed_marker(C.c_uint32(seed), C.c_uint32(j0 + j), C.c_uint32(att), _p(thresholds[j]), C.c_uint32(N), _p(out[j]))
+    return out
+
+
+# --------------------------------------------------------------------------- chain
+class _BrrArgs(C.Structure):
+    _fields_ = (
+        [(n, C.c_int32) for n in ("N", "Mtot", "T", "K", "G", "sync_rate", "n_iter", "iter0")]
+        + [(n, C.c_void_p) for n in ("I1", "N1S", "N1L", "I2", "N2S", "N2L", "IM", "NMS", "NML", "usebed", "bed")]
+        + [("snpLenByt", c_sz)]
+        + [(n, C.c_void_p) for n in ("y_raw", "groups", "mS", "tape_zmu", "tape_perm", "tape_u", "tape_z",
+                                     "tape_sigmaG0", "tape_sigmaG", "tape_sigmaE", "tape_pi")]
+        + [("hyper_seed", C.c_uint32)]
+        + [(n, C.c_void_p) for n in ("out_beta", "out_comp", "out_acum", "out_mu", "out_eps", "out_sigmaG", "out_sigmaE",
+                                     "out_pi", "out_bsq", "out_cass", "out_esqn", "out_epssum", "out_nsync", "out_loop_seconds")]
+    )
+
+
+def brr_chain(N, Mtot, T, K, G, sync_rate, n_iter, sp: SparseLists, y_raw, groups, mS, tape, sigmaG0,
+              usebed=None, bed=None, hyper=None, hyper_seed=0, want_eps=True, fast=False, want_marker_out=True):
+    """Run the BayesRRm oracle chain. `tape` = dict(zmu, perm, u, z); `hyper` =
+    dict(sigmaG, sigmaE, pi) to replay hyper-parameter VALUES, or None to draw
+    them with mt19937(hyper_seed) (RNG spec v1).  Returns dict of per-iteration outputs."""
+    keep = []
+
+    def k(a, dt):
+        if a is None:
+            return None
+        a = _c(a, dt)
+        keep.append(a)
+        return a.ctypes.data
+
+    out = dict(
+        beta=np.zeros((n_iter, Mtot)) if want_marker_out else None,
+        comp=np.zeros((n_iter, Mtot), np.int32) if want_marker_out else None,
+        acum=np.zeros((n_iter, Mtot)) if want_marker_out else None,
+        mu=np.zeros((n_iter, T)),
+        eps=np.zeros((n_iter, T, N)) if want_eps else None,
+        sigmaG=np.zeros((n_iter, G)), sigmaE=np.zeros(n_iter), pi=np.zeros((n_iter, G, K)),
+        bsq=np.zeros((n_iter, G)), cass=np.zeros((n_iter, G, K), np.int32), esqn=np.zeros(n_iter),
+        epssum=np.zeros((n_iter, T)), nsync=np.zeros(n_iter, np.int64), loop_seconds=np.zeros(n_iter),
+    )
+    a = _BrrArgs()
+    a.N, a.Mtot, a.T, a.K, a.G, a.sync_rate, a.n_iter, a.iter0 = N, Mtot, T, K, G, sync_rate, n_iter, 0
+    a.I1, a.N1S, a.N1L = k(sp.I1 if len(sp.I1) else np.zeros(1), np.uint32), k(sp.N1S, np.uint64), k(sp.N1L, np.uint64)
+    a.I2, a.N2S, a.N2L = k(sp.I2 if len(sp.I2) else np.zeros(1), np.uint32), k(sp.N2S, np.uint64), k(sp.N2L, np.uint64)
+    a.IM, a.NMS, a.NML = k(sp.IM if len(sp.IM) else np.zeros(1), np.uint32), k(sp.NMS, np.uint64), k(sp.NML, np.uint64)
+    a.usebed = k(usebed, np.uint8)
+    a.bed = k(bed, np.uint8)
+    a.snpLenByt = snp_len_byt(N)
+    a.y_raw, a.groups, a.mS = k(y_raw, np.float64), k(groups, np.int32), k(mS, np.float64)
+    a.tape_zmu, a.tape_perm = k(tape["zmu"], np.float64), k(tape["perm"], np.int32)
+    a.tape_u, a.tape_z = k(tape["u"], np.float64), k(tape["z"], np.float64)
+    a.tape_sigmaG0 = k(sigmaG0, np.float64)
+    if hyper is not None:
+        a.tape_sigmaG, a.tape_sigmaE, a.tape_pi = k(hyper["sigmaG"], np.float64), k(hyper["sigmaE"], np.float64), k(hyper["pi"], np.float64)
+    a.hyper_seed = hyper_seed & 0xFFFFFFFF
+    for name in ("beta", "comp", "acum", "mu", "eps", "sigmaG", "sigmaE", "pi", "bsq", "cass", "esqn", "epssum", "nsync", "loop_seconds"):
+        v = out[name]
+        setattr(a, "out_" + name, None if v is None else v.ctypes.data)
+    rc = lib(fast).ho_brr_chain(C.byref(a))
+    if rc != 0:
+        raise RuntimeError(f"ho_brr_chain failed rc={rc}")
+    return out
+
+
+def num_threads(fast=True):
+    return lib(fast).ho_num_threads()

@@ -1,0 +1,16 @@
+#!/bin/bash
+# Compiles the few reference sources that build standalone FROM
+# WHERE THEY LIE under /root/reference into oracle/_ref/ (git-ignored, travels
+# with gpurun).  No reference source is copied into the repo.  The full
+# reference (src/Makefile*) needs MPI + Eigen + Boost, none installed: unbuildable.
+set -e
+REF=${1:-/root/reference}
+OUT="$(cd "$(dirname "$0")" && pwd)/_ref"
+mkdir -p "$OUT"
+CXX=/usr/bin/g++
+# LUT generator: its stdout is the text of src/dotp_lut.h
+$CXX -O1 -w -o "$OUT/mk_lut" "$REF/src/mk_lut.cpp"
+"$OUT/mk_lut" > "$OUT/dotp_lut_generated.h"
+# ARMS sampler (BayesW): libc only
+$CXX -O2 -w -fPIC -shared -o "$OUT/libarms_ref.so" "$REF/src/BayesW_arms.cpp"
+echo "built: $(ls "$OUT")"
