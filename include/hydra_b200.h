@@ -1,0 +1,173 @@
+/*
+ * hydra_b200.h -- C ABI of the B200-native (sm_100a) per-marker Gibbs hot path
+ * of medical-genomics-group/hydra (BayesRRm / BayesW).
+ *
+ * hydra has no plugin/FFI interface: its seam is the member-function set of
+ * class BayesRRm (reference src/BayesRRm.h:116-150) plus the state of the marker
+ * loop in BayesRRm::runMpiGibbs (src/BayesRRm.cpp:933-2939).  Every entry point
+ * below names the reference code it replaces.  Plain pointers and sizes only;
+ * all host buffers are owned by the caller, all device memory by hb_ctx.
+ * The ABI is not re-entrant per ctx (one host thread per GPU, like one MPI rank).
+ *
+ * Every function returns HB_OK (0) or a negative error code; hb_last_error()
+ * returns the message of the last failure on the calling thread (the host maps
+ * it to the reference's "FATAL  : ..." line + non-zero exit, cf.
+ * src/mpi_utils.hpp:19-36 check_mpi/check_malloc -> MPI_Abort).
+ * There is NO CPU fallback: without a CUDA device every call fails loudly.
+ */
+#ifndef HYDRA_B200_H
+#define HYDRA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_OK 0
+#define HB_ERR_CUDA -1
+#define HB_ERR_ARG -2
+#define HB_ERR_STATE -3
+#define HB_ERR_NCCL -4
+#define HB_ERR_NOMEM -5
+
+#define HB_ABI_VERSION 1
+
+typedef struct hb_ctx hb_ctx;
+
+/* Genotype representation choice, src/data.cpp:886-1069 (mixed), options.hpp:86 */
+#define HB_REPR_SPARSE 0 /* all markers as index lists      (--sparse-dir/--sparse-basename) */
+#define HB_REPR_BED 1    /* all markers as 2-bit BED bytes  (dotp_lut path)                   */
+#define HB_REPR_MIXED 2  /* BED iff (n1+n2+nm)/N > threshold_fnz (src/data.cpp:931-932)       */
+
+typedef struct hb_config {
+    int32_t device;           /* CUDA device ordinal */
+    uint32_t n_ind_raw;       /* individuals in the genotype files (--number-individuals) */
+    uint32_t n_na;            /* individuals with NA phenotype (data.numNAs) */
+    const uint32_t *na_inds;  /* their raw indices, ascending (data.NAsInds, src/data.cpp:1827) */
+    uint32_t m_total;         /* Mtot (--number-markers) */
+    uint32_t n_tasks_total;   /* hydra "tasks" (= MPI ranks of the reference run being reproduced) */
+    uint32_t task_first;      /* first task hosted by this device */
+    uint32_t n_tasks_local;   /* tasks hosted by this device (contiguous) */
+    const int32_t *block_starts; /* optional --marker-blocks-file (src/data.cpp:1391-1440): n_tasks_total */
+    const int32_t *block_lens;   /*   starts (0-based) / lengths; NULL = even split, BayesRRm.cpp:396-413 */
+    uint32_t sync_rate;       /* --sync-rate (0 behaves as 1, src/BayesRRm.cpp:2044) */
+    uint32_t n_groups;        /* numGroups */
+    uint32_t n_mix;           /* K = mixtures + 1 (zero component first) */
+    int32_t repr_mode;        /* HB_REPR_* */
+    double threshold_fnz;     /* --threshold-fnz (default 0.06) */
+    uint32_t n_slices;        /* 0 = auto; individuals are split in n_slices shared-memory slices */
+    uint32_t max_ctas;        /* 0 = one CTA per SM */
+    uint32_t model;           /* 0 = BayesRRm, 1 = BayesW */
+    uint32_t reserved[7];
+} hb_config;
+
+/* ---- life cycle ------------------------------------------------------- */
+int hb_abi_version(void);
+const char *hb_last_error(void);
+int hb_create(const hb_config *cfg, hb_ctx **out);
+void hb_destroy(hb_ctx *ctx);
+/* layout facts: N after NA removal, local marker range, slices, slice length, replica groups */
+int hb_get_layout(hb_ctx *ctx, uint32_t *n_ind, uint32_t *m_start, uint32_t *m_local, uint32_t *n_slices,
+                  uint32_t *slice_len, uint32_t *n_groups_of_ctas, uint32_t *lmax);
+/* task blocks, src/BayesRRm.cpp:781-827 mpi_assign_blocks_to_tasks: arrays of n_tasks_total */
+int hb_get_task_blocks(hb_ctx *ctx, int32_t *starts, int32_t *lens);
+
+/* ---- genotype staging (replaces src/data.cpp:671-1313) ----------------- */
+/* Raw PLINK BED columns (3-byte header already skipped, snpLenByt = ceil(n_ind_raw/4) bytes
+ * per marker, src/data.cpp:685,700) for local markers [m_first, m_first+n). Decoding rule and
+ * index order are those of Data::sparse_data_fill_indices (src/data.cpp:1224-1290); NA-phenotype
+ * individuals are compacted away as in sparse_data_correct_for_missing_phenotype (:1112-1158). */
+int hb_stage_bed(hb_ctx *ctx, uint32_t m_first, uint32_t n, const uint8_t *bed_cols);
+/* Reference sparse triple (raw, i.e. NOT NA-corrected indices), src/data.cpp:742-823:
+ * starts N?S are relative to the passed I? arrays. */
+int hb_stage_sparse(hb_ctx *ctx, uint32_t m_first, uint32_t n,
+                    const uint32_t *I1, const uint64_t *N1S, const uint64_t *N1L,
+                    const uint32_t *I2, const uint64_t *N2S, const uint64_t *N2L,
+                    const uint32_t *IM, const uint64_t *NMS, const uint64_t *NML);
+/* Bench/test scaffold: counter-based synthetic genotypes generated on the device
+ * (SURVEY.md 8(d)); thresholds[n][3], attempts[n] (NULL = 0); j_global0 = global id of m_first. */
+int hb_stage_synth(hb_ctx *ctx, uint32_t m_first, uint32_t n, uint32_t seed,
+                   const uint32_t *thresholds, const uint32_t *attempts);
+/* After all local markers are staged: mave/mstd (src/BayesRRm.cpp:1502-1508; BayesW: :1211-1232) */
+int hb_stage_finalize(hb_ctx *ctx);
+
+int hb_marker_counts(hb_ctx *ctx, uint32_t *n1, uint32_t *n2, uint32_t *nm); /* m_local each */
+int hb_marker_stats(hb_ctx *ctx, double *mave, double *mstd);                /* m_local each */
+int hb_marker_is_bed(hb_ctx *ctx, uint8_t *flags);                           /* USEBED, m_local */
+uint64_t hb_genotype_bytes(hb_ctx *ctx);                                     /* HBM bytes of marker records */
+/* Round trip back to the reference representation (bit-exact parity checks and --bed-to-sparse):
+ * lists for local markers [m_first, m_first+n); starts relative to the output arrays. */
+int hb_export_sparse(hb_ctx *ctx, uint32_t m_first, uint32_t n,
+                     uint32_t *I1, uint64_t *N1S, uint64_t *N1L,
+                     uint32_t *I2, uint64_t *N2S, uint64_t *N2L,
+                     uint32_t *IM, uint64_t *NMS, uint64_t *NML);
+/* NA-compacted BED bytes of one marker (ceil(N/4) bytes, pad bits 00), src/data.cpp:826-865 */
+int hb_export_bed(hb_ctx *ctx, uint32_t m, uint8_t *out);
+
+/* ---- unit-level kernels (parity tests; reference member functions) ------ */
+int hb_set_epsilon(hb_ctx *ctx, const double *eps); /* N doubles */
+int hb_get_epsilon(hb_ctx *ctx, double *eps);
+/* num[i] = mstd*(x_j . eps), centred/scaled column: BayesRRm::sparse_dotprod (src/BayesRRm.cpp:316-342)
+ * for list markers, the dotp_lut loop (:1757-1809) for BED markers */
+int hb_dot_markers(hb_ctx *ctx, const uint32_t *markers, uint32_t n, double *num);
+/* eps += sum_i deltaEps(marker_i, dbeta_i): sparse_scaadd (:250-281) / LUT deltaEps (:1976-2010)
+ * followed by sum_vectors_f64 (:2022) and the epsilon update (:2460-2471) */
+int hb_scaadd_markers(hb_ctx *ctx, const uint32_t *markers, const double *dbeta, uint32_t n);
+
+/* ---- BayesRRm chain (src/BayesRRm.cpp:1565-2731) ------------------------- */
+/* y: N raw phenotypes (centred and scaled inside, :371-388); groups: m_total ints; mS: n_groups*n_mix
+ * row-major with column 0 = 0; sigmaG0: initial sigmaG per group (:1233), NULL = draw by RNG spec v1 */
+int hb_brr_init(hb_ctx *ctx, const double *y, const int32_t *groups, const double *mS,
+                const double *sigmaG0, uint32_t seed);
+
+typedef struct hb_brr_tape {
+    /* positional draw tape for ONE iteration, local tasks only (DESIGN.md "Draw tape") */
+    const double *zmu;    /* n_tasks_local standard normals for mu (:1682) */
+    const int32_t *perm;  /* m_local: marker order of each local task block, task-local indices (:1692) */
+    const double *u;      /* m_local: U(0,1) of the marker processed at step j of each task (:1880) */
+    const double *z;      /* m_local: standard normal for beta (:1901), used iff component > 0 */
+    const double *sigmaG; /* n_groups values AFTER this iteration (:2570), NULL = draw */
+    const double *pi;     /* n_groups*n_mix (:2577), NULL = draw */
+    const double *sigmaE; /* 1 value (:2690), NULL = draw */
+} hb_brr_tape;
+
+typedef struct hb_brr_iter_out {
+    double sigmaE;        /* after the iteration */
+    double e_sqn;         /* sum eps^2 of task 0 (:2685-2686) */
+    double epssum;        /* sum of (eps + mu) at iteration start (:1677-1678) */
+    double loop_ms;       /* device time of the marker loop (CUDA events) */
+    double iter_ms;       /* device time of the whole iteration */
+    uint64_t n_sync;      /* epsilon synchronisations performed (:2069) */
+    uint64_t n_windows;   /* sync windows processed */
+    uint64_t n_launches;  /* kernels launched by this call */
+    uint64_t nnz_processed;   /* stored non-zeros visited by the dot products */
+    uint64_t nnz_updated;     /* stored non-zeros visited by epsilon updates */
+    uint64_t bed_markers;     /* markers processed through the BED path */
+    uint64_t markers_changed; /* markers with deltaBeta != 0 */
+} hb_brr_iter_out;
+
+/* One Gibbs iteration: mu, marker loop (sync windows), group statistics, hyper-parameters.
+ * tape == NULL: RNG spec v1 (host mt19937 streams + device Philox). Per-group / per-task results
+ * are fetched with hb_brr_get_hyper / hb_brr_get_state. */
+int hb_brr_iteration(hb_ctx *ctx, const hb_brr_tape *tape, hb_brr_iter_out *out);
+int hb_brr_get_hyper(hb_ctx *ctx, double *sigmaG, double *pi, double *sigmaE, double *mu_tasks_local,
+                     double *bsq, int32_t *cass, int32_t *m0);
+/* Beta, components, Acum of the local markers (the slices written to .bet/.cpn/.acu, :2779-2785) */
+int hb_brr_get_state(hb_ctx *ctx, double *beta, int32_t *components, double *acum);
+int hb_brr_set_state(hb_ctx *ctx, const double *beta, const int32_t *components); /* --restart */
+/* epsilon of local task t as the reference dumps it to .eps.<rank> (:2827) */
+int hb_brr_get_task_epsilon(hb_ctx *ctx, uint32_t task_local, double *eps);
+/* current marker order of local task t (.mrk.<rank>, :2828) */
+int hb_brr_get_task_perm(hb_ctx *ctx, uint32_t task_local, int32_t *perm);
+
+/* ---- multi-GPU (replaces MPI_Allreduce, src/BayesRRm.cpp:2051,2456,2517-2518) --- */
+#define HB_NCCL_ID_BYTES 128
+int hb_comm_get_unique_id(uint8_t id[HB_NCCL_ID_BYTES]);
+int hb_comm_init(hb_ctx *ctx, const uint8_t id[HB_NCCL_ID_BYTES], int rank, int nranks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYDRA_B200_H */
