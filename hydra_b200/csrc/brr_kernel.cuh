@@ -217,7 +217,7 @@ __device__ void draw_marker(const BrrParams &P, uint32_t p, uint32_t q, int32_t 
         atomicAdd(&P.cass[g * K + comp], 1);                                         // :1904
     }
     P.beta[m] = beta_new;
-    P.comp[m] = comp;
+    if (P.grp_active[g]) P.comp[m] = comp;  // :1924-1925 leave components untouched
     P.acum[m] = acum;
     const double dbeta = beta_old - beta_new;                                        // :1933
     P.dB[(size_t)dbuf * P.Wmax + p] = (dbeta != 0.0) ? __dmul_rn(dbeta, mstd) : 0.0;
@@ -423,14 +423,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
 }
 
 // ---------------------------------------------------------------------------------
-// Per-marker positional draws of RNG spec v1, written in window order q = j*T + t.
-__global__ void k_marker_draws(uint32_t seed, uint32_t iteration, uint32_t task_first, uint32_t T,
-                               const int32_t *__restrict__ task_len, uint32_t lmax, double *__restrict__ u,
-                               double *__restrict__ z) {
+// Window-ordered inputs of one iteration: order[q], u[q], z[q] with q = j*T + t.
+// perm holds the task-local marker order of every local task block (concatenated);
+// ut/zt != NULL: positional tape values indexed like perm; else RNG spec v1 (Philox).
+__global__ void k_window_order(const int32_t *__restrict__ perm, const double *__restrict__ ut,
+                               const double *__restrict__ zt, const int32_t *__restrict__ task_len,
+                               const int32_t *__restrict__ task_off, uint32_t T, uint32_t lmax, uint32_t seed,
+                               uint32_t iteration, uint32_t task_first, int32_t *__restrict__ order,
+                               double *__restrict__ u, double *__restrict__ z) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= lmax * T) return;
     const uint32_t t = q % T, j = q / T;
-    if ((int32_t)j >= task_len[t]) { u[q] = 0.0; z[q] = 0.0; return; }
+    if ((int32_t)j >= task_len[t]) { order[q] = -1; u[q] = 0.0; z[q] = 0.0; return; }  // :2029-2034
+    const uint32_t o = (uint32_t)task_off[t] + j;
+    order[q] = task_off[t] + perm[o];
+    if (ut) { u[q] = ut[o]; z[q] = zt[o]; return; }
     uint32_t w[4];
     philox4x32(j, iteration, 0x48594452u, 0u, seed, task_first + t, w);
     u[q] = ((double)(w[0] >> 5) * 67108864.0 + (double)(w[1] >> 6)) * (1.0 / 9007199254740992.0);

@@ -57,7 +57,7 @@ __host__ __device__ inline uint32_t dir_bytes(uint32_t S) { return (12u * S + 15
 
 constexpr int kMaxMix = 16;      // K <= 16 mixture components (incl. zero)
 constexpr int kThreads = 1024;   // threads per CTA of the sampler kernel
-constexpr int kTabCap = 1024;    // window items staged per table chunk
+constexpr int kTabCap = 128;     // window items staged per table chunk
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- device helpers

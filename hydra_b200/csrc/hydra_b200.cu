@@ -1,0 +1,1018 @@
+// hydra_b200.cu -- C ABI (include/hydra_b200.h) of the B200-native BayesRRm hot path.
+// Host side: context, genotype staging, per-iteration driver of the window kernel.
+// There is no CPU fallback in this file: every entry point needs a CUDA device.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <memory>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "brr_kernel.cuh"
+#include "common.cuh"
+#include "convert.cuh"
+#include "host_rng.hpp"
+
+namespace hb {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    int alloc(size_t count) {
+        release();
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+            p = nullptr;
+            return HB_ERR_NOMEM;
+        }
+        n = count;
+        return HB_OK;
+    }
+    int ensure(size_t count) { return (count <= n && p) ? HB_OK : alloc(count); }
+    int zero(cudaStream_t s) {
+        HB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+        return HB_OK;
+    }
+};
+
+}  // namespace hb
+
+using namespace hb;
+
+struct hb_ctx {
+    hb_config cfg{};
+    int dev = 0, n_sms = 0;
+    uint32_t Nraw = 0, N = 0, S = 0, L = 0, R = 0;
+    uint32_t Mtot = 0, M = 0, m_start = 0;          // local markers [m_start, m_start+M)
+    uint32_t Ttot = 0, T = 0, t_first = 0, lmax = 0; // tasks
+    uint32_t K = 0, G = 0, SR = 1;
+    std::vector<int32_t> blkS, blkL;                // all tasks (global marker ids)
+    std::vector<uint32_t> na;
+    size_t smem_bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
+    // genotype records
+    DevBuf<uint32_t> d_rmap;
+    DevBuf<uint64_t> d_rec;
+    DevBuf<double> d_mave, d_mstd;
+    DevBuf<int32_t> d_grp;
+    std::vector<void *> arenas;
+    std::vector<uint32_t> n1, n2, nm;
+    std::vector<uint8_t> is_bed, staged;
+    std::vector<uint64_t> rec_h;
+    std::vector<double> mave_h, mstd_h;
+    uint64_t geno_bytes = 0;
+    bool finalized = false;
+    // staging scratch
+    DevBuf<uint8_t> d_raw;
+    DevBuf<uint32_t> d_cnt3, d_start, d_meta;
+
+    // epsilon
+    DevBuf<double> d_E[2];
+    int cur = 0;
+    double shift = 0.0;  // true eps(task 0) = E + shift
+    DevBuf<double> d_small;  // [0]=off, [1..S]=slice_sum, [1+S..2S]=slice_sq, then bsq[G]
+    std::vector<double> slice_sum_h;
+    bool eps_set = false;
+
+    // marker state
+    DevBuf<double> d_beta, d_acum;
+    DevBuf<int32_t> d_comp, d_cass;
+    // per-iteration inputs
+    DevBuf<int32_t> d_order, d_perm, d_task_len, d_task_off;
+    DevBuf<double> d_u, d_z, d_ut, d_zt;
+    DevBuf<double> d_hyp;
+    DevBuf<uint8_t> d_active;
+    // scratch
+    DevBuf<double> d_partial, d_dB, d_num;
+    DevBuf<uint32_t> d_cntr, d_bar, d_markers;
+    DevBuf<unsigned long long> d_stats;
+    uint32_t Wmax = 0;
+
+    // chain (host)
+    bool brr_ready = false;
+    uint32_t seed = 0, iteration = 0;
+    std::vector<double> cVa, cVaI, pi, sigmaG, mu, bsq;
+    std::vector<int32_t> cass, m0, MtotGrp, groups_local;
+    std::vector<uint8_t> active;
+    double sigmaE = 0.0;
+    std::vector<HostRng> task_rng;
+    HostRng hyper_rng;
+    std::vector<int32_t> perm;  // M: task-local order per local task block
+    double *pin = nullptr;      // pinned host scratch
+    size_t pin_n = 0;
+
+    ~hb_ctx() {
+        for (void *a : arenas) cudaFree(a);
+        if (pin) cudaFreeHost(pin);
+        for (auto &e : ev)
+            if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace hb {
+
+// contiguous blocks, first Mtot % n tasks get one extra marker (src/BayesRRm.cpp:396-413)
+static void define_blocks(uint32_t Mtot, uint32_t nblocks, std::vector<int32_t> &S, std::vector<int32_t> &Lb) {
+    S.resize(nblocks);
+    Lb.resize(nblocks);
+    const uint32_t modu = Mtot % nblocks;
+    uint32_t start = 0;
+    for (uint32_t i = 0; i < nblocks; ++i) {
+        Lb[i] = (int32_t)(Mtot / nblocks) + ((modu != 0 && i < modu) ? 1 : 0);
+        S[i] = (int32_t)start;
+        start += (uint32_t)Lb[i];
+    }
+}
+
+static size_t smem_for(uint32_t L) { return (((size_t)L + 2) * 8 + 15) / 16 * 16 + sizeof(ItemTab); }
+
+static int ensure_scratch(hb_ctx *c, uint32_t W) {
+    if (W <= c->Wmax) return HB_OK;
+    W = (W + 255u) & ~255u;
+    HB_TRY(c->d_partial.alloc((size_t)W * c->S));
+    HB_TRY(c->d_cntr.alloc(W));
+    HB_TRY(c->d_dB.alloc((size_t)2 * W));
+    HB_TRY(c->d_cntr.zero(c->stream));
+    HB_TRY(c->d_dB.zero(c->stream));
+    c->Wmax = W;
+    return HB_OK;
+}
+
+static int ensure_pin(hb_ctx *c, size_t n) {
+    if (n <= c->pin_n) return HB_OK;
+    if (c->pin) cudaFreeHost(c->pin);
+    c->pin = nullptr;
+    HB_CUDA(cudaMallocHost((void **)&c->pin, n * sizeof(double)));
+    c->pin_n = n;
+    return HB_OK;
+}
+
+static void fill_params(hb_ctx *c, BrrParams &P) {
+    memset(&P, 0, sizeof(P));
+    P.N = c->N; P.S = c->S; P.L = c->L; P.R = c->R; P.M = c->M;
+    P.rec = c->d_rec.p; P.mave = c->d_mave.p; P.mstd = c->d_mstd.p; P.grp = c->d_grp.p;
+    P.E_in = c->d_E[c->cur].p; P.E_out = c->d_E[c->cur ^ 1].p;
+    P.shift_in = 0.0;
+    P.off_out = c->d_small.p;
+    P.slice_sum_out = c->d_small.p + 1;
+    P.slice_sq_out = c->d_small.p + 1 + c->S;
+    P.beta = c->d_beta.p; P.comp = c->d_comp.p; P.acum = c->d_acum.p; P.cass = c->d_cass.p;
+    P.order = c->d_order.p; P.u = c->d_u.p; P.z = c->d_z.p;
+    P.T = 1; P.SR = 1; P.lmax = 0; P.K = c->K; P.G = c->G;
+    const size_t gk = (size_t)c->G * c->K;
+    P.logPi = c->d_hyp.p; P.chalf = c->d_hyp.p + gk; P.denom = c->d_hyp.p + 2 * gk; P.sdk = c->d_hyp.p + 3 * gk;
+    P.grp_active = c->d_active.p;
+    P.dNm1 = (double)(c->N - 1);
+    P.partial = c->d_partial.p; P.cnt = c->d_cntr.p; P.dB = c->d_dB.p; P.Wmax = c->Wmax;
+    P.bar = c->d_bar.p; P.stats = c->d_stats.p;
+    P.mode = MODE_CHAIN;
+    P.num_out = c->d_num.p;
+}
+
+static int launch_window_kernel(hb_ctx *c, BrrParams &P) {
+    HB_CUDA(cudaMemsetAsync(c->d_bar.p, 0, sizeof(uint32_t), c->stream));
+    void *args[] = {(void *)&P};
+    dim3 grid(c->S * c->R), block(kThreads);
+    HB_CUDA(cudaLaunchCooperativeKernel((const void *)k_brr_iteration, grid, block, args, c->smem_bytes, c->stream));
+    return HB_OK;
+}
+
+}  // namespace hb
+
+extern "C" {
+
+int hb_abi_version(void) { return HB_ABI_VERSION; }
+int hb_sizeof_config(void) { return (int)sizeof(hb_config); }
+int hb_sizeof_iter_out(void) { return (int)sizeof(hb_brr_iter_out); }
+const char *hb_last_error(void) { return g_err; }
+
+int hb_create(const hb_config *cfg, hb_ctx **out) {
+    HB_CHECK(cfg && out, HB_ERR_ARG, "hb_create: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    HB_CHECK(e == cudaSuccess && ndev > 0, HB_ERR_CUDA,
+             "hb_create: no CUDA device (%s); hydra_b200 has no CPU fallback", cudaGetErrorString(e));
+    HB_CHECK(cfg->device >= 0 && cfg->device < ndev, HB_ERR_ARG, "hb_create: device %d out of range (%d devices)", cfg->device, ndev);
+    HB_CHECK(cfg->n_ind_raw > cfg->n_na + 1, HB_ERR_ARG, "hb_create: need at least 2 individuals with a phenotype");
+    HB_CHECK(cfg->m_total > 0, HB_ERR_ARG, "hb_create: m_total == 0");
+    HB_CHECK(cfg->n_tasks_total > 0 && cfg->n_tasks_local > 0 && cfg->task_first + cfg->n_tasks_local <= cfg->n_tasks_total,
+             HB_ERR_ARG, "hb_create: bad task layout (total %u first %u local %u)", cfg->n_tasks_total, cfg->task_first, cfg->n_tasks_local);
+    HB_CHECK(cfg->n_tasks_total <= cfg->m_total, HB_ERR_ARG, "hb_create: more tasks than markers");
+    HB_CHECK(cfg->n_groups >= 1 && cfg->n_mix >= 2 && cfg->n_mix <= (uint32_t)kMaxMix, HB_ERR_ARG,
+             "hb_create: n_groups >= 1 and 2 <= n_mix <= %d required", kMaxMix);
+    HB_CHECK(cfg->repr_mode >= 0 && cfg->repr_mode <= 2, HB_ERR_ARG, "hb_create: bad repr_mode");
+    HB_CHECK(cfg->n_na == 0 || cfg->na_inds, HB_ERR_ARG, "hb_create: n_na > 0 but na_inds == NULL");
+    HB_CHECK(cfg->model == 0, HB_ERR_ARG, "hb_create: model %u not available in this build", cfg->model);
+
+    std::unique_ptr<hb_ctx> c(new (std::nothrow) hb_ctx);
+    HB_CHECK(c, HB_ERR_NOMEM, "hb_create: out of host memory");
+    c->cfg = *cfg;
+    c->cfg.na_inds = nullptr; c->cfg.block_starts = nullptr; c->cfg.block_lens = nullptr;
+    c->dev = cfg->device;
+    HB_CUDA(cudaSetDevice(c->dev));
+    cudaDeviceProp prop;
+    HB_CUDA(cudaGetDeviceProperties(&prop, c->dev));
+    HB_CHECK(prop.major >= 10, HB_ERR_CUDA, "hb_create: device %d is sm_%d%d; this library is built for sm_100a only", c->dev, prop.major, prop.minor);
+    HB_CHECK(prop.cooperativeLaunch, HB_ERR_CUDA, "hb_create: device lacks cooperative launch");
+    c->n_sms = prop.multiProcessorCount;
+    c->Nraw = cfg->n_ind_raw;
+    c->N = cfg->n_ind_raw - cfg->n_na;
+    c->Mtot = cfg->m_total; c->Ttot = cfg->n_tasks_total; c->T = cfg->n_tasks_local; c->t_first = cfg->task_first;
+    c->K = cfg->n_mix; c->G = cfg->n_groups; c->SR = cfg->sync_rate == 0 ? 1u : cfg->sync_rate;
+
+    // NA individuals (ascending, unique)
+    c->na.assign(cfg->na_inds, cfg->na_inds + cfg->n_na);
+    for (uint32_t i = 0; i < cfg->n_na; i++) {
+        HB_CHECK(c->na[i] < c->Nraw && (i == 0 || c->na[i] > c->na[i - 1]), HB_ERR_ARG, "hb_create: na_inds must be ascending, unique, < n_ind_raw");
+    }
+    // task blocks
+    if (cfg->block_starts && cfg->block_lens) {
+        c->blkS.assign(cfg->block_starts, cfg->block_starts + c->Ttot);
+        c->blkL.assign(cfg->block_lens, cfg->block_lens + c->Ttot);
+        int64_t pos = 0;
+        for (uint32_t t = 0; t < c->Ttot; t++) {
+            HB_CHECK(c->blkS[t] == pos && c->blkL[t] >= 0, HB_ERR_ARG, "hb_create: marker blocks must be contiguous and ordered (task %u)", t);
+            pos += c->blkL[t];
+        }
+        HB_CHECK(pos == (int64_t)c->Mtot, HB_ERR_ARG, "hb_create: marker blocks do not cover m_total");
+    } else {
+        define_blocks(c->Mtot, c->Ttot, c->blkS, c->blkL);
+    }
+    c->lmax = 0;
+    for (uint32_t t = 0; t < c->Ttot; t++) c->lmax = std::max(c->lmax, (uint32_t)c->blkL[t]);  // global lmax (lock-step)
+    c->m_start = (uint32_t)c->blkS[c->t_first];
+    c->M = 0;
+    for (uint32_t t = 0; t < c->T; t++) c->M += (uint32_t)c->blkL[c->t_first + t];
+    HB_CHECK(c->M > 0, HB_ERR_ARG, "hb_create: no local markers");
+
+    // slices: smallest S whose slice fits in shared memory next to the item table
+    int max_smem = 0;
+    HB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->dev));
+    cudaFuncAttributes fa;
+    HB_CUDA(cudaFuncGetAttributes(&fa, (const void *)k_brr_iteration));
+    const size_t avail = (size_t)max_smem - fa.sharedSizeBytes;
+    uint32_t max_ctas = cfg->max_ctas ? std::min<uint32_t>(cfg->max_ctas, c->n_sms) : (uint32_t)c->n_sms;
+    uint32_t S = cfg->n_slices ? cfg->n_slices : 1;
+    for (;; S++) {
+        uint32_t L = ((c->N + S - 1) / S + 63u) & ~63u;
+        if (L <= 65472u && smem_for(L) <= avail) { c->S = S; c->L = L; break; }
+        HB_CHECK(cfg->n_slices == 0, HB_ERR_ARG, "hb_create: n_slices=%u gives slices of %u individuals, too large for shared memory", S, L);
+        HB_CHECK(S < max_ctas, HB_ERR_ARG, "hb_create: %u individuals do not fit in the shared memory of %u CTAs", c->N, max_ctas);
+    }
+    HB_CHECK(c->S <= max_ctas, HB_ERR_ARG, "hb_create: %u slices > %u CTAs", c->S, max_ctas);
+    c->R = max_ctas / c->S;
+    c->smem_bytes = smem_for(c->L);
+    HB_CUDA(cudaFuncSetAttribute((const void *)k_brr_iteration, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    int occ = 0;
+    HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)k_brr_iteration, kThreads, c->smem_bytes));
+    HB_CHECK(occ >= 1, HB_ERR_CUDA, "hb_create: sampler kernel does not fit on an SM (smem %zu)", c->smem_bytes);
+    // with small slices several CTAs may share an SM; co-residency only needs S*R <= occ*SMs (true: S*R <= SMs)
+
+    HB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto &ev : c->ev) HB_CUDA(cudaEventCreate(&ev));
+
+    // compacted individual -> raw individual
+    if (c->na.size()) {
+        std::vector<uint32_t> rmap(c->N);
+        uint32_t k = 0, w = 0;
+        for (uint32_t i = 0; i < c->Nraw; i++) {
+            if (k < c->na.size() && c->na[k] == i) { k++; continue; }
+            rmap[w++] = i;
+        }
+        HB_TRY(c->d_rmap.alloc(c->N));
+        HB_CUDA(cudaMemcpy(c->d_rmap.p, rmap.data(), sizeof(uint32_t) * c->N, cudaMemcpyHostToDevice));
+    }
+    const size_t M = c->M;
+    HB_TRY(c->d_rec.alloc(M)); HB_TRY(c->d_mave.alloc(M)); HB_TRY(c->d_mstd.alloc(M)); HB_TRY(c->d_grp.alloc(M));
+    HB_CUDA(cudaMemset(c->d_grp.p, 0, sizeof(int32_t) * M));
+    c->n1.assign(M, 0); c->n2.assign(M, 0); c->nm.assign(M, 0);
+    c->is_bed.assign(M, 0); c->staged.assign(M, 0); c->rec_h.assign(M, 0);
+    HB_TRY(c->d_E[0].alloc((size_t)c->S * c->L)); HB_TRY(c->d_E[1].alloc((size_t)c->S * c->L));
+    HB_CUDA(cudaMemset(c->d_E[0].p, 0, sizeof(double) * c->S * c->L));
+    HB_CUDA(cudaMemset(c->d_E[1].p, 0, sizeof(double) * c->S * c->L));
+    HB_TRY(c->d_small.alloc(1 + 2 * (size_t)c->S + c->G));
+    HB_CUDA(cudaMemset(c->d_small.p, 0, sizeof(double) * c->d_small.n));
+    c->slice_sum_h.assign(c->S, 0.0);
+    HB_TRY(c->d_beta.alloc(M)); HB_TRY(c->d_acum.alloc(M)); HB_TRY(c->d_comp.alloc(M));
+    HB_CUDA(cudaMemset(c->d_beta.p, 0, sizeof(double) * M));
+    HB_CUDA(cudaMemset(c->d_acum.p, 0, sizeof(double) * M));
+    HB_CUDA(cudaMemset(c->d_comp.p, 0, sizeof(int32_t) * M));
+    const size_t gk = (size_t)c->G * c->K;
+    HB_TRY(c->d_cass.alloc(gk)); HB_TRY(c->d_hyp.alloc(4 * gk)); HB_TRY(c->d_active.alloc(c->G));
+    HB_CUDA(cudaMemset(c->d_cass.p, 0, sizeof(int32_t) * gk));
+    HB_CUDA(cudaMemset(c->d_hyp.p, 0, sizeof(double) * 4 * gk));
+    HB_CUDA(cudaMemset(c->d_active.p, 0, c->G));
+    HB_TRY(c->d_bar.alloc(1)); HB_TRY(c->d_stats.alloc(8));
+    HB_CUDA(cudaMemset(c->d_stats.p, 0, 8 * sizeof(unsigned long long)));
+    HB_TRY(c->d_order.alloc(1)); HB_TRY(c->d_u.alloc(1)); HB_TRY(c->d_z.alloc(1)); HB_TRY(c->d_num.alloc(1));
+    HB_TRY(ensure_scratch(c.get(), 256));
+    HB_TRY(ensure_pin(c.get(), 4096));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    *out = c.release();
+    return HB_OK;
+}
+
+void hb_destroy(hb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->dev);
+    cudaDeviceSynchronize();
+    delete ctx;
+}
+
+int hb_get_layout(hb_ctx *c, uint32_t *n_ind, uint32_t *m_start, uint32_t *m_local, uint32_t *n_slices,
+                  uint32_t *slice_len, uint32_t *n_groups_of_ctas, uint32_t *lmax) {
+    HB_CHECK(c, HB_ERR_ARG, "null ctx");
+    if (n_ind) *n_ind = c->N;
+    if (m_start) *m_start = c->m_start;
+    if (m_local) *m_local = c->M;
+    if (n_slices) *n_slices = c->S;
+    if (slice_len) *slice_len = c->L;
+    if (n_groups_of_ctas) *n_groups_of_ctas = c->R;
+    if (lmax) *lmax = c->lmax;
+    return HB_OK;
+}
+
+int hb_get_task_blocks(hb_ctx *c, int32_t *starts, int32_t *lens) {
+    HB_CHECK(c && starts && lens, HB_ERR_ARG, "null argument");
+    std::copy(c->blkS.begin(), c->blkS.end(), starts);
+    std::copy(c->blkL.begin(), c->blkL.end(), lens);
+    return HB_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------
+// staging
+// ------------------------------------------------------------------------------------
+namespace hb {
+
+static inline size_t raw_stride(uint32_t Nraw) { return ((size_t)(Nraw + 3) / 4 + 15) & ~(size_t)15; }
+
+// d_raw holds n raw BED columns (stride raw_stride): build the records of local markers [m_first, m_first+n)
+static int records_from_raw(hb_ctx *c, uint32_t m_first, uint32_t n) {
+    const size_t stride = raw_stride(c->Nraw);
+    const uint32_t S = c->S, L = c->L;
+    HB_TRY(c->d_cnt3.ensure((size_t)n * S * 3));
+    HB_TRY(c->d_start.ensure((size_t)n * S));
+    HB_TRY(c->d_meta.ensure((size_t)n * 4));
+    k_count<<<n, 256, 0, c->stream>>>(c->d_raw.p, stride, c->d_rmap.p, c->N, S, L, c->d_cnt3.p, c->d_start.p, c->d_meta.p);
+    HB_CUDA(cudaGetLastError());
+    std::vector<uint32_t> meta((size_t)n * 4);
+    HB_CUDA(cudaMemcpyAsync(meta.data(), c->d_meta.p, sizeof(uint32_t) * 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    size_t total = 0;
+    std::vector<size_t> off(n);
+    const size_t bed_bytes = (size_t)S * L / 4;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t m = m_first + i;
+        c->n1[m] = meta[i * 4 + 0]; c->n2[m] = meta[i * 4 + 1]; c->nm[m] = meta[i * 4 + 2];
+        bool bed = false;
+        if (c->cfg.repr_mode == HB_REPR_BED) bed = true;
+        else if (c->cfg.repr_mode == HB_REPR_MIXED)  // src/data.cpp:931-932
+            bed = ((double)(c->n1[m] + c->n2[m] + c->nm[m]) / (double)c->N) > c->cfg.threshold_fnz;
+        c->is_bed[m] = bed ? 1 : 0;
+        const size_t bytes = bed ? bed_bytes : (dir_bytes(S) + 8 * (size_t)meta[i * 4 + 3]);
+        off[i] = total;
+        total += (bytes + 15) & ~(size_t)15;
+    }
+    void *arena = nullptr;
+    cudaError_t e = cudaMalloc(&arena, std::max<size_t>(total, 16));
+    HB_CHECK(e == cudaSuccess, HB_ERR_NOMEM, "genotype arena of %zu bytes: %s", total, cudaGetErrorString(e));
+    c->arenas.push_back(arena);
+    c->geno_bytes += total;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t m = m_first + i;
+        c->rec_h[m] = (uint64_t)((uintptr_t)arena + off[i]) | (c->is_bed[m] ? 1ull : 0ull);
+        c->staged[m] = 1;
+    }
+    HB_CUDA(cudaMemcpyAsync(c->d_rec.p + m_first, c->rec_h.data() + m_first, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, c->stream));
+    k_fill_sparse<<<n, 256, 0, c->stream>>>(c->d_raw.p, stride, c->d_rmap.p, c->N, S, L, c->d_cnt3.p, c->d_start.p, c->d_meta.p,
+                                            c->d_rec.p + m_first);
+    HB_CUDA(cudaGetLastError());
+    dim3 g((S * L / 16 + 255) / 256, n);
+    k_fill_bed<<<g, 256, 0, c->stream>>>(c->d_raw.p, stride, c->d_rmap.p, c->N, S, L, c->d_rec.p + m_first);
+    HB_CUDA(cudaGetLastError());
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    c->finalized = false;
+    return HB_OK;
+}
+
+static uint32_t stage_chunk(hb_ctx *c) {
+    const size_t stride = raw_stride(c->Nraw);
+    size_t ch = ((size_t)768 << 20) / stride;
+    ch = std::max<size_t>(1, std::min<size_t>(ch, 32768));
+    return (uint32_t)ch;
+}
+
+static int check_range(hb_ctx *c, uint32_t m_first, uint32_t n) {
+    HB_CHECK(c, HB_ERR_ARG, "null ctx");
+    HB_CHECK((uint64_t)m_first + n <= c->M, HB_ERR_ARG, "marker range [%u,+%u) outside the %u local markers", m_first, n, c->M);
+    return HB_OK;
+}
+
+}  // namespace hb
+
+extern "C" {
+
+int hb_stage_bed(hb_ctx *c, uint32_t m_first, uint32_t n, const uint8_t *bed_cols) {
+    HB_TRY(check_range(c, m_first, n));
+    HB_CHECK(bed_cols || n == 0, HB_ERR_ARG, "hb_stage_bed: null data");
+    HB_CUDA(cudaSetDevice(c->dev));
+    const size_t nb = (size_t)(c->Nraw + 3) / 4, stride = raw_stride(c->Nraw);
+    const uint32_t ch = stage_chunk(c);
+    for (uint32_t o = 0; o < n; o += ch) {
+        const uint32_t k = std::min(ch, n - o);
+        HB_TRY(c->d_raw.ensure((size_t)k * stride));
+        HB_CUDA(cudaMemcpy2DAsync(c->d_raw.p, stride, bed_cols + (size_t)o * nb, nb, nb, k, cudaMemcpyHostToDevice, c->stream));
+        HB_TRY(records_from_raw(c, m_first + o, k));
+    }
+    return HB_OK;
+}
+
+int hb_stage_sparse(hb_ctx *c, uint32_t m_first, uint32_t n,
+                    const uint32_t *I1, const uint64_t *N1S, const uint64_t *N1L,
+                    const uint32_t *I2, const uint64_t *N2S, const uint64_t *N2L,
+                    const uint32_t *IM, const uint64_t *NMS, const uint64_t *NML) {
+    HB_TRY(check_range(c, m_first, n));
+    HB_CHECK(N1S && N1L && N2S && N2L && NMS && NML, HB_ERR_ARG, "hb_stage_sparse: null start/length arrays");
+    HB_CUDA(cudaSetDevice(c->dev));
+    const size_t stride = raw_stride(c->Nraw);
+    const uint32_t ch = stage_chunk(c);
+    const uint32_t *I[3] = {I1, I2, IM};
+    const uint64_t *NS[3] = {N1S, N2S, NMS}, *NL[3] = {N1L, N2L, NML};
+    const uint32_t mask[3] = {1u, 3u, 2u};  // XOR masks of src/data.cpp:839-864
+    DevBuf<uint32_t> d_I;
+    DevBuf<uint64_t> d_S, d_L;
+    for (uint32_t o = 0; o < n; o += ch) {
+        const uint32_t k = std::min(ch, n - o);
+        HB_TRY(c->d_raw.ensure((size_t)k * stride));
+        HB_CUDA(cudaMemsetAsync(c->d_raw.p, 0xFF, (size_t)k * stride, c->stream));
+        HB_TRY(d_S.ensure(k)); HB_TRY(d_L.ensure(k));
+        for (int w = 0; w < 3; w++) {
+            // the chunk's entries span [lo, hi) of the list array
+            uint64_t lo = ~0ull, hi = 0, maxl = 0;
+            for (uint32_t i = 0; i < k; i++) {
+                const uint64_t s = NS[w][o + i], l = NL[w][o + i];
+                if (l == 0) continue;
+                lo = std::min(lo, s); hi = std::max(hi, s + l); maxl = std::max(maxl, l);
+            }
+            if (hi == 0) continue;
+            HB_CHECK(I[w], HB_ERR_ARG, "hb_stage_sparse: null index array with non-empty lists");
+            std::vector<uint64_t> rs(k);
+            for (uint32_t i = 0; i < k; i++) rs[i] = NL[w][o + i] ? NS[w][o + i] - lo : 0;
+            HB_TRY(d_I.ensure(hi - lo));
+            HB_CUDA(cudaMemcpyAsync(d_I.p, I[w] + lo, sizeof(uint32_t) * (hi - lo), cudaMemcpyHostToDevice, c->stream));
+            HB_CUDA(cudaMemcpyAsync(d_S.p, rs.data(), sizeof(uint64_t) * k, cudaMemcpyHostToDevice, c->stream));
+            HB_CUDA(cudaMemcpyAsync(d_L.p, NL[w] + o, sizeof(uint64_t) * k, cudaMemcpyHostToDevice, c->stream));
+            // index validity is checked on the host (cheap, and a bad index would corrupt device memory)
+            for (uint64_t x = lo; x < hi; x++)
+                HB_CHECK(I[w][x] < c->Nraw, HB_ERR_ARG, "hb_stage_sparse: index %u >= number of individuals %u", I[w][x], c->Nraw);
+            dim3 g((unsigned)std::min<uint64_t>((maxl + 255) / 256, 64), k);
+            k_lists_to_bed<<<g, 256, 0, c->stream>>>(c->d_raw.p, stride, d_I.p, d_S.p, d_L.p, mask[w]);
+            HB_CUDA(cudaGetLastError());
+            HB_CUDA(cudaStreamSynchronize(c->stream));  // rs / host arrays reused
+        }
+        HB_TRY(records_from_raw(c, m_first + o, k));
+    }
+    return HB_OK;
+}
+
+int hb_stage_synth(hb_ctx *c, uint32_t m_first, uint32_t n, uint32_t seed, const uint32_t *thresholds,
+                   const uint32_t *attempts) {
+    HB_TRY(check_range(c, m_first, n));
+    HB_CHECK(thresholds, HB_ERR_ARG, "hb_stage_synth: null thresholds");
+    HB_CUDA(cudaSetDevice(c->dev));
+    const size_t stride = raw_stride(c->Nraw);
+    const uint32_t nb = (c->Nraw + 3) / 4;
+    const uint32_t ch = std::min<uint32_t>(stage_chunk(c), 65535u);
+    DevBuf<uint32_t> d_thr, d_att;
+    for (uint32_t o = 0; o < n; o += ch) {
+        const uint32_t k = std::min(ch, n - o);
+        HB_TRY(c->d_raw.ensure((size_t)k * stride));
+        HB_TRY(d_thr.ensure((size_t)k * 3));
+        HB_CUDA(cudaMemcpyAsync(d_thr.p, thresholds + (size_t)o * 3, sizeof(uint32_t) * 3 * k, cudaMemcpyHostToDevice, c->stream));
+        if (attempts) {
+            HB_TRY(d_att.ensure(k));
+            HB_CUDA(cudaMemcpyAsync(d_att.p, attempts + o, sizeof(uint32_t) * k, cudaMemcpyHostToDevice, c->stream));
+        }
+        dim3 g(std::min<uint32_t>((nb + 255) / 256, 64), k);
+        k_synth_bed<<<g, 256, 0, c->stream>>>(c->d_raw.p, stride, nb, c->Nraw, seed, c->m_start + m_first + o, d_thr.p,
+                                              attempts ? d_att.p : nullptr);
+        HB_CUDA(cudaGetLastError());
+        HB_TRY(records_from_raw(c, m_first + o, k));
+    }
+    return HB_OK;
+}
+
+int hb_stage_finalize(hb_ctx *c) {
+    HB_CHECK(c, HB_ERR_ARG, "null ctx");
+    HB_CUDA(cudaSetDevice(c->dev));
+    for (uint32_t m = 0; m < c->M; m++) HB_CHECK(c->staged[m], HB_ERR_STATE, "hb_stage_finalize: local marker %u was never staged", m);
+    c->mave_h.resize(c->M); c->mstd_h.resize(c->M);
+    const double dN = (double)c->N;
+    for (uint32_t i = 0; i < c->M; i++) {  // src/BayesRRm.cpp:1502-1508
+        const double a = (double)c->n1[i], b = (double)c->n2[i], nm = (double)c->nm[i];
+        const double mave = (a + 2.0 * b) / (dN - nm);
+        const double tmp1 = a * (1.0 - mave) * (1.0 - mave);
+        const double tmp2 = b * (2.0 - mave) * (2.0 - mave);
+        const double tmp0 = (double)(c->N - c->n1[i] - c->n2[i] - c->nm[i]) * (0.0 - mave) * (0.0 - mave);
+        c->mave_h[i] = mave;
+        c->mstd_h[i] = sqrt((double)(c->N - 1) / (tmp0 + tmp1 + tmp2));
+    }
+    HB_CUDA(cudaMemcpy(c->d_mave.p, c->mave_h.data(), sizeof(double) * c->M, cudaMemcpyHostToDevice));
+    HB_CUDA(cudaMemcpy(c->d_mstd.p, c->mstd_h.data(), sizeof(double) * c->M, cudaMemcpyHostToDevice));
+    c->d_raw.release(); c->d_cnt3.release(); c->d_start.release(); c->d_meta.release();
+    c->finalized = true;
+    return HB_OK;
+}
+
+int hb_marker_counts(hb_ctx *c, uint32_t *n1, uint32_t *n2, uint32_t *nm) {
+    HB_CHECK(c, HB_ERR_ARG, "null ctx");
+    if (n1) std::copy(c->n1.begin(), c->n1.end(), n1);
+    if (n2) std::copy(c->n2.begin(), c->n2.end(), n2);
+    if (nm) std::copy(c->nm.begin(), c->nm.end(), nm);
+    return HB_OK;
+}
+
+int hb_marker_stats(hb_ctx *c, double *mave, double *mstd) {
+    HB_CHECK(c && c->finalized, HB_ERR_STATE, "hb_marker_stats: call hb_stage_finalize first");
+    if (mave) std::copy(c->mave_h.begin(), c->mave_h.end(), mave);
+    if (mstd) std::copy(c->mstd_h.begin(), c->mstd_h.end(), mstd);
+    return HB_OK;
+}
+
+int hb_marker_is_bed(hb_ctx *c, uint8_t *flags) {
+    HB_CHECK(c && flags, HB_ERR_ARG, "null argument");
+    std::copy(c->is_bed.begin(), c->is_bed.end(), flags);
+    return HB_OK;
+}
+
+uint64_t hb_genotype_bytes(hb_ctx *c) { return c ? c->geno_bytes : 0; }
+
+int hb_export_bed(hb_ctx *c, uint32_t m, uint8_t *out) {
+    HB_TRY(check_range(c, m, 1));
+    HB_CHECK(out && c->staged[m], HB_ERR_STATE, "hb_export_bed: marker %u not staged", m);
+    HB_CUDA(cudaSetDevice(c->dev));
+    const size_t ostride = (size_t)c->S * c->L / 4;
+    DevBuf<uint8_t> d;
+    HB_TRY(d.alloc(ostride));
+    HB_CUDA(cudaMemsetAsync(d.p, 0xFF, ostride, c->stream));
+    k_record_to_bed<<<1, 256, 0, c->stream>>>(c->d_rec.p, m, c->S, c->L, d.p, ostride);
+    HB_CUDA(cudaGetLastError());
+    const size_t nb = (size_t)(c->N + 3) / 4;
+    std::vector<uint8_t> tmp(ostride);
+    HB_CUDA(cudaMemcpyAsync(tmp.data(), d.p, ostride, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(out, tmp.data(), nb);
+    // PLINK pads the last byte with 00; internal pad positions hold 11
+    if (c->N % 4) out[nb - 1] &= (uint8_t)((1u << (2 * (c->N % 4))) - 1u);
+    return HB_OK;
+}
+
+int hb_export_sparse(hb_ctx *c, uint32_t m_first, uint32_t n,
+                     uint32_t *I1, uint64_t *N1S, uint64_t *N1L,
+                     uint32_t *I2, uint64_t *N2S, uint64_t *N2L,
+                     uint32_t *IM, uint64_t *NMS, uint64_t *NML) {
+    HB_TRY(check_range(c, m_first, n));
+    HB_CHECK(N1S && N1L && N2S && N2L && NMS && NML, HB_ERR_ARG, "hb_export_sparse: null start/length arrays");
+    HB_CUDA(cudaSetDevice(c->dev));
+    uint64_t t1 = 0, t2 = 0, tm = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t m = m_first + i;
+        HB_CHECK(c->staged[m], HB_ERR_STATE, "hb_export_sparse: marker %u not staged", m);
+        N1S[i] = t1; N1L[i] = c->n1[m]; t1 += c->n1[m];
+        N2S[i] = t2; N2L[i] = c->n2[m]; t2 += c->n2[m];
+        NMS[i] = tm; NML[i] = c->nm[m]; tm += c->nm[m];
+    }
+    const size_t ostride = (size_t)c->S * c->L / 4;
+    size_t chm = std::max<size_t>(1, ((size_t)256 << 20) / ostride);
+    DevBuf<uint8_t> d;
+    DevBuf<uint32_t> dI[3];
+    DevBuf<uint64_t> dS[3];
+    uint32_t *outI[3] = {I1, I2, IM};
+    const uint64_t *NS[3] = {N1S, N2S, NMS}, *NL[3] = {N1L, N2L, NML};
+    for (uint32_t o = 0; o < n; o += (uint32_t)chm) {
+        const uint32_t k = (uint32_t)std::min<size_t>(chm, n - o);
+        HB_TRY(d.ensure((size_t)k * ostride));
+        HB_CUDA(cudaMemsetAsync(d.p, 0xFF, (size_t)k * ostride, c->stream));
+        k_record_to_bed<<<k, 256, 0, c->stream>>>(c->d_rec.p, m_first + o, c->S, c->L, d.p, ostride);
+        HB_CUDA(cudaGetLastError());
+        uint64_t base[3], cntw[3];
+        std::vector<uint64_t> rs[3];
+        for (int w = 0; w < 3; w++) {
+            base[w] = NS[w][o];
+            cntw[w] = NS[w][o + k - 1] + NL[w][o + k - 1] - base[w];
+            rs[w].resize(k);
+            for (uint32_t i = 0; i < k; i++) rs[w][i] = NS[w][o + i] - base[w];
+            HB_TRY(dI[w].ensure(std::max<uint64_t>(cntw[w], 1)));
+            HB_TRY(dS[w].ensure(k));
+            HB_CUDA(cudaMemcpyAsync(dS[w].p, rs[w].data(), sizeof(uint64_t) * k, cudaMemcpyHostToDevice, c->stream));
+        }
+        k_bed_to_lists<<<k, 256, 0, c->stream>>>(d.p, ostride, c->N, dI[0].p, dS[0].p, dI[1].p, dS[1].p, dI[2].p, dS[2].p);
+        HB_CUDA(cudaGetLastError());
+        for (int w = 0; w < 3; w++) {
+            if (cntw[w]) {
+                HB_CHECK(outI[w], HB_ERR_ARG, "hb_export_sparse: null index output");
+                HB_CUDA(cudaMemcpyAsync(outI[w] + base[w], dI[w].p, sizeof(uint32_t) * cntw[w], cudaMemcpyDeviceToHost, c->stream));
+            }
+        }
+        HB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return HB_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// epsilon + unit-level kernels
+// ------------------------------------------------------------------------------------
+int hb_set_epsilon(hb_ctx *c, const double *eps) {
+    HB_CHECK(c && eps, HB_ERR_ARG, "null argument");
+    HB_CUDA(cudaSetDevice(c->dev));
+    HB_CUDA(cudaMemsetAsync(c->d_E[c->cur].p, 0, sizeof(double) * c->S * c->L, c->stream));
+    HB_CUDA(cudaMemcpyAsync(c->d_E[c->cur].p, eps, sizeof(double) * c->N, cudaMemcpyHostToDevice, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    c->shift = 0.0;
+    c->eps_set = true;
+    return HB_OK;
+}
+
+int hb_get_epsilon(hb_ctx *c, double *eps) {
+    HB_CHECK(c && eps, HB_ERR_ARG, "null argument");
+    HB_CUDA(cudaSetDevice(c->dev));
+    HB_CUDA(cudaMemcpyAsync(eps, c->d_E[c->cur].p, sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->shift != 0.0)
+        for (uint32_t i = 0; i < c->N; i++) eps[i] += c->shift;
+    return HB_OK;
+}
+
+static int upload_markers(hb_ctx *c, const uint32_t *markers, uint32_t n) {
+    for (uint32_t i = 0; i < n; i++) HB_CHECK(markers[i] < c->M, HB_ERR_ARG, "marker %u out of range", markers[i]);
+    HB_TRY(c->d_order.ensure(n));
+    HB_CUDA(cudaMemcpyAsync(c->d_order.p, markers, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+    return HB_OK;
+}
+
+int hb_dot_markers(hb_ctx *c, const uint32_t *markers, uint32_t n, double *num) {
+    HB_CHECK(c && markers && num, HB_ERR_ARG, "null argument");
+    HB_CHECK(c->finalized, HB_ERR_STATE, "hb_dot_markers: call hb_stage_finalize first");
+    if (n == 0) return HB_OK;
+    HB_CUDA(cudaSetDevice(c->dev));
+    HB_TRY(upload_markers(c, markers, n));
+    HB_TRY(ensure_scratch(c, n));
+    HB_TRY(c->d_num.ensure(n));
+    BrrParams P;
+    fill_params(c, P);
+    P.mode = MODE_DOT; P.T = 1; P.lmax = n; P.SR = 1;
+    HB_TRY(launch_window_kernel(c, P));
+    HB_CUDA(cudaMemcpyAsync(num, c->d_num.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    return HB_OK;
+}
+
+int hb_scaadd_markers(hb_ctx *c, const uint32_t *markers, const double *dbeta, uint32_t n) {
+    HB_CHECK(c && markers && dbeta, HB_ERR_ARG, "null argument");
+    HB_CHECK(c->finalized, HB_ERR_STATE, "hb_scaadd_markers: call hb_stage_finalize first");
+    if (n == 0) return HB_OK;
+    HB_CUDA(cudaSetDevice(c->dev));
+    HB_TRY(upload_markers(c, markers, n));
+    HB_TRY(ensure_scratch(c, n));
+    std::vector<double> dbs(n);
+    for (uint32_t i = 0; i < n; i++) dbs[i] = dbeta[i] * c->mstd_h[markers[i]];  // mstd*deltaBeta (:1982)
+    HB_CUDA(cudaMemcpyAsync(c->d_dB.p, dbs.data(), sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    BrrParams P;
+    fill_params(c, P);
+    P.mode = MODE_SCAADD; P.T = 1; P.lmax = n; P.SR = 1;
+    P.shift_in = 0.0;
+    HB_TRY(launch_window_kernel(c, P));
+    double off = 0.0;
+    HB_CUDA(cudaMemcpyAsync(&off, c->d_small.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    c->cur ^= 1;
+    c->shift += off;
+    return HB_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// BayesRRm chain
+// ------------------------------------------------------------------------------------
+int hb_brr_init(hb_ctx *c, const double *y, const int32_t *groups, const double *mS, const double *sigmaG0, uint32_t seed) {
+    HB_CHECK(c && y && mS, HB_ERR_ARG, "null argument");
+    HB_CHECK(c->finalized, HB_ERR_STATE, "hb_brr_init: call hb_stage_finalize first");
+    HB_CUDA(cudaSetDevice(c->dev));
+    const uint32_t N = c->N, K = c->K, G = c->G;
+    // groups (global array of m_total; NULL = single group)
+    c->MtotGrp.assign(G, 0);
+    c->groups_local.assign(c->M, 0);
+    if (groups) {
+        for (uint32_t m = 0; m < c->Mtot; m++) {
+            HB_CHECK(groups[m] >= 0 && (uint32_t)groups[m] < G, HB_ERR_ARG, "hb_brr_init: group %d of marker %u out of range", groups[m], m);
+            c->MtotGrp[groups[m]]++;
+        }
+        for (uint32_t m = 0; m < c->M; m++) c->groups_local[m] = groups[c->m_start + m];
+    } else {
+        HB_CHECK(G == 1, HB_ERR_ARG, "hb_brr_init: groups == NULL needs n_groups == 1");
+        c->MtotGrp[0] = (int32_t)c->Mtot;
+    }
+    HB_CUDA(cudaMemcpy(c->d_grp.p, c->groups_local.data(), sizeof(int32_t) * c->M, cudaMemcpyHostToDevice));
+    // mixture variances and prior pi (src/BayesRRm.cpp:1097-1110)
+    c->cVa.assign((size_t)G * K, 0.0); c->cVaI.assign((size_t)G * K, 0.0); c->pi.assign((size_t)G * K, 0.0);
+    for (uint32_t g = 0; g < G; g++) {
+        double s = 0.0;
+        for (uint32_t k = 1; k < K; k++) {
+            const double v = mS[g * K + k];
+            HB_CHECK(v > 0.0, HB_ERR_ARG, "hb_brr_init: mixture variance must be > 0 (group %u, k %u)", g, k);
+            c->cVa[g * K + k] = v; c->cVaI[g * K + k] = 1.0 / v; s += v;
+        }
+        c->pi[g * K] = 0.5;
+        for (uint32_t k = 1; k < K; k++) c->pi[g * K + k] = 0.5 * c->cVa[g * K + k] / s;
+    }
+    // RNG spec v1 streams (seeding rule of :1228: seed + 1000*rank)
+    c->seed = seed;
+    c->task_rng.clear();
+    for (uint32_t t = 0; t < c->T; t++) c->task_rng.emplace_back(seed + 1000u * (c->t_first + t));
+    c->hyper_rng.seed(seed ^ 0x5bd1e995u);
+    c->sigmaG.assign(G, 0.0);
+    for (uint32_t g = 0; g < G; g++) {
+        c->sigmaG[g] = sigmaG0 ? sigmaG0[g] : c->hyper_rng.res53();  // beta_rng(1,1) == U(0,1)  (:1233)
+        if (c->MtotGrp[g] == 0) c->sigmaG[g] = 0.0;  // :1239-1240
+    }
+    c->active.assign(G, 0);
+    for (uint32_t g = 0; g < G; g++) c->active[g] = (c->sigmaG[g] != 0.0) ? 1 : 0;  // adaV, :1592-1597
+    // y -> centred, scaled (:371-388); eps = y; sigmaE = sum(eps^2)/N*0.5 (:1575-1579)
+    std::vector<double> e(y, y + N);
+    double mean = 0.0;
+    for (uint32_t i = 0; i < N; i++) mean += e[i];
+    mean /= (double)(int)N;
+    for (uint32_t i = 0; i < N; i++) e[i] -= mean;
+    double sqn = 0.0;
+    for (uint32_t i = 0; i < N; i++) sqn += e[i] * e[i];
+    HB_CHECK(sqn > 0.0, HB_ERR_ARG, "hb_brr_init: phenotype has zero variance");
+    sqn = sqrt((double)(N - 1) / sqn);
+    for (uint32_t i = 0; i < N; i++) e[i] *= sqn;
+    double s2 = 0.0, s1 = 0.0;
+    for (uint32_t i = 0; i < N; i++) { s2 += e[i] * e[i]; s1 += e[i]; }
+    c->sigmaE = s2 / (double)N * 0.5;
+    HB_TRY(hb_set_epsilon(c, e.data()));
+    // slice sums of the initial residual
+    for (uint32_t s = 0; s < c->S; s++) {
+        double v = 0.0;
+        for (uint32_t i = s * c->L; i < std::min(N, (s + 1) * c->L); i++) v += e[i];
+        c->slice_sum_h[s] = v;
+    }
+    c->mu.assign(c->T, 0.0);
+    c->bsq.assign(G, 0.0); c->cass.assign((size_t)G * K, 0); c->m0.assign(G, 0);
+    HB_CUDA(cudaMemset(c->d_beta.p, 0, sizeof(double) * c->M));
+    HB_CUDA(cudaMemset(c->d_acum.p, 0, sizeof(double) * c->M));
+    HB_CUDA(cudaMemset(c->d_comp.p, 0, sizeof(int32_t) * c->M));
+    // identity marker order per task (markerI, :1615-1617)
+    c->perm.resize(c->M);
+    {
+        size_t o = 0;
+        for (uint32_t t = 0; t < c->T; t++)
+            for (int32_t j = 0; j < c->blkL[c->t_first + t]; j++) c->perm[o++] = j;
+    }
+    std::vector<int32_t> tl(c->T), to(c->T);
+    for (uint32_t t = 0; t < c->T; t++) { tl[t] = c->blkL[c->t_first + t]; to[t] = c->blkS[c->t_first + t] - (int32_t)c->m_start; }
+    HB_TRY(c->d_task_len.alloc(c->T)); HB_TRY(c->d_task_off.alloc(c->T));
+    HB_CUDA(cudaMemcpy(c->d_task_len.p, tl.data(), sizeof(int32_t) * c->T, cudaMemcpyHostToDevice));
+    HB_CUDA(cudaMemcpy(c->d_task_off.p, to.data(), sizeof(int32_t) * c->T, cudaMemcpyHostToDevice));
+    const size_t Q = (size_t)c->lmax * c->T;
+    HB_TRY(c->d_order.ensure(Q)); HB_TRY(c->d_u.ensure(Q)); HB_TRY(c->d_z.ensure(Q));
+    HB_TRY(c->d_perm.ensure(c->M)); HB_TRY(c->d_ut.ensure(c->M)); HB_TRY(c->d_zt.ensure(c->M));
+    HB_TRY(ensure_scratch(c, c->SR * c->T));
+    HB_TRY(ensure_pin(c, 8 + 2 * (size_t)c->S + G + (size_t)G * K + 16));
+    c->iteration = 0;
+    c->brr_ready = true;
+    return HB_OK;
+}
+
+int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
+    HB_CHECK(c && c->brr_ready, HB_ERR_STATE, "hb_brr_iteration: call hb_brr_init first");
+    HB_CUDA(cudaSetDevice(c->dev));
+    if (tape) HB_CHECK(tape->zmu && tape->perm && tape->u && tape->z, HB_ERR_ARG, "hb_brr_iteration: tape needs zmu, perm, u and z");
+    const uint32_t N = c->N, K = c->K, G = c->G, T = c->T, M = c->M;
+    const double dN = (double)N, dNm1 = (double)(N - 1);
+    const double v0E = 0.0001, s02E = 0.0001, v0G = 0.0001, s02G = 0.0001;  // src/BayesRRm.h:30-33
+    cudaStream_t st = c->stream;
+    HB_CUDA(cudaEventRecord(c->ev[0], st));
+
+    // ---- mu (:1675-1686): eps_r + mu_r is the same vector for every task
+    double ssum = 0.0;
+    for (uint32_t s = 0; s < c->S; s++) ssum += c->slice_sum_h[s];
+    const double epssum = ssum + dN * c->shift + dN * c->mu[0];
+    const double mu0_old = c->mu[0];
+    for (uint32_t t = 0; t < T; t++) {
+        const double z = tape ? tape->zmu[t] : c->task_rng[t].normal();
+        c->mu[t] = epssum / dN + sqrt(c->sigmaE / dN) * z;
+    }
+    c->shift += mu0_old - c->mu[0];
+
+    // ---- marker order (:1691-1694) and per-marker draws, laid out in window order q = j*T + t
+    if (tape) {
+        size_t o = 0;
+        for (uint32_t t = 0; t < T; t++) {
+            const int32_t len = c->blkL[c->t_first + t];
+            for (int32_t j = 0; j < len; j++, o++) {
+                HB_CHECK(tape->perm[o] >= 0 && tape->perm[o] < len, HB_ERR_ARG, "hb_brr_iteration: tape perm[%zu]=%d out of range", o, tape->perm[o]);
+                c->perm[o] = tape->perm[o];
+            }
+        }
+    } else {
+        size_t o = 0;
+        for (uint32_t t = 0; t < T; t++) {
+            const int32_t len = c->blkL[c->t_first + t];
+            if (c->cfg.reserved[0] == 0) c->task_rng[t].shuffle(c->perm.data() + o, len);  // reserved[0]: --shuf-mark 0
+            o += (size_t)len;
+        }
+    }
+    HB_CUDA(cudaMemcpyAsync(c->d_perm.p, c->perm.data(), sizeof(int32_t) * M, cudaMemcpyHostToDevice, st));
+    const uint32_t Q = c->lmax * T;
+    if (tape) {
+        HB_CUDA(cudaMemcpyAsync(c->d_ut.p, tape->u, sizeof(double) * M, cudaMemcpyHostToDevice, st));
+        HB_CUDA(cudaMemcpyAsync(c->d_zt.p, tape->z, sizeof(double) * M, cudaMemcpyHostToDevice, st));
+    }
+    k_window_order<<<(Q + 255) / 256, 256, 0, st>>>(c->d_perm.p, tape ? c->d_ut.p : nullptr, tape ? c->d_zt.p : nullptr,
+                                                     c->d_task_len.p, c->d_task_off.p, T, c->lmax, c->seed, c->iteration,
+                                                     c->t_first, c->d_order.p, c->d_u.p, c->d_z.p);
+    HB_CUDA(cudaGetLastError());
+
+    // ---- hyper-parameter tables (:1721-1723, 1750, 1863-1876, 1901)
+    const size_t gk = (size_t)G * K;
+    std::vector<double> hyp(4 * gk, 0.0);
+    for (uint32_t g = 0; g < G; g++) {
+        const double sigE_G = c->sigmaE / c->sigmaG[g], sigG_E = c->sigmaG[g] / c->sigmaE;
+        for (uint32_t k = 0; k < K; k++) {
+            hyp[g * K + k] = log(c->pi[g * K + k]);
+            if (k == 0 || !c->active[g]) continue;
+            hyp[gk + g * K + k] = 0.5 * log(sigG_E * dNm1 * c->cVa[g * K + k] + 1.0);
+            const double den = dNm1 + sigE_G * c->cVaI[g * K + k];
+            hyp[2 * gk + g * K + k] = den;
+            hyp[3 * gk + g * K + k] = sqrt(c->sigmaE / den);
+        }
+    }
+    memcpy(c->pin, hyp.data(), sizeof(double) * 4 * gk);
+    HB_CUDA(cudaMemcpyAsync(c->d_hyp.p, c->pin, sizeof(double) * 4 * gk, cudaMemcpyHostToDevice, st));
+    HB_CUDA(cudaMemcpyAsync(c->d_active.p, c->active.data(), G, cudaMemcpyHostToDevice, st));
+    HB_CUDA(cudaMemsetAsync(c->d_cass.p, 0, sizeof(int32_t) * gk, st));  // :1697
+    HB_CUDA(cudaMemsetAsync(c->d_stats.p, 0, sizeof(unsigned long long) * 8, st));
+
+    // ---- marker loop
+    BrrParams P;
+    fill_params(c, P);
+    P.mode = MODE_CHAIN; P.T = T; P.SR = c->SR; P.lmax = c->lmax;
+    P.shift_in = c->shift;  // fold the accumulated constant into the stored residual
+    P.i_2sigE = 1.0 / (2.0 * c->sigmaE);
+    HB_CUDA(cudaEventRecord(c->ev[1], st));
+    HB_TRY(launch_window_kernel(c, P));
+    HB_CUDA(cudaEventRecord(c->ev[2], st));
+    c->cur ^= 1;
+
+    // ---- group statistics (:2496-2521)
+    double *d_bsq = c->d_small.p + 1 + 2 * c->S;
+    k_beta_sqnorm<<<G, 1024, 0, st>>>(c->d_beta.p, c->d_grp.p, M, d_bsq);
+    HB_CUDA(cudaGetLastError());
+    const size_t nsmall = 1 + 2 * (size_t)c->S + G;
+    double *pin_small = c->pin;
+    int32_t *pin_cass = reinterpret_cast<int32_t *>(c->pin + nsmall);
+    unsigned long long *pin_stats = reinterpret_cast<unsigned long long *>(c->pin + nsmall + (gk + 1) / 2 + 1);
+    HB_CUDA(cudaMemcpyAsync(pin_small, c->d_small.p, sizeof(double) * nsmall, cudaMemcpyDeviceToHost, st));
+    HB_CUDA(cudaMemcpyAsync(pin_cass, c->d_cass.p, sizeof(int32_t) * gk, cudaMemcpyDeviceToHost, st));
+    HB_CUDA(cudaMemcpyAsync(pin_stats, c->d_stats.p, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
+    HB_CUDA(cudaEventRecord(c->ev[3], st));
+    HB_CUDA(cudaStreamSynchronize(st));
+
+    const double off = pin_small[0];
+    c->shift = off;  // the launch folded the old shift into E; the new constant is this launch's base terms
+    double s1 = 0.0, s2 = 0.0;
+    for (uint32_t s = 0; s < c->S; s++) { c->slice_sum_h[s] = pin_small[1 + s]; s1 += pin_small[1 + s]; s2 += pin_small[1 + c->S + s]; }
+    // sum (E+off)^2 over the N individuals
+    const double e_sqn = s2 + 2.0 * off * s1 + dN * off * off;
+    for (uint32_t g = 0; g < G; g++) c->bsq[g] = pin_small[1 + 2 * c->S + g];
+    for (size_t x = 0; x < gk; x++) c->cass[x] = pin_cass[x];
+
+    // ---- hyper-parameters (:2525-2578, 2685-2731)
+    for (uint32_t g = 0; g < G; g++) {
+        c->m0[g] = 0;
+        if (c->MtotGrp[g] == 0) continue;
+        c->m0[g] = c->MtotGrp[g] - c->cass[g * K];
+        int rowsum = 0;
+        for (uint32_t k = 0; k < K; k++) rowsum += c->cass[g * K + k];
+        if (c->m0[g] == 0 || rowsum == 0) {  // :2534-2542
+            c->active[g] = 0;
+            c->sigmaG[g] = 0.0;
+            continue;
+        }
+        if (tape && tape->sigmaG && tape->pi) {
+            c->sigmaG[g] = tape->sigmaG[g];
+            for (uint32_t k = 0; k < K; k++) c->pi[g * K + k] = tape->pi[g * K + k];
+        } else {
+            const double m0 = (double)c->m0[g];
+            c->sigmaG[g] = c->hyper_rng.inv_scaled_chisq(v0G + m0, (c->bsq[g] * m0 + v0G * s02G) / (v0G + m0));  // :2570
+            double s = 0.0;
+            for (uint32_t k = 0; k < K; k++) { c->pi[g * K + k] = c->hyper_rng.gamma((double)c->cass[g * K + k] + 1.0); s += c->pi[g * K + k]; }
+            for (uint32_t k = 0; k < K; k++) c->pi[g * K + k] /= s;  // dirichlet(cass+1), :2577
+        }
+    }
+    if (tape && tape->sigmaE) c->sigmaE = tape->sigmaE[0];
+    else c->sigmaE = c->hyper_rng.inv_scaled_chisq(v0E + dN, (e_sqn + v0E * s02E) / (v0E + dN));  // :2690
+    c->iteration++;
+
+    if (out) {
+        memset(out, 0, sizeof(*out));
+        out->sigmaE = c->sigmaE; out->e_sqn = e_sqn; out->epssum = epssum;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); out->loop_ms = ms;
+        cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); out->iter_ms = ms;
+        out->n_sync = pin_stats[0]; out->n_windows = pin_stats[1];
+        out->n_launches = 3;
+        out->nnz_processed = pin_stats[2]; out->nnz_updated = pin_stats[3];
+        out->bed_markers = pin_stats[4]; out->markers_changed = pin_stats[5];
+    }
+    return HB_OK;
+}
+
+int hb_brr_get_hyper(hb_ctx *c, double *sigmaG, double *pi, double *sigmaE, double *mu_tasks_local, double *bsq,
+                     int32_t *cass, int32_t *m0) {
+    HB_CHECK(c && c->brr_ready, HB_ERR_STATE, "hb_brr_get_hyper: call hb_brr_init first");
+    if (sigmaG) std::copy(c->sigmaG.begin(), c->sigmaG.end(), sigmaG);
+    if (pi) std::copy(c->pi.begin(), c->pi.end(), pi);
+    if (sigmaE) *sigmaE = c->sigmaE;
+    if (mu_tasks_local) std::copy(c->mu.begin(), c->mu.end(), mu_tasks_local);
+    if (bsq) std::copy(c->bsq.begin(), c->bsq.end(), bsq);
+    if (cass) std::copy(c->cass.begin(), c->cass.end(), cass);
+    if (m0) std::copy(c->m0.begin(), c->m0.end(), m0);
+    return HB_OK;
+}
+
+int hb_brr_get_state(hb_ctx *c, double *beta, int32_t *components, double *acum) {
+    HB_CHECK(c && c->brr_ready, HB_ERR_STATE, "hb_brr_get_state: call hb_brr_init first");
+    HB_CUDA(cudaSetDevice(c->dev));
+    if (beta) HB_CUDA(cudaMemcpyAsync(beta, c->d_beta.p, sizeof(double) * c->M, cudaMemcpyDeviceToHost, c->stream));
+    if (components) HB_CUDA(cudaMemcpyAsync(components, c->d_comp.p, sizeof(int32_t) * c->M, cudaMemcpyDeviceToHost, c->stream));
+    if (acum) HB_CUDA(cudaMemcpyAsync(acum, c->d_acum.p, sizeof(double) * c->M, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    return HB_OK;
+}
+
+int hb_brr_set_state(hb_ctx *c, const double *beta, const int32_t *components) {
+    HB_CHECK(c && c->brr_ready, HB_ERR_STATE, "hb_brr_set_state: call hb_brr_init first");
+    HB_CUDA(cudaSetDevice(c->dev));
+    if (beta) HB_CUDA(cudaMemcpyAsync(c->d_beta.p, beta, sizeof(double) * c->M, cudaMemcpyHostToDevice, c->stream));
+    if (components) HB_CUDA(cudaMemcpyAsync(c->d_comp.p, components, sizeof(int32_t) * c->M, cudaMemcpyHostToDevice, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    return HB_OK;
+}
+
+int hb_brr_get_task_epsilon(hb_ctx *c, uint32_t task_local, double *eps) {
+    HB_CHECK(c && c->brr_ready && eps, HB_ERR_STATE, "hb_brr_get_task_epsilon: call hb_brr_init first");
+    HB_CHECK(task_local < c->T, HB_ERR_ARG, "task %u out of range", task_local);
+    HB_TRY(hb_get_epsilon(c, eps));  // eps of local task 0
+    const double d = c->mu[0] - c->mu[task_local];
+    if (d != 0.0)
+        for (uint32_t i = 0; i < c->N; i++) eps[i] += d;
+    return HB_OK;
+}
+
+int hb_brr_get_task_perm(hb_ctx *c, uint32_t task_local, int32_t *perm) {
+    HB_CHECK(c && c->brr_ready && perm, HB_ERR_STATE, "hb_brr_get_task_perm: call hb_brr_init first");
+    HB_CHECK(task_local < c->T, HB_ERR_ARG, "task %u out of range", task_local);
+    size_t o = 0;
+    for (uint32_t t = 0; t < task_local; t++) o += (size_t)c->blkL[c->t_first + t];
+    std::copy(c->perm.begin() + o, c->perm.begin() + o + c->blkL[c->t_first + task_local], perm);
+    return HB_OK;
+}
+
+int hb_comm_get_unique_id(uint8_t id[HB_NCCL_ID_BYTES]) {
+    (void)id;
+    set_error("hb_comm_get_unique_id: multi-GPU exchange is not part of this build yet");
+    return HB_ERR_NCCL;
+}
+int hb_comm_init(hb_ctx *ctx, const uint8_t id[HB_NCCL_ID_BYTES], int rank, int nranks) {
+    (void)ctx; (void)id; (void)rank; (void)nranks;
+    set_error("hb_comm_init: multi-GPU exchange is not part of this build yet");
+    return HB_ERR_NCCL;
+}
+
+}  // extern "C"

@@ -1,0 +1,219 @@
+"""Host-side mirror of the reference's interface for the per-marker Gibbs hot path.
+
+hydra has no plugin API; its seam is class BayesRRm (reference src/BayesRRm.h:116-150) and the
+Data loaders (src/data.hpp:88-357).  `GenotypeStore` plays the role of `Data` for the genotype
+representations (load_data_from_bed_file / _sparse_files / _mixed_representations) and
+`BayesRRm` that of the sampler (sparse_dotprod, sparse_scaadd, runMpiGibbs' iteration body).
+Everything numeric happens in libhydra_b200.so on the GPU, through the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import arr, check, ptr
+
+_REPR = {"sparse": capi.REPR_SPARSE, "bed": capi.REPR_BED, "mixed": capi.REPR_MIXED}
+
+
+class GenotypeStore:
+    """Device-resident genotypes of the markers owned by this GPU + the residual vector epsilon."""
+
+    def __init__(self, n_ind, m_total, *, na_inds=None, tasks=1, task_first=0, tasks_local=None, sync_rate=1,
+                 n_groups=1, n_mix=4, repr_mode="sparse", threshold_fnz=0.06, device=0, n_slices=0, max_ctas=0,
+                 block_starts=None, block_lens=None, shuffle=True):
+        self._lib = capi.load()
+        cfg = capi.HbConfig()
+        self._na = arr(na_inds if na_inds is not None else np.zeros(0), np.uint32)
+        self._bs = arr(block_starts, np.int32)
+        self._bl = arr(block_lens, np.int32)
+        cfg.device, cfg.n_ind_raw, cfg.n_na = device, n_ind, len(self._na)
+        cfg.na_inds = self._na.ctypes.data if len(self._na) else None
+        cfg.m_total, cfg.n_tasks_total, cfg.task_first = m_total, tasks, task_first
+        cfg.n_tasks_local = tasks if tasks_local is None else tasks_local
+        cfg.block_starts = None if self._bs is None else self._bs.ctypes.data
+        cfg.block_lens = None if self._bl is None else self._bl.ctypes.data
+        cfg.sync_rate, cfg.n_groups, cfg.n_mix = sync_rate, n_groups, n_mix
+        cfg.repr_mode, cfg.threshold_fnz = _REPR[repr_mode], threshold_fnz
+        cfg.n_slices, cfg.max_ctas, cfg.model = n_slices, max_ctas, 0
+        cfg.reserved[0] = 0 if shuffle else 1
+        self._h = C.c_void_p()
+        check(self._lib.hb_create(C.byref(cfg), C.byref(self._h)))
+        v = [C.c_uint32() for _ in range(7)]
+        check(self._lib.hb_get_layout(self._h, *[C.byref(x) for x in v]))
+        (self.n_ind, self.m_start, self.m_local, self.n_slices, self.slice_len, self.n_cta_groups, self.lmax) = [x.value for x in v]
+        self.n_ind_raw, self.m_total, self.tasks, self.tasks_local, self.task_first = n_ind, m_total, tasks, cfg.n_tasks_local, task_first
+        self.n_groups, self.n_mix, self.sync_rate = n_groups, n_mix, sync_rate
+
+    # -- life cycle
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.hb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def task_blocks(self):
+        s = np.zeros(self.tasks, np.int32)
+        l = np.zeros(self.tasks, np.int32)
+        check(self._lib.hb_get_task_blocks(self._h, ptr(s), ptr(l)))
+        return s, l
+
+    # -- staging (Data::load_data_from_*)
+    def load_data_from_bed(self, bed_cols, m_first=0):
+        """bed_cols: (n, ceil(n_ind_raw/4)) uint8, PLINK columns without the 3-byte header."""
+        b = arr(bed_cols, np.uint8)
+        assert b.ndim == 2 and b.shape[1] == (self.n_ind_raw + 3) // 4, b.shape
+        check(self._lib.hb_stage_bed(self._h, C.c_uint32(m_first), C.c_uint32(b.shape[0]), ptr(b)))
+
+    def load_data_from_sparse(self, I1, N1S, N1L, I2, N2S, N2L, IM, NMS, NML, m_first=0):
+        a = [arr(I1, np.uint32), arr(N1S, np.uint64), arr(N1L, np.uint64), arr(I2, np.uint32), arr(N2S, np.uint64),
+             arr(N2L, np.uint64), arr(IM, np.uint32), arr(NMS, np.uint64), arr(NML, np.uint64)]
+        n = len(a[1])
+        check(self._lib.hb_stage_sparse(self._h, C.c_uint32(m_first), C.c_uint32(n), *[ptr(x) if len(x) else None for x in a]))
+
+    def load_synthetic(self, seed, thresholds, attempts=None, m_first=0):
+        t = arr(thresholds, np.uint32)
+        at = arr(attempts, np.uint32)
+        check(self._lib.hb_stage_synth(self._h, C.c_uint32(m_first), C.c_uint32(t.shape[0]), C.c_uint32(seed), ptr(t), ptr(at)))
+
+    def finalize(self):
+        check(self._lib.hb_stage_finalize(self._h))
+
+    def marker_counts(self):
+        o = [np.zeros(self.m_local, np.uint32) for _ in range(3)]
+        check(self._lib.hb_marker_counts(self._h, *[ptr(x) for x in o]))
+        return o
+
+    def marker_stats(self):
+        a, s = np.zeros(self.m_local), np.zeros(self.m_local)
+        check(self._lib.hb_marker_stats(self._h, ptr(a), ptr(s)))
+        return a, s
+
+    def marker_is_bed(self):
+        f = np.zeros(self.m_local, np.uint8)
+        check(self._lib.hb_marker_is_bed(self._h, ptr(f)))
+        return f
+
+    @property
+    def genotype_bytes(self):
+        return int(self._lib.hb_genotype_bytes(self._h))
+
+    def export_sparse(self, m_first=0, n=None):
+        n = self.m_local - m_first if n is None else n
+        c1, c2, cm = self.marker_counts()
+        sl = slice(m_first, m_first + n)
+        I = [np.zeros(max(int(c[sl].sum()), 1), np.uint32) for c in (c1, c2, cm)]
+        SL = [np.zeros(n, np.uint64) for _ in range(6)]
+        check(self._lib.hb_export_sparse(self._h, C.c_uint32(m_first), C.c_uint32(n), ptr(I[0]), ptr(SL[0]), ptr(SL[1]),
+                                         ptr(I[1]), ptr(SL[2]), ptr(SL[3]), ptr(I[2]), ptr(SL[4]), ptr(SL[5])))
+        return (I[0][: int(c1[sl].sum())], SL[0], SL[1], I[1][: int(c2[sl].sum())], SL[2], SL[3], I[2][: int(cm[sl].sum())], SL[4], SL[5])
+
+    def export_bed(self, m):
+        out = np.zeros((self.n_ind + 3) // 4, np.uint8)
+        check(self._lib.hb_export_bed(self._h, C.c_uint32(m), ptr(out)))
+        return out
+
+    # -- epsilon and the unit kernels (BayesRRm::sparse_dotprod / sparse_scaadd, LUT variants)
+    def set_epsilon(self, eps):
+        e = arr(eps, np.float64)
+        assert e.shape == (self.n_ind,)
+        check(self._lib.hb_set_epsilon(self._h, ptr(e)))
+
+    def get_epsilon(self):
+        e = np.zeros(self.n_ind)
+        check(self._lib.hb_get_epsilon(self._h, ptr(e)))
+        return e
+
+    def sparse_dotprod(self, markers):
+        """num_j = mstd_j * (x_j . eps) for centred columns (src/BayesRRm.cpp:316-342 / :1757-1809)."""
+        m = arr(markers, np.uint32)
+        out = np.zeros(len(m))
+        check(self._lib.hb_dot_markers(self._h, ptr(m), C.c_uint32(len(m)), ptr(out)))
+        return out
+
+    def sparse_scaadd(self, markers, dbeta):
+        """eps += sum_j dbeta_j * mstd_j * (x_j - mave_j) (src/BayesRRm.cpp:250-281, :1976-2010, :2460-2471)."""
+        m = arr(markers, np.uint32)
+        d = arr(dbeta, np.float64)
+        assert len(m) == len(d)
+        check(self._lib.hb_scaadd_markers(self._h, ptr(m), ptr(d), C.c_uint32(len(m))))
+
+
+class BayesRRm:
+    """The BayesRRm chain on one GPU (src/BayesRRm.cpp:933-2939, marker loop :1709-2490)."""
+
+    def __init__(self, store: GenotypeStore, y, mS, groups=None, sigmaG0=None, seed=0):
+        self.store = store
+        self._lib = store._lib
+        G, K = store.n_groups, store.n_mix
+        mS = np.asarray(mS, dtype=np.float64).reshape(G, -1)
+        if mS.shape[1] == K - 1:  # the zero component is implicit in .mS files (src/data.cpp:1981-2007)
+            mS = np.concatenate([np.zeros((G, 1)), mS], axis=1)
+        assert mS.shape == (G, K), (mS.shape, G, K)
+        self.mS = np.ascontiguousarray(mS)
+        y = arr(y, np.float64)
+        assert y.shape == (store.n_ind,)
+        g = arr(groups, np.int32)
+        s0 = arr(sigmaG0, np.float64)
+        check(self._lib.hb_brr_init(store._h, ptr(y), ptr(g), ptr(self.mS), ptr(s0), C.c_uint32(seed & 0xFFFFFFFF)))
+        self.iteration_index = 0
+
+    def iteration(self, tape=None):
+        """One Gibbs iteration. tape = dict(zmu, perm, u, z[, sigmaG, pi, sigmaE]) for deterministic replay."""
+        out = capi.HbBrrIterOut()
+        keep = []
+        tp = None
+        if tape is not None:
+            t = capi.HbBrrTape()
+            for name, dt in (("zmu", np.float64), ("perm", np.int32), ("u", np.float64), ("z", np.float64),
+                             ("sigmaG", np.float64), ("pi", np.float64), ("sigmaE", np.float64)):
+                v = tape.get(name)
+                if v is not None:
+                    a = arr(np.atleast_1d(v), dt)
+                    keep.append(a)
+                    setattr(t, name, a.ctypes.data)
+            tp = C.byref(t)
+        check(self._lib.hb_brr_iteration(self.store._h, tp, C.byref(out)))
+        self.iteration_index += 1
+        return {n: getattr(out, n) for n, _ in out._fields_}
+
+    def hyper(self):
+        s = self.store
+        G, K = s.n_groups, s.n_mix
+        sigmaG, pi, sigmaE = np.zeros(G), np.zeros((G, K)), C.c_double()
+        mu, bsq, cass, m0 = np.zeros(s.tasks_local), np.zeros(G), np.zeros((G, K), np.int32), np.zeros(G, np.int32)
+        check(self._lib.hb_brr_get_hyper(s._h, ptr(sigmaG), ptr(pi), C.byref(sigmaE), ptr(mu), ptr(bsq), ptr(cass), ptr(m0)))
+        return dict(sigmaG=sigmaG, pi=pi, sigmaE=sigmaE.value, mu=mu, bsq=bsq, cass=cass, m0=m0)
+
+    def state(self):
+        s = self.store
+        beta, comp, acum = np.zeros(s.m_local), np.zeros(s.m_local, np.int32), np.zeros(s.m_local)
+        check(self._lib.hb_brr_get_state(s._h, ptr(beta), ptr(comp), ptr(acum)))
+        return beta, comp, acum
+
+    def set_state(self, beta=None, components=None):
+        check(self._lib.hb_brr_set_state(self.store._h, ptr(arr(beta, np.float64)), ptr(arr(components, np.int32))))
+
+    def task_epsilon(self, task_local=0):
+        e = np.zeros(self.store.n_ind)
+        check(self._lib.hb_brr_get_task_epsilon(self.store._h, C.c_uint32(task_local), ptr(e)))
+        return e
+
+    def task_perm(self, task_local=0):
+        _, l = self.store.task_blocks()
+        p = np.zeros(int(l[self.store.task_first + task_local]), np.int32)
+        check(self._lib.hb_brr_get_task_perm(self.store._h, C.c_uint32(task_local), ptr(p)))
+        return p

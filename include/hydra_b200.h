@@ -24,6 +24,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
 
 #define HB_OK 0
 #define HB_ERR_CUDA -1
@@ -65,6 +68,8 @@ typedef struct hb_config {
 
 /* ---- life cycle ------------------------------------------------------- */
 int hb_abi_version(void);
+int hb_sizeof_config(void);   /* sizeof(hb_config): lets a foreign-language binding check its struct layout */
+int hb_sizeof_iter_out(void); /* sizeof(hb_brr_iter_out) */
 const char *hb_last_error(void);
 int hb_create(const hb_config *cfg, hb_ctx **out);
 void hb_destroy(hb_ctx *ctx);
@@ -167,6 +172,9 @@ int hb_brr_get_task_perm(hb_ctx *ctx, uint32_t task_local, int32_t *perm);
 int hb_comm_get_unique_id(uint8_t id[HB_NCCL_ID_BYTES]);
 int hb_comm_init(hb_ctx *ctx, const uint8_t id[HB_NCCL_ID_BYTES], int rank, int nranks);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif
