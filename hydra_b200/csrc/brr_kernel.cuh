@@ -55,45 +55,104 @@ struct BrrParams {
     double *partial;       // [Wmax*S]
     uint32_t *cnt;         // [Wmax] arrival counters (monotonic)
     double *dB;            // [2*Wmax] deltaBeta*mstd per window position, double buffered
+    double *dMave;         // [2*Wmax] mave of the changed marker
+    uint64_t *dRec;        // [2*Wmax] its record
     uint32_t Wmax;
     uint32_t *bar;         // grid barrier counter
-    unsigned long long *stats; // [8]: 0 nsync 1 nwindows 2 nnz dot 3 nnz upd 4 bed markers 5 changed
+    unsigned long long *stats; // [16]: 0 nsync 1 nwindows 2 nnz dot 3 nnz upd 4 bed markers 5 changed, 8.. phase cycles
     // unit modes
     int mode;
     double *num_out;       // MODE_DOT: [W]
+    uint32_t flags;        // bit 0: no L2 prefetch of the next window (developer knob)
+    unsigned long long *cta_cycles;  // optional [gridDim*8] per-CTA phase cycles (HB_DEBUG_CYCLES=1)
 };
 
-struct ItemTab {
+struct ItemTab {  // the window positions this CTA group works on, with everything the draw needs
     const uint64_t *ptr[kTabCap];
-    double mave[kTabCap];
+    uint64_t rec[kTabCap];
+    double mave[kTabCap], mstd[kTabCap], beta[kTabCap], u[kTabCap], z[kTabCap];
     double part[kTabCap];
     uint32_t nw[kTabCap];   // u64 words of the slice block
     uint32_t b1[kTabCap];   // first word of class 2   (0xFFFFFFFF = BED block)
     uint32_t b2[kTabCap];   // first word of class "missing"
     int32_t m[kTabCap];
+    int32_t grp[kTabCap];
+    uint32_t tag_base, tag_W, tag_k0, tag_valid;  // which window chunk the table describes
 };
 
+struct ChgTab {  // changed markers of a window, staged for the epsilon update
+    const uint64_t *ptr[kChgCap];
+    double dbs[kChgCap];
+    double mave[kChgCap];
+    uint32_t nw[kChgCap], b1[kChgCap], b2[kChgCap];
+    uint32_t cum[kChgCap + 1];  // exclusive prefix of nw
+};
+
+struct Blk {
+    const uint64_t *ptr;
+    uint32_t nw, b1, b2;
+};
+
+// slice block c of a marker record (common.cuh "record layout")
+__device__ __forceinline__ Blk decode_block(uint64_t rr, uint32_t c, uint32_t S, uint32_t L) {
+    Blk b;
+    if (rr & 1ull) {
+        b.ptr = reinterpret_cast<const uint64_t *>(rr & ~15ull) + (size_t)c * (L / 32);
+        b.nw = L / 32;
+        b.b1 = 0xFFFFFFFFu;
+        b.b2 = 0xFFFFFFFFu;
+    } else {
+        const uint8_t *bp = reinterpret_cast<const uint8_t *>(rr);
+        const uint32_t *dir = reinterpret_cast<const uint32_t *>(bp) + c * 3;
+        const uint32_t st = __ldg(dir), n12 = __ldg(dir + 1), nm = __ldg(dir + 2);
+        const uint32_t w1 = ((n12 & 0xFFFFu) + 3) / 4, w2 = ((n12 >> 16) + 3) / 4, wm = (nm + 3) / 4;
+        b.ptr = reinterpret_cast<const uint64_t *>(bp + dir_bytes(S)) + st;
+        b.b1 = w1;
+        b.b2 = w1 + w2;
+        b.nw = w1 + w2 + wm;
+    }
+    return b;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ---- slice block dot product: sum_w weight(w) * sum_4 E_s[idx] ------------------
+__device__ __forceinline__ double gather4(uint64_t x, const double *__restrict__ E_s) {
+    return (E_s[x & 0xFFFFu] + E_s[(x >> 16) & 0xFFFFu]) + (E_s[(x >> 32) & 0xFFFFu] + E_s[x >> 48]);
+}
 __device__ __forceinline__ double dot_sparse_block(const uint64_t *__restrict__ ptr, uint32_t nw, uint32_t b1,
                                                    uint32_t b2, double mave, const double *__restrict__ E_s,
                                                    uint32_t lane) {
     double acc = 0.0;
     uint32_t w = lane;
-    // two independent 64-bit loads in flight per lane
-    for (; w + 32 < nw; w += 64) {
-        uint64_t x0 = ld_stream_u64(ptr + w), x1 = ld_stream_u64(ptr + w + 32);
-        double wt0 = (w < b1) ? 1.0 : ((w < b2) ? 2.0 : mave);
-        double wt1 = (w + 32 < b1) ? 1.0 : ((w + 32 < b2) ? 2.0 : mave);
-        double s0 = (E_s[x0 & 0xFFFFu] + E_s[(x0 >> 16) & 0xFFFFu]) + (E_s[(x0 >> 32) & 0xFFFFu] + E_s[x0 >> 48]);
-        double s1 = (E_s[x1 & 0xFFFFu] + E_s[(x1 >> 16) & 0xFFFFu]) + (E_s[(x1 >> 32) & 0xFFFFu] + E_s[x1 >> 48]);
-        acc = fma(wt0, s0, acc);
-        acc = fma(wt1, s1, acc);
+    // four independent 64-bit loads in flight per lane
+    for (; w + 96 < nw; w += 128) {
+        const uint64_t x0 = ld_stream_u64(ptr + w), x1 = ld_stream_u64(ptr + w + 32);
+        const uint64_t x2 = ld_stream_u64(ptr + w + 64), x3 = ld_stream_u64(ptr + w + 96);
+        const double wt0 = (w < b1) ? 1.0 : ((w < b2) ? 2.0 : mave);
+        const double wt1 = (w + 32 < b1) ? 1.0 : ((w + 32 < b2) ? 2.0 : mave);
+        const double wt2 = (w + 64 < b1) ? 1.0 : ((w + 64 < b2) ? 2.0 : mave);
+        const double wt3 = (w + 96 < b1) ? 1.0 : ((w + 96 < b2) ? 2.0 : mave);
+        acc = fma(wt0, gather4(x0, E_s), acc);
+        acc = fma(wt1, gather4(x1, E_s), acc);
+        acc = fma(wt2, gather4(x2, E_s), acc);
+        acc = fma(wt3, gather4(x3, E_s), acc);
     }
-    if (w < nw) {
-        uint64_t x0 = ld_stream_u64(ptr + w);
-        double wt0 = (w < b1) ? 1.0 : ((w < b2) ? 2.0 : mave);
-        double s0 = (E_s[x0 & 0xFFFFu] + E_s[(x0 >> 16) & 0xFFFFu]) + (E_s[(x0 >> 32) & 0xFFFFu] + E_s[x0 >> 48]);
-        acc = fma(wt0, s0, acc);
+    // tail: up to four words, loads issued together
+    uint64_t x[4];
+    uint32_t n = 0;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        x[t] = 0;
+        if (w + 32u * t < nw) { x[t] = ld_stream_u64(ptr + w + 32u * t); n = t + 1; }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        if ((uint32_t)t < n) {
+            const uint32_t ww = w + 32u * t;
+            const double wt = (ww < b1) ? 1.0 : ((ww < b2) ? 2.0 : mave);
+            acc = fma(wt, gather4(x[t], E_s), acc);
+        }
     }
     return acc;
 }
@@ -120,31 +179,35 @@ __device__ __forceinline__ double dot_bed_block(const uint64_t *__restrict__ ptr
     return acc;
 }
 
-// ---- epsilon update of one marker on the CTA's slice (all threads) --------------
-__device__ __forceinline__ void apply_marker(uint64_t r, uint32_t c, uint32_t S, uint32_t L, double dbs,
-                                             double mave, double *__restrict__ E_s) {
-    if (r & 1ull) {
-        const uint64_t *ptr = reinterpret_cast<const uint64_t *>(r & ~15ull) + (size_t)c * (L / 32);
-        for (uint32_t i = threadIdx.x; i < L; i += blockDim.x) {
-            const uint64_t bits = ptr[i >> 5];
-            const uint32_t code = (uint32_t)(bits >> (2u * (i & 31u))) & 3u;
-            if (code != 3u) {
-                const double wt = (code == 0u) ? 2.0 : ((code == 2u) ? 1.0 : mave);
-                E_s[i] += wt * dbs;
-            }
+// ---- epsilon update with one 64-bit word of a marker's slice block; both return the sum of
+//      what was added to real individuals (keeps the slice sum current without a rescan)
+// BED: word w covers individuals 32w .. 32w+31
+__device__ __forceinline__ double apply_bed_word(uint64_t x, uint32_t w, double dbs, double mave, double *__restrict__ E_s,
+                                                 uint32_t lane) {
+    if (x == ~0ull) return 0.0;
+    double *e = E_s + 32u * w;
+    const double d1 = dbs, d2 = 2.0 * dbs, dm = mave * dbs;
+    double added = 0.0;
+#pragma unroll 8
+    for (uint32_t t = 0; t < 32; t++) {
+        const uint32_t idx = (t + lane) & 31u;
+        const uint32_t code = (uint32_t)(x >> (2u * idx)) & 3u;
+        if (code != 3u) {
+            const double d = (code == 0u) ? d2 : ((code == 2u) ? d1 : dm);
+            e[idx] += d;
+            added += d;
         }
-    } else {
-        const uint8_t *base = reinterpret_cast<const uint8_t *>(r);
-        const uint32_t *dir = reinterpret_cast<const uint32_t *>(base) + c * 3;
-        const uint32_t st = dir[0], n1 = dir[1] & 0xFFFFu, n2 = dir[1] >> 16, nm = dir[2];
-        const uint16_t *blk = reinterpret_cast<const uint16_t *>(base + dir_bytes(S)) + (size_t)st * 4;
-        const uint32_t o2 = ((n1 + 3) / 4) * 4, om = o2 + ((n2 + 3) / 4) * 4;
-        const double d1 = dbs, d2 = 2.0 * dbs, dm = mave * dbs;
-        // indices are unique inside one marker: no write conflicts
-        for (uint32_t e = threadIdx.x; e < n1; e += blockDim.x) E_s[blk[e]] += d1;
-        for (uint32_t e = threadIdx.x; e < n2; e += blockDim.x) E_s[blk[o2 + e]] += d2;
-        for (uint32_t e = threadIdx.x; e < nm; e += blockDim.x) E_s[blk[om + e]] += dm;
     }
+    return added;
+}
+// sparse: four u16 indices, unique inside a marker; unused lanes of a word point at the dummy slot L
+__device__ __forceinline__ double apply_word(uint64_t x, double d, double *__restrict__ E_s, uint32_t L) {
+    const uint32_t i0 = (uint32_t)(x & 0xFFFFu), i1 = (uint32_t)((x >> 16) & 0xFFFFu);
+    const uint32_t i2 = (uint32_t)((x >> 32) & 0xFFFFu), i3 = (uint32_t)(x >> 48);
+    const double e0 = E_s[i0], e1 = E_s[i1], e2 = E_s[i2], e3 = E_s[i3];  // independent loads
+    E_s[i0] = e0 + d; E_s[i1] = e1 + d; E_s[i2] = e2 + d; E_s[i3] = e3 + d;
+    const uint32_t real = (i0 != L) + (i1 != L) + (i2 != L) + (i3 != L);
+    return d * (double)real;
 }
 
 __device__ __forceinline__ double block_sum(double v, double *red /*[32]*/) {
@@ -159,80 +222,134 @@ __device__ __forceinline__ double block_sum(double v, double *red /*[32]*/) {
     return s;
 }
 
+struct HypTabs {
+    const double *logPi, *chalf, *denom, *sdk;
+};
+
 // ---- mixture draw of one marker (src/BayesRRm.cpp:1721-1933) ---------------------
-// Executed by the thread that delivered the last slice partial of window position p.
-__device__ void draw_marker(const BrrParams &P, uint32_t p, uint32_t q, int32_t m, uint32_t dbuf) {
+// Executed by the thread that delivered the last slice partial of table entry k (window position p).
+__device__ void draw_marker(const BrrParams &P, const ItemTab *tab, uint32_t k, const HypTabs &H, uint32_t p, uint32_t q,
+                            uint32_t dbuf) {
     // sum the S slice partials in slice order (deterministic)
     const double *pp = P.partial + (size_t)p * P.S;
     double sum = 0.0;
     for (uint32_t c = 0; c < P.S; c++) sum += __ldcg(pp + c);
-    const double mstd = P.mstd[m];
+    const double mstd = tab->mstd[k];
+    const size_t slot = (size_t)dbuf * P.Wmax + p;
     if (P.mode == MODE_DOT) {
         P.num_out[q] = __dmul_rn(mstd, sum);
-        P.dB[(size_t)dbuf * P.Wmax + p] = 0.0;
+        P.dB[slot] = 0.0;
         return;
     }
-    const int g = P.grp[m];
+    const int32_t m = tab->m[k];
+    const int g = tab->grp[k];
     const uint32_t K = P.K;
-    const double beta_old = P.beta[m];
+    const double beta_old = tab->beta[k];
     double beta_new = 0.0, acum = 1.0;
-    int comp = 0;
     if (P.grp_active[g]) {
         // num = mstd*(...) ; num += beta*(N-1)            (:1809/:316-342, :1855)
         const double num = __dadd_rn(__dmul_rn(mstd, sum), __dmul_rn(beta_old, P.dNm1));
-        double logL[kMaxMix], muk[kMaxMix];
-        const double *lp = P.logPi + g * K, *ch = P.chalf + g * K, *dn = P.denom + g * K;
+        double logL[kMaxMix];
+        const double *lp = H.logPi + g * K, *ch = H.chalf + g * K, *dn = H.denom + g * K;
         logL[0] = lp[0];
-        muk[0] = 0.0;
-        for (uint32_t k = 1; k < K; k++) {
-            muk[k] = num / dn[k];                                                    // :1859
-            logL[k] = __dadd_rn(__dadd_rn(lp[k], -ch[k]), __dmul_rn(__dmul_rn(muk[k], num), P.i_2sigE));  // :1874-1876
-        }
-        const double prob = P.u[q];                                                  // :1880
         bool big = false;
-        for (uint32_t k = 1; k < K; k++) big |= (fabs(logL[k] - logL[0]) > 700.0);   // :1884
-        if (big) acum = 0.0;
-        else {
-            double s = 0.0;
-            for (uint32_t k = 0; k < K; k++) s += exp(logL[k] - logL[0]);
-            acum = 1.0 / s;
+        double s = 1.0;  // exp(logL[0]-logL[0])
+        for (uint32_t kk = 1; kk < K; kk++) {
+            const double muk = num / dn[kk];                                          // :1859
+            // logL = log(pi) - 0.5*log(...) + muk*num*i_2sigE, evaluated left to right   (:1874-1876)
+            logL[kk] = __dadd_rn(__dadd_rn(lp[kk], -ch[kk]), __dmul_rn(__dmul_rn(muk, num), P.i_2sigE));
+            big |= (fabs(logL[kk] - logL[0]) > 700.0);                                // :1884
+            s += exp(logL[kk] - logL[0]);
         }
-        const double acum0 = acum;
-        for (uint32_t k = 0; k < K; k++) {                                           // :1894-1921
-            if (prob <= acum || k == K - 1) {
-                if (k > 0) beta_new = __dadd_rn(muk[k], __dmul_rn(P.sdk[g * K + k], P.z[q]));  // :1901
-                comp = (int)k;
+        acum = big ? 0.0 : 1.0 / s;
+        const double acum0 = acum;                                                   // Acum(marker), :1892
+        const double prob = tab->u[k];                                               // :1880
+        int comp = 0;
+        for (uint32_t kk = 0; kk < K; kk++) {                                        // :1894-1921
+            if (prob <= acum || kk == K - 1) {
+                if (kk > 0) beta_new = __dadd_rn(num / dn[kk], __dmul_rn(H.sdk[g * K + kk], tab->z[k]));  // :1901
+                comp = (int)kk;
                 break;
             } else {
                 bool big2 = false;
-                for (uint32_t i = k + 1; i < K; i++) big2 |= (fabs(logL[i] - logL[k + 1]) > 700.0);
+                for (uint32_t i = kk + 1; i < K; i++) big2 |= (fabs(logL[i] - logL[kk + 1]) > 700.0);
                 if (!big2) {
-                    double s = 0.0;
-                    for (uint32_t i = 0; i < K; i++) s += exp(logL[i] - logL[k + 1]);
-                    acum += 1.0 / s;
+                    double s2 = 0.0;
+                    for (uint32_t i = 0; i < K; i++) s2 += exp(logL[i] - logL[kk + 1]);
+                    acum += 1.0 / s2;
                 }
             }
         }
-        acum = acum0;                                                                // Acum(marker), :1892
+        acum = acum0;
         atomicAdd(&P.cass[g * K + comp], 1);                                         // :1904
+        P.comp[m] = comp;
+    }                                                                                // else :1924-1925
+    const double dbeta = beta_old - beta_new;                                        // :1933
+    if (dbeta != 0.0) {
+        P.dMave[slot] = tab->mave[k];
+        P.dRec[slot] = tab->rec[k];
+        P.dB[slot] = __dmul_rn(dbeta, mstd);
+        atomicAdd(&P.stats[5], 1ull);
+    } else {
+        P.dB[slot] = 0.0;
     }
     P.beta[m] = beta_new;
-    if (P.grp_active[g]) P.comp[m] = comp;  // :1924-1925 leave components untouched
     P.acum[m] = acum;
-    const double dbeta = beta_old - beta_new;                                        // :1933
-    P.dB[(size_t)dbuf * P.Wmax + p] = (dbeta != 0.0) ? __dmul_rn(dbeta, mstd) : 0.0;
-    if (dbeta != 0.0) atomicAdd(&P.stats[5], 1ull);
 }
+
+// Item table of one window chunk: one thread per window position of this CTA group.
+// Threads [t0, t0+nt) take part; the blocks are prefetched into L2.
+__device__ __forceinline__ void build_table(ItemTab *tab, const BrrParams &P, uint32_t r, uint32_t c, uint32_t base,
+                                            uint32_t W, uint32_t k0, uint32_t t0, uint32_t nt, bool prefetch) {
+    const uint32_t n_items = (W > r) ? (W - r + P.R - 1) / P.R : 0;
+    const uint32_t nk = (n_items > k0) ? min((uint32_t)kTabCap, n_items - k0) : 0;
+    const uint32_t tl = threadIdx.x - t0;
+    for (uint32_t k = tl; k < nk; k += nt) {
+        const uint32_t p = r + P.R * (k0 + k);
+        const int32_t m = P.order[base + p];
+        tab->m[k] = m;
+        tab->nw[k] = 0;
+        if (m >= 0) {
+            const uint64_t rr = P.rec[m];
+            const Blk b = decode_block(rr, c, P.S, P.L);
+            tab->rec[k] = rr;
+            tab->mave[k] = P.mave[m]; tab->mstd[k] = P.mstd[m]; tab->beta[k] = P.beta[m];
+            tab->grp[k] = P.grp[m];
+            tab->u[k] = P.u[base + p]; tab->z[k] = P.z[base + p];
+            tab->ptr[k] = b.ptr; tab->nw[k] = b.nw; tab->b1[k] = b.b1; tab->b2[k] = b.b2;
+            if (prefetch) {
+                const char *a = reinterpret_cast<const char *>(b.ptr);
+                const char *e = a + (size_t)b.nw * 8;
+                for (a = reinterpret_cast<const char *>((uintptr_t)a & ~(uintptr_t)127); a < e; a += 128) prefetch_l2(a);
+            }
+        }
+    }
+    if (tl == 0) { tab->tag_base = base; tab->tag_W = W; tab->tag_k0 = k0; tab->tag_valid = 1; }
+}
+
+// last index x with cum[x] <= f (cum ascending, cum[0] = 0, f < cum[n])
+__device__ __forceinline__ uint32_t find_entry(const uint32_t *cum, uint32_t n, uint32_t f) {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (cum[mid] <= f) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+constexpr uint32_t kApplyQ = 4;          // 64-bit words staged in registers per thread and round
+constexpr uint32_t kHypSmem = 64;        // G*K up to this: hyper-parameter tables live in shared memory
 
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *E_s = reinterpret_cast<double *>(smem_raw);                 // [L+1], slot L = dummy for PAD
-    ItemTab *tab = reinterpret_cast<ItemTab *>(smem_raw + (((size_t)P.L + 2) * 8 + 15) / 16 * 16);
+    ItemTab *tabs = reinterpret_cast<ItemTab *>(smem_raw + (((size_t)P.L + 2) * 8 + 15) / 16 * 16);
+    ChgTab *chg = reinterpret_cast<ChgTab *>(tabs + 2);
     __shared__ double red[32];
+    __shared__ double hyp_s[4 * kHypSmem];
     __shared__ uint32_t work_ctr;
     __shared__ uint32_t chg_n;
-    __shared__ uint32_t chg_p[kThreads];
     __shared__ uint32_t chg_base[33];
 
     const uint32_t S = P.S, L = P.L, R = P.R;
@@ -240,6 +357,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t nctas = gridDim.x;
 
+    if (tid == 0) { tabs[0].tag_valid = 0; tabs[1].tag_valid = 0; }
+    HypTabs H{P.logPi, P.chalf, P.denom, P.sdk};
+    {
+        const uint32_t gk = P.G * P.K;
+        if (gk <= kHypSmem) {
+            for (uint32_t i = tid; i < gk; i += blockDim.x) {
+                hyp_s[i] = P.logPi[i]; hyp_s[kHypSmem + i] = P.chalf[i];
+                hyp_s[2 * kHypSmem + i] = P.denom[i]; hyp_s[3 * kHypSmem + i] = P.sdk[i];
+            }
+            H = HypTabs{hyp_s, hyp_s + kHypSmem, hyp_s + 2 * kHypSmem, hyp_s + 3 * kHypSmem};
+        }
+    }
     // ---- load the slice (fold the base terms of the previous launch) -------------
     for (uint32_t i = tid; i < L; i += blockDim.x) {
         const uint32_t gi = c * L + i;
@@ -255,6 +384,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
     }
 
     uint32_t bar_target = 0;
+    long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tclk = clock64();
+    unsigned long long gts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define HB_PHASE(i) do { if (tid == 0) { long long t_ = clock64(); tph[i] += t_ - tclk; tclk = t_; \
+        if (P.cta_cycles && win == 10) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); gts[i] = g_; } } } while (0)
     double off = 0.0;
     uint32_t j0 = 0, since = 0, win = 0;
     unsigned long long nnz_dot = 0, nnz_upd = 0, n_bed = 0, n_sync = 0;
@@ -270,36 +403,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
         if (P.mode != MODE_SCAADD) {
             for (uint32_t k0 = 0; k0 < n_items; k0 += kTabCap) {
                 const uint32_t nk = min((uint32_t)kTabCap, n_items - k0);
-                // ---- 1. item table: one thread per window position of this group ------
-                for (uint32_t k = tid; k < nk; k += blockDim.x) {
-                    const uint32_t p = r + R * (k0 + k);
-                    const int32_t m = P.order[base + p];
-                    tab->m[k] = m;
-                    tab->nw[k] = 0;
-                    if (m >= 0) {
-                        const uint64_t rr = P.rec[m];
-                        tab->mave[k] = P.mave[m];
-                        if (rr & 1ull) {
-                            tab->ptr[k] = reinterpret_cast<const uint64_t *>(rr & ~15ull) + (size_t)c * (L / 32);
-                            tab->nw[k] = L / 32;
-                            tab->b1[k] = 0xFFFFFFFFu;
-                            tab->b2[k] = 0xFFFFFFFFu;
-                        } else {
-                            const uint8_t *bp = reinterpret_cast<const uint8_t *>(rr);
-                            const uint32_t *dir = reinterpret_cast<const uint32_t *>(bp) + c * 3;
-                            const uint32_t st = dir[0], n12 = dir[1], nm = dir[2];
-                            const uint32_t w1 = ((n12 & 0xFFFFu) + 3) / 4, w2 = ((n12 >> 16) + 3) / 4, wm = (nm + 3) / 4;
-                            tab->ptr[k] = reinterpret_cast<const uint64_t *>(bp + dir_bytes(S)) + st;
-                            tab->b1[k] = w1;
-                            tab->b2[k] = w1 + w2;
-                            tab->nw[k] = w1 + w2 + wm;
-                        }
-                    } else if (P.mode == MODE_CHAIN) {
-                        P.dB[(size_t)dbuf * P.Wmax + p] = 0.0;  // padded task step (:2029-2034); every slice CTA writes 0
-                    }
+                ItemTab *tab = &tabs[win & 1u];
+                // ---- 1. item table (normally prebuilt during the previous window) -------
+                if (!(tab->tag_valid && tab->tag_base == base && tab->tag_W == W && tab->tag_k0 == k0)) {
+                    __syncthreads();
+                    build_table(tab, P, r, c, base, W, k0, 0, blockDim.x, false);
                 }
                 if (tid == 0) work_ctr = 0;
                 __syncthreads();
+                HB_PHASE(0);
                 // ---- 2. phase A: warps pull items -------------------------------------
                 for (;;) {
                     uint32_t k = 0;
@@ -321,35 +433,68 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                     if (lane == 0) tab->part[k] = acc;
                 }
                 __syncthreads();
+                HB_PHASE(1);
                 // ---- 3. publish slice partials; last arriver draws ---------------------
-                for (uint32_t k = tid; k < nk; k += blockDim.x) {
-                    const int32_t m = tab->m[k];
-                    if (m < 0) continue;
-                    const uint32_t p = r + R * (k0 + k);
-                    // partial of num/mstd: sum_1 + 2 sum_2 + mave*sum_M - mave*sum_slice   (:327-339)
-                    const double val = fma(-tab->mave[k], slice_sum, tab->part[k]);
-                    __stcg(P.partial + (size_t)p * S + c, val);
-                    __threadfence();
-                    const uint32_t old = atomicAdd(P.cnt + p, 1u);
-                    if ((old + 1u) % S == 0u) {
-                        __threadfence();
-                        draw_marker(P, p, base + p, m, dbuf);
+                //         meanwhile the upper warps prepare the next window's table
+                if (tid < kTabCap) {
+                    const uint32_t k = tid;
+                    if (k < nk) {
+                        const int32_t m = tab->m[k];
+                        const uint32_t p = r + R * (k0 + k);
+                        if (m < 0) {
+                            if (P.mode == MODE_CHAIN) P.dB[(size_t)dbuf * P.Wmax + p] = 0.0;  // padded task step (:2029-2034)
+                        } else {
+                            // partial of num/mstd: sum_1 + 2 sum_2 + mave*sum_M - mave*sum_slice   (:327-339)
+                            const double val = fma(-tab->mave[k], slice_sum, tab->part[k]);
+                            __stcg(P.partial + (size_t)p * S + c, val);
+                            __threadfence();
+                            const uint32_t old = atomicAdd(P.cnt + p, 1u);
+                            if ((old + 1u) % S == 0u) {
+                                __threadfence();
+                                draw_marker(P, tab, k, H, p, base + p, dbuf);
+                            }
+                        }
+                    }
+                } else if (P.mode == MODE_CHAIN && k0 + kTabCap >= n_items) {
+                    // speculate that this window ends with a synchronisation: next window = SR steps
+                    const uint32_t j1 = j0 + n;
+                    if (j1 < P.lmax) {
+                        const uint32_t n1 = min(SR, P.lmax - j1);
+                        build_table(&tabs[(win + 1u) & 1u], P, r, c, j1 * P.T, n1 * P.T, 0, kTabCap, blockDim.x - kTabCap, !(P.flags & 1u));
                     }
                 }
                 __syncthreads();  // table reuse
+                HB_PHASE(2);
             }
             if (P.mode == MODE_DOT) break;  // single window, nothing to apply
             // ---- 4. the one grid barrier of the window --------------------------------
             grid_barrier(P.bar, bar_target, nctas);
+            HB_PHASE(3);
         }
 
         // ---- 5. apply the window's non-zero deltaBetas in window order ---------------
         bool any = false;
-        const double *dB = P.dB + (size_t)dbuf * P.Wmax;
+        double added = 0.0;
+        const size_t dslot = (size_t)dbuf * P.Wmax;
         for (uint32_t p0 = 0; p0 < W; p0 += blockDim.x) {
             const uint32_t p = p0 + tid;
-            const double d = (p < W) ? __ldcg(dB + p) : 0.0;
+            const double d = (p < W) ? __ldcg(P.dB + dslot + p) : 0.0;
             const bool ch = (d != 0.0);
+            // every changed position decodes its own record: one dependent-load chain for all of them
+            Blk b;
+            double mv = 0.0;
+            if (ch) {
+                uint64_t rr;
+                if (P.mode == MODE_SCAADD) {
+                    const int32_t m = P.order[base + p];
+                    rr = P.rec[m];
+                    mv = P.mave[m];
+                } else {
+                    rr = __ldcg(P.dRec + dslot + p);
+                    mv = __ldcg(P.dMave + dslot + p);
+                }
+                b = decode_block(rr, c, S, L);
+            }
             const uint32_t bal = __ballot_sync(0xffffffffu, ch);
             if (lane == 0) chg_base[warp] = __popc(bal);
             __syncthreads();
@@ -359,32 +504,86 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                 chg_n = a;
             }
             __syncthreads();
-            if (ch) chg_p[chg_base[warp] + __popc(bal & ((1u << lane) - 1u))] = p;
-            __syncthreads();
             const uint32_t nchg = chg_n;
-            for (uint32_t x = 0; x < nchg; x++) {
-                const uint32_t pc = chg_p[x];
-                const int32_t m = P.order[base + pc];
-                const double dbs = __ldcg(dB + pc);
-                const double mv = P.mave[m];
-                const uint64_t rr = P.rec[m];
-                apply_marker(rr, c, S, L, dbs, mv, E_s);
-                off = fma(-mv, dbs, off);  // base term -mave*mstd*deltaBeta of every individual (:265-267)
-                if (tid == 0 && !(rr & 1ull)) {
-                    const uint32_t *dir = reinterpret_cast<const uint32_t *>(rr) + c * 3;
-                    nnz_upd += (dir[1] & 0xFFFFu) + (dir[1] >> 16) + dir[2];
+            const uint32_t slot = chg_base[warp] + __popc(bal & ((1u << lane) - 1u));
+            for (uint32_t x0 = 0; x0 < nchg; x0 += kChgCap) {
+                const uint32_t nx = min((uint32_t)kChgCap, nchg - x0);
+                if (ch && slot >= x0 && slot < x0 + nx) {
+                    const uint32_t x = slot - x0;
+                    chg->ptr[x] = b.ptr; chg->nw[x] = b.nw; chg->b1[x] = b.b1; chg->b2[x] = b.b2;
+                    chg->dbs[x] = d; chg->mave[x] = mv;
+                }
+                __syncthreads();
+                if (warp == 0) {  // exclusive prefix of the block lengths (nx <= 64)
+                    const uint32_t a0 = (lane < nx && chg->b1[lane] != 0xFFFFFFFFu) ? chg->nw[lane] : 0u;
+                    const uint32_t a1 = (lane + 32 < nx && chg->b1[lane + 32] != 0xFFFFFFFFu) ? chg->nw[lane + 32] : 0u;
+                    uint32_t s0 = a0, s1 = a1;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t0 = __shfl_up_sync(0xffffffffu, s0, o), t1 = __shfl_up_sync(0xffffffffu, s1, o);
+                        if (lane >= (uint32_t)o) { s0 += t0; s1 += t1; }
+                    }
+                    const uint32_t tot0 = __shfl_sync(0xffffffffu, s0, 31);
+                    chg->cum[lane + 1] = s0;
+                    chg->cum[lane + 33] = tot0 + s1;
+                    if (lane == 0) chg->cum[0] = 0;
+                }
+                __syncthreads();
+                const uint32_t total = chg->cum[nx];
+                HB_PHASE(4);
+                // sparse words of all staged markers, flattened: loaded together, applied in marker order
+                // (BED blocks have length 0 in the flattened space and are applied by the whole CTA in their turn)
+                uint32_t xdone = 0;  // entries [0, xdone) are complete
+                for (uint32_t f0 = 0; f0 < total || xdone < nx; f0 += kApplyQ * kThreads) {
+                    uint64_t wd[kApplyQ];
+                    uint32_t we[kApplyQ];
+                    double dd[kApplyQ];
+#pragma unroll
+                    for (uint32_t i = 0; i < kApplyQ; i++) {
+                        const uint32_t f = f0 + tid + i * kThreads;
+                        we[i] = 0xFFFFFFFFu; wd[i] = 0; dd[i] = 0.0;
+                        if (f < total) {
+                            const uint32_t x = find_entry(chg->cum, nx, f);
+                            const uint32_t w = f - chg->cum[x];
+                            we[i] = x;
+                            wd[i] = ld_stream_u64(chg->ptr[x] + w);
+                            dd[i] = ((w < chg->b1[x]) ? 1.0 : ((w < chg->b2[x]) ? 2.0 : chg->mave[x])) * chg->dbs[x];
+                        }
+                    }
+                    HB_PHASE(6);
+                    const uint32_t fend = min(total, f0 + kApplyQ * kThreads);
+                    // last entry touched by this round; trailing entries without flattened words (BED, empty) follow it
+                    uint32_t xhi = (f0 < total) ? find_entry(chg->cum, nx, fend - 1u) : xdone;
+                    if (fend == total) xhi = nx - 1u;
+                    for (uint32_t x = xdone; x <= xhi; x++) {
+                        if (chg->b1[x] == 0xFFFFFFFFu) {
+                            const uint32_t nwb = chg->nw[x];
+                            const double dbs = chg->dbs[x], mave = chg->mave[x];
+                            for (uint32_t w = tid; w < nwb; w += blockDim.x)
+                                added += apply_bed_word(ld_stream_u64(chg->ptr[x] + w), w, dbs, mave, E_s, lane);
+                        } else {
+#pragma unroll
+                            for (uint32_t i = 0; i < kApplyQ; i++)
+                                if (we[i] == x) added += apply_word(wd[i], dd[i], E_s, L);
+                        }
+                        __syncthreads();
+                    }
+                    // an entry cut by the round boundary continues in the next round
+                    xdone = (fend < total && chg->cum[xhi + 1] > fend) ? xhi : xhi + 1u;
+                    HB_PHASE(7);
+                }
+                for (uint32_t x = 0; x < nx; x++) {
+                    off = fma(-chg->mave[x], chg->dbs[x], off);  // base term -mave*mstd*deltaBeta of every individual (:265-267)
+                    if (tid == 0 && chg->b1[x] != 0xFFFFFFFFu) nnz_upd += 4ull * chg->nw[x];
                 }
                 __syncthreads();
             }
             any |= (nchg > 0);
-            __syncthreads();
         }
+        HB_PHASE(4);
         if (any) {
-            if (tid == 0) E_s[L] = 0.0;  // PAD slot
-            __syncthreads();
-            double v = 0.0;
-            for (uint32_t i = tid; i < L; i += blockDim.x) v += E_s[i];
-            slice_sum = block_sum(v, red);
+            if (tid == 0) E_s[L] = 0.0;  // the dummy slot collected the PAD lanes
+            slice_sum += block_sum(added, red);
             since = 0;
             n_sync++;
         } else {
@@ -392,6 +591,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
         }
         j0 += n;
         win++;
+        HB_PHASE(5);
     }
 
     // ---- epilogue: group 0 stores the slices and their sums ----------------------------
@@ -412,8 +612,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
             *P.off_out = off;
             P.stats[0] = n_sync;
             P.stats[1] = win;
+            for (int i = 0; i < 8; i++) P.stats[8 + i] = (unsigned long long)tph[i];
         }
     }
+    if (P.cta_cycles && tid == 0)
+        for (int i = 0; i < 8; i++) P.cta_cycles[(size_t)blockIdx.x * 8 + i] = gts[i];
     // traffic counters (lane 0 of every warp holds a share)
     if (lane == 0) {
         if (nnz_dot) atomicAdd(&P.stats[2], nnz_dot);

@@ -56,8 +56,9 @@ constexpr uint32_t kDirWordsPerSlice = 3;
 __host__ __device__ inline uint32_t dir_bytes(uint32_t S) { return (12u * S + 15u) & ~15u; }
 
 constexpr int kMaxMix = 16;      // K <= 16 mixture components (incl. zero)
-constexpr int kThreads = 1024;   // threads per CTA of the sampler kernel
+constexpr int kThreads = 512;    // threads per CTA of the sampler kernel
 constexpr int kTabCap = 128;     // window items staged per table chunk
+constexpr int kChgCap = 64;      // changed markers staged per epsilon-update round
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- device helpers
@@ -87,11 +88,10 @@ __device__ __forceinline__ void grid_barrier(uint32_t *bar, uint32_t &target, ui
     __syncthreads();
     target += nctas;
     if (threadIdx.x == 0) {
-        __threadfence();
+        // release: makes the CTA's writes (ordered before by bar.sync) visible; acquire: the other CTAs'
         red_release_add_u32(bar, 1u);
         while (ld_acquire_u32(bar) < target) {
         }
-        __threadfence();
     }
     __syncthreads();
 }

@@ -103,9 +103,11 @@ struct hb_ctx {
     DevBuf<double> d_hyp;
     DevBuf<uint8_t> d_active;
     // scratch
-    DevBuf<double> d_partial, d_dB, d_num;
+    DevBuf<double> d_partial, d_dB, d_dMave, d_num;
+    DevBuf<uint64_t> d_dRec;
     DevBuf<uint32_t> d_cntr, d_bar, d_markers;
-    DevBuf<unsigned long long> d_stats;
+    DevBuf<unsigned long long> d_stats, d_ctacyc;
+    bool debug_cycles = false;
     uint32_t Wmax = 0;
 
     // chain (host)
@@ -145,7 +147,7 @@ static void define_blocks(uint32_t Mtot, uint32_t nblocks, std::vector<int32_t> 
     }
 }
 
-static size_t smem_for(uint32_t L) { return (((size_t)L + 2) * 8 + 15) / 16 * 16 + sizeof(ItemTab); }
+static size_t smem_for(uint32_t L) { return (((size_t)L + 2) * 8 + 15) / 16 * 16 + 2 * sizeof(ItemTab) + sizeof(ChgTab); }
 
 static int ensure_scratch(hb_ctx *c, uint32_t W) {
     if (W <= c->Wmax) return HB_OK;
@@ -153,6 +155,8 @@ static int ensure_scratch(hb_ctx *c, uint32_t W) {
     HB_TRY(c->d_partial.alloc((size_t)W * c->S));
     HB_TRY(c->d_cntr.alloc(W));
     HB_TRY(c->d_dB.alloc((size_t)2 * W));
+    HB_TRY(c->d_dMave.alloc((size_t)2 * W));
+    HB_TRY(c->d_dRec.alloc((size_t)2 * W));
     HB_TRY(c->d_cntr.zero(c->stream));
     HB_TRY(c->d_dB.zero(c->stream));
     c->Wmax = W;
@@ -184,10 +188,12 @@ static void fill_params(hb_ctx *c, BrrParams &P) {
     P.logPi = c->d_hyp.p; P.chalf = c->d_hyp.p + gk; P.denom = c->d_hyp.p + 2 * gk; P.sdk = c->d_hyp.p + 3 * gk;
     P.grp_active = c->d_active.p;
     P.dNm1 = (double)(c->N - 1);
-    P.partial = c->d_partial.p; P.cnt = c->d_cntr.p; P.dB = c->d_dB.p; P.Wmax = c->Wmax;
+    P.partial = c->d_partial.p; P.cnt = c->d_cntr.p; P.dB = c->d_dB.p; P.dMave = c->d_dMave.p; P.dRec = c->d_dRec.p; P.Wmax = c->Wmax;
     P.bar = c->d_bar.p; P.stats = c->d_stats.p;
     P.mode = MODE_CHAIN;
     P.num_out = c->d_num.p;
+    P.cta_cycles = c->debug_cycles ? c->d_ctacyc.p : nullptr;
+    P.flags = getenv("HB_NO_PREFETCH") ? 1u : 0u;
 }
 
 static int launch_window_kernel(hb_ctx *c, BrrParams &P) {
@@ -274,13 +280,23 @@ int hb_create(const hb_config *cfg, hb_ctx **out) {
     HB_CUDA(cudaFuncGetAttributes(&fa, (const void *)k_brr_iteration));
     const size_t avail = (size_t)max_smem - fa.sharedSizeBytes;
     uint32_t max_ctas = cfg->max_ctas ? std::min<uint32_t>(cfg->max_ctas, c->n_sms) : (uint32_t)c->n_sms;
-    uint32_t S = cfg->n_slices ? cfg->n_slices : 1;
-    for (;; S++) {
-        uint32_t L = ((c->N + S - 1) / S + 63u) & ~63u;
-        if (L <= 65472u && smem_for(L) <= avail) { c->S = S; c->L = L; break; }
-        HB_CHECK(cfg->n_slices == 0, HB_ERR_ARG, "hb_create: n_slices=%u gives slices of %u individuals, too large for shared memory", S, L);
-        HB_CHECK(S < max_ctas, HB_ERR_ARG, "hb_create: %u individuals do not fit in the shared memory of %u CTAs", c->N, max_ctas);
+    auto slice_len = [&](uint32_t S) { return ((c->N + S - 1) / S + 63u) & ~63u; };
+    auto fits = [&](uint32_t S) { const uint32_t L = slice_len(S); return L <= 65472u && smem_for(L) <= avail; };
+    if (cfg->n_slices) {
+        HB_CHECK(fits(cfg->n_slices), HB_ERR_ARG, "hb_create: n_slices=%u gives slices of %u individuals, too large for shared memory",
+                 cfg->n_slices, slice_len(cfg->n_slices));
+        c->S = cfg->n_slices;
+    } else {
+        uint32_t smin = 1;
+        while (smin <= max_ctas && !fits(smin)) smin++;
+        HB_CHECK(smin <= max_ctas, HB_ERR_ARG, "hb_create: %u individuals do not fit in the shared memory of %u CTAs", c->N, max_ctas);
+        // among the slice counts near the minimum, take the one that leaves the fewest SMs idle
+        uint32_t best = smin;
+        for (uint32_t S = smin; S <= std::min(max_ctas, smin + smin / 4); S++)
+            if (S * (max_ctas / S) > best * (max_ctas / best)) best = S;
+        c->S = best;
     }
+    c->L = slice_len(c->S);
     HB_CHECK(c->S <= max_ctas, HB_ERR_ARG, "hb_create: %u slices > %u CTAs", c->S, max_ctas);
     c->R = max_ctas / c->S;
     c->smem_bytes = smem_for(c->L);
@@ -324,8 +340,10 @@ int hb_create(const hb_config *cfg, hb_ctx **out) {
     HB_CUDA(cudaMemset(c->d_cass.p, 0, sizeof(int32_t) * gk));
     HB_CUDA(cudaMemset(c->d_hyp.p, 0, sizeof(double) * 4 * gk));
     HB_CUDA(cudaMemset(c->d_active.p, 0, c->G));
-    HB_TRY(c->d_bar.alloc(1)); HB_TRY(c->d_stats.alloc(8));
-    HB_CUDA(cudaMemset(c->d_stats.p, 0, 8 * sizeof(unsigned long long)));
+    HB_TRY(c->d_bar.alloc(1)); HB_TRY(c->d_stats.alloc(16));
+    c->debug_cycles = getenv("HB_DEBUG_CYCLES") != nullptr;
+    HB_TRY(c->d_ctacyc.alloc((size_t)c->S * c->R * 8));
+    HB_CUDA(cudaMemset(c->d_stats.p, 0, 16 * sizeof(unsigned long long)));
     HB_TRY(c->d_order.alloc(1)); HB_TRY(c->d_u.alloc(1)); HB_TRY(c->d_z.alloc(1)); HB_TRY(c->d_num.alloc(1));
     HB_TRY(ensure_scratch(c.get(), 256));
     HB_TRY(ensure_pin(c.get(), 4096));
@@ -670,6 +688,8 @@ int hb_get_epsilon(hb_ctx *c, double *eps) {
 static int upload_markers(hb_ctx *c, const uint32_t *markers, uint32_t n) {
     for (uint32_t i = 0; i < n; i++) HB_CHECK(markers[i] < c->M, HB_ERR_ARG, "marker %u out of range", markers[i]);
     HB_TRY(c->d_order.ensure(n));
+    HB_TRY(c->d_u.ensure(n));  // the item table reads u/z of every position, also in the unit modes
+    HB_TRY(c->d_z.ensure(n));
     HB_CUDA(cudaMemcpyAsync(c->d_order.p, markers, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
     return HB_OK;
 }
@@ -802,7 +822,7 @@ int hb_brr_init(hb_ctx *c, const double *y, const int32_t *groups, const double 
     HB_TRY(c->d_order.ensure(Q)); HB_TRY(c->d_u.ensure(Q)); HB_TRY(c->d_z.ensure(Q));
     HB_TRY(c->d_perm.ensure(c->M)); HB_TRY(c->d_ut.ensure(c->M)); HB_TRY(c->d_zt.ensure(c->M));
     HB_TRY(ensure_scratch(c, c->SR * c->T));
-    HB_TRY(ensure_pin(c, 8 + 2 * (size_t)c->S + G + (size_t)G * K + 16));
+    HB_TRY(ensure_pin(c, 8 + 2 * (size_t)c->S + G + (size_t)G * K + 32));
     c->iteration = 0;
     c->brr_ready = true;
     return HB_OK;
@@ -876,7 +896,7 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
     HB_CUDA(cudaMemcpyAsync(c->d_hyp.p, c->pin, sizeof(double) * 4 * gk, cudaMemcpyHostToDevice, st));
     HB_CUDA(cudaMemcpyAsync(c->d_active.p, c->active.data(), G, cudaMemcpyHostToDevice, st));
     HB_CUDA(cudaMemsetAsync(c->d_cass.p, 0, sizeof(int32_t) * gk, st));  // :1697
-    HB_CUDA(cudaMemsetAsync(c->d_stats.p, 0, sizeof(unsigned long long) * 8, st));
+    HB_CUDA(cudaMemsetAsync(c->d_stats.p, 0, sizeof(unsigned long long) * 16, st));
 
     // ---- marker loop
     BrrParams P;
@@ -899,10 +919,25 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
     unsigned long long *pin_stats = reinterpret_cast<unsigned long long *>(c->pin + nsmall + (gk + 1) / 2 + 1);
     HB_CUDA(cudaMemcpyAsync(pin_small, c->d_small.p, sizeof(double) * nsmall, cudaMemcpyDeviceToHost, st));
     HB_CUDA(cudaMemcpyAsync(pin_cass, c->d_cass.p, sizeof(int32_t) * gk, cudaMemcpyDeviceToHost, st));
-    HB_CUDA(cudaMemcpyAsync(pin_stats, c->d_stats.p, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
+    HB_CUDA(cudaMemcpyAsync(pin_stats, c->d_stats.p, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost, st));
     HB_CUDA(cudaEventRecord(c->ev[3], st));
     HB_CUDA(cudaStreamSynchronize(st));
 
+    if (c->debug_cycles) {  // developer aid: spread of the per-CTA phase cycles
+        const size_t nc = (size_t)c->S * c->R;
+        std::vector<unsigned long long> cy(nc * 8);
+        cudaMemcpy(cy.data(), c->d_ctacyc.p, sizeof(unsigned long long) * nc * 8, cudaMemcpyDeviceToHost);
+        // globaltimer stamps (ns) of window 10 at the end of each phase, relative to the earliest "table done"
+        unsigned long long t0 = ~0ull;
+        for (size_t b = 0; b < nc; b++) t0 = std::min(t0, cy[b * 8 + 0]);
+        const int ord[7] = {0, 1, 2, 3, 4, 7, 5};
+        const char *nm[7] = {"tab", "dot", "pub", "bar", "upd0", "updA", "sum"};
+        for (int i = 0; i < 7; i++) {
+            double mn = 1e300, mx = 0, sm = 0;
+            for (size_t b = 0; b < nc; b++) { const double v = (double)(cy[b * 8 + ord[i]] - t0); mn = std::min(mn, v); mx = std::max(mx, v); sm += v; }
+            fprintf(stderr, "[hb window 10, ns since first CTA started its dot] end of %-5s min %8.0f mean %8.0f max %8.0f\n", nm[i], mn, sm / (double)nc, mx);
+        }
+    }
     const double off = pin_small[0];
     c->shift = off;  // the launch folded the old shift into E; the new constant is this launch's base terms
     double s1 = 0.0, s2 = 0.0;
@@ -949,6 +984,7 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
         out->n_launches = 3;
         out->nnz_processed = pin_stats[2]; out->nnz_updated = pin_stats[3];
         out->bed_markers = pin_stats[4]; out->markers_changed = pin_stats[5];
+        for (int i = 0; i < 8; i++) out->phase_cycles[i] = pin_stats[8 + i];
     }
     return HB_OK;
 }

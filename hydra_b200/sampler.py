@@ -188,7 +188,9 @@ class BayesRRm:
             tp = C.byref(t)
         check(self._lib.hb_brr_iteration(self.store._h, tp, C.byref(out)))
         self.iteration_index += 1
-        return {n: getattr(out, n) for n, _ in out._fields_}
+        d = {n: getattr(out, n) for n, _ in out._fields_}
+        d["phase_cycles"] = list(out.phase_cycles)
+        return d
 
     def hyper(self):
         s = self.store

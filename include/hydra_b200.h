@@ -151,6 +151,7 @@ typedef struct hb_brr_iter_out {
     uint64_t nnz_updated;     /* stored non-zeros visited by epsilon updates */
     uint64_t bed_markers;     /* markers processed through the BED path */
     uint64_t markers_changed; /* markers with deltaBeta != 0 */
+    uint64_t phase_cycles[8]; /* CTA 0 SM cycles: table, dot, publish+draw, grid barrier, update set-up, slice sum, update loads, update apply */
 } hb_brr_iter_out;
 
 /* One Gibbs iteration: mu, marker loop (sync windows), group statistics, hyper-parameters.

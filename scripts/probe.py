@@ -39,5 +39,5 @@ for ns in a.slices:
                 tw = time.time() - tw
                 print(f"  it {it}: loop {o['loop_ms']:.3f} ms iter {o['iter_ms']:.3f} ms wall {tw*1e3:.1f} ms  {a.m/o['loop_ms']/1e3:.2f} M markers/s  "
                       f"windows {o['n_windows']} syncs {o['n_sync']} changed {o['markers_changed']} us/window {o['loop_ms']*1e3/max(1,o['n_windows']):.2f} "
-                      f"sigmaE {o['sigmaE']:.4f} sigmaG {brr.hyper()['sigmaG'][0]:.4f}", flush=True)
+                      f"sigmaE {o['sigmaE']:.4f} sigmaG {brr.hyper()['sigmaG'][0]:.4f}\n      cyc/window: " + " ".join(f"{n}={v/max(1,o['n_windows']):.0f}" for n, v in zip(["tab","dot","pub","bar","upd0","sum","updL","updA"], o["phase_cycles"])), flush=True)
             st.close()
