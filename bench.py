@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- marker updates/sec and sec/iteration of the BayesRRm marker loop (BASELINE.json metric).
+
+One "step" = one Gibbs iteration over all M markers of the synthetic workload:
+N=500K individuals, spectrum-B sparse genotypes generated on the device, T hydra tasks x sync_rate.
+At --gpus N the markers (and tasks) are partitioned over the N ranks (M = m_per_gpu * N: weak scaling).
+
+Prints ONE JSON line on rank 0 (see the field list in DESIGN.md "Measurement").
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+`--impl reference` times the CPU oracle (the reference loop restated, OpenMP "tasks as threads";
+the reference itself needs MPI+Eigen+Boost and cannot be built in this image) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "marker_updates_per_sec"
+UNIT = "marker updates/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="hydra_b200", choices=["hydra_b200", "reference"])
+    ap.add_argument("--n", type=int, default=500_000, help="individuals")
+    ap.add_argument("--m-per-gpu", type=int, default=1_000_000, help="markers per GPU (M = this x gpus)")
+    ap.add_argument("--spectrum", default="B")
+    ap.add_argument("--tasks-per-gpu", type=int, default=64)
+    ap.add_argument("--sync-rate", type=int, default=10)
+    ap.add_argument("--cpu-sample-markers", type=int, default=16384)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--n-slices", type=int, default=0)
+    return ap.parse_args()
+
+
+def workload_config(a, world):
+    return {
+        "workload": f"BayesRRm sparse, synthetic N={a.n} M={a.m_per_gpu * world} (spectrum {a.spectrum}: log-uniform MAF, "
+                    f"0.1% missing), 1 group, S=0.0001,0.001,0.01, {a.tasks_per_gpu * world} tasks x sync_rate {a.sync_rate}",
+        "n_individuals": a.n, "m_markers": a.m_per_gpu * world, "spectrum": a.spectrum,
+        "tasks": a.tasks_per_gpu * world, "sync_rate": a.sync_rate, "partition": f"markers/tasks over {world} GPU(s)",
+        "l2_policy": "inputs larger than L2 (genotype records >> 126 MB, each read once per step)",
+    }
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.stop_flag, self.index = [], False, index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.t.start()
+
+    def stop(self):
+        self.stop_flag = True
+        self.t.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU oracle leg
+def cpu_sample_lists(a, n_markers, m_total):
+    """Reference-format lists (I1/I2/IM) of the first n_markers markers of the workload, from the oracle's own CPU copy of
+    the synthetic generator (bit-identical to the device generator: tests/test_gpu_parity.py)."""
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    from hydra_b200 import synth  # host-side recipe only (numpy): MAF spectrum and thresholds
+    p = synth.maf_spectrum(m_total, *synth.SPECTRA[a.spectrum])[:n_markers]
+    thr = synth.thresholds(p)
+    chunk = 256
+    jobs = [(o, min(chunk, n_markers - o)) for o in range(0, n_markers, chunk)]
+
+    def work(job):
+        o, k = job
+        bed = oracle.synth_bed(synth.SEED_GENO, a.n, thr[o:o + k], None, j0=o, fast=True)
+        return oracle.sparse_fill_indices(bed, a.n)
+
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+        parts = list(ex.map(work, jobs))
+    I, S, Ln = [[], [], []], [[], [], []], [[], [], []]
+    base = [0, 0, 0]
+    for sp in parts:
+        for w, (ii, ss, ll) in enumerate(((sp.I1, sp.N1S, sp.N1L), (sp.I2, sp.N2S, sp.N2L), (sp.IM, sp.NMS, sp.NML))):
+            I[w].append(ii); S[w].append(ss + np.uint64(base[w])); Ln[w].append(ll)
+            base[w] += len(ii)
+    c = np.concatenate
+    return oracle.SparseLists(c(I[0]), c(S[0]), c(Ln[0]), c(I[1]), c(S[1]), c(Ln[1]), c(I[2]), c(S[2]), c(Ln[2]))
+
+
+def cpu_reference_run(a, n_ind, n_markers, m_total, steps, warmup):
+    """Times the CPU restatement of the reference loop on the first n_markers markers (same spectrum, same N).
+    Layout: T = host cores tasks x 1 thread each (the reference's '12 tasks x 1 thread' MPI layout as OpenMP threads)."""
+    import oracle
+    cores = oracle.num_threads(True)
+    t_prep = time.time()
+    sp = cpu_sample_lists(a, n_markers, m_total)
+    t_prep = time.time() - t_prep
+    T = max(1, min(cores, n_markers))
+    rng = np.random.default_rng(20240902)
+    y = rng.normal(size=n_ind)
+    mS = np.array([[0.0, 0.0001, 0.001, 0.01]])
+    n_iter = steps + warmup
+    tape = oracle.TapeMaker(1222, T, n_markers).make(n_iter)
+    t0 = time.time()
+    out = oracle.brr_chain(n_ind, n_markers, T, 4, 1, a.sync_rate, n_iter, sp, y, np.zeros(n_markers, np.int32), mS, tape,
+                           np.array([0.5]), hyper_seed=7, want_eps=False, fast=True, want_marker_out=False)
+    wall = time.time() - t0
+    loop = out["loop_seconds"][warmup:]
+    rate = n_markers * len(loop) / float(loop.sum())
+    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_markers} markers of the same workload (N={n_ind}), {T} tasks x 1 OpenMP thread, sync_rate {a.sync_rate}, "
+                      f"{len(loop)} timed iteration(s) after {warmup} warm-up; marker loop only; chain {wall:.1f} s + data generation {t_prep:.1f} s",
+            "ms_per_step_sample": float(loop.mean() * 1e3), "compile": "gcc -Ofast -march=native -fopenmp (reference src/Makefile_G flags)"}
+
+
+# ----------------------------------------------------------------------------- main
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus and world > 1:
+        a.gpus = world
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        return reference_arm(a, world)
+
+    import torch
+    import hydra_b200
+    from hydra_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; hydra_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    T_total = a.tasks_per_gpu * world
+    M_total = a.m_per_gpu * world
+    store = hydra_b200.GenotypeStore(a.n, M_total, tasks=T_total, task_first=rank * a.tasks_per_gpu, tasks_local=a.tasks_per_gpu,
+                                     sync_rate=a.sync_rate, n_groups=1, n_mix=4, repr_mode="sparse", device=local_rank,
+                                     n_slices=a.n_slices)
+    t0 = time.time()
+    synth.stage_synthetic(store, a.spectrum)
+    stage_s = time.time() - t0
+    if world > 1:
+        store.comm_init(dist)  # exchange of the epsilon updates between the GPUs (DESIGN.md "Multi-GPU")
+    # phenotype: every rank needs the same y; simulate from rank-local causal markers and sum the genetic values
+    y, _, _ = synth.simulate_phenotype(store, n_causal=5000 // world, seed=synth.SEED_PHEN + rank)
+    if world > 1:
+        e = np.random.Generator(np.random.Philox(key=synth.SEED_PHEN + rank)).normal(0.0, np.sqrt(0.5), size=store.n_ind)
+        g = torch.from_numpy(y - e).cuda()
+        dist.all_reduce(g)
+        e0 = np.random.Generator(np.random.Philox(key=synth.SEED_PHEN)).normal(0.0, np.sqrt(0.5), size=store.n_ind)
+        y = g.cpu().numpy() + e0
+    brr = hydra_b200.BayesRRm(store, y, [[0.0001, 0.001, 0.01]], seed=1222)
+    n1, n2, nm = store.marker_counts()
+    nnz = n1.astype(np.int64) + n2 + nm
+    nnz_total = int(nnz.sum())
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident leg: K iterations, inputs in HBM
+    for _ in range(a.warmup):
+        brr.iteration()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    sync_all()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    t_wall = time.perf_counter()
+    outs = [brr.iteration() for _ in range(a.steps)]
+    ev1.record()
+    sync_all()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    loop_ms = float(sum(o["loop_ms"] for o in outs))
+    iter_ms = float(sum(o["iter_ms"] for o in outs))
+    t = torch.tensor([wall_ms, loop_ms, iter_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall_ms, loop_ms, iter_ms = [float(x) for x in t.cpu()]
+
+    # ---- end-to-end leg through the host API: per step H2D of the marker order (+hyper tables), D2H of beta/components/acum
+    sync_all()
+    t_e2e = time.perf_counter()
+    for _ in range(a.steps):
+        brr.iteration()
+        brr.state()
+        brr.hyper()
+    sync_all()
+    e2e_ms = (time.perf_counter() - t_e2e) * 1e3
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.cpu()[0])
+    clocks = sampler.stop() if sampler else None
+
+    # ---- roofline of the dominant kernel (k_brr_iteration): algorithmic bytes of SURVEY.md 8(d)
+    #      12 B per stored non-zero visited by a dot product + 16 B per non-zero of a changed marker + 24*N per synchronisation
+    pad_ratio = nnz_total / max(1.0, float(np.mean([o["nnz_processed"] for o in outs])))
+    alg_bytes = [12.0 * nnz_total + 16.0 * o["nnz_updated"] * pad_ratio + 24.0 * store.n_ind * o["n_sync"] for o in outs]
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
+    peak = float(peaks["hbm_gbs"]) if peaks else 6650.0
+    achieved = float(np.sum(alg_bytes)) / (loop_ms * 1e-3) / 1e9  # per-rank bytes / max-over-ranks kernel time
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+
+    if rank == 0:
+        res = {
+            "metric": METRIC, "value": M_total * a.steps / (wall_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": wall_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic (device-generated genotypes, simulated phenotype)", "config": workload_config(a, world),
+            "sec_per_iteration": wall_ms / a.steps * 1e-3,
+            "marker_loop": {"ms_per_step": loop_ms / a.steps, "marker_updates_per_sec": M_total * a.steps / (loop_ms * 1e-3),
+                            "windows_per_step": outs[-1]["n_windows"], "syncs_per_step": outs[-1]["n_sync"],
+                            "markers_changed_last_step": outs[-1]["markers_changed"], "us_per_window": loop_ms * 1e3 / sum(o["n_windows"] for o in outs)},
+            "e2e": {"value": M_total * a.steps / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(4 * store.m_local + 8 * 4 * 4 + 1), "d2h_bytes_per_step": int(20 * store.m_local + 8 * (3 + 2 * store.n_slices) + 16 + 128),
+                    "ms_per_step": e2e_ms / a.steps, "what": "BayesRRm.iteration() + state() + hyper() through the C ABI: marker order H2D, beta/components/acum D2H every step (thin=1)"},
+            "gpu_launches": 3 * a.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                         "kernel": "k_brr_iteration (one cooperative launch per step)",
+                         "algorithmic_bytes_per_launch": float(np.mean(alg_bytes)),
+                         "note": "epsilon lives in shared memory and indices are 16-bit, so real DRAM traffic is ~2 B per stored non-zero; "
+                                 "achieved counts the reference's algorithmic 12/16 B per non-zero"},
+            "clocks": clocks,
+            "layout": {"slices": store.n_slices, "slice_len": store.slice_len, "cta_groups": store.n_cta_groups,
+                       "genotype_bytes_per_gpu": store.genotype_bytes, "mean_nnz_per_marker": nnz_total / store.m_local, "stage_seconds": stage_s},
+        }
+        if not a.no_cpu_baseline and world == 1:
+            try:
+                res["cpu_baseline"] = cpu_reference_run(a, a.n, min(a.cpu_sample_markers, M_total), M_total, 1, 1)
+            except Exception as e:  # the bench line must still print
+                res["cpu_baseline"] = {"error": repr(e)}
+        print(json.dumps(res), flush=True)
+    store.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def reference_arm(a, world):
+    """CPU leg as its own arm: same metric/config, bounded sample per step, all host threads."""
+    n_markers = min(a.cpu_sample_markers, a.m_per_gpu * world)
+    r = cpu_reference_run(a, a.n, n_markers, a.m_per_gpu * world, a.steps, a.warmup)
+    res = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+           "ms_per_step": r["ms_per_step_sample"] * (a.m_per_gpu * world / n_markers), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(a, world),
+           "cpu_baseline": r, "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "note": "ms_per_step extrapolated linearly from the sample to the full M; the reference binary needs MPI+Eigen+Boost (absent), "
+                   "so this is the CPU restatement of its loop (oracle/hydra_oracle.c)"}
+    print(json.dumps(res), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

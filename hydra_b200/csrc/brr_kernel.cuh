@@ -23,6 +23,12 @@ namespace hb {
 
 enum : int { MODE_CHAIN = 0, MODE_DOT = 1, MODE_SCAADD = 2 };
 
+struct ChgEnt {  // 32 bytes
+    uint32_t p, pad;
+    double dbs, mave;
+    uint64_t rec;
+};
+
 struct BrrParams {
     // layout
     uint32_t N, S, L, R, M;
@@ -52,8 +58,9 @@ struct BrrParams {
     const uint8_t *grp_active; // [G]
     double i_2sigE, dNm1;
     // scratch
-    double *partial;       // [Wmax*S]
-    uint32_t *cnt;         // [Wmax] arrival counters (monotonic)
+    uint4 *slots;          // [Wmax*S] slice partials as {lo, tag, hi, tag}: data and flag travel together
+    uint32_t *chg_cnt;     // [3] changed markers of a window (triple buffered)
+    ChgEnt *chg_list;      // [3*Wmax] their (position, deltaBeta*mstd, mave, record), in arrival order
     double *dB;            // [2*Wmax] deltaBeta*mstd per window position, double buffered
     double *dMave;         // [2*Wmax] mave of the changed marker
     uint64_t *dRec;        // [2*Wmax] its record
@@ -226,75 +233,96 @@ struct HypTabs {
     const double *logPi, *chalf, *denom, *sdk;
 };
 
-// ---- mixture draw of one marker (src/BayesRRm.cpp:1721-1933) ---------------------
-// Executed by the thread that delivered the last slice partial of table entry k (window position p).
-__device__ void draw_marker(const BrrParams &P, const ItemTab *tab, uint32_t k, const HypTabs &H, uint32_t p, uint32_t q,
-                            uint32_t dbuf) {
-    // sum the S slice partials in slice order (deterministic)
-    const double *pp = P.partial + (size_t)p * P.S;
-    double sum = 0.0;
-    for (uint32_t c = 0; c < P.S; c++) sum += __ldcg(pp + c);
+__device__ __forceinline__ uint4 ld_slot(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_slot(uint4 *p, double val, uint32_t tag) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(val);
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"((uint32_t)b), "r"(tag), "r"((uint32_t)(b >> 32)), "r"(tag) : "memory");
+}
+
+// ---- mixture draw of one marker (src/BayesRRm.cpp:1721-1933), by one warp ---------
+// The warp first collects the S slice partials of table entry k (window position p): every slot carries
+// the window tag next to the data, so no fence or arrival counter is needed. Lane kk < K then evaluates
+// mixture component kk; sums over components are taken in component order (same order as the reference).
+__device__ void draw_marker_warp(const BrrParams &P, const ItemTab *tab, uint32_t k, const HypTabs &H, uint32_t p, uint32_t q,
+                                 uint32_t dbuf, uint32_t buf3, uint32_t tag, uint32_t lane) {
+    const uint4 *sl = P.slots + (size_t)p * P.S;
+    double acc = 0.0;
+    for (uint32_t c0 = 0; c0 < P.S; c0 += 32) {
+        const uint32_t cc = c0 + lane;
+        if (cc < P.S) {
+            uint4 v;
+            do { v = ld_slot(sl + cc); } while (v.y != tag || v.w != tag);
+            acc += __longlong_as_double((long long)(((unsigned long long)v.z << 32) | v.x));
+        }
+    }
+    const double sum = warp_sum(acc);  // xor tree: fixed order
     const double mstd = tab->mstd[k];
     const size_t slot = (size_t)dbuf * P.Wmax + p;
     if (P.mode == MODE_DOT) {
-        P.num_out[q] = __dmul_rn(mstd, sum);
-        P.dB[slot] = 0.0;
+        if (lane == 0) P.num_out[q] = __dmul_rn(mstd, sum);
         return;
     }
     const int32_t m = tab->m[k];
     const int g = tab->grp[k];
     const uint32_t K = P.K;
     const double beta_old = tab->beta[k];
-    double beta_new = 0.0, acum = 1.0;
+    double beta_new = 0.0, acum0 = 1.0;
+    int comp = -1;
     if (P.grp_active[g]) {
         // num = mstd*(...) ; num += beta*(N-1)            (:1809/:316-342, :1855)
         const double num = __dadd_rn(__dmul_rn(mstd, sum), __dmul_rn(beta_old, P.dNm1));
-        double logL[kMaxMix];
-        const double *lp = H.logPi + g * K, *ch = H.chalf + g * K, *dn = H.denom + g * K;
-        logL[0] = lp[0];
-        bool big = false;
-        double s = 1.0;  // exp(logL[0]-logL[0])
-        for (uint32_t kk = 1; kk < K; kk++) {
-            const double muk = num / dn[kk];                                          // :1859
-            // logL = log(pi) - 0.5*log(...) + muk*num*i_2sigE, evaluated left to right   (:1874-1876)
-            logL[kk] = __dadd_rn(__dadd_rn(lp[kk], -ch[kk]), __dmul_rn(__dmul_rn(muk, num), P.i_2sigE));
-            big |= (fabs(logL[kk] - logL[0]) > 700.0);                                // :1884
-            s += exp(logL[kk] - logL[0]);
+        const uint32_t kk = (lane < K) ? lane : 0;
+        double muk = 0.0, logL = H.logPi[g * K + kk];
+        if (kk > 0) {
+            muk = num / H.denom[g * K + kk];                                          // :1859
+            // log(pi) - 0.5*log(...) + muk*num*i_2sigE, evaluated left to right        (:1874-1876)
+            logL = __dadd_rn(__dadd_rn(logL, -H.chalf[g * K + kk]), __dmul_rn(__dmul_rn(muk, num), P.i_2sigE));
         }
-        acum = big ? 0.0 : 1.0 / s;
-        const double acum0 = acum;                                                   // Acum(marker), :1892
         const double prob = tab->u[k];                                               // :1880
-        int comp = 0;
-        for (uint32_t kk = 0; kk < K; kk++) {                                        // :1894-1921
-            if (prob <= acum || kk == K - 1) {
-                if (kk > 0) beta_new = __dadd_rn(num / dn[kk], __dmul_rn(H.sdk[g * K + kk], tab->z[k]));  // :1901
-                comp = (int)kk;
-                break;
-            } else {
-                bool big2 = false;
-                for (uint32_t i = kk + 1; i < K; i++) big2 |= (fabs(logL[i] - logL[kk + 1]) > 700.0);
-                if (!big2) {
-                    double s2 = 0.0;
-                    for (uint32_t i = 0; i < K; i++) s2 += exp(logL[i] - logL[kk + 1]);
-                    acum += 1.0 / s2;
-                }
-            }
+        double ref = __shfl_sync(0xffffffffu, logL, 0);
+        bool big = __ballot_sync(0xffffffffu, lane > 0 && lane < K && fabs(logL - ref) > 700.0) != 0u;  // :1884
+        double e = exp(logL - ref), s = 0.0;
+        for (uint32_t i = 0; i < K; i++) s += __shfl_sync(0xffffffffu, e, i);
+        double acum = big ? 0.0 : 1.0 / s;
+        acum0 = acum;                                                                // Acum(marker), :1892
+        for (uint32_t c = 0; c < K; c++) {                                           // :1894-1921 (uniform across the warp)
+            if (prob <= acum || c == K - 1) { comp = (int)c; break; }
+            ref = __shfl_sync(0xffffffffu, logL, c + 1);
+            big = __ballot_sync(0xffffffffu, lane > c && lane < K && fabs(logL - ref) > 700.0) != 0u;   // :1915
+            e = exp(logL - ref);
+            s = 0.0;
+            for (uint32_t i = 0; i < K; i++) s += __shfl_sync(0xffffffffu, e, i);
+            if (!big) acum += 1.0 / s;
         }
-        acum = acum0;
-        atomicAdd(&P.cass[g * K + comp], 1);                                         // :1904
-        P.comp[m] = comp;
+        const double muc = __shfl_sync(0xffffffffu, muk, comp);
+        if (comp > 0) beta_new = __dadd_rn(muc, __dmul_rn(H.sdk[g * K + comp], tab->z[k]));  // :1901
     }                                                                                // else :1924-1925
-    const double dbeta = beta_old - beta_new;                                        // :1933
-    if (dbeta != 0.0) {
-        P.dMave[slot] = tab->mave[k];
-        P.dRec[slot] = tab->rec[k];
-        P.dB[slot] = __dmul_rn(dbeta, mstd);
-        atomicAdd(&P.stats[5], 1ull);
-    } else {
-        P.dB[slot] = 0.0;
+    if (lane == 0) {
+        if (comp >= 0) {
+            atomicAdd(&P.cass[g * K + comp], 1);                                     // :1904
+            P.comp[m] = comp;
+        }
+        const double dbeta = beta_old - beta_new;                                    // :1933
+        if (dbeta != 0.0) {
+            const double dbs = __dmul_rn(dbeta, mstd);
+            P.dMave[slot] = tab->mave[k];
+            P.dRec[slot] = tab->rec[k];
+            P.dB[slot] = dbs;
+            const uint32_t idx = atomicAdd(P.chg_cnt + buf3, 1u);
+            ChgEnt en;
+            en.p = p; en.pad = 0; en.dbs = dbs; en.mave = tab->mave[k]; en.rec = tab->rec[k];
+            P.chg_list[(size_t)buf3 * P.Wmax + idx] = en;
+            atomicAdd(&P.stats[5], 1ull);
+        } else {
+            P.dB[slot] = 0.0;
+        }
+        P.beta[m] = beta_new;
+        P.acum[m] = acum0;
     }
-    P.beta[m] = beta_new;
-    P.acum[m] = acum;
 }
 
 // Item table of one window chunk: one thread per window position of this CTA group.
@@ -339,6 +367,74 @@ __device__ __forceinline__ uint32_t find_entry(const uint32_t *cum, uint32_t n, 
 
 constexpr uint32_t kApplyQ = 4;          // 64-bit words staged in registers per thread and round
 constexpr uint32_t kHypSmem = 64;        // G*K up to this: hyper-parameter tables live in shared memory
+constexpr uint32_t kDrawWarps = 8;       // warps that collect partials and draw; the others prebuild the next table
+
+// Epsilon update with the nx markers staged in chg[0..nx) (window order). All threads of the CTA call it.
+// Sparse words of all staged markers are flattened, loaded together and applied marker by marker (one CTA
+// barrier per marker keeps the order of additions to an individual fixed); BED blocks have length 0 in the
+// flattened space and are applied by the whole CTA in their turn.
+__device__ __forceinline__ void apply_staged(ChgTab *chg, uint32_t nx, double *__restrict__ E_s, uint32_t L, double &added,
+                                             double &off, unsigned long long &nnz_upd) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (warp == 0) {  // exclusive prefix of the block lengths (nx <= 64)
+        const uint32_t a0 = (lane < nx && chg->b1[lane] != 0xFFFFFFFFu) ? chg->nw[lane] : 0u;
+        const uint32_t a1 = (lane + 32 < nx && chg->b1[lane + 32] != 0xFFFFFFFFu) ? chg->nw[lane + 32] : 0u;
+        uint32_t s0 = a0, s1 = a1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t0 = __shfl_up_sync(0xffffffffu, s0, o), t1 = __shfl_up_sync(0xffffffffu, s1, o);
+            if (lane >= (uint32_t)o) { s0 += t0; s1 += t1; }
+        }
+        const uint32_t tot0 = __shfl_sync(0xffffffffu, s0, 31);
+        chg->cum[lane + 1] = s0;
+        chg->cum[lane + 33] = tot0 + s1;
+        if (lane == 0) chg->cum[0] = 0;
+    }
+    __syncthreads();
+    const uint32_t total = chg->cum[nx];
+    uint32_t xdone = 0;  // entries [0, xdone) are complete
+    for (uint32_t f0 = 0; f0 < total || xdone < nx; f0 += kApplyQ * kThreads) {
+        uint64_t wd[kApplyQ];
+        uint32_t we[kApplyQ];
+        double dd[kApplyQ];
+#pragma unroll
+        for (uint32_t i = 0; i < kApplyQ; i++) {
+            const uint32_t f = f0 + tid + i * kThreads;
+            we[i] = 0xFFFFFFFFu; wd[i] = 0; dd[i] = 0.0;
+            if (f < total) {
+                const uint32_t x = find_entry(chg->cum, nx, f);
+                const uint32_t w = f - chg->cum[x];
+                we[i] = x;
+                wd[i] = ld_stream_u64(chg->ptr[x] + w);
+                dd[i] = ((w < chg->b1[x]) ? 1.0 : ((w < chg->b2[x]) ? 2.0 : chg->mave[x])) * chg->dbs[x];
+            }
+        }
+        const uint32_t fend = min(total, f0 + kApplyQ * kThreads);
+        // last entry touched by this round; trailing entries without flattened words (BED, empty) follow it
+        uint32_t xhi = (f0 < total) ? find_entry(chg->cum, nx, fend - 1u) : xdone;
+        if (fend == total) xhi = nx - 1u;
+        for (uint32_t x = xdone; x <= xhi; x++) {
+            if (chg->b1[x] == 0xFFFFFFFFu) {
+                const uint32_t nwb = chg->nw[x];
+                const double dbs = chg->dbs[x], mave = chg->mave[x];
+                for (uint32_t w = tid; w < nwb; w += blockDim.x)
+                    added += apply_bed_word(ld_stream_u64(chg->ptr[x] + w), w, dbs, mave, E_s, lane);
+            } else {
+#pragma unroll
+                for (uint32_t i = 0; i < kApplyQ; i++)
+                    if (we[i] == x) added += apply_word(wd[i], dd[i], E_s, L);
+            }
+            __syncthreads();
+        }
+        // an entry cut by the round boundary continues in the next round
+        xdone = (fend < total && chg->cum[xhi + 1] > fend) ? xhi : xhi + 1u;
+    }
+    for (uint32_t x = 0; x < nx; x++) {
+        off = fma(-chg->mave[x], chg->dbs[x], off);  // base term -mave*mstd*deltaBeta of every individual (:265-267)
+        if (tid == 0 && chg->b1[x] != 0xFFFFFFFFu) nnz_upd += 4ull * chg->nw[x];
+    }
+    __syncthreads();
+}
 
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P) {
@@ -434,33 +530,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                 }
                 __syncthreads();
                 HB_PHASE(1);
-                // ---- 3. publish slice partials; last arriver draws ---------------------
-                //         meanwhile the upper warps prepare the next window's table
-                if (tid < kTabCap) {
-                    const uint32_t k = tid;
-                    if (k < nk) {
-                        const int32_t m = tab->m[k];
-                        const uint32_t p = r + R * (k0 + k);
-                        if (m < 0) {
-                            if (P.mode == MODE_CHAIN) P.dB[(size_t)dbuf * P.Wmax + p] = 0.0;  // padded task step (:2029-2034)
-                        } else {
-                            // partial of num/mstd: sum_1 + 2 sum_2 + mave*sum_M - mave*sum_slice   (:327-339)
-                            const double val = fma(-tab->mave[k], slice_sum, tab->part[k]);
-                            __stcg(P.partial + (size_t)p * S + c, val);
-                            __threadfence();
-                            const uint32_t old = atomicAdd(P.cnt + p, 1u);
-                            if ((old + 1u) % S == 0u) {
-                                __threadfence();
-                                draw_marker(P, tab, k, H, p, base + p, dbuf);
-                            }
-                        }
+                // ---- 3. publish the slice partials (data + tag in one 16-byte store, no fence) ----
+                const uint32_t tag = win + 1u;
+                if (tid < nk) {
+                    const uint32_t k = tid, p = r + R * (k0 + k);
+                    if (tab->m[k] < 0) {
+                        if (P.mode == MODE_CHAIN) P.dB[(size_t)dbuf * P.Wmax + p] = 0.0;  // padded task step (:2029-2034)
+                    } else {
+                        // partial of num/mstd: sum_1 + 2 sum_2 + mave*sum_M - mave*sum_slice   (:327-339)
+                        st_slot(P.slots + (size_t)p * S + c, fma(-tab->mave[k], slice_sum, tab->part[k]), tag);
                     }
+                }
+                // ---- 4. draws: item kk of the group is drawn by slice-CTA kk % S, one warp per item;
+                //         meanwhile the upper warps prepare the next window's table
+                if (warp < kDrawWarps) {
+                    const uint32_t kf = (c + S - (k0 % S)) % S;  // first table entry owned by this CTA
+                    for (uint32_t k = kf + warp * S; k < nk; k += kDrawWarps * S)
+                        if (tab->m[k] >= 0) draw_marker_warp(P, tab, k, H, r + R * (k0 + k), base + r + R * (k0 + k), dbuf, win % 3u, tag, lane);
                 } else if (P.mode == MODE_CHAIN && k0 + kTabCap >= n_items) {
                     // speculate that this window ends with a synchronisation: next window = SR steps
                     const uint32_t j1 = j0 + n;
                     if (j1 < P.lmax) {
                         const uint32_t n1 = min(SR, P.lmax - j1);
-                        build_table(&tabs[(win + 1u) & 1u], P, r, c, j1 * P.T, n1 * P.T, 0, kTabCap, blockDim.x - kTabCap, !(P.flags & 1u));
+                        build_table(&tabs[(win + 1u) & 1u], P, r, c, j1 * P.T, n1 * P.T, 0, kDrawWarps * 32, blockDim.x - kDrawWarps * 32, !(P.flags & 1u));
                     }
                 }
                 __syncthreads();  // table reuse
@@ -476,111 +568,85 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
         bool any = false;
         double added = 0.0;
         const size_t dslot = (size_t)dbuf * P.Wmax;
-        for (uint32_t p0 = 0; p0 < W; p0 += blockDim.x) {
-            const uint32_t p = p0 + tid;
-            const double d = (p < W) ? __ldcg(P.dB + dslot + p) : 0.0;
-            const bool ch = (d != 0.0);
-            // every changed position decodes its own record: one dependent-load chain for all of them
-            Blk b;
-            double mv = 0.0;
-            if (ch) {
-                uint64_t rr;
-                if (P.mode == MODE_SCAADD) {
-                    const int32_t m = P.order[base + p];
-                    rr = P.rec[m];
-                    mv = P.mave[m];
-                } else {
-                    rr = __ldcg(P.dRec + dslot + p);
-                    mv = __ldcg(P.dMave + dslot + p);
-                }
-                b = decode_block(rr, c, S, L);
+        uint32_t nlist = 0xFFFFFFFFu;
+        if (P.mode == MODE_CHAIN) {
+            // fast path: the drawers appended the changed markers to a list; one round trip brings count + entries
+            const uint32_t buf3 = win % 3u;
+            ChgEnt en;
+            en.p = 0; en.dbs = 0.0; en.mave = 0.0; en.rec = 0;
+            if (tid < kChgCap) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(P.chg_list + (size_t)buf3 * P.Wmax + tid);
+                const uint4 a = __ldcg(src), b = __ldcg(src + 1);
+                en.p = a.x;
+                en.dbs = __longlong_as_double((long long)(((unsigned long long)a.w << 32) | a.z));
+                en.mave = __longlong_as_double((long long)(((unsigned long long)b.y << 32) | b.x));
+                en.rec = ((unsigned long long)b.w << 32) | b.z;
             }
-            const uint32_t bal = __ballot_sync(0xffffffffu, ch);
-            if (lane == 0) chg_base[warp] = __popc(bal);
-            __syncthreads();
-            if (tid == 0) {
-                uint32_t a = 0;
-                for (uint32_t w = 0; w < (blockDim.x >> 5); w++) { uint32_t t = chg_base[w]; chg_base[w] = a; a += t; }
-                chg_n = a;
-            }
-            __syncthreads();
-            const uint32_t nchg = chg_n;
-            const uint32_t slot = chg_base[warp] + __popc(bal & ((1u << lane) - 1u));
-            for (uint32_t x0 = 0; x0 < nchg; x0 += kChgCap) {
-                const uint32_t nx = min((uint32_t)kChgCap, nchg - x0);
-                if (ch && slot >= x0 && slot < x0 + nx) {
-                    const uint32_t x = slot - x0;
-                    chg->ptr[x] = b.ptr; chg->nw[x] = b.nw; chg->b1[x] = b.b1; chg->b2[x] = b.b2;
-                    chg->dbs[x] = d; chg->mave[x] = mv;
+            nlist = __ldcg(P.chg_cnt + buf3);
+            if (blockIdx.x == 0 && tid == 0) P.chg_cnt[(win + 2u) % 3u] = 0;  // free since the previous grid barrier
+            if (nlist > 0 && nlist <= kChgCap) {
+                uint32_t *sp = chg->cum;  // scratch for the positions (cum is rebuilt afterwards)
+                if (tid < nlist) sp[tid] = en.p;
+                __syncthreads();
+                if (tid < nlist) {
+                    uint32_t rank = 0;
+                    for (uint32_t i = 0; i < nlist; i++) rank += (sp[i] < en.p) ? 1u : 0u;  // window order
+                    const Blk b = decode_block(en.rec, c, S, L);
+                    chg->ptr[rank] = b.ptr; chg->nw[rank] = b.nw; chg->b1[rank] = b.b1; chg->b2[rank] = b.b2;
+                    chg->dbs[rank] = en.dbs; chg->mave[rank] = en.mave;
                 }
                 __syncthreads();
-                if (warp == 0) {  // exclusive prefix of the block lengths (nx <= 64)
-                    const uint32_t a0 = (lane < nx && chg->b1[lane] != 0xFFFFFFFFu) ? chg->nw[lane] : 0u;
-                    const uint32_t a1 = (lane + 32 < nx && chg->b1[lane + 32] != 0xFFFFFFFFu) ? chg->nw[lane + 32] : 0u;
-                    uint32_t s0 = a0, s1 = a1;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t t0 = __shfl_up_sync(0xffffffffu, s0, o), t1 = __shfl_up_sync(0xffffffffu, s1, o);
-                        if (lane >= (uint32_t)o) { s0 += t0; s1 += t1; }
-                    }
-                    const uint32_t tot0 = __shfl_sync(0xffffffffu, s0, 31);
-                    chg->cum[lane + 1] = s0;
-                    chg->cum[lane + 33] = tot0 + s1;
-                    if (lane == 0) chg->cum[0] = 0;
-                }
-                __syncthreads();
-                const uint32_t total = chg->cum[nx];
                 HB_PHASE(4);
-                // sparse words of all staged markers, flattened: loaded together, applied in marker order
-                // (BED blocks have length 0 in the flattened space and are applied by the whole CTA in their turn)
-                uint32_t xdone = 0;  // entries [0, xdone) are complete
-                for (uint32_t f0 = 0; f0 < total || xdone < nx; f0 += kApplyQ * kThreads) {
-                    uint64_t wd[kApplyQ];
-                    uint32_t we[kApplyQ];
-                    double dd[kApplyQ];
-#pragma unroll
-                    for (uint32_t i = 0; i < kApplyQ; i++) {
-                        const uint32_t f = f0 + tid + i * kThreads;
-                        we[i] = 0xFFFFFFFFu; wd[i] = 0; dd[i] = 0.0;
-                        if (f < total) {
-                            const uint32_t x = find_entry(chg->cum, nx, f);
-                            const uint32_t w = f - chg->cum[x];
-                            we[i] = x;
-                            wd[i] = ld_stream_u64(chg->ptr[x] + w);
-                            dd[i] = ((w < chg->b1[x]) ? 1.0 : ((w < chg->b2[x]) ? 2.0 : chg->mave[x])) * chg->dbs[x];
-                        }
+                apply_staged(chg, nlist, E_s, L, added, off, nnz_upd);
+                HB_PHASE(7);
+                any = true;
+            }
+        }
+        if (nlist > kChgCap) {  // many changes (or a unit mode): scan the dense per-position arrays
+            for (uint32_t p0 = 0; p0 < W; p0 += blockDim.x) {
+                const uint32_t p = p0 + tid;
+                const double d = (p < W) ? __ldcg(P.dB + dslot + p) : 0.0;
+                const bool ch = (d != 0.0);
+                // every changed position decodes its own record: one dependent-load chain for all of them
+                Blk b;
+                double mv = 0.0;
+                if (ch) {
+                    uint64_t rr;
+                    if (P.mode == MODE_SCAADD) {
+                        const int32_t m = P.order[base + p];
+                        rr = P.rec[m];
+                        mv = P.mave[m];
+                    } else {
+                        rr = __ldcg(P.dRec + dslot + p);
+                        mv = __ldcg(P.dMave + dslot + p);
                     }
-                    HB_PHASE(6);
-                    const uint32_t fend = min(total, f0 + kApplyQ * kThreads);
-                    // last entry touched by this round; trailing entries without flattened words (BED, empty) follow it
-                    uint32_t xhi = (f0 < total) ? find_entry(chg->cum, nx, fend - 1u) : xdone;
-                    if (fend == total) xhi = nx - 1u;
-                    for (uint32_t x = xdone; x <= xhi; x++) {
-                        if (chg->b1[x] == 0xFFFFFFFFu) {
-                            const uint32_t nwb = chg->nw[x];
-                            const double dbs = chg->dbs[x], mave = chg->mave[x];
-                            for (uint32_t w = tid; w < nwb; w += blockDim.x)
-                                added += apply_bed_word(ld_stream_u64(chg->ptr[x] + w), w, dbs, mave, E_s, lane);
-                        } else {
-#pragma unroll
-                            for (uint32_t i = 0; i < kApplyQ; i++)
-                                if (we[i] == x) added += apply_word(wd[i], dd[i], E_s, L);
-                        }
-                        __syncthreads();
-                    }
-                    // an entry cut by the round boundary continues in the next round
-                    xdone = (fend < total && chg->cum[xhi + 1] > fend) ? xhi : xhi + 1u;
-                    HB_PHASE(7);
+                    b = decode_block(rr, c, S, L);
                 }
-                for (uint32_t x = 0; x < nx; x++) {
-                    off = fma(-chg->mave[x], chg->dbs[x], off);  // base term -mave*mstd*deltaBeta of every individual (:265-267)
-                    if (tid == 0 && chg->b1[x] != 0xFFFFFFFFu) nnz_upd += 4ull * chg->nw[x];
+                const uint32_t bal = __ballot_sync(0xffffffffu, ch);
+                if (lane == 0) chg_base[warp] = __popc(bal);
+                __syncthreads();
+                if (tid == 0) {
+                    uint32_t a = 0;
+                    for (uint32_t w = 0; w < (blockDim.x >> 5); w++) { uint32_t t = chg_base[w]; chg_base[w] = a; a += t; }
+                    chg_n = a;
                 }
                 __syncthreads();
+                const uint32_t nchg = chg_n;
+                const uint32_t slot = chg_base[warp] + __popc(bal & ((1u << lane) - 1u));
+                for (uint32_t x0 = 0; x0 < nchg; x0 += kChgCap) {
+                    const uint32_t nx = min((uint32_t)kChgCap, nchg - x0);
+                    if (ch && slot >= x0 && slot < x0 + nx) {
+                        const uint32_t x = slot - x0;
+                        chg->ptr[x] = b.ptr; chg->nw[x] = b.nw; chg->b1[x] = b.b1; chg->b2[x] = b.b2;
+                        chg->dbs[x] = d; chg->mave[x] = mv;
+                    }
+                    __syncthreads();
+                    apply_staged(chg, nx, E_s, L, added, off, nnz_upd);
+                }
+                any |= (nchg > 0);
             }
-            any |= (nchg > 0);
+            HB_PHASE(4);
         }
-        HB_PHASE(4);
         if (any) {
             if (tid == 0) E_s[L] = 0.0;  // the dummy slot collected the PAD lanes
             slice_sum += block_sum(added, red);

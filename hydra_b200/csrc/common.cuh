@@ -70,6 +70,11 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
 __device__ __forceinline__ void red_release_add_u32(uint32_t *p, uint32_t v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t atom_add_acq_rel_u32(uint32_t *p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
 // streaming read of genotype words: read-only path, do not pollute L1
 __device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t *p) {
     uint64_t v;

@@ -103,9 +103,11 @@ struct hb_ctx {
     DevBuf<double> d_hyp;
     DevBuf<uint8_t> d_active;
     // scratch
-    DevBuf<double> d_partial, d_dB, d_dMave, d_num;
+    DevBuf<uint4> d_slots;
+    DevBuf<ChgEnt> d_chg_list;
+    DevBuf<double> d_dB, d_dMave, d_num;
     DevBuf<uint64_t> d_dRec;
-    DevBuf<uint32_t> d_cntr, d_bar, d_markers;
+    DevBuf<uint32_t> d_chg_cnt, d_bar, d_markers;
     DevBuf<unsigned long long> d_stats, d_ctacyc;
     bool debug_cycles = false;
     uint32_t Wmax = 0;
@@ -152,12 +154,13 @@ static size_t smem_for(uint32_t L) { return (((size_t)L + 2) * 8 + 15) / 16 * 16
 static int ensure_scratch(hb_ctx *c, uint32_t W) {
     if (W <= c->Wmax) return HB_OK;
     W = (W + 255u) & ~255u;
-    HB_TRY(c->d_partial.alloc((size_t)W * c->S));
-    HB_TRY(c->d_cntr.alloc(W));
+    HB_TRY(c->d_slots.alloc((size_t)W * c->S));
+    HB_TRY(c->d_chg_list.alloc((size_t)3 * W));
+    HB_TRY(c->d_chg_cnt.alloc(4));
     HB_TRY(c->d_dB.alloc((size_t)2 * W));
     HB_TRY(c->d_dMave.alloc((size_t)2 * W));
     HB_TRY(c->d_dRec.alloc((size_t)2 * W));
-    HB_TRY(c->d_cntr.zero(c->stream));
+    HB_TRY(c->d_chg_list.zero(c->stream));
     HB_TRY(c->d_dB.zero(c->stream));
     c->Wmax = W;
     return HB_OK;
@@ -188,7 +191,7 @@ static void fill_params(hb_ctx *c, BrrParams &P) {
     P.logPi = c->d_hyp.p; P.chalf = c->d_hyp.p + gk; P.denom = c->d_hyp.p + 2 * gk; P.sdk = c->d_hyp.p + 3 * gk;
     P.grp_active = c->d_active.p;
     P.dNm1 = (double)(c->N - 1);
-    P.partial = c->d_partial.p; P.cnt = c->d_cntr.p; P.dB = c->d_dB.p; P.dMave = c->d_dMave.p; P.dRec = c->d_dRec.p; P.Wmax = c->Wmax;
+    P.slots = c->d_slots.p; P.chg_cnt = c->d_chg_cnt.p; P.chg_list = c->d_chg_list.p; P.dB = c->d_dB.p; P.dMave = c->d_dMave.p; P.dRec = c->d_dRec.p; P.Wmax = c->Wmax;
     P.bar = c->d_bar.p; P.stats = c->d_stats.p;
     P.mode = MODE_CHAIN;
     P.num_out = c->d_num.p;
@@ -198,6 +201,10 @@ static void fill_params(hb_ctx *c, BrrParams &P) {
 
 static int launch_window_kernel(hb_ctx *c, BrrParams &P) {
     HB_CUDA(cudaMemsetAsync(c->d_bar.p, 0, sizeof(uint32_t), c->stream));
+    HB_CUDA(cudaMemsetAsync(c->d_chg_cnt.p, 0, 4 * sizeof(uint32_t), c->stream));
+    // the slots carry window tags starting at 1: clear what this launch can touch
+    const size_t wuse = std::min<size_t>(c->Wmax, (P.mode == MODE_CHAIN) ? (size_t)std::max(1u, P.SR) * P.T : (size_t)P.lmax * P.T);
+    HB_CUDA(cudaMemsetAsync(c->d_slots.p, 0, wuse * c->S * sizeof(uint4), c->stream));
     void *args[] = {(void *)&P};
     dim3 grid(c->S * c->R), block(kThreads);
     HB_CUDA(cudaLaunchCooperativeKernel((const void *)k_brr_iteration, grid, block, args, c->smem_bytes, c->stream));
@@ -697,17 +704,20 @@ static int upload_markers(hb_ctx *c, const uint32_t *markers, uint32_t n) {
 int hb_dot_markers(hb_ctx *c, const uint32_t *markers, uint32_t n, double *num) {
     HB_CHECK(c && markers && num, HB_ERR_ARG, "null argument");
     HB_CHECK(c->finalized, HB_ERR_STATE, "hb_dot_markers: call hb_stage_finalize first");
-    if (n == 0) return HB_OK;
     HB_CUDA(cudaSetDevice(c->dev));
-    HB_TRY(upload_markers(c, markers, n));
-    HB_TRY(ensure_scratch(c, n));
-    HB_TRY(c->d_num.ensure(n));
-    BrrParams P;
-    fill_params(c, P);
-    P.mode = MODE_DOT; P.T = 1; P.lmax = n; P.SR = 1;
-    HB_TRY(launch_window_kernel(c, P));
-    HB_CUDA(cudaMemcpyAsync(num, c->d_num.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
-    HB_CUDA(cudaStreamSynchronize(c->stream));
+    const uint32_t chunk = 1u << 16;
+    for (uint32_t o = 0; o < n; o += chunk) {
+        const uint32_t k = std::min(chunk, n - o);
+        HB_TRY(upload_markers(c, markers + o, k));
+        HB_TRY(ensure_scratch(c, k));
+        HB_TRY(c->d_num.ensure(k));
+        BrrParams P;
+        fill_params(c, P);
+        P.mode = MODE_DOT; P.T = 1; P.lmax = k; P.SR = 1;
+        HB_TRY(launch_window_kernel(c, P));
+        HB_CUDA(cudaMemcpyAsync(num + o, c->d_num.p, sizeof(double) * k, cudaMemcpyDeviceToHost, c->stream));
+        HB_CUDA(cudaStreamSynchronize(c->stream));
+    }
     return HB_OK;
 }
 
