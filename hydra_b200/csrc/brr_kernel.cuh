@@ -24,9 +24,31 @@ namespace hb {
 enum : int { MODE_CHAIN = 0, MODE_DOT = 1, MODE_SCAADD = 2 };
 
 struct ChgEnt {  // 32 bytes
-    uint32_t p, pad;
+    uint32_t p;      // GLOBAL window position: step * T_total + global task (the order hydra's ranks are summed in)
+    uint32_t m;      // local marker
     double dbs, mave;
-    uint64_t rec;
+    uint64_t rec;    // record address on the owning GPU / payload offset inside an inbox region
+};
+
+constexpr uint32_t kMaxRanks = 8;
+constexpr uint32_t kMaxMerged = 1024;        // changed markers of one window over all GPUs (shared-memory sort)
+constexpr size_t kInboxHeader = 16 + (size_t)kMaxMerged * sizeof(ChgEnt);
+
+// Exchange of the changed markers between the GPUs of one node (replaces MPI_Allreduce of deltaEps,
+// src/BayesRRm.cpp:2051, 2456): every GPU pushes (position, deltaBeta*mstd, mave, genotype record) of its
+// changed markers into every peer's inbox over NVLink, then raises a flag in the peer's memory.
+struct PeerComm {
+    uint32_t nranks, rank;
+    uint32_t T_total, t_first;
+    unsigned char *inbox_local;               // [2 parities][nranks sources] regions of inbox_stride bytes
+    unsigned char *inbox_peer[kMaxRanks];     // peer-mapped inbox of rank h (unused for self)
+    unsigned long long *flags_local;          // [nranks] sequence numbers raised by the peers
+    unsigned long long *flags_peer[kMaxRanks];
+    size_t inbox_stride;
+    unsigned long long seq_base;              // sequence number of this launch's window 0, minus 1
+    const uint32_t *rec_bytes;                // [M] bytes of each local record
+    uint32_t *err;                            // != 0: exchange failed (capacity / timeout)
+    long long timeout_cycles;
 };
 
 struct BrrParams {
@@ -70,6 +92,7 @@ struct BrrParams {
     // unit modes
     int mode;
     double *num_out;       // MODE_DOT: [W]
+    PeerComm pc;
     uint32_t flags;        // bit 0: no L2 prefetch of the next window (developer knob)
     unsigned long long *cta_cycles;  // optional [gridDim*8] per-CTA phase cycles (HB_DEBUG_CYCLES=1)
 };
@@ -101,6 +124,7 @@ struct Blk {
 };
 
 // slice block c of a marker record (common.cuh "record layout")
+template <bool kCoherent = false>
 __device__ __forceinline__ Blk decode_block(uint64_t rr, uint32_t c, uint32_t S, uint32_t L) {
     Blk b;
     if (rr & 1ull) {
@@ -111,7 +135,9 @@ __device__ __forceinline__ Blk decode_block(uint64_t rr, uint32_t c, uint32_t S,
     } else {
         const uint8_t *bp = reinterpret_cast<const uint8_t *>(rr);
         const uint32_t *dir = reinterpret_cast<const uint32_t *>(bp) + c * 3;
-        const uint32_t st = __ldg(dir), n12 = __ldg(dir + 1), nm = __ldg(dir + 2);
+        // kCoherent: the record may sit in an inbox that a peer GPU rewrites during the launch -> read through L2
+        const uint32_t st = kCoherent ? __ldcg(dir) : __ldg(dir), n12 = kCoherent ? __ldcg(dir + 1) : __ldg(dir + 1);
+        const uint32_t nm = kCoherent ? __ldcg(dir + 2) : __ldg(dir + 2);
         const uint32_t w1 = ((n12 & 0xFFFFu) + 3) / 4, w2 = ((n12 >> 16) + 3) / 4, wm = (nm + 3) / 4;
         b.ptr = reinterpret_cast<const uint64_t *>(bp + dir_bytes(S)) + st;
         b.b1 = w1;
@@ -121,6 +147,9 @@ __device__ __forceinline__ Blk decode_block(uint64_t rr, uint32_t c, uint32_t S,
     return b;
 }
 
+__device__ __forceinline__ uint64_t ld_l2_u64(const uint64_t *p) {  // coherent at L2 (peer-written inbox data)
+    return __ldcg(reinterpret_cast<const unsigned long long *>(p));
+}
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- slice block dot product: sum_w weight(w) * sum_4 E_s[idx] ------------------
@@ -233,6 +262,24 @@ struct HypTabs {
     const double *logPi, *chalf, *denom, *sdk;
 };
 
+__device__ __forceinline__ ChgEnt ld_chg_ent(const ChgEnt *e) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(e);
+    const uint4 a = __ldcg(src), b = __ldcg(src + 1);
+    ChgEnt en;
+    en.p = a.x; en.m = a.y;
+    en.dbs = __longlong_as_double((long long)(((unsigned long long)a.w << 32) | a.z));
+    en.mave = __longlong_as_double((long long)(((unsigned long long)b.y << 32) | b.x));
+    en.rec = ((unsigned long long)b.w << 32) | b.z;
+    return en;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint4 ld_slot(const uint4 *p) {
     uint4 v;
     asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
@@ -314,7 +361,8 @@ __device__ void draw_marker_warp(const BrrParams &P, const ItemTab *tab, uint32_
             P.dB[slot] = dbs;
             const uint32_t idx = atomicAdd(P.chg_cnt + buf3, 1u);
             ChgEnt en;
-            en.p = p; en.pad = 0; en.dbs = dbs; en.mave = tab->mave[k]; en.rec = tab->rec[k];
+            en.p = (P.pc.nranks > 1) ? (p / P.T) * P.pc.T_total + P.pc.t_first + (p % P.T) : p;
+            en.m = (uint32_t)m; en.dbs = dbs; en.mave = tab->mave[k]; en.rec = tab->rec[k];
             P.chg_list[(size_t)buf3 * P.Wmax + idx] = en;
             atomicAdd(&P.stats[5], 1ull);
         } else {
@@ -405,7 +453,7 @@ __device__ __forceinline__ void apply_staged(ChgTab *chg, uint32_t nx, double *_
                 const uint32_t x = find_entry(chg->cum, nx, f);
                 const uint32_t w = f - chg->cum[x];
                 we[i] = x;
-                wd[i] = ld_stream_u64(chg->ptr[x] + w);
+                wd[i] = ld_l2_u64(chg->ptr[x] + w);
                 dd[i] = ((w < chg->b1[x]) ? 1.0 : ((w < chg->b2[x]) ? 2.0 : chg->mave[x])) * chg->dbs[x];
             }
         }
@@ -418,7 +466,7 @@ __device__ __forceinline__ void apply_staged(ChgTab *chg, uint32_t nx, double *_
                 const uint32_t nwb = chg->nw[x];
                 const double dbs = chg->dbs[x], mave = chg->mave[x];
                 for (uint32_t w = tid; w < nwb; w += blockDim.x)
-                    added += apply_bed_word(ld_stream_u64(chg->ptr[x] + w), w, dbs, mave, E_s, lane);
+                    added += apply_bed_word(ld_l2_u64(chg->ptr[x] + w), w, dbs, mave, E_s, lane);
             } else {
 #pragma unroll
                 for (uint32_t i = 0; i < kApplyQ; i++)
@@ -447,6 +495,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
     __shared__ uint32_t work_ctr;
     __shared__ uint32_t chg_n;
     __shared__ uint32_t chg_base[33];
+    __shared__ uint32_t psort[kMaxMerged + 1];
+    __shared__ uint32_t pcnt[kMaxRanks];
 
     const uint32_t S = P.S, L = P.L, R = P.R;
     const uint32_t c = blockIdx.x % S, r = blockIdx.x / S;
@@ -570,39 +620,129 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
         const size_t dslot = (size_t)dbuf * P.Wmax;
         uint32_t nlist = 0xFFFFFFFFu;
         if (P.mode == MODE_CHAIN) {
-            // fast path: the drawers appended the changed markers to a list; one round trip brings count + entries
-            const uint32_t buf3 = win % 3u;
-            ChgEnt en;
-            en.p = 0; en.dbs = 0.0; en.mave = 0.0; en.rec = 0;
-            if (tid < kChgCap) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(P.chg_list + (size_t)buf3 * P.Wmax + tid);
-                const uint4 a = __ldcg(src), b = __ldcg(src + 1);
-                en.p = a.x;
-                en.dbs = __longlong_as_double((long long)(((unsigned long long)a.w << 32) | a.z));
-                en.mave = __longlong_as_double((long long)(((unsigned long long)b.y << 32) | b.x));
-                en.rec = ((unsigned long long)b.w << 32) | b.z;
-            }
-            nlist = __ldcg(P.chg_cnt + buf3);
+            const uint32_t buf3 = win % 3u, par = win & 1u, NR = P.pc.nranks, me = P.pc.rank;
+            const uint32_t nloc = __ldcg(P.chg_cnt + buf3);
+            const ChgEnt *llist = P.chg_list + (size_t)buf3 * P.Wmax;
             if (blockIdx.x == 0 && tid == 0) P.chg_cnt[(win + 2u) % 3u] = 0;  // free since the previous grid barrier
-            if (nlist > 0 && nlist <= kChgCap) {
-                uint32_t *sp = chg->cum;  // scratch for the positions (cum is rebuilt afterwards)
-                if (tid < nlist) sp[tid] = en.p;
-                __syncthreads();
-                if (tid < nlist) {
-                    uint32_t rank = 0;
-                    for (uint32_t i = 0; i < nlist; i++) rank += (sp[i] < en.p) ? 1u : 0u;  // window order
-                    const Blk b = decode_block(en.rec, c, S, L);
-                    chg->ptr[rank] = b.ptr; chg->nw[rank] = b.nw; chg->b1[rank] = b.b1; chg->b2[rank] = b.b2;
-                    chg->dbs[rank] = en.dbs; chg->mave[rank] = en.mave;
+            uint32_t ntot = nloc;
+            if (NR > 1) {
+                // ---- 5a. push the changed markers (list + genotype records) into every peer's inbox over NVLink
+                const unsigned long long seq = P.pc.seq_base + win + 1ull;
+                uint32_t *sp = psort;  // scratch: exclusive prefix of the record sizes (16-byte units)
+                const bool fits = nloc <= kMaxMerged;
+                if (fits) {
+                    for (uint32_t i = tid; i < nloc; i += blockDim.x) sp[i] = (P.pc.rec_bytes[__ldcg(&llist[i].m)] + 15u) >> 4;
+                    __syncthreads();
+                    if (tid == 0) {
+                        uint32_t a = 0;
+                        for (uint32_t i = 0; i < nloc; i++) { const uint32_t t = sp[i]; sp[i] = a; a += t; }
+                        sp[nloc] = a;
+                    }
+                    __syncthreads();
+                }
+                const uint32_t units = fits ? sp[nloc] : 0u;
+                const bool ok = fits && (kInboxHeader + (size_t)units * 16 <= P.pc.inbox_stride);
+                if (!ok && blockIdx.x == 0 && tid == 0) atomicExch(P.pc.err, 1u);
+                const size_t region = ((size_t)par * NR + me) * P.pc.inbox_stride;
+                if (ok) {
+                    for (uint32_t f = blockIdx.x * blockDim.x + tid; f < units; f += nctas * blockDim.x) {
+                        const uint32_t e = find_entry(sp, nloc, f);
+                        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(__ldcg(&llist[e].rec) & ~15ull) + (f - sp[e]));
+                        for (uint32_t h = 0; h < NR; h++)
+                            if (h != me) reinterpret_cast<uint4 *>(P.pc.inbox_peer[h] + region + kInboxHeader)[f] = v;
+                    }
+                    if (blockIdx.x == 0) {
+                        for (uint32_t i = tid; i < nloc; i += blockDim.x) {
+                            ChgEnt en = ld_chg_ent(llist + i);
+                            en.rec = (en.rec & 1ull) | ((unsigned long long)sp[i] << 4);  // offset inside the region's payload | BED flag
+                            for (uint32_t h = 0; h < NR; h++)
+                                if (h != me) reinterpret_cast<ChgEnt *>(P.pc.inbox_peer[h] + region + 16)[i] = en;
+                        }
+                    }
+                }
+                __threadfence_system();
+                grid_barrier(P.bar, bar_target, nctas);
+                if (blockIdx.x == 0 && tid < NR && tid != me) {
+                    // the count travels with the flag's region header; flag last (release at system scope)
+                    *reinterpret_cast<volatile uint32_t *>(P.pc.inbox_peer[tid] + region) = ok ? nloc : 0xFFFFFFFFu;
+                    __threadfence_system();
+                    st_release_sys_u64(P.pc.flags_peer[tid] + me, seq);
+                }
+                // ---- 5b. wait for every peer's flag of this window
+                if (tid < NR) {
+                    uint32_t nh = ok ? nloc : 0xFFFFFFFFu;
+                    if (tid != me) {
+                        const long long t0 = clock64();
+                        bool late = false;
+                        while (ld_acquire_sys_u64(P.pc.flags_local + tid) < seq) {
+                            if (clock64() - t0 > P.pc.timeout_cycles) { late = true; break; }
+                        }
+                        nh = late ? 0xFFFFFFFFu
+                                  : *reinterpret_cast<volatile uint32_t *>(P.pc.inbox_local + ((size_t)par * NR + tid) * P.pc.inbox_stride);
+                        if (late) atomicExch(P.pc.err, 2u);
+                    }
+                    pcnt[tid] = nh;
                 }
                 __syncthreads();
+                ntot = 0;
+                bool bad = false;
+                for (uint32_t h = 0; h < NR; h++) { bad |= (pcnt[h] == 0xFFFFFFFFu); ntot += bad ? 0u : pcnt[h]; }
+                if (bad || ntot > kMaxMerged) {  // give up: the host reports the failure after the launch
+                    if (blockIdx.x == 0 && tid == 0) atomicExch(P.pc.err, bad ? 3u : 4u);
+                    break;
+                }
+            } else if (tid == 0) {
+                pcnt[0] = nloc;
+            }
+            nlist = ntot;
+            if (ntot > 0 && ntot <= kMaxMerged) {
+                // ---- 5c. merge: sort the changed markers of all GPUs by global window position
+                ChgEnt en[2];
+                const unsigned char *rbase[2] = {nullptr, nullptr};
+#pragma unroll
+                for (uint32_t u = 0; u < 2; u++) {
+                    const uint32_t i = tid + u * kThreads;
+                    en[u].p = 0xFFFFFFFFu;
+                    if (i < ntot) {
+                        uint32_t h = 0, o = i;
+                        if (NR > 1) { while (o >= pcnt[h]) { o -= pcnt[h]; h++; } }
+                        if (h == me) {
+                            en[u] = ld_chg_ent(llist + o);
+                        } else {
+                            const unsigned char *reg = P.pc.inbox_local + ((size_t)par * NR + h) * P.pc.inbox_stride;
+                            en[u] = ld_chg_ent(reinterpret_cast<const ChgEnt *>(reg + 16) + o);
+                            rbase[u] = reg + kInboxHeader;
+                        }
+                        psort[i] = en[u].p;
+                    }
+                }
+                __syncthreads();
+                uint32_t rank[2] = {0, 0};
+#pragma unroll
+                for (uint32_t u = 0; u < 2; u++)
+                    if (en[u].p != 0xFFFFFFFFu)
+                        for (uint32_t i = 0; i < ntot; i++) rank[u] += (psort[i] < en[u].p) ? 1u : 0u;
                 HB_PHASE(4);
-                apply_staged(chg, nlist, E_s, L, added, off, nnz_upd);
+                for (uint32_t x0 = 0; x0 < ntot; x0 += kChgCap) {
+                    const uint32_t nx = min((uint32_t)kChgCap, ntot - x0);
+#pragma unroll
+                    for (uint32_t u = 0; u < 2; u++) {
+                        if (en[u].p != 0xFFFFFFFFu && rank[u] >= x0 && rank[u] < x0 + nx) {
+                            const uint64_t rr = rbase[u] ? (((uint64_t)(uintptr_t)rbase[u] + (en[u].rec & ~15ull)) | (en[u].rec & 1ull)) : en[u].rec;
+                            const Blk b = decode_block<true>(rr, c, S, L);
+                            const uint32_t x = rank[u] - x0;
+                            chg->ptr[x] = b.ptr; chg->nw[x] = b.nw; chg->b1[x] = b.b1; chg->b2[x] = b.b2;
+                            chg->dbs[x] = en[u].dbs; chg->mave[x] = en[u].mave;
+                        }
+                    }
+                    __syncthreads();
+                    apply_staged(chg, nx, E_s, L, added, off, nnz_upd);
+                }
                 HB_PHASE(7);
                 any = true;
             }
         }
-        if (nlist > kChgCap) {  // many changes (or a unit mode): scan the dense per-position arrays
+        if (nlist > kMaxMerged) {  // very many changes on a single GPU (or a unit mode): scan the dense per-position arrays
             for (uint32_t p0 = 0; p0 < W; p0 += blockDim.x) {
                 const uint32_t p = p0 + tid;
                 const double d = (p < W) ? __ldcg(P.dB + dslot + p) : 0.0;

@@ -14,6 +14,18 @@
 #include "convert.cuh"
 #include "host_rng.hpp"
 
+#include <nccl.h>
+
+#define HB_NCCL(x)                                                                                  \
+    do {                                                                                            \
+        ncclResult_t r_ = (x);                                                                      \
+        if (r_ != ncclSuccess) {                                                                    \
+            hb::set_error("%s:%d NCCL error in %s: %s", __FILE__, __LINE__, #x, ncclGetErrorString(r_)); \
+            return HB_ERR_NCCL;                                                                     \
+        }                                                                                           \
+    } while (0)
+
+
 namespace hb {
 
 static thread_local char g_err[1024] = "";
@@ -125,7 +137,23 @@ struct hb_ctx {
     double *pin = nullptr;      // pinned host scratch
     size_t pin_n = 0;
 
+    // multi-GPU (one process per GPU)
+    ncclComm_t nccl = nullptr;
+    int rank = 0, nranks = 1;
+    unsigned char *inbox = nullptr;             // this GPU's inbox, written by the peers over NVLink
+    unsigned long long *flags = nullptr;        // [nranks] peers' sequence numbers (same allocation as the inbox)
+    unsigned char *peer_inbox[kMaxRanks] = {};  // IPC mappings of the peers' inboxes
+    size_t inbox_stride = 0, comm_bytes = 0;
+    unsigned long long seq_base = 0;
+    DevBuf<uint32_t> d_rec_bytes, d_err;
+    DevBuf<double> d_red;                       // per-iteration statistics that are summed over the GPUs
+    std::vector<uint32_t> rec_bytes_h;
+
     ~hb_ctx() {
+        for (int h = 0; h < nranks; h++)
+            if (h != rank && peer_inbox[h]) cudaIpcCloseMemHandle(peer_inbox[h]);
+        if (inbox) cudaFree(inbox);
+        if (nccl) ncclCommDestroy(nccl);
         for (void *a : arenas) cudaFree(a);
         if (pin) cudaFreeHost(pin);
         for (auto &e : ev)
@@ -197,6 +225,19 @@ static void fill_params(hb_ctx *c, BrrParams &P) {
     P.num_out = c->d_num.p;
     P.cta_cycles = c->debug_cycles ? c->d_ctacyc.p : nullptr;
     P.flags = getenv("HB_NO_PREFETCH") ? 1u : 0u;
+    P.pc.nranks = (uint32_t)c->nranks; P.pc.rank = (uint32_t)c->rank;
+    P.pc.T_total = c->Ttot; P.pc.t_first = c->t_first;
+    P.pc.inbox_local = c->inbox; P.pc.flags_local = c->flags;
+    for (int h = 0; h < c->nranks; h++) {
+        P.pc.inbox_peer[h] = c->peer_inbox[h];
+        P.pc.flags_peer[h] = c->peer_inbox[h] ? reinterpret_cast<unsigned long long *>(c->peer_inbox[h] + c->comm_bytes - 256) : nullptr;
+    }
+    P.pc.inbox_stride = c->inbox_stride; P.pc.seq_base = c->seq_base;
+    P.pc.rec_bytes = c->d_rec_bytes.p; P.pc.err = c->d_err.p;
+    {
+        const char *t = getenv("HB_PEER_TIMEOUT_S");
+        P.pc.timeout_cycles = (long long)((t ? atof(t) : 10.0) * 1.9e9);
+    }
 }
 
 static int launch_window_kernel(hb_ctx *c, BrrParams &P) {
@@ -331,7 +372,10 @@ int hb_create(const hb_config *cfg, hb_ctx **out) {
     HB_TRY(c->d_rec.alloc(M)); HB_TRY(c->d_mave.alloc(M)); HB_TRY(c->d_mstd.alloc(M)); HB_TRY(c->d_grp.alloc(M));
     HB_CUDA(cudaMemset(c->d_grp.p, 0, sizeof(int32_t) * M));
     c->n1.assign(M, 0); c->n2.assign(M, 0); c->nm.assign(M, 0);
-    c->is_bed.assign(M, 0); c->staged.assign(M, 0); c->rec_h.assign(M, 0);
+    c->is_bed.assign(M, 0); c->staged.assign(M, 0); c->rec_h.assign(M, 0); c->rec_bytes_h.assign(M, 0);
+    HB_TRY(c->d_rec_bytes.alloc(M)); HB_TRY(c->d_err.alloc(1));
+    HB_CUDA(cudaMemset(c->d_err.p, 0, sizeof(uint32_t)));
+    HB_TRY(c->d_red.alloc(2 * ((size_t)cfg->n_groups * (1 + cfg->n_mix) + 4)));
     HB_TRY(c->d_E[0].alloc((size_t)c->S * c->L)); HB_TRY(c->d_E[1].alloc((size_t)c->S * c->L));
     HB_CUDA(cudaMemset(c->d_E[0].p, 0, sizeof(double) * c->S * c->L));
     HB_CUDA(cudaMemset(c->d_E[1].p, 0, sizeof(double) * c->S * c->L));
@@ -419,6 +463,7 @@ static int records_from_raw(hb_ctx *c, uint32_t m_first, uint32_t n) {
             bed = ((double)(c->n1[m] + c->n2[m] + c->nm[m]) / (double)c->N) > c->cfg.threshold_fnz;
         c->is_bed[m] = bed ? 1 : 0;
         const size_t bytes = bed ? bed_bytes : (dir_bytes(S) + 8 * (size_t)meta[i * 4 + 3]);
+        c->rec_bytes_h[m] = (uint32_t)((bytes + 15) & ~(size_t)15);
         off[i] = total;
         total += (bytes + 15) & ~(size_t)15;
     }
@@ -568,6 +613,7 @@ int hb_stage_finalize(hb_ctx *c) {
     }
     HB_CUDA(cudaMemcpy(c->d_mave.p, c->mave_h.data(), sizeof(double) * c->M, cudaMemcpyHostToDevice));
     HB_CUDA(cudaMemcpy(c->d_mstd.p, c->mstd_h.data(), sizeof(double) * c->M, cudaMemcpyHostToDevice));
+    HB_CUDA(cudaMemcpy(c->d_rec_bytes.p, c->rec_bytes_h.data(), sizeof(uint32_t) * c->M, cudaMemcpyHostToDevice));
     c->d_raw.release(); c->d_cnt3.release(); c->d_start.release(); c->d_meta.release();
     c->finalized = true;
     return HB_OK;
@@ -948,6 +994,14 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
             fprintf(stderr, "[hb window 10, ns since first CTA started its dot] end of %-5s min %8.0f mean %8.0f max %8.0f\n", nm[i], mn, sm / (double)nc, mx);
         }
     }
+    {
+        uint32_t err = 0;
+        HB_CUDA(cudaMemcpy(&err, c->d_err.p, sizeof(err), cudaMemcpyDeviceToHost));
+        HB_CHECK(err == 0, HB_ERR_NCCL, "hb_brr_iteration: exchange between the GPUs failed (code %u: 1 = inbox too small (HB_INBOX_MB), "
+                 "2 = a peer did not answer in time (HB_PEER_TIMEOUT_S), 3 = a peer reported a failure, 4 = more than %u changed markers in one window)",
+                 err, kMaxMerged);
+        c->seq_base += pin_stats[1];
+    }
     const double off = pin_small[0];
     c->shift = off;  // the launch folded the old shift into E; the new constant is this launch's base terms
     double s1 = 0.0, s2 = 0.0;
@@ -956,6 +1010,26 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
     const double e_sqn = s2 + 2.0 * off * s1 + dN * off * off;
     for (uint32_t g = 0; g < G; g++) c->bsq[g] = pin_small[1 + 2 * c->S + g];
     for (size_t x = 0; x < gk; x++) c->cass[x] = pin_cass[x];
+    double e_sqn_g = e_sqn;
+    unsigned long long changed_all = pin_stats[5];
+    if (c->nranks > 1) {
+        // group statistics summed over the GPUs (MPI_Allreduce of beta_squaredNorm and cass, :2517-2518); e_sqn is that
+        // of global task 0, whose sigmaE draw the reference broadcasts (:2705)
+        const size_t nr = G + gk + 2;
+        std::vector<double> red(nr, 0.0);
+        for (uint32_t g = 0; g < G; g++) red[g] = c->bsq[g];
+        for (size_t x = 0; x < gk; x++) red[G + x] = (double)c->cass[x];
+        red[G + gk] = (c->t_first == 0) ? e_sqn : 0.0;
+        red[G + gk + 1] = (double)pin_stats[5];
+        HB_CUDA(cudaMemcpyAsync(c->d_red.p, red.data(), sizeof(double) * nr, cudaMemcpyHostToDevice, st));
+        HB_NCCL(ncclAllReduce(c->d_red.p, c->d_red.p + nr, nr, ncclDouble, ncclSum, c->nccl, st));
+        HB_CUDA(cudaMemcpyAsync(red.data(), c->d_red.p + nr, sizeof(double) * nr, cudaMemcpyDeviceToHost, st));
+        HB_CUDA(cudaStreamSynchronize(st));
+        for (uint32_t g = 0; g < G; g++) c->bsq[g] = red[g];
+        for (size_t x = 0; x < gk; x++) c->cass[x] = (int32_t)llround(red[G + x]);
+        e_sqn_g = red[G + gk];
+        changed_all = (unsigned long long)llround(red[G + gk + 1]);
+    }
 
     // ---- hyper-parameters (:2525-2578, 2685-2731)
     for (uint32_t g = 0; g < G; g++) {
@@ -981,19 +1055,19 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
         }
     }
     if (tape && tape->sigmaE) c->sigmaE = tape->sigmaE[0];
-    else c->sigmaE = c->hyper_rng.inv_scaled_chisq(v0E + dN, (e_sqn + v0E * s02E) / (v0E + dN));  // :2690
+    else c->sigmaE = c->hyper_rng.inv_scaled_chisq(v0E + dN, (e_sqn_g + v0E * s02E) / (v0E + dN));  // :2690
     c->iteration++;
 
     if (out) {
         memset(out, 0, sizeof(*out));
-        out->sigmaE = c->sigmaE; out->e_sqn = e_sqn; out->epssum = epssum;
+        out->sigmaE = c->sigmaE; out->e_sqn = e_sqn_g; out->epssum = epssum;
         float ms = 0.f;
         cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); out->loop_ms = ms;
         cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); out->iter_ms = ms;
         out->n_sync = pin_stats[0]; out->n_windows = pin_stats[1];
         out->n_launches = 3;
         out->nnz_processed = pin_stats[2]; out->nnz_updated = pin_stats[3];
-        out->bed_markers = pin_stats[4]; out->markers_changed = pin_stats[5];
+        out->bed_markers = pin_stats[4]; out->markers_changed = changed_all;
         for (int i = 0; i < 8; i++) out->phase_cycles[i] = pin_stats[8 + i];
     }
     return HB_OK;
@@ -1051,14 +1125,57 @@ int hb_brr_get_task_perm(hb_ctx *c, uint32_t task_local, int32_t *perm) {
 }
 
 int hb_comm_get_unique_id(uint8_t id[HB_NCCL_ID_BYTES]) {
-    (void)id;
-    set_error("hb_comm_get_unique_id: multi-GPU exchange is not part of this build yet");
-    return HB_ERR_NCCL;
+    HB_CHECK(id, HB_ERR_ARG, "null argument");
+    static_assert(sizeof(ncclUniqueId) <= HB_NCCL_ID_BYTES, "ncclUniqueId larger than HB_NCCL_ID_BYTES");
+    ncclUniqueId u;
+    HB_NCCL(ncclGetUniqueId(&u));
+    memset(id, 0, HB_NCCL_ID_BYTES);
+    memcpy(id, &u, sizeof(u));
+    return HB_OK;
 }
-int hb_comm_init(hb_ctx *ctx, const uint8_t id[HB_NCCL_ID_BYTES], int rank, int nranks) {
-    (void)ctx; (void)id; (void)rank; (void)nranks;
-    set_error("hb_comm_init: multi-GPU exchange is not part of this build yet");
-    return HB_ERR_NCCL;
+
+// One process per GPU. Sets up (1) an NCCL communicator for the per-iteration statistics that hydra all-reduces
+// (src/BayesRRm.cpp:2517-2518) and the bootstrap, and (2) the NVLink peer mapping of every GPU's inbox, through
+// which the marker kernel exchanges the changed markers of a synchronisation window (replaces :2051, :2456).
+int hb_comm_init(hb_ctx *c, const uint8_t id[HB_NCCL_ID_BYTES], int rank, int nranks) {
+    HB_CHECK(c && id, HB_ERR_ARG, "null argument");
+    HB_CHECK(nranks >= 1 && nranks <= (int)kMaxRanks && rank >= 0 && rank < nranks, HB_ERR_ARG, "hb_comm_init: rank %d of %d (max %u GPUs)", rank, nranks, kMaxRanks);
+    HB_CHECK(!c->nccl, HB_ERR_STATE, "hb_comm_init: already initialised");
+    HB_CUDA(cudaSetDevice(c->dev));
+    if (nranks == 1) return HB_OK;
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    HB_NCCL(ncclCommInitRank(&c->nccl, nranks, u, rank));
+    c->rank = rank; c->nranks = nranks;
+    const char *mb = getenv("HB_INBOX_MB");
+    c->inbox_stride = ((size_t)(mb ? atoi(mb) : 16) << 20);
+    HB_CHECK(c->inbox_stride >= kInboxHeader + (1u << 20), HB_ERR_ARG, "hb_comm_init: HB_INBOX_MB too small");
+    c->comm_bytes = 2 * (size_t)nranks * c->inbox_stride + 256;
+    cudaError_t e = cudaMalloc((void **)&c->inbox, c->comm_bytes);
+    HB_CHECK(e == cudaSuccess, HB_ERR_NOMEM, "hb_comm_init: inbox of %zu bytes: %s", c->comm_bytes, cudaGetErrorString(e));
+    HB_CUDA(cudaMemset(c->inbox, 0, c->comm_bytes));
+    c->flags = reinterpret_cast<unsigned long long *>(c->inbox + c->comm_bytes - 256);
+    // exchange the IPC handles of the inboxes with NCCL itself (no MPI / torch needed by the C ABI)
+    cudaIpcMemHandle_t mine;
+    HB_CUDA(cudaIpcGetMemHandle(&mine, c->inbox));
+    DevBuf<unsigned char> d_h;
+    HB_TRY(d_h.alloc((size_t)nranks * sizeof(mine)));
+    HB_CUDA(cudaMemcpy(d_h.p + (size_t)rank * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    HB_NCCL(ncclAllGather(d_h.p + (size_t)rank * sizeof(mine), d_h.p, sizeof(mine), ncclChar, c->nccl, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    std::vector<cudaIpcMemHandle_t> all(nranks);
+    HB_CUDA(cudaMemcpy(all.data(), d_h.p, (size_t)nranks * sizeof(mine), cudaMemcpyDeviceToHost));
+    for (int h = 0; h < nranks; h++) {
+        if (h == rank) continue;
+        void *ptr = nullptr;
+        e = cudaIpcOpenMemHandle(&ptr, all[h], cudaIpcMemLazyEnablePeerAccess);
+        HB_CHECK(e == cudaSuccess, HB_ERR_CUDA, "hb_comm_init: cannot map the inbox of rank %d over NVLink/PCIe (%s); the GPUs must be peers on one node", h, cudaGetErrorString(e));
+        c->peer_inbox[h] = static_cast<unsigned char *>(ptr);
+    }
+    // nobody may write into an inbox before everybody has mapped (and cleared) theirs
+    HB_NCCL(ncclAllReduce(d_h.p, d_h.p, 1, ncclChar, ncclSum, c->nccl, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    return HB_OK;
 }
 
 }  // extern "C"

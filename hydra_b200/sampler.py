@@ -65,6 +65,27 @@ class GenotypeStore:
     def __exit__(self, *a):
         self.close()
 
+    def comm_init(self, dist=None, unique_id=None, rank=None, world=None):
+        """Join the GPUs of one node (one process each): NCCL communicator for the per-iteration statistics and the
+        NVLink peer mapping used by the marker kernel to exchange changed markers (replaces the MPI_Allreduce of deltaEps,
+        src/BayesRRm.cpp:2051, 2456, 2517-2518). `dist` = an initialised torch.distributed (any backend) used only to
+        broadcast the NCCL unique id; or pass unique_id/rank/world explicitly."""
+        uid = np.zeros(capi.NCCL_ID_BYTES, np.uint8)
+        if dist is not None:
+            import torch
+            rank, world = dist.get_rank(), dist.get_world_size()
+            if rank == 0:
+                check(self._lib.hb_comm_get_unique_id(ptr(uid)))
+            t = torch.from_numpy(uid)
+            if dist.get_backend() == "nccl":
+                t = t.cuda()
+            dist.broadcast(t, src=0)
+            uid = t.cpu().numpy().copy()
+        else:
+            uid[:] = np.frombuffer(bytes(unique_id), np.uint8)[: capi.NCCL_ID_BYTES]
+        check(self._lib.hb_comm_init(self._h, ptr(uid), C.c_int(rank), C.c_int(world)))
+        self.rank, self.world = rank, world
+
     def task_blocks(self):
         s = np.zeros(self.tasks, np.int32)
         l = np.zeros(self.tasks, np.int32)

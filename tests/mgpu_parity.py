@@ -1,0 +1,68 @@
+"""Multi-GPU replay parity (launched by torchrun from tests/test_gpu_multi.py, one process per GPU):
+G GPUs x T_local tasks each must reproduce the CPU oracle run with T_total = G*T_local tasks."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import hydra_b200  # noqa: E402
+import oracle  # noqa: E402
+from helpers import bed_from_lists, random_bed, reference_lists, simulate_y  # noqa: E402
+
+
+def main():
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    for case, (N, M, TL, SR, G, K, repr_mode, n_iter, seed) in enumerate([
+        (1500, 403, 2, 10, 2, 4, "sparse", 4, 7),
+        (1200, 300, 1, 1, 1, 4, "bed", 3, 1222),
+        (2000, 1000, 8, 8, 1, 3, "mixed", 2, 5),
+    ]):
+        T = TL * world
+        rng = np.random.default_rng(seed)
+        bed, g = random_bed(rng, M, N, pmiss=0.01)
+        sp = reference_lists(bed, N)
+        y = simulate_y(rng, g, n_causal=max(3, M // 10))
+        groups = (np.arange(M) % G).astype(np.int32)
+        mS = np.tile(np.array([0.0] + [10.0 ** (-(K - 1 - k)) for k in range(1, K)]), (G, 1))
+        sigmaG0 = rng.uniform(0.2, 0.8, size=G)
+        tape = oracle.TapeMaker(seed, T, M).make(n_iter)
+        fnz = (sp.N1L + sp.N2L + sp.NML).astype(np.float64) / N
+        usebed = {"sparse": np.zeros(M, np.uint8), "bed": np.ones(M, np.uint8), "mixed": (fnz > 0.35).astype(np.uint8)}[repr_mode]
+        ref = oracle.brr_chain(N, M, T, K, G, SR, n_iter, sp, y, groups, mS, tape, sigmaG0, usebed=usebed, bed=bed_from_lists(sp, N))
+        st = hydra_b200.GenotypeStore(N, M, tasks=T, task_first=rank * TL, tasks_local=TL, sync_rate=SR, n_groups=G, n_mix=K,
+                                      repr_mode=repr_mode, threshold_fnz=0.35, device=lr)
+        ms, ml = st.m_start, st.m_local
+        st.load_data_from_bed(bed[ms:ms + ml])
+        st.finalize()
+        st.comm_init(dist)
+        brr = hydra_b200.BayesRRm(st, y, mS, groups=groups, sigmaG0=sigmaG0, seed=seed)
+        for it in range(n_iter):
+            tp = dict(zmu=tape["zmu"][it][rank * TL:(rank + 1) * TL], perm=tape["perm"][it][ms:ms + ml], u=tape["u"][it][ms:ms + ml],
+                      z=tape["z"][it][ms:ms + ml], sigmaG=ref["sigmaG"][it], pi=ref["pi"][it], sigmaE=ref["sigmaE"][it:it + 1])
+            o = brr.iteration(tp)
+            beta, comp, acum = brr.state()
+            h = brr.hyper()
+            assert np.array_equal(comp, ref["comp"][it][ms:ms + ml]), f"case {case} rank {rank}: components differ at iteration {it}"
+            np.testing.assert_allclose(beta, ref["beta"][it][ms:ms + ml], rtol=1e-10, atol=1e-15)
+            assert np.array_equal(h["cass"], ref["cass"][it])
+            np.testing.assert_allclose(h["bsq"], ref["bsq"][it], rtol=1e-10)
+            np.testing.assert_allclose(o["e_sqn"], ref["esqn"][it], rtol=1e-10)
+            assert o["n_sync"] == ref["nsync"][it]
+            for t in range(TL):
+                np.testing.assert_allclose(brr.task_epsilon(t), ref["eps"][it, rank * TL + t], rtol=1e-10, atol=1e-12)
+        st.close()
+        dist.barrier()
+        if rank == 0:
+            print(f"multi-GPU parity case {case} ok on {world} GPUs", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,25 @@
+"""Multi-GPU parity: runs tests/mgpu_parity.py under torchrun when the box has >= 2 GPUs."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_multi_gpu_replay_matches_oracle(world):
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29500 + world), os.path.join(ROOT, "tests", "mgpu_parity.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "HB_PEER_TIMEOUT_S": "20"})
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "case 2 ok" in r.stdout
