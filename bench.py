@@ -147,6 +147,7 @@ def cpu_reference_run(a, n_ind, n_markers, m_total, steps, warmup):
 
 # ----------------------------------------------------------------------------- main
 def main():
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep NCCL's version banner off stdout (one JSON line only)
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -181,14 +182,8 @@ def main():
     stage_s = time.time() - t0
     if world > 1:
         store.comm_init(dist)  # exchange of the epsilon updates between the GPUs (DESIGN.md "Multi-GPU")
-    # phenotype: every rank needs the same y; simulate from rank-local causal markers and sum the genetic values
-    y, _, _ = synth.simulate_phenotype(store, n_causal=5000 // world, seed=synth.SEED_PHEN + rank)
-    if world > 1:
-        e = np.random.Generator(np.random.Philox(key=synth.SEED_PHEN + rank)).normal(0.0, np.sqrt(0.5), size=store.n_ind)
-        g = torch.from_numpy(y - e).cuda()
-        dist.all_reduce(g)
-        e0 = np.random.Generator(np.random.Philox(key=synth.SEED_PHEN)).normal(0.0, np.sqrt(0.5), size=store.n_ind)
-        y = g.cpu().numpy() + e0
+    # phenotype: every rank needs the same y (causal markers spread over the ranks, genetic values summed)
+    y, _, _ = synth.simulate_phenotype(store, n_causal=5000, dist=dist)
     brr = hydra_b200.BayesRRm(store, y, [[0.0001, 0.001, 0.01]], seed=1222)
     n1, n2, nm = store.marker_counts()
     nnz = n1.astype(np.int64) + n2 + nm

@@ -275,6 +275,9 @@ __device__ __forceinline__ ChgEnt ld_chg_ent(const ChgEnt *e) {
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void red_release_sys_add_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -660,25 +663,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                         }
                     }
                 }
-                __threadfence_system();
-                grid_barrier(P.bar, bar_target, nctas);
-                if (blockIdx.x == 0 && tid < NR && tid != me) {
-                    // the count travels with the flag's region header; flag last (release at system scope)
+                // Every CTA signals every peer once per window, after its share of the copy (the release at system scope
+                // orders the signal after the CTA's stores, which bar.sync ordered before it): the receiver waits until the
+                // cumulative arrival counter of a source reaches (sequence number) x (CTAs per GPU). No second grid
+                // barrier and no per-thread system fence.
+                if (blockIdx.x == 0 && tid < NR && tid != me)
                     *reinterpret_cast<volatile uint32_t *>(P.pc.inbox_peer[tid] + region) = ok ? nloc : 0xFFFFFFFFu;
-                    __threadfence_system();
-                    st_release_sys_u64(P.pc.flags_peer[tid] + me, seq);
-                }
-                // ---- 5b. wait for every peer's flag of this window
+                __syncthreads();
+                if (tid < NR && tid != me) red_release_sys_add_u64(P.pc.flags_peer[tid] + me, 1ull);
+                // ---- 5b. wait for every peer's pushes of this window
                 if (tid < NR) {
                     uint32_t nh = ok ? nloc : 0xFFFFFFFFu;
                     if (tid != me) {
                         const long long t0 = clock64();
                         bool late = false;
-                        while (ld_acquire_sys_u64(P.pc.flags_local + tid) < seq) {
+                        while (ld_acquire_sys_u64(P.pc.flags_local + tid) < seq * nctas) {
                             if (clock64() - t0 > P.pc.timeout_cycles) { late = true; break; }
                         }
                         nh = late ? 0xFFFFFFFFu
-                                  : *reinterpret_cast<volatile uint32_t *>(P.pc.inbox_local + ((size_t)par * NR + tid) * P.pc.inbox_stride);
+                                  : __ldcg(reinterpret_cast<const uint32_t *>(P.pc.inbox_local + ((size_t)par * NR + tid) * P.pc.inbox_stride));
                         if (late) atomicExch(P.pc.err, 2u);
                     }
                     pcnt[tid] = nh;

@@ -1172,9 +1172,17 @@ int hb_comm_init(hb_ctx *c, const uint8_t id[HB_NCCL_ID_BYTES], int rank, int nr
         HB_CHECK(e == cudaSuccess, HB_ERR_CUDA, "hb_comm_init: cannot map the inbox of rank %d over NVLink/PCIe (%s); the GPUs must be peers on one node", h, cudaGetErrorString(e));
         c->peer_inbox[h] = static_cast<unsigned char *>(ptr);
     }
-    // nobody may write into an inbox before everybody has mapped (and cleared) theirs
-    HB_NCCL(ncclAllReduce(d_h.p, d_h.p, 1, ncclChar, ncclSum, c->nccl, c->stream));
+    // nobody may write into an inbox before everybody has mapped (and cleared) theirs; and all GPUs must run the same
+    // grid, because the arrival counters of the exchange count CTAs
+    DevBuf<int32_t> d_g;
+    HB_TRY(d_g.alloc(2));
+    const int32_t mine_g[2] = {(int32_t)(c->S * c->R), -(int32_t)(c->S * c->R)};
+    int32_t mx[2] = {0, 0};
+    HB_CUDA(cudaMemcpy(d_g.p, mine_g, sizeof(mine_g), cudaMemcpyHostToDevice));
+    HB_NCCL(ncclAllReduce(d_g.p, d_g.p, 2, ncclInt32, ncclMax, c->nccl, c->stream));
     HB_CUDA(cudaStreamSynchronize(c->stream));
+    HB_CUDA(cudaMemcpy(mx, d_g.p, sizeof(mx), cudaMemcpyDeviceToHost));
+    HB_CHECK(mx[0] == -mx[1], HB_ERR_ARG, "hb_comm_init: the GPUs run different grids (%d vs %d CTAs); use the same n_slices / max_ctas", mx[0], -mx[1]);
     return HB_OK;
 }
 

@@ -54,13 +54,31 @@ def stage_synthetic(store, spectrum="B", pmiss=0.001, seed=SEED_GENO, chunk=1 <<
     return p, thr, attempts
 
 
-def simulate_phenotype(store, n_causal=5000, h2=0.5, seed=SEED_PHEN):
-    """y = X beta + e on standardised columns, computed on the device with the sampler's own update kernel."""
+def genetic_values(store, n_causal, h2, seed):
+    """g = X beta for n_causal local markers with beta ~ N(0, h2/n_causal_total-ish), on standardised columns, computed
+    on the device with the sampler's own update kernel."""
     rng = np.random.Generator(np.random.Philox(key=seed))
     n_causal = min(n_causal, store.m_local)
     causal = np.sort(rng.choice(store.m_local, size=n_causal, replace=False)).astype(np.uint32)
-    beta = rng.normal(0.0, np.sqrt(h2 / n_causal), size=n_causal)
-    e = rng.normal(0.0, np.sqrt(1.0 - h2), size=store.n_ind)
-    store.set_epsilon(e)
+    beta = rng.normal(0.0, 1.0, size=n_causal)
+    store.set_epsilon(np.zeros(store.n_ind))
     store.sparse_scaadd(causal, beta)
     return store.get_epsilon(), causal, beta
+
+
+def simulate_phenotype(store, n_causal=5000, h2=0.5, seed=SEED_PHEN, dist=None):
+    """y = X beta + e with var(X beta) ~ h2. With `dist` (torch.distributed) the causal markers are spread over the ranks
+    and the genetic values are summed, so that every rank ends up with the same phenotype."""
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    g, causal, beta = genetic_values(store, max(1, n_causal // world), h2, seed + 1 + rank)
+    if dist is not None:
+        import torch
+        t = torch.from_numpy(g)
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.all_reduce(t)
+        g = t.cpu().numpy()
+    g = g * np.sqrt(h2 / max(g.var(), 1e-300))
+    e = np.random.Generator(np.random.Philox(key=seed)).normal(0.0, np.sqrt(1.0 - h2), size=store.n_ind)
+    return g + e, causal, beta
