@@ -1,0 +1,426 @@
+// hydra_b200 -- C++ host of the B200-native per-marker Gibbs hot path.
+//
+// Keeps hydra's command line (reference src/options.cpp:5-333), input formats (PLINK .bed/.bim/.fam, sparse
+// .si?/.ss?/.sl? sets, .phen, .group, .mS; src/data.cpp:671-823, 1443-2007) and output files (.csv .bet .cpn .acu
+// .mus.<task> .eps.<task> .mrk.<task> .xbet .xcpn; src/BayesRRm.cpp:2736-2877) and drives the CUDA kernels only
+// through the C ABI of include/hydra_b200.h.  One process per GPU; `--tasks T` sets the number of hydra tasks that
+// the reference would have been started with (`mpirun -np T`).  Everything numeric happens on the device: without a
+// CUDA device the run fails (no CPU fallback); `--dry-run` only parses the options and the input files.
+#include <algorithm>
+#include <cerrno>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <sys/stat.h>
+#include <vector>
+
+#include "../../include/hydra_b200.h"
+
+namespace {
+
+struct Options {  // names follow the reference's Options class (src/options.hpp:20-138)
+    std::string bayesType, bedFile, phenotypeFile, groupIndexFile, groupMixtureFile, mcmcOutDir, mcmcOutNam, sparseDir, sparseBsn,
+        markerBlocksFile;
+    bool bedToSparse = false, dryRun = false, readFromBedFile = false, readFromSparseFiles = false;
+    uint32_t numberMarkers = 0, numberIndividuals = 0, chainLength = 10000, burnin = 5000, thin = 5, save = 10, syncRate = 1,
+             shuffleMarkers = 1, tasks = 1, device = 0, blocksPerRank = 1;
+    uint32_t seed = 0;
+    bool seedSet = false;
+    double thresholdFnz = 0.06;
+    std::vector<double> S{0.01, 0.001, 0.0001};  // src/options.hpp:102-110
+    std::string mcmcOut() const { return mcmcOutDir + "/" + mcmcOutNam; }
+};
+
+[[noreturn]] void fatal(const std::string &msg) {
+    printf("FATAL  : %s\n", msg.c_str());
+    fflush(stdout);
+    exit(1);
+}
+
+#define HB(x)                                                     \
+    do {                                                          \
+        if ((x) != HB_OK) fatal(std::string(hb_last_error()));    \
+    } while (0)
+
+std::vector<std::string> split(const std::string &s, const char *seps) {
+    std::vector<std::string> out;
+    size_t i = 0;
+    while (i < s.size()) {
+        size_t j = s.find_first_of(seps, i);
+        if (j == std::string::npos) j = s.size();
+        if (j > i) out.push_back(s.substr(i, j - i));
+        i = j + 1;
+    }
+    return out;
+}
+
+Options parse(int argc, const char **argv) {
+    Options o;
+    auto need = [&](int &i) -> const char * {
+        if (i + 1 >= argc) throw std::runtime_error(std::string("option ") + argv[i] + " needs a value");
+        return argv[++i];
+    };
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        if (a == "--mpibayes") o.bayesType = need(i);
+        else if (a == "--bfile") { o.readFromBedFile = true; o.bedFile = need(i); }
+        else if (a == "--pheno") o.phenotypeFile = need(i);
+        else if (a == "--groupIndexFile") o.groupIndexFile = need(i);
+        else if (a == "--groupMixtureFile") o.groupMixtureFile = need(i);
+        else if (a == "--mcmc-out-dir") o.mcmcOutDir = need(i);
+        else if (a == "--mcmc-out-name") o.mcmcOutNam = need(i);
+        else if (a == "--shuf-mark") o.shuffleMarkers = (uint32_t)atoi(need(i));
+        else if (a == "--marker-blocks-file") o.markerBlocksFile = need(i);
+        else if (a == "--sync-rate") o.syncRate = (uint32_t)atoi(need(i));
+        else if (a == "--sparse-dir") { o.readFromSparseFiles = true; o.sparseDir = need(i); }
+        else if (a == "--sparse-basename") o.sparseBsn = need(i);
+        else if (a == "--number-markers") o.numberMarkers = (uint32_t)atoi(need(i));
+        else if (a == "--number-individuals") o.numberIndividuals = (uint32_t)atoi(need(i));
+        else if (a == "--chain-length") o.chainLength = (uint32_t)atoi(need(i));
+        else if (a == "--burn-in") o.burnin = (uint32_t)atoi(need(i));
+        else if (a == "--seed") { o.seed = (uint32_t)atoi(need(i)); o.seedSet = true; }
+        else if (a == "--thin") o.thin = (uint32_t)atoi(need(i));
+        else if (a == "--save") o.save = (uint32_t)atoi(need(i));
+        else if (a == "--threshold-fnz") o.thresholdFnz = atof(need(i));
+        else if (a == "--bed-to-sparse") o.bedToSparse = true;
+        else if (a == "--blocks-per-rank") o.blocksPerRank = (uint32_t)atoi(need(i));
+        else if (a == "--S") {
+            o.S.clear();
+            for (auto &t : split(need(i), " ,")) o.S.push_back(std::stod(t));
+        }
+        // additions of this host (the reference takes the task count from mpirun)
+        else if (a == "--tasks") o.tasks = (uint32_t)atoi(need(i));
+        else if (a == "--device") o.device = (uint32_t)atoi(need(i));
+        else if (a == "--dry-run") o.dryRun = true;
+        // reference options outside the accelerated path: recognised, refused with a clear message
+        else if (a == "--restart" || a == "--ignore-xfiles" || a == "--sparse-sync" || a == "--bed-sync" || a == "--covariates" ||
+                 a == "--failure" || a == "--quad_points" || a == "--check-RAM" || a == "--groupPriorsFile" || a == "--dPriorsFile")
+            throw std::runtime_error("option \"" + a + "\" of hydra is not supported by hydra_b200 yet (see DESIGN.md, out of scope)");
+        else
+            throw std::runtime_error("\nError: invalid option \"" + a + "\".\n");  // src/options.cpp:292-296
+    }
+    if (!o.bedToSparse) {  // src/options.cpp:302-323
+        if (o.mcmcOutDir.empty()) throw std::runtime_error("--mcmc-out-dir CL option has to be set!");
+        if (o.mcmcOutNam.empty()) throw std::runtime_error("--mcmc-out-nam CL option has to be set!");
+    }
+    if (o.sparseBsn.empty() != o.sparseDir.empty())  // :330-331
+        throw std::runtime_error("--sparse-dir and --sparse-basename must either be both set or unset");
+    if (o.groupIndexFile.empty() != o.groupMixtureFile.empty())  // src/main.cpp:147-149
+        throw std::runtime_error("--groupIndexFile and --groupMixtureFile must either be both set or unset");
+    if (o.numberIndividuals == 0) throw std::runtime_error("--number-individuals has to be set (src/BayesRRm.cpp:3125-3143)");
+    if (o.numberMarkers == 0) throw std::runtime_error("--number-markers has to be set (src/BayesRRm.cpp:3125-3143)");
+    if (o.tasks == 0) throw std::runtime_error("--tasks must be >= 1");
+    if (o.thin == 0) o.thin = 1;
+    if (o.save % o.thin != 0) o.save = std::max(o.thin, o.save / o.thin * o.thin);  // :1058-1066 save is a multiple of thin
+    return o;
+}
+
+size_t count_lines(const std::string &path) {
+    std::ifstream in(path);
+    if (!in) throw std::runtime_error("Error: can not open the file [" + path + "] to read.");
+    size_t n = 0;
+    std::string l;
+    while (std::getline(in, l))
+        if (!l.empty()) n++;
+    return n;
+}
+
+// src/data.cpp:1806-1833: third token, "NA" -> individual dropped, its line number recorded
+void read_phen(const std::string &path, uint32_t n_ind, std::vector<double> &y, std::vector<uint32_t> &na) {
+    std::ifstream in(path);
+    if (!in) throw std::runtime_error("Error: can not open the phenotype file [" + path + "] to read.");
+    std::string l;
+    uint32_t line = 0;
+    while (std::getline(in, l)) {
+        auto t = split(l, " \t\r");
+        if (t.empty()) continue;
+        if (t.size() < 3) throw std::runtime_error("phenotype file [" + path + "]: line " + std::to_string(line + 1) + " has fewer than 3 columns");
+        if (t[2] != "NA") y.push_back(atof(t[2].c_str()));
+        else na.push_back(line);
+        line++;
+    }
+    if (line != n_ind) throw std::runtime_error("phenotype file [" + path + "] has " + std::to_string(line) + " lines, --number-individuals is " + std::to_string(n_ind));
+}
+
+// src/data.cpp:1944-1960: one integer per marker
+std::vector<int32_t> read_group_file(const std::string &path, uint32_t m) {
+    std::ifstream in(path);
+    if (!in) throw std::runtime_error("Error: can not open the group file [" + path + "] to read.");
+    std::vector<int32_t> g;
+    std::string l;
+    while (std::getline(in, l)) {
+        auto t = split(l, " \t\r");
+        if (t.empty()) continue;
+        g.push_back(atoi(t.back().c_str()));
+    }
+    if (g.size() != m) throw std::runtime_error("group file [" + path + "] has " + std::to_string(g.size()) + " entries, --number-markers is " + std::to_string(m));
+    return g;
+}
+
+// src/data.cpp:1975-2007: "a,b,c;a,b,c" -- one ';'-separated row per group, strictly positive, zero component implicit
+std::vector<std::vector<double>> read_mS_file(const std::string &path) {
+    std::ifstream in(path);
+    if (!in) throw std::runtime_error("Error: can not open the mixture file [" + path + "] to read.");
+    std::stringstream ss;
+    ss << in.rdbuf();
+    std::vector<std::vector<double>> rows;
+    for (auto &r : split(ss.str(), ";\n\r")) {
+        std::vector<double> row;
+        for (auto &t : split(r, ", \t")) {
+            const double v = std::stod(t);
+            if (!(v > 0.0)) throw std::runtime_error("mixture file [" + path + "]: variances must be strictly positive");
+            row.push_back(v);
+        }
+        if (!row.empty()) rows.push_back(row);
+    }
+    if (rows.empty()) throw std::runtime_error("mixture file [" + path + "] is empty");
+    for (auto &r : rows)
+        if (r.size() != rows[0].size()) throw std::runtime_error("mixture file [" + path + "]: all groups need the same number of components");
+    return rows;
+}
+
+template <class T>
+std::vector<T> read_binary(const std::string &path, size_t offset_elems, size_t count) {
+    std::vector<T> v(count);
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("Error: can not open [" + path + "]: " + strerror(errno));
+    if (fseeko(f, (off_t)(offset_elems * sizeof(T)), SEEK_SET) != 0 || fread(v.data(), sizeof(T), count, f) != count) {
+        fclose(f);
+        throw std::runtime_error("Error: short read from [" + path + "]");
+    }
+    fclose(f);
+    return v;
+}
+
+struct OutFile {
+    FILE *f = nullptr;
+    void open(const std::string &path) {
+        f = fopen(path.c_str(), "wb");  // the reference deletes old files and creates new ones (:1269-1309)
+        if (!f) fatal("cannot create output file " + path + ": " + strerror(errno));
+    }
+    template <class T>
+    void put(const T *p, size_t n) {
+        if (fwrite(p, sizeof(T), n, f) != n) fatal("write failed");
+    }
+    ~OutFile() {
+        if (f) fclose(f);
+    }
+};
+
+template <class T>
+void dump_file(const std::string &path, uint32_t it, uint32_t n, const T *data) {  // .eps/.mrk: u32 it, u32 n, data[n]
+    OutFile o;
+    o.open(path);
+    o.put(&it, 1);
+    o.put(&n, 1);
+    o.put(data, n);
+}
+
+}  // namespace
+
+int main(int argc, const char **argv) {
+    Options opt;
+    try {
+        opt = parse(argc, argv);
+    } catch (const std::exception &e) {  // the reference prints the thrown message and returns (src/main.cpp:179-184)
+        std::cerr << e.what() << std::endl;
+        return 1;
+    }
+    try {
+        const uint32_t Nraw = opt.numberIndividuals, Mtot = opt.numberMarkers;
+        if (opt.readFromBedFile) {  // src/main.cpp:69-70: .fam / .bim only give the dimensions here
+            const size_t nf = count_lines(opt.bedFile + ".fam"), nb = count_lines(opt.bedFile + ".bim");
+            if (nf != Nraw) throw std::runtime_error(".fam file has " + std::to_string(nf) + " individuals, --number-individuals is " + std::to_string(Nraw));
+            if (nb != Mtot) throw std::runtime_error(".bim file has " + std::to_string(nb) + " markers, --number-markers is " + std::to_string(Mtot));
+        }
+        if (!opt.readFromBedFile && !opt.readFromSparseFiles) throw std::runtime_error("either --bfile or --sparse-dir/--sparse-basename is needed");
+
+        std::vector<double> y;
+        std::vector<uint32_t> na;
+        if (!opt.bedToSparse) {
+            if (opt.phenotypeFile.empty()) throw std::runtime_error("--pheno has to be set");
+            read_phen(opt.phenotypeFile, Nraw, y, na);
+        }
+        // groups and mixtures (src/BayesRRm.cpp:981-996)
+        std::vector<int32_t> groups;
+        std::vector<std::vector<double>> mS;
+        if (!opt.groupIndexFile.empty()) {
+            groups = read_group_file(opt.groupIndexFile, Mtot);
+            mS = read_mS_file(opt.groupMixtureFile);
+            for (auto g : groups)
+                if (g < 0 || (size_t)g >= mS.size()) throw std::runtime_error("group index out of range of the mixture file");
+        } else {
+            mS.push_back(opt.S);
+        }
+        const uint32_t G = (uint32_t)mS.size(), K = (uint32_t)mS[0].size() + 1;
+        const int repr = (opt.readFromBedFile && opt.readFromSparseFiles) ? HB_REPR_MIXED : (opt.readFromBedFile ? HB_REPR_BED : HB_REPR_SPARSE);
+
+        printf("INFO   : hydra_b200: %s, N = %u (%zu NA phenotypes), M = %u, %u task(s), sync rate %u, %u group(s) x %u mixtures, input %s\n",
+               opt.bedToSparse ? "bed-to-sparse" : opt.bayesType.c_str(), Nraw, na.size(), Mtot, opt.tasks, opt.syncRate, G, K - 1,
+               repr == HB_REPR_MIXED ? "mixed" : (repr == HB_REPR_BED ? "bed" : "sparse"));
+        if (opt.dryRun) {
+            printf("INFO   : dry run: options and input files parsed, nothing computed\n");
+            return 0;
+        }
+        if (!opt.bedToSparse && opt.bayesType != "bayesMPI")
+            throw std::runtime_error("--mpibayes " + opt.bayesType + ": only bayesMPI (BayesRRm) is available in this build");
+
+        // ---- device context
+        hb_config cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.device = (int32_t)opt.device;
+        cfg.n_ind_raw = Nraw; cfg.n_na = (uint32_t)na.size(); cfg.na_inds = na.data();
+        cfg.m_total = Mtot; cfg.n_tasks_total = opt.tasks; cfg.task_first = 0; cfg.n_tasks_local = opt.tasks;
+        cfg.sync_rate = opt.syncRate; cfg.n_groups = G; cfg.n_mix = K;
+        cfg.repr_mode = opt.bedToSparse ? HB_REPR_SPARSE : repr;
+        cfg.threshold_fnz = opt.thresholdFnz;
+        cfg.reserved[0] = opt.shuffleMarkers ? 0u : 1u;
+        hb_ctx *ctx = nullptr;
+        HB(hb_create(&cfg, &ctx));
+        uint32_t N = 0, m_local = 0, lmax = 0;
+        HB(hb_get_layout(ctx, &N, nullptr, &m_local, nullptr, nullptr, nullptr, &lmax));
+
+        // ---- genotypes -> HBM (src/data.cpp:671-739 bed, :742-823 sparse; mixed mode reads the sparse files, :991-996)
+        const size_t chunk = std::max<size_t>(1, ((size_t)256 << 20) / std::max<size_t>(1, (Nraw + 3) / 4));
+        if (opt.readFromSparseFiles && !opt.bedToSparse) {
+            const std::string b = opt.sparseDir + "/" + opt.sparseBsn;
+            for (size_t m0 = 0; m0 < Mtot; m0 += chunk) {
+                const size_t n = std::min(chunk, (size_t)Mtot - m0);
+                std::vector<uint64_t> S[3], Ln[3];
+                std::vector<uint32_t> I[3];
+                const char *ext[3] = {"1", "2", "m"};
+                for (int w = 0; w < 3; w++) {
+                    S[w] = read_binary<uint64_t>(b + ".ss" + ext[w], m0, n);
+                    Ln[w] = read_binary<uint64_t>(b + ".sl" + ext[w], m0, n);
+                    const uint64_t lo = S[w][0], hi = S[w][n - 1] + Ln[w][n - 1];  // src/data.cpp:1101-1105
+                    I[w] = read_binary<uint32_t>(b + ".si" + ext[w], lo, hi - lo);
+                    for (auto &s : S[w]) s -= lo;  // :820-822
+                }
+                HB(hb_stage_sparse(ctx, (uint32_t)m0, (uint32_t)n, I[0].data(), S[0].data(), Ln[0].data(), I[1].data(), S[1].data(),
+                                   Ln[1].data(), I[2].data(), S[2].data(), Ln[2].data()));
+            }
+        } else {
+            const size_t nb = (Nraw + 3) / 4;
+            for (size_t m0 = 0; m0 < Mtot; m0 += chunk) {
+                const size_t n = std::min(chunk, (size_t)Mtot - m0);
+                // 3 magic bytes are skipped, never validated (src/data.cpp:700)
+                auto cols = read_binary<uint8_t>(opt.bedFile + ".bed", 3 + m0 * nb, n * nb);
+                HB(hb_stage_bed(ctx, (uint32_t)m0, (uint32_t)n, cols.data()));
+            }
+        }
+        HB(hb_stage_finalize(ctx));
+        printf("INFO   : genotypes staged: %.3f GB in HBM\n", (double)hb_genotype_bytes(ctx) / 1e9);
+
+        if (opt.bedToSparse) {  // src/BayesRRm.cpp:437-770: .dim .si? .ss? .sl?
+            if (opt.sparseDir.empty()) throw std::runtime_error("--bed-to-sparse needs --sparse-dir and --sparse-basename");
+            mkdir(opt.sparseDir.c_str(), 0755);
+            const std::string b = opt.sparseDir + "/" + opt.sparseBsn;
+            std::vector<uint32_t> n1(Mtot), n2(Mtot), nm(Mtot);
+            HB(hb_marker_counts(ctx, n1.data(), n2.data(), nm.data()));
+            OutFile fi[3], fs[3], fl[3];
+            const char *ext[3] = {"1", "2", "m"};
+            for (int w = 0; w < 3; w++) { fi[w].open(b + ".si" + ext[w]); fs[w].open(b + ".ss" + ext[w]); fl[w].open(b + ".sl" + ext[w]); }
+            uint64_t base[3] = {0, 0, 0};
+            for (size_t m0 = 0; m0 < Mtot; m0 += chunk) {
+                const size_t n = std::min(chunk, (size_t)Mtot - m0);
+                size_t t[3] = {0, 0, 0};
+                for (size_t i = 0; i < n; i++) { t[0] += n1[m0 + i]; t[1] += n2[m0 + i]; t[2] += nm[m0 + i]; }
+                std::vector<uint32_t> I[3];
+                std::vector<uint64_t> S[3], Ln[3];
+                for (int w = 0; w < 3; w++) { I[w].resize(std::max<size_t>(t[w], 1)); S[w].resize(n); Ln[w].resize(n); }
+                HB(hb_export_sparse(ctx, (uint32_t)m0, (uint32_t)n, I[0].data(), S[0].data(), Ln[0].data(), I[1].data(), S[1].data(),
+                                    Ln[1].data(), I[2].data(), S[2].data(), Ln[2].data()));
+                for (int w = 0; w < 3; w++) {
+                    for (auto &s : S[w]) s += base[w];  // absolute starts, in elements (:680-684)
+                    fi[w].put(I[w].data(), t[w]); fs[w].put(S[w].data(), n); fl[w].put(Ln[w].data(), n);
+                    base[w] += t[w];
+                }
+            }
+            std::ofstream dim(b + ".dim");
+            dim << N << " " << Mtot << "\n";
+            printf("INFO   : wrote sparse files %s.{dim,si?,ss?,sl?}: %llu ones, %llu twos, %llu missing\n", b.c_str(),
+                   (unsigned long long)base[0], (unsigned long long)base[1], (unsigned long long)base[2]);
+            hb_destroy(ctx);
+            return 0;
+        }
+
+        // ---- chain (src/BayesRRm.cpp:1565-2877)
+        std::vector<double> mSflat((size_t)G * K, 0.0);
+        for (uint32_t g = 0; g < G; g++)
+            for (uint32_t k = 1; k < K; k++) mSflat[g * K + k] = mS[g][k - 1];
+        const uint32_t seed = opt.seedSet ? opt.seed : (uint32_t)time(nullptr);
+        HB(hb_brr_init(ctx, y.data(), groups.empty() ? nullptr : groups.data(), mSflat.data(), nullptr, seed));
+
+        struct stat sb;
+        if (stat(opt.mcmcOutDir.c_str(), &sb) != 0 && system(("mkdir -p " + opt.mcmcOutDir).c_str()) != 0)
+            throw std::runtime_error("could not create output directory --mcmc-out-dir " + opt.mcmcOutDir);
+        const std::string out = opt.mcmcOut();
+        OutFile csv, bet, acu, cpn;
+        csv.open(out + ".csv"); bet.open(out + ".bet"); acu.open(out + ".acu"); cpn.open(out + ".cpn");
+        bet.put(&Mtot, 1); acu.put(&Mtot, 1); cpn.put(&Mtot, 1);  // :1304-1308
+        std::vector<OutFile> mus(opt.tasks);
+        for (uint32_t t = 0; t < opt.tasks; t++) mus[t].open(out + ".mus." + std::to_string(t));
+
+        std::vector<double> beta(Mtot), acum(Mtot), sigmaG(G), pi((size_t)G * K), mu(opt.tasks), bsq(G), eps(N);
+        std::vector<int32_t> comp(Mtot), cass((size_t)G * K), m0(G), perm;
+        double tot_loop_ms = 0.0, tot_iter_ms = 0.0;
+        for (uint32_t it = 0; it < opt.chainLength; it++) {
+            hb_brr_iter_out io;
+            HB(hb_brr_iteration(ctx, nullptr, &io));
+            tot_loop_ms += io.loop_ms; tot_iter_ms += io.iter_ms;
+            double sigmaE = 0.0;
+            HB(hb_brr_get_hyper(ctx, sigmaG.data(), pi.data(), &sigmaE, mu.data(), bsq.data(), cass.data(), m0.data()));
+            double sG = 0.0; int m0s = 0;
+            for (uint32_t g = 0; g < G; g++) { sG += sigmaG[g]; m0s += m0[g]; }
+            printf("RESULT : it %4u, rank %4d: proc = %9.3f s, sync = %9.3f (%9.3f + %9.3f), n_sync = %8llu (%8llu + %8llu) (%7.3f / %7.3f), sigmaG = %15.10f, sigmaE = %15.10f, betasq = %15.10f, m0 = %10d\n",
+                   it, 0, io.iter_ms * 1e-3, 0.0, 0.0, 0.0, (unsigned long long)io.n_sync, (unsigned long long)io.n_windows, (unsigned long long)io.n_sync,
+                   0.0, 0.0, sG, sigmaE, bsq[0], m0s);  // :2714-2720
+            if (it % opt.thin == 0) {
+                char buff[65536];
+                int n = snprintf(buff, sizeof(buff), "%5d, %4d", (int)it, (int)G);  // :2742-2764
+                for (uint32_t g = 0; g < G; g++) n += snprintf(buff + n, sizeof(buff) - n, ", %20.15f", sigmaG[g]);
+                n += snprintf(buff + n, sizeof(buff) - n, ", %20.15f, %20.15f, %7d, %4d, %2d", sigmaE, sG / (sigmaE + sG), m0s, (int)G, (int)K);
+                for (size_t x = 0; x < (size_t)G * K; x++) n += snprintf(buff + n, sizeof(buff) - n, ", %20.15f", pi[x]);
+                n += snprintf(buff + n, sizeof(buff) - n, "\n");
+                csv.put(buff, (size_t)n);
+                HB(hb_brr_get_state(ctx, beta.data(), comp.data(), acum.data()));
+                bet.put(&it, 1); bet.put(beta.data(), Mtot);  // records {u32 it; f64[Mtot]} (:2768-2780)
+                acu.put(&it, 1); acu.put(acum.data(), Mtot);
+                cpn.put(&it, 1); cpn.put(comp.data(), Mtot);  // {u32 it; i32[Mtot]} (:2772-2785)
+                for (uint32_t t = 0; t < opt.tasks; t++) { mus[t].put(&it, 1); mus[t].put(&mu[t], 1); }  // :2788-2791
+                fflush(csv.f);
+            }
+            if (it > 0 && it % opt.save == 0) {  // :2808-2838, overwritten at every save
+                int32_t starts[4096], lens[4096];
+                std::vector<int32_t> bs(opt.tasks), bl(opt.tasks);
+                (void)starts; (void)lens;
+                HB(hb_get_task_blocks(ctx, bs.data(), bl.data()));
+                for (uint32_t t = 0; t < opt.tasks; t++) {
+                    HB(hb_brr_get_task_epsilon(ctx, t, eps.data()));
+                    dump_file(out + ".eps." + std::to_string(t), it, N, eps.data());
+                    perm.resize((size_t)bl[t]);
+                    HB(hb_brr_get_task_perm(ctx, t, perm.data()));
+                    dump_file(out + ".mrk." + std::to_string(t), it, (uint32_t)bl[t], perm.data());
+                }
+                HB(hb_brr_get_state(ctx, beta.data(), comp.data(), nullptr));
+                OutFile xb, xc;
+                xb.open(out + ".xbet"); xc.open(out + ".xcpn");  // u32 Mtot; u32 it; data[Mtot] (:2818-2838)
+                xb.put(&Mtot, 1); xb.put(&it, 1); xb.put(beta.data(), Mtot);
+                xc.put(&Mtot, 1); xc.put(&it, 1); xc.put(comp.data(), Mtot);
+            }
+        }
+        printf("INFO   : time to process the data: %.3f sec (marker loops %.3f sec: %.3f M marker updates/s)\n", tot_iter_ms * 1e-3,
+               tot_loop_ms * 1e-3, (double)Mtot * opt.chainLength / (tot_loop_ms * 1e3));
+        hb_destroy(ctx);
+    } catch (const std::exception &e) {
+        fatal(e.what());
+    }
+    return 0;
+}

@@ -1,0 +1,160 @@
+"""The C++ host: hydra's command line and file formats on top of the C ABI.
+CPU part: option parsing / input readers (--dry-run). GPU part: the reference's own test strategy:
+run-vs-run equality -- BED input vs sparse input vs the Python front-end, compared through the output files."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import random_bed, simulate_y
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "hydra_b200", "bin", "hydra_b200")
+
+
+def _exe():
+    if not os.path.exists(EXE):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "hydra_b200", "csrc")], check=True, capture_output=True)
+        subprocess.run(["make", "-C", os.path.join(ROOT, "hydra_b200", "host")], check=True, capture_output=True)
+    return EXE
+
+
+def write_dataset(d, N=600, M=150, G=2, n_na=7, seed=3):
+    rng = np.random.default_rng(seed)
+    bed, g = random_bed(rng, M, N, pmiss=0.01)
+    with open(os.path.join(d, "t.bed"), "wb") as f:
+        f.write(bytes([0x6C, 0x1B, 0x01]))
+        f.write(bed.tobytes())
+    with open(os.path.join(d, "t.bim"), "w") as f:
+        for j in range(M):
+            f.write(f"1\trs{j}\t0\t{j + 1}\tA\tC\n")
+    with open(os.path.join(d, "t.fam"), "w") as f:
+        for i in range(N):
+            f.write(f"F{i} I{i} 0 0 1 -9\n")
+    y = simulate_y(rng, g)
+    na = np.sort(rng.choice(N, n_na, replace=False))
+    with open(os.path.join(d, "t.phen"), "w") as f:
+        for i in range(N):
+            f.write(f"F{i} I{i} {'NA' if i in set(na.tolist()) else repr(float(y[i]))}\n")
+    groups = (np.arange(M) % G).astype(np.int32)
+    with open(os.path.join(d, "t.group"), "w") as f:
+        for j in range(M):
+            f.write(f"rs{j} {groups[j]}\n")
+    with open(os.path.join(d, "t.mS"), "w") as f:
+        f.write(";".join(["0.001,0.01,0.1"] * G) + "\n")
+    return bed, y, na.astype(np.uint32), groups
+
+
+def read_bet(path, M, dtype=np.float64):
+    raw = open(path, "rb").read()
+    (m,) = struct.unpack("<I", raw[:4])
+    assert m == M
+    rec = 4 + M * np.dtype(dtype).itemsize
+    n = (len(raw) - 4) // rec
+    its, vals = [], []
+    for r in range(n):
+        o = 4 + r * rec
+        its.append(struct.unpack("<I", raw[o:o + 4])[0])
+        vals.append(np.frombuffer(raw[o + 4:o + rec], dtype=dtype))
+    return np.array(its), np.array(vals)
+
+
+def base_args(d, out, extra=()):
+    return [_exe(), "--mpibayes", "bayesMPI", "--pheno", os.path.join(d, "t.phen"), "--number-individuals", "600", "--number-markers", "150",
+            "--chain-length", "6", "--thin", "2", "--save", "4", "--seed", "1222", "--shuf-mark", "1", "--sync-rate", "5", "--tasks", "3",
+            "--groupIndexFile", os.path.join(d, "t.group"), "--groupMixtureFile", os.path.join(d, "t.mS"),
+            "--mcmc-out-dir", os.path.join(d, out), "--mcmc-out-name", "run", *extra]
+
+
+def test_cli_rejects_unknown_and_incomplete_options(tmp_path):
+    r = subprocess.run([_exe(), "--no-such-flag"], capture_output=True, text=True)
+    assert r.returncode != 0 and "invalid option" in r.stderr
+    r = subprocess.run([_exe(), "--mpibayes", "bayesMPI", "--mcmc-out-dir", str(tmp_path), "--mcmc-out-name", "x"], capture_output=True, text=True)
+    assert r.returncode != 0 and "--number-individuals" in r.stderr
+    r = subprocess.run([_exe(), "--mpibayes", "bayesMPI", "--sparse-dir", "x", "--mcmc-out-dir", str(tmp_path), "--mcmc-out-name", "x",
+                        "--number-individuals", "5", "--number-markers", "5"], capture_output=True, text=True)
+    assert r.returncode != 0 and "--sparse-dir and --sparse-basename" in r.stderr
+
+
+def test_cli_dry_run_reads_reference_formats(tmp_path):
+    d = str(tmp_path)
+    write_dataset(d)
+    r = subprocess.run(base_args(d, "o", ["--bfile", os.path.join(d, "t"), "--dry-run"]), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "N = 600 (7 NA phenotypes), M = 150, 3 task(s), sync rate 5, 2 group(s) x 3 mixtures, input bed" in r.stdout
+    # a wrong --number-markers is caught against the .bim file
+    a = base_args(d, "o", ["--bfile", os.path.join(d, "t"), "--dry-run"])
+    a[a.index("--number-markers") + 1] = "151"
+    r = subprocess.run(a, capture_output=True, text=True)
+    assert r.returncode != 0 and ".bim file has 150 markers" in r.stdout
+
+
+def test_cli_reads_the_reference_example_files():
+    # parser fixtures shipped with the reference (SURVEY 8c iv): copied line counts only, no reference file is read at GPU time
+    ex = "/root/reference/example"
+    if not os.path.isdir(ex):
+        pytest.skip("reference checkout not present")
+    r = subprocess.run([_exe(), "--mpibayes", "bayesMPI", "--sparse-dir", "/tmp", "--sparse-basename", "none", "--pheno", ex + "/normal.phen",
+                        "--number-individuals", "5000", "--number-markers", "10000", "--groupIndexFile", ex + "/normal.group",
+                        "--groupMixtureFile", ex + "/normal.mS", "--mcmc-out-dir", "/tmp/hb_o", "--mcmc-out-name", "x", "--dry-run"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "N = 5000 (0 NA phenotypes), M = 10000" in r.stdout and "2 group(s) x 3 mixtures" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cli_bed_vs_sparse_vs_python_runs_are_identical(tmp_path):
+    import hydra_b200
+    d = str(tmp_path)
+    bed, y, na, groups = write_dataset(d)
+    N, M = 600, 150
+    r = subprocess.run(base_args(d, "bed", ["--bfile", os.path.join(d, "t")]), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    # bed -> sparse files -> sparse-input run
+    r = subprocess.run([_exe(), "--bed-to-sparse", "--bfile", os.path.join(d, "t"), "--sparse-dir", os.path.join(d, "sp"), "--sparse-basename", "t",
+                        "--number-individuals", str(N), "--number-markers", str(M)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert open(os.path.join(d, "sp", "t.dim")).read().split() == [str(N), str(M)]
+    import oracle
+    sp = oracle.sparse_fill_indices(bed, N)   # the sparse files hold the raw (not NA-corrected) lists, ascending, absolute starts
+    assert np.array_equal(np.fromfile(os.path.join(d, "sp", "t.si1"), np.uint32), sp.I1)
+    assert np.array_equal(np.fromfile(os.path.join(d, "sp", "t.ss2"), np.uint64), sp.N2S)
+    assert np.array_equal(np.fromfile(os.path.join(d, "sp", "t.slm"), np.uint64), sp.NML)
+    r = subprocess.run(base_args(d, "sparse", ["--sparse-dir", os.path.join(d, "sp"), "--sparse-basename", "t"]), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    for ext in ("bet", "cpn", "acu", "csv", "xbet", "xcpn", "eps.0", "eps.2", "mrk.1", "mus.0"):
+        a = open(os.path.join(d, "bed", "run." + ext), "rb").read()
+        b = open(os.path.join(d, "sparse", "run." + ext), "rb").read()
+        if ext in ("bet", "acu", "eps.0", "eps.2", "xbet", "mus.0"):  # list vs 2-bit dot products round differently: values, not bytes
+            hdr = 8 if ext.startswith("eps") or ext == "xbet" else 0
+            assert a[:hdr] == b[:hdr] and len(a) == len(b)
+        elif ext == "csv":
+            va = np.array([[float(x) for x in l.split(",")] for l in a.decode().strip().split("\n")])
+            vb = np.array([[float(x) for x in l.split(",")] for l in b.decode().strip().split("\n")])
+            np.testing.assert_allclose(va, vb, rtol=1e-9)
+        else:
+            assert a == b, ext  # components, marker order: integers, identical
+    its, beta = read_bet(os.path.join(d, "bed", "run.bet"), M)
+    its2, beta2 = read_bet(os.path.join(d, "sparse", "run.bet"), M)
+    assert its.tolist() == [0, 2, 4] and its2.tolist() == [0, 2, 4]
+    np.testing.assert_allclose(beta, beta2, rtol=1e-9, atol=1e-14)
+    # the same chain through the Python front-end
+    keep = np.setdiff1d(np.arange(N), na)
+    with hydra_b200.GenotypeStore(N, M, na_inds=na, tasks=3, sync_rate=5, n_groups=2, n_mix=4, repr_mode="bed") as st:
+        st.load_data_from_bed(bed)
+        st.finalize()
+        brr = hydra_b200.BayesRRm(st, y[keep], [[0.001, 0.01, 0.1]] * 2, groups=groups, seed=1222)
+        for it in range(5):
+            brr.iteration()
+            if it % 2 == 0:
+                b, c, _ = brr.state()
+                assert np.array_equal(b, beta[it // 2]), f"python vs CLI beta at iteration {it}"
+    _, comp = read_bet(os.path.join(d, "bed", "run.cpn"), M, np.int32)
+    assert comp.shape == (3, M) and comp.min() >= 0 and comp.max() <= 3
+    lines = open(os.path.join(d, "bed", "run.csv")).read().split("\n")[:-1]
+    assert len(lines) == 3 and len({len(l) for l in lines}) == 1   # fixed line length (the reference seeks by n*strlen)
+    assert len(lines[0].split(",")) == 2 + 2 + 5 + 8
+    raw = open(os.path.join(d, "bed", "run.eps.0"), "rb").read()
+    assert struct.unpack("<II", raw[:8]) == (4, N - len(na)) and len(raw) == 8 + 8 * (N - len(na))
