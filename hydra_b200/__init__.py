@@ -6,6 +6,6 @@ No CPU fallback: importing works anywhere, computing needs the CUDA library and 
 """
 from . import capi, synth
 from .capi import HydraError
-from .sampler import BayesRRm, GenotypeStore
+from .sampler import BayesRRm, BayesW, GenotypeStore
 
-__all__ = ["GenotypeStore", "BayesRRm", "HydraError", "capi", "synth"]
+__all__ = ["GenotypeStore", "BayesRRm", "BayesW", "HydraError", "capi", "synth"]

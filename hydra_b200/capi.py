@@ -46,6 +46,15 @@ class HbBrrIterOut(C.Structure):
     ] + [("phase_cycles", C.c_uint64 * 8)]
 
 
+class HbBwTape(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("perm", "p", "sigmaG", "pi")]
+
+
+class HbBwIterOut(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("mu", "alpha", "loop_ms", "iter_ms")] + [
+        (n, C.c_uint64) for n in ("n_sync", "n_windows", "n_launches", "markers_changed", "density_evals")]
+
+
 class HydraError(RuntimeError):
     pass
 
@@ -83,6 +92,8 @@ EXPORTS = [
     "hb_genotype_bytes", "hb_export_sparse", "hb_export_bed", "hb_set_epsilon", "hb_get_epsilon", "hb_dot_markers",
     "hb_scaadd_markers", "hb_brr_init", "hb_brr_iteration", "hb_brr_get_hyper", "hb_brr_get_state", "hb_brr_set_state",
     "hb_brr_get_task_epsilon", "hb_brr_get_task_perm", "hb_comm_get_unique_id", "hb_comm_init",
+    "hb_bw_init", "hb_bw_iteration", "hb_bw_get_hyper", "hb_bw_marker_stats", "hb_bw_vi_sums", "hb_bw_sum_exp",
+    "hb_bw_marginal_likelihoods", "hb_bw_arms_beta",
 ]
 
 

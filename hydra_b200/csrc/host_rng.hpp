@@ -52,4 +52,27 @@ struct HostRng {
     }
 };
 
+// Philox4x32-10 on the host (same function as the device's philox4x32 in common.cuh)
+inline void philox4x32_host(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// ARMS uniforms of RNG spec v1: 31-bit integers r, u = (r + 0.5) / 2^31 (the form of src/BayesW_arms.cpp:913-918)
+struct ArmsStream {
+    uint32_t seed, task, c1, c2, tag, idx;
+    double operator()() {
+        uint32_t w[4];
+        philox4x32_host(idx >> 2, c1, c2, tag, seed, task, w);
+        const uint32_t r = w[idx & 3u] >> 1;
+        idx++;
+        return ((double)r + 0.5) / 2147483648.0;
+    }
+};
+
 }  // namespace hb

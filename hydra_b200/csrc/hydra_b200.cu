@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "brr_kernel.cuh"
+#include "bw_kernels.cuh"
 #include "common.cuh"
 #include "convert.cuh"
 #include "host_rng.hpp"
@@ -124,6 +125,14 @@ struct hb_ctx {
     bool debug_cycles = false;
     uint32_t Wmax = 0;
 
+    // BayesW
+    bool bw_ready = false;
+    int bw_rule = -1;
+    double bw_alpha = 0.0, bw_mu = 0.0, bw_d = 0.0, bw_sumSigmaG = 0.0;
+    uint64_t bw_evals = 0;
+    DevBuf<double> d_sd, d_sumfail, d_fail, d_bwsc;
+    std::vector<double> sd_h, sumfail_h;
+
     // chain (host)
     bool brr_ready = false;
     uint32_t seed = 0, iteration = 0;
@@ -184,7 +193,7 @@ static int ensure_scratch(hb_ctx *c, uint32_t W) {
     W = (W + 255u) & ~255u;
     HB_TRY(c->d_slots.alloc((size_t)W * c->S));
     HB_TRY(c->d_chg_list.alloc((size_t)3 * W));
-    HB_TRY(c->d_chg_cnt.alloc(4));
+    HB_TRY(c->d_chg_cnt.alloc(16));
     HB_TRY(c->d_dB.alloc((size_t)2 * W));
     HB_TRY(c->d_dMave.alloc((size_t)2 * W));
     HB_TRY(c->d_dRec.alloc((size_t)2 * W));
@@ -242,7 +251,7 @@ static void fill_params(hb_ctx *c, BrrParams &P) {
 
 static int launch_window_kernel(hb_ctx *c, BrrParams &P) {
     HB_CUDA(cudaMemsetAsync(c->d_bar.p, 0, sizeof(uint32_t), c->stream));
-    HB_CUDA(cudaMemsetAsync(c->d_chg_cnt.p, 0, 4 * sizeof(uint32_t), c->stream));
+    HB_CUDA(cudaMemsetAsync(c->d_chg_cnt.p, 0, 16 * sizeof(uint32_t), c->stream));
     // the slots carry window tags starting at 1: clear what this launch can touch
     const size_t wuse = std::min<size_t>(c->Wmax, (P.mode == MODE_CHAIN) ? (size_t)std::max(1u, P.SR) * P.T : (size_t)P.lmax * P.T);
     HB_CUDA(cudaMemsetAsync(c->d_slots.p, 0, wuse * c->S * sizeof(uint4), c->stream));
@@ -278,7 +287,7 @@ int hb_create(const hb_config *cfg, hb_ctx **out) {
              "hb_create: n_groups >= 1 and 2 <= n_mix <= %d required", kMaxMix);
     HB_CHECK(cfg->repr_mode >= 0 && cfg->repr_mode <= 2, HB_ERR_ARG, "hb_create: bad repr_mode");
     HB_CHECK(cfg->n_na == 0 || cfg->na_inds, HB_ERR_ARG, "hb_create: n_na > 0 but na_inds == NULL");
-    HB_CHECK(cfg->model == 0, HB_ERR_ARG, "hb_create: model %u not available in this build", cfg->model);
+    HB_CHECK(cfg->model <= 1, HB_ERR_ARG, "hb_create: model %u unknown (0 = BayesRRm, 1 = BayesW)", cfg->model);
 
     std::unique_ptr<hb_ctx> c(new (std::nothrow) hb_ctx);
     HB_CHECK(c, HB_ERR_NOMEM, "hb_create: out of host memory");
@@ -610,6 +619,15 @@ int hb_stage_finalize(hb_ctx *c) {
         const double tmp0 = (double)(c->N - c->n1[i] - c->n2[i] - c->nm[i]) * (0.0 - mave) * (0.0 - mave);
         c->mave_h[i] = mave;
         c->mstd_h[i] = sqrt((double)(c->N - 1) / (tmp0 + tmp1 + tmp2));
+        if (c->cfg.model == 1) {  // BayesW: mstd is the SD; the update multiplies by 1/mstd (src/BayesW.cpp:1218, 1506, 1619)
+            c->sd_h.resize(c->M);
+            c->sd_h[i] = sqrt((tmp0 + tmp1 + tmp2) / (double)(c->N - 1));
+            c->mstd_h[i] = 1 / c->sd_h[i];
+        }
+    }
+    if (c->cfg.model == 1) {
+        HB_TRY(c->d_sd.alloc(c->M));
+        HB_CUDA(cudaMemcpy(c->d_sd.p, c->sd_h.data(), sizeof(double) * c->M, cudaMemcpyHostToDevice));
     }
     HB_CUDA(cudaMemcpy(c->d_mave.p, c->mave_h.data(), sizeof(double) * c->M, cudaMemcpyHostToDevice));
     HB_CUDA(cudaMemcpy(c->d_mstd.p, c->mstd_h.data(), sizeof(double) * c->M, cudaMemcpyHostToDevice));
@@ -1187,3 +1205,5 @@ int hb_comm_init(hb_ctx *c, const uint8_t id[HB_NCCL_ID_BYTES], int rank, int nr
 }
 
 }  // extern "C"
+
+#include "hydra_b200_bw.inc"

@@ -23,7 +23,7 @@ class GenotypeStore:
 
     def __init__(self, n_ind, m_total, *, na_inds=None, tasks=1, task_first=0, tasks_local=None, sync_rate=1,
                  n_groups=1, n_mix=4, repr_mode="sparse", threshold_fnz=0.06, device=0, n_slices=0, max_ctas=0,
-                 block_starts=None, block_lens=None, shuffle=True):
+                 block_starts=None, block_lens=None, shuffle=True, model="bayesRRm"):
         self._lib = capi.load()
         cfg = capi.HbConfig()
         self._na = arr(na_inds if na_inds is not None else np.zeros(0), np.uint32)
@@ -37,7 +37,7 @@ class GenotypeStore:
         cfg.block_lens = None if self._bl is None else self._bl.ctypes.data
         cfg.sync_rate, cfg.n_groups, cfg.n_mix = sync_rate, n_groups, n_mix
         cfg.repr_mode, cfg.threshold_fnz = _REPR[repr_mode], threshold_fnz
-        cfg.n_slices, cfg.max_ctas, cfg.model = n_slices, max_ctas, 0
+        cfg.n_slices, cfg.max_ctas, cfg.model = n_slices, max_ctas, {"bayesRRm": 0, "bayesW": 1}[model]
         cfg.reserved[0] = 0 if shuffle else 1
         self._h = C.c_void_p()
         check(self._lib.hb_create(C.byref(cfg), C.byref(self._h)))
@@ -240,3 +240,90 @@ class BayesRRm:
         p = np.zeros(int(l[self.store.task_first + task_local]), np.int32)
         check(self._lib.hb_brr_get_task_perm(self.store._h, C.c_uint32(task_local), ptr(p)))
         return p
+
+
+class BayesW:
+    """The BayesW (Weibull survival) chain on one GPU (src/BayesW.cpp:905-1907). `store` must be created with model="bayesW"."""
+
+    def __init__(self, store: GenotypeStore, y, failure, mS, groups=None, quad_points=25, seed=0):
+        self.store = store
+        self._lib = store._lib
+        G, K = store.n_groups, store.n_mix
+        mS = np.asarray(mS, dtype=np.float64).reshape(G, -1)
+        if mS.shape[1] == K - 1:
+            mS = np.concatenate([np.zeros((G, 1)), mS], axis=1)
+        assert mS.shape == (G, K), (mS.shape, G, K)
+        self.mS = np.ascontiguousarray(mS)
+        y = arr(y, np.float64)
+        f = arr(failure, np.float64)
+        assert y.shape == (store.n_ind,) and f.shape == (store.n_ind,)
+        g = arr(groups, np.int32)
+        check(self._lib.hb_bw_init(store._h, ptr(y), ptr(f), ptr(g), ptr(self.mS), C.c_uint32(quad_points), C.c_uint32(seed & 0xFFFFFFFF)))
+
+    def iteration(self, tape=None):
+        out = capi.HbBwIterOut()
+        keep = []
+        tp = None
+        if tape is not None:
+            t = capi.HbBwTape()
+            for name, dt in (("perm", np.int32), ("p", np.float64), ("sigmaG", np.float64), ("pi", np.float64)):
+                v = tape.get(name)
+                if v is not None:
+                    a = arr(np.atleast_1d(v), dt)
+                    keep.append(a)
+                    setattr(t, name, a.ctypes.data)
+            tp = C.byref(t)
+        check(self._lib.hb_bw_iteration(self.store._h, tp, C.byref(out)))
+        return {n: getattr(out, n) for n, _ in out._fields_}
+
+    def hyper(self):
+        s = self.store
+        G, K = s.n_groups, s.n_mix
+        sigmaG, pi, mu, alpha = np.zeros(G), np.zeros((G, K)), C.c_double(), C.c_double()
+        bsq, cass, m0 = np.zeros(G), np.zeros((G, K), np.int32), np.zeros(G, np.int32)
+        check(self._lib.hb_bw_get_hyper(s._h, ptr(sigmaG), ptr(pi), C.byref(mu), C.byref(alpha), ptr(bsq), ptr(cass), ptr(m0)))
+        return dict(sigmaG=sigmaG, pi=pi, mu=mu.value, alpha=alpha.value, bsq=bsq, cass=cass, m0=m0)
+
+    def state(self):
+        s = self.store
+        beta, comp = np.zeros(s.m_local), np.zeros(s.m_local, np.int32)
+        check(self._lib.hb_brr_get_state(s._h, ptr(beta), ptr(comp), None))
+        return beta, comp
+
+    def epsilon(self):
+        return self.store.get_epsilon()
+
+    def marker_stats(self):
+        s = self.store
+        sd, sf = np.zeros(s.m_local), np.zeros(s.m_local)
+        check(self._lib.hb_bw_marker_stats(s._h, ptr(sd), ptr(sf)))
+        return sd, sf
+
+
+def bw_vi_sums(store, markers, beta_old, alpha):
+    m = arr(markers, np.uint32)
+    b = arr(beta_old, np.float64)
+    out = np.zeros((len(m), 4))
+    check(store._lib.hb_bw_vi_sums(store._h, ptr(m), ptr(b), C.c_uint32(len(m)), C.c_double(alpha), ptr(out)))
+    return out
+
+
+def bw_sum_exp(store, a, b):
+    o = C.c_double()
+    check(store._lib.hb_bw_sum_exp(store._h, C.c_double(a), C.c_double(b), C.byref(o)))
+    return o.value
+
+
+def bw_marginal_likelihoods(store, quad_points, pars, prior, cVa):
+    pars, prior, cVa = arr(pars, np.float64), arr(prior, np.float64), arr(cVa, np.float64)
+    post = np.zeros(len(prior))
+    check(store._lib.hb_bw_marginal_likelihoods(store._h, C.c_uint32(quad_points), ptr(pars), ptr(prior), ptr(cVa), C.c_uint32(len(cVa)), ptr(post)))
+    return post
+
+
+def bw_arms_beta(store, pars, C_k, sum_sigmaG, beta_old, seed, task, iteration, j):
+    pars = arr(pars, np.float64)
+    out = np.zeros(4)
+    check(store._lib.hb_bw_arms_beta(store._h, ptr(pars), C.c_double(C_k), C.c_double(sum_sigmaG), C.c_double(beta_old), C.c_uint32(seed),
+                                     C.c_uint32(task), C.c_uint32(iteration), C.c_uint32(j), ptr(out)))
+    return dict(beta=out[0], err=int(out[1]), neval=int(out[2]), nrand=int(out[3]))

@@ -168,6 +168,45 @@ int hb_brr_get_task_epsilon(hb_ctx *ctx, uint32_t task_local, double *eps);
 /* current marker order of local task t (.mrk.<rank>, :2828) */
 int hb_brr_get_task_perm(hb_ctx *ctx, uint32_t task_local, int32_t *perm);
 
+/* ---- BayesW chain (Weibull survival; src/BayesW.cpp:905-1907), single GPU in this version ------------- */
+/* hb_config.model = 1. y: N log-times, fail: N failure indicators (0/1; src/data.cpp:1779), mS as for BayesRRm,
+ * quad_points in {3,5,7,9,11,13,15,17,25} (--quad_points, :706-709). Initial values as BayesW::init (:728-853). */
+int hb_bw_init(hb_ctx *ctx, const double *y, const double *fail, const int32_t *groups, const double *mS,
+               uint32_t quad_points, uint32_t seed);
+
+typedef struct hb_bw_tape {
+    const int32_t *perm;  /* m_local: marker order of each local task block (:1457-1459) */
+    const double *p;      /* m_local: U(0,1) of the marker processed at step j of each task (:1528) */
+    const double *sigmaG; /* n_groups values AFTER this iteration (:1893), NULL = draw */
+    const double *pi;     /* n_groups*n_mix (:1899-1903), NULL = draw */
+} hb_bw_tape;
+
+typedef struct hb_bw_iter_out {
+    double mu, alpha;     /* after the iteration's ARMS draws (:1336-1363, :1421-1447) */
+    double loop_ms, iter_ms;
+    uint64_t n_sync, n_windows, n_launches, markers_changed;
+    uint64_t density_evals; /* N-sum evaluations of the mu / alpha log-densities (K11) */
+} hb_bw_iter_out;
+
+/* One Gibbs iteration: ARMS for mu and alpha (N-sums of exp on the device), marker loop, sigmaG / pi_L draws.
+ * ARMS uniforms: RNG spec v1 (Philox, 31-bit integers in the form of src/BayesW_arms.cpp:913-918). */
+int hb_bw_iteration(hb_ctx *ctx, const hb_bw_tape *tape, hb_bw_iter_out *out);
+int hb_bw_get_hyper(hb_ctx *ctx, double *sigmaG, double *pi, double *mu, double *alpha, double *bsq, int32_t *cass, int32_t *m0);
+/* marker statistics of BayesW: mstd is the SD (not its inverse), sum_failure (:1211-1232); m_local each */
+int hb_bw_marker_stats(hb_ctx *ctx, double *sd, double *sum_failure);
+/* unit-level kernels for parity tests */
+/* (vi_sum, vi_1, vi_2, vi_0) of markers against the current epsilon with the marker's own effect beta_old removed
+ * (partial_sum :49-65 and :1499-1525); out: n*4 */
+int hb_bw_vi_sums(hb_ctx *ctx, const uint32_t *markers, const double *beta_old, uint32_t n, double alpha, double *out);
+/* sum_i exp(a*eps_i + b): the N-sum inside mu_dens / alpha_dens / gamma_dens (:77-142) */
+int hb_bw_sum_exp(hb_ctx *ctx, double a, double b, double *out);
+/* pars[10] = alpha, sigmaG, sum_failure, vi_sum, vi_0, vi_1, vi_2, mean, sd, mean/sd */
+int hb_bw_marginal_likelihoods(hb_ctx *ctx, uint32_t quad_points, const double *pars, const double *prior, const double *cVa,
+                               uint32_t km1, double *post);
+/* one ARMS draw of beta on the device (:1562-1582); out[4] = beta, error code, density evaluations, uniforms used */
+int hb_bw_arms_beta(hb_ctx *ctx, const double *pars, double C_k, double sum_sigmaG, double beta_old, uint32_t seed, uint32_t task,
+                    uint32_t iteration, uint32_t j, double *out);
+
 /* ---- multi-GPU (replaces MPI_Allreduce, src/BayesRRm.cpp:2051,2456,2517-2518) --- */
 #define HB_NCCL_ID_BYTES 128
 int hb_comm_get_unique_id(uint8_t id[HB_NCCL_ID_BYTES]);

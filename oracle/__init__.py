@@ -23,11 +23,8 @@ P = C.POINTER
 def build(fast: bool = False, force: bool = False) -> str:
     name = "libhydra_oracle_fast.so" if fast else "libhydra_oracle.so"
     path = os.path.join(_HERE, name)
-    if force or not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(
-        os.path.join(_HERE, "hydra_oracle.c")
-    ):
-        args = ["make", "-C", _HERE, name] + (["-B"] if force else [])
-        subprocess.run(args, check=True, capture_output=True)
+    args = ["make", "-C", _HERE, name] + (["-B"] if force else [])  # make tracks the sources
+    subprocess.run(args, check=True, capture_output=True)
     return path
 
 
@@ -42,6 +39,10 @@ def lib(fast: bool = False, rebuild: bool = False) -> C.CDLL:
         L.ho_mt_gamma.restype = C.c_double
         L.ho_mt_gamma.argtypes = [C.c_void_p, C.c_double]
         L.ho_mt_u32.restype = C.c_uint32
+        L.ho_bw_beta_dens.restype = C.c_double
+        L.ho_bw_gh_integral.restype = C.c_double
+        L.ho_bw_mu_dens.restype = C.c_double
+        L.ho_bw_alpha_dens.restype = C.c_double
         _LIBS[key] = L
     return _LIBS[key]
 
@@ -322,3 +323,97 @@ def brr_chain(N, Mtot, T, K, G, sync_rate, n_iter, sp: SparseLists, y_raw, group
 
 def num_threads(fast=True):
     return lib(fast).ho_num_threads()
+
+
+# --------------------------------------------------------------------------- BayesW
+_ARMS = None
+
+
+def arms_ref():
+    """The reference's own ARMS object code (oracle/_ref/libarms_ref.so, built by oracle/build_ref.sh from
+    /root/reference/src/BayesW_arms.cpp with rand() wrapped). None if it was never built."""
+    global _ARMS
+    if _ARMS is None:
+        p = os.path.join(_HERE, "_ref", "libarms_ref.so")
+        if not os.path.exists(p):
+            return None
+        _ARMS = C.CDLL(p)
+    return _ARMS
+
+
+class _BwPars(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("alpha", "sigmaG", "sum_failure", "vi_sum", "vi_0", "vi_1", "vi_2", "mean", "sd", "mean_sd_ratio", "mixture_value")]
+
+
+def bw_pars(pars10, mixture_value=0.0):
+    return _BwPars(*[float(x) for x in pars10], float(mixture_value))
+
+
+def bw_marginal_likelihoods(quad_points, pars10, prior, cVa):
+    prior, cVa = _c(prior, np.float64), _c(cVa, np.float64)
+    post = np.zeros(len(prior))
+    p = bw_pars(pars10)
+    lib().ho_bw_marginal_likelihoods(C.c_int(quad_points), _p(prior), _p(cVa), C.c_int(len(cVa)), C.byref(p), _p(post))
+    post[0] = prior[0] * 1.77245385090552
+    return post
+
+
+def bw_sample_beta(pars10, C_k, sum_sigmaG, beta_old, seed, task, iteration, j):
+    a = arms_ref()
+    p = bw_pars(pars10, C_k)
+    bn, ne, nr = C.c_double(), C.c_int(), C.c_int()
+    fn = C.cast(a.ho_ref_arms, C.c_void_p)
+    err = lib().ho_bw_sample_beta(fn, C.byref(p), C.c_double(sum_sigmaG), C.c_double(beta_old), C.c_uint32(seed), C.c_uint32(task),
+                                  C.c_uint32(iteration), C.c_uint32(j), C.byref(bn), C.byref(ne), C.byref(nr))
+    return dict(beta=bn.value, err=err, neval=ne.value, nrand=nr.value)
+
+
+def bw_marker_stats(N, sp: SparseLists, fail):
+    M = len(sp.N1S)
+    fail = _c(fail, np.float64)
+    mave, mstd, sf = np.zeros(M), np.zeros(M), np.zeros(M)
+    lib().ho_bw_marker_stats(C.c_int(M), C.c_uint(N), _p(sp.I1 if len(sp.I1) else np.zeros(1, np.uint32)), _p(sp.N1S), _p(sp.N1L),
+                             _p(sp.I2 if len(sp.I2) else np.zeros(1, np.uint32)), _p(sp.N2S), _p(sp.N2L), _p(sp.NML), _p(fail), _p(mave), _p(mstd), _p(sf))
+    return mave, mstd, sf
+
+
+class _BwArgs(C.Structure):
+    _fields_ = ([(n, C.c_int32) for n in ("N", "Mtot", "T", "K", "G", "sync_rate", "n_iter", "quad_points")]
+                + [(n, C.c_void_p) for n in ("I1", "N1S", "N1L", "I2", "N2S", "N2L", "IM", "NMS", "NML", "y", "fail", "groups", "mS",
+                                             "tape_perm", "tape_p", "tape_sigmaG", "tape_pi")]
+                + [("seed", C.c_uint32), ("hyper_seed", C.c_uint32), ("arms", C.c_void_p)]
+                + [(n, C.c_void_p) for n in ("out_beta", "out_comp", "out_eps", "out_mu", "out_alpha", "out_sigmaG", "out_pi", "out_bsq",
+                                             "out_cass", "out_nsync", "out_err")])
+
+
+def bw_chain(N, Mtot, T, K, G, sync_rate, n_iter, quad_points, sp: SparseLists, y, fail, groups, mS, tape, seed, hyper=None, hyper_seed=0):
+    """BayesW oracle chain; tape = dict(perm, p); hyper = dict(sigmaG, pi) to replay values, else drawn with mt19937(hyper_seed)."""
+    keep = []
+
+    def k(a, dt):
+        if a is None:
+            return None
+        a = _c(a, dt)
+        keep.append(a)
+        return a.ctypes.data
+
+    out = dict(beta=np.zeros((n_iter, Mtot)), comp=np.zeros((n_iter, Mtot), np.int32), eps=np.zeros((n_iter, N)), mu=np.zeros(n_iter),
+               alpha=np.zeros(n_iter), sigmaG=np.zeros((n_iter, G)), pi=np.zeros((n_iter, G, K)), bsq=np.zeros((n_iter, G)),
+               cass=np.zeros((n_iter, G, K), np.int32), nsync=np.zeros(n_iter, np.int64), err=np.zeros(1, np.int32))
+    a = _BwArgs()
+    a.N, a.Mtot, a.T, a.K, a.G, a.sync_rate, a.n_iter, a.quad_points = N, Mtot, T, K, G, sync_rate, n_iter, quad_points
+    a.I1, a.N1S, a.N1L = k(sp.I1 if len(sp.I1) else np.zeros(1), np.uint32), k(sp.N1S, np.uint64), k(sp.N1L, np.uint64)
+    a.I2, a.N2S, a.N2L = k(sp.I2 if len(sp.I2) else np.zeros(1), np.uint32), k(sp.N2S, np.uint64), k(sp.N2L, np.uint64)
+    a.IM, a.NMS, a.NML = k(sp.IM if len(sp.IM) else np.zeros(1), np.uint32), k(sp.NMS, np.uint64), k(sp.NML, np.uint64)
+    a.y, a.fail, a.groups, a.mS = k(y, np.float64), k(fail, np.float64), k(groups, np.int32), k(mS, np.float64)
+    a.tape_perm, a.tape_p = k(tape["perm"], np.int32), k(tape["p"], np.float64)
+    if hyper is not None:
+        a.tape_sigmaG, a.tape_pi = k(hyper["sigmaG"], np.float64), k(hyper["pi"], np.float64)
+    a.seed, a.hyper_seed = seed & 0xFFFFFFFF, hyper_seed & 0xFFFFFFFF
+    a.arms = C.cast(arms_ref().ho_ref_arms, C.c_void_p)
+    for name in ("beta", "comp", "eps", "mu", "alpha", "sigmaG", "pi", "bsq", "cass", "nsync", "err"):
+        setattr(a, "out_" + name, out[name].ctypes.data)
+    rc = lib().ho_bw_chain(C.byref(a))
+    if rc != 0:
+        raise RuntimeError(f"ho_bw_chain: ARMS error code {rc}")
+    return out
