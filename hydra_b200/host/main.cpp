@@ -26,7 +26,7 @@
 namespace {
 
 struct Options {  // names follow the reference's Options class (src/options.hpp:20-138)
-    std::string bayesType, bedFile, phenotypeFile, groupIndexFile, groupMixtureFile, mcmcOutDir, mcmcOutNam, sparseDir, sparseBsn,
+    std::string bayesType, bedFile, phenotypeFile, failureFile, quad_points, groupIndexFile, groupMixtureFile, mcmcOutDir, mcmcOutNam, sparseDir, sparseBsn,
         markerBlocksFile;
     bool bedToSparse = false, dryRun = false, readFromBedFile = false, readFromSparseFiles = false;
     uint32_t numberMarkers = 0, numberIndividuals = 0, chainLength = 10000, burnin = 5000, thin = 5, save = 10, syncRate = 1,
@@ -72,6 +72,8 @@ Options parse(int argc, const char **argv) {
         if (a == "--mpibayes") o.bayesType = need(i);
         else if (a == "--bfile") { o.readFromBedFile = true; o.bedFile = need(i); }
         else if (a == "--pheno") o.phenotypeFile = need(i);
+        else if (a == "--failure") o.failureFile = need(i);
+        else if (a == "--quad_points") o.quad_points = need(i);
         else if (a == "--groupIndexFile") o.groupIndexFile = need(i);
         else if (a == "--groupMixtureFile") o.groupMixtureFile = need(i);
         else if (a == "--mcmc-out-dir") o.mcmcOutDir = need(i);
@@ -101,7 +103,7 @@ Options parse(int argc, const char **argv) {
         else if (a == "--dry-run") o.dryRun = true;
         // reference options outside the accelerated path: recognised, refused with a clear message
         else if (a == "--restart" || a == "--ignore-xfiles" || a == "--sparse-sync" || a == "--bed-sync" || a == "--covariates" ||
-                 a == "--failure" || a == "--quad_points" || a == "--check-RAM" || a == "--groupPriorsFile" || a == "--dPriorsFile")
+                 a == "--check-RAM" || a == "--groupPriorsFile" || a == "--dPriorsFile")
             throw std::runtime_error("option \"" + a + "\" of hydra is not supported by hydra_b200 yet (see DESIGN.md, out of scope)");
         else
             throw std::runtime_error("\nError: invalid option \"" + a + "\".\n");  // src/options.cpp:292-296
@@ -147,6 +149,27 @@ void read_phen(const std::string &path, uint32_t n_ind, std::vector<double> &y, 
         line++;
     }
     if (line != n_ind) throw std::runtime_error("phenotype file [" + path + "] has " + std::to_string(line) + " lines, --number-individuals is " + std::to_string(n_ind));
+}
+
+// src/data.cpp:1753-1803: phenotype and failure files read together; NA phenotype or failure "-9" drops the individual
+void read_phen_fail(const std::string &phen, const std::string &failf, uint32_t n_ind, std::vector<double> &y, std::vector<double> &fail,
+                    std::vector<uint32_t> &na) {
+    std::ifstream inp(phen), inf(failf);
+    if (!inp) throw std::runtime_error("Error: can not open the phenotype file [" + phen + "] to read.");
+    if (!inf) throw std::runtime_error("Error: can not open the file [" + failf + "] to read.");
+    std::string lp, lf;
+    uint32_t line = 0;
+    while (std::getline(inp, lp)) {
+        auto tp = split(lp, " \t\r");
+        if (tp.empty()) continue;
+        if (!std::getline(inf, lf)) throw std::runtime_error("failure file [" + failf + "] is shorter than the phenotype file");
+        auto tf = split(lf, " \t\r");
+        if (tp.size() < 3 || tf.empty()) throw std::runtime_error("phenotype / failure files: malformed line " + std::to_string(line + 1));
+        if (tp[2] != "NA" && tf[0] != "-9") { y.push_back(atof(tp[2].c_str())); fail.push_back(atof(tf[0].c_str())); }
+        else na.push_back(line);
+        line++;
+    }
+    if (line != n_ind) throw std::runtime_error("phenotype file [" + phen + "] has " + std::to_string(line) + " lines, --number-individuals is " + std::to_string(n_ind));
 }
 
 // src/data.cpp:1944-1960: one integer per marker
@@ -242,11 +265,18 @@ int main(int argc, const char **argv) {
         }
         if (!opt.readFromBedFile && !opt.readFromSparseFiles) throw std::runtime_error("either --bfile or --sparse-dir/--sparse-basename is needed");
 
-        std::vector<double> y;
+        std::vector<double> y, fail;
         std::vector<uint32_t> na;
+        const bool bayesW = (opt.bayesType == "bayesWMPI");
         if (!opt.bedToSparse) {
             if (opt.phenotypeFile.empty()) throw std::runtime_error("--pheno has to be set");
-            read_phen(opt.phenotypeFile, Nraw, y, na);
+            if (bayesW) {
+                if (opt.failureFile.empty()) throw std::runtime_error("--failure has to be set for bayesWMPI");
+                if (opt.quad_points.empty()) throw std::runtime_error("--quad_points has to be set for bayesWMPI (3,5,7,9,11,13,15,17,25)");
+                read_phen_fail(opt.phenotypeFile, opt.failureFile, Nraw, y, fail, na);
+            } else {
+                read_phen(opt.phenotypeFile, Nraw, y, na);
+            }
         }
         // groups and mixtures (src/BayesRRm.cpp:981-996)
         std::vector<int32_t> groups;
@@ -269,8 +299,9 @@ int main(int argc, const char **argv) {
             printf("INFO   : dry run: options and input files parsed, nothing computed\n");
             return 0;
         }
-        if (!opt.bedToSparse && opt.bayesType != "bayesMPI")
-            throw std::runtime_error("--mpibayes " + opt.bayesType + ": only bayesMPI (BayesRRm) is available in this build");
+        if (!opt.bedToSparse && opt.bayesType != "bayesMPI" && !bayesW)
+            throw std::runtime_error("--mpibayes " + opt.bayesType + ": bayesMPI (BayesRRm) and bayesWMPI (BayesW) are available in this build");
+        if (bayesW && repr == HB_REPR_MIXED) throw std::runtime_error("bayesWMPI reads bed or sparse input, not both (src/BayesW.cpp:1149-1192)");
 
         // ---- device context
         hb_config cfg;
@@ -282,6 +313,7 @@ int main(int argc, const char **argv) {
         cfg.repr_mode = opt.bedToSparse ? HB_REPR_SPARSE : repr;
         cfg.threshold_fnz = opt.thresholdFnz;
         cfg.reserved[0] = opt.shuffleMarkers ? 0u : 1u;
+        cfg.model = bayesW ? 1u : 0u;
         hb_ctx *ctx = nullptr;
         HB(hb_create(&cfg, &ctx));
         uint32_t N = 0, m_local = 0, lmax = 0;
@@ -351,11 +383,54 @@ int main(int argc, const char **argv) {
             return 0;
         }
 
-        // ---- chain (src/BayesRRm.cpp:1565-2877)
+        // ---- chain (src/BayesRRm.cpp:1565-2877, src/BayesW.cpp:1326-2090)
         std::vector<double> mSflat((size_t)G * K, 0.0);
         for (uint32_t g = 0; g < G; g++)
             for (uint32_t k = 1; k < K; k++) mSflat[g * K + k] = mS[g][k - 1];
         const uint32_t seed = opt.seedSet ? opt.seed : (uint32_t)time(nullptr);
+        if (bayesW) {
+            HB(hb_bw_init(ctx, y.data(), fail.data(), groups.empty() ? nullptr : groups.data(), mSflat.data(), (uint32_t)atoi(opt.quad_points.c_str()), seed));
+            struct stat sbw;
+            if (stat(opt.mcmcOutDir.c_str(), &sbw) != 0 && system(("mkdir -p " + opt.mcmcOutDir).c_str()) != 0)
+                throw std::runtime_error("could not create output directory --mcmc-out-dir " + opt.mcmcOutDir);
+            const std::string out = opt.mcmcOut();
+            OutFile csv, bet, cpn;
+            csv.open(out + ".csv"); bet.open(out + ".bet"); cpn.open(out + ".cpn");
+            bet.put(&Mtot, 1); cpn.put(&Mtot, 1);
+            std::vector<double> beta(Mtot), sigmaG(G), pi((size_t)G * K), bsq(G), eps(N);
+            std::vector<int32_t> comp(Mtot), cass((size_t)G * K), m0(G);
+            double tot_ms = 0.0;
+            for (uint32_t it = 0; it < opt.chainLength; it++) {
+                hb_bw_iter_out io;
+                HB(hb_bw_iteration(ctx, nullptr, &io));
+                tot_ms += io.iter_ms;
+                double mu = 0, alpha = 0;
+                HB(hb_bw_get_hyper(ctx, sigmaG.data(), pi.data(), &mu, &alpha, bsq.data(), cass.data(), m0.data()));
+                double sG = 0.0; int m0s = 0;
+                for (uint32_t g = 0; g < G; g++) { sG += sigmaG[g]; m0s += m0[g]; }
+                printf("%u. %d; %.7g; %.7g; %.7g\n", it, m0s, mu, alpha, sG);  // src/BayesW.cpp:1909-1911
+                if (it % opt.thin == 0) {
+                    char buff[65536];
+                    int n = snprintf(buff, sizeof(buff), "%5d, %20.15f, %20.15f, %20.15f, %20.15f, %7d, %7d, %2d", (int)it, mu, sG, alpha,
+                                     sG / (sG + 9.86960440109 / (6 * alpha * alpha)), m0s, (int)G, (int)K);  // :1942
+                    for (uint32_t g = 0; g < G; g++) n += snprintf(buff + n, sizeof(buff) - n, ", %20.15f", sigmaG[g]);
+                    for (size_t x = 0; x < (size_t)G * K; x++) n += snprintf(buff + n, sizeof(buff) - n, ", %20.15f", pi[x]);
+                    n += snprintf(buff + n, sizeof(buff) - n, "\n");
+                    csv.put(buff, (size_t)n);
+                    HB(hb_brr_get_state(ctx, beta.data(), comp.data(), nullptr));
+                    bet.put(&it, 1); bet.put(beta.data(), Mtot);
+                    cpn.put(&it, 1); cpn.put(comp.data(), Mtot);
+                    fflush(csv.f);
+                }
+                if (it > 0 && it % opt.save == 0) {
+                    HB(hb_get_epsilon(ctx, eps.data()));
+                    dump_file(out + ".eps.0", it, N, eps.data());
+                }
+            }
+            printf("INFO   : time to process the data: %.3f sec\n", tot_ms * 1e-3);
+            hb_destroy(ctx);
+            return 0;
+        }
         HB(hb_brr_init(ctx, y.data(), groups.empty() ? nullptr : groups.data(), mSflat.data(), nullptr, seed));
 
         struct stat sb;

@@ -158,3 +158,50 @@ def test_cli_bed_vs_sparse_vs_python_runs_are_identical(tmp_path):
     assert len(lines[0].split(",")) == 2 + 2 + 5 + 8
     raw = open(os.path.join(d, "bed", "run.eps.0"), "rb").read()
     assert struct.unpack("<II", raw[:8]) == (4, N - len(na)) and len(raw) == 8 + 8 * (N - len(na))
+
+
+def test_cli_reads_the_weibull_example_files():
+    ex = "/root/reference/example"
+    if not os.path.isdir(ex):
+        pytest.skip("reference checkout not present")
+    r = subprocess.run([_exe(), "--mpibayes", "bayesWMPI", "--sparse-dir", "/tmp", "--sparse-basename", "none", "--pheno", ex + "/Weibull.phen",
+                        "--failure", ex + "/Weibull.fail", "--quad_points", "25", "--number-individuals", "5000", "--number-markers", "10000",
+                        "--S", "0.001,0.01,0.1", "--mcmc-out-dir", "/tmp/hb_o", "--mcmc-out-name", "x", "--dry-run"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "bayesWMPI, N = 5000 (0 NA phenotypes), M = 10000" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cli_bayesw_run_equals_python_run(tmp_path):
+    import hydra_b200
+    d = str(tmp_path)
+    N, M = 600, 80
+    rng = np.random.default_rng(21)
+    bed, g = random_bed(rng, M, N, pmiss=0.01)
+    with open(os.path.join(d, "w.bed"), "wb") as f:
+        f.write(bytes([0x6C, 0x1B, 0x01]) + bed.tobytes())
+    open(os.path.join(d, "w.bim"), "w").write("".join(f"1\trs{j}\t0\t{j + 1}\tA\tC\n" for j in range(M)))
+    open(os.path.join(d, "w.fam"), "w").write("".join(f"F{i} I{i} 0 0 1 -9\n" for i in range(N)))
+    y = 4.1 + 0.1 * np.log(rng.exponential(size=N))
+    fail = (rng.random(N) > 0.1).astype(int)
+    na_p, na_f = {5, 17}, {40}
+    open(os.path.join(d, "w.phen"), "w").write("".join(f"F{i} I{i} {'NA' if i in na_p else repr(float(y[i]))}\n" for i in range(N)))
+    open(os.path.join(d, "w.fail"), "w").write("".join(f"{-9 if i in na_f else fail[i]}\n" for i in range(N)))
+    r = subprocess.run([_exe(), "--mpibayes", "bayesWMPI", "--bfile", os.path.join(d, "w"), "--pheno", os.path.join(d, "w.phen"),
+                        "--failure", os.path.join(d, "w.fail"), "--quad_points", "11", "--number-individuals", str(N), "--number-markers", str(M),
+                        "--S", "0.001,0.01,0.1", "--chain-length", "4", "--thin", "1", "--save", "2", "--seed", "9", "--sync-rate", "3", "--tasks", "2",
+                        "--mcmc-out-dir", os.path.join(d, "o"), "--mcmc-out-name", "w"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    its, beta = read_bet(os.path.join(d, "o", "w.bet"), M)
+    assert its.tolist() == [0, 1, 2, 3]
+    na = np.array(sorted(na_p | na_f), np.uint32)
+    keep = np.setdiff1d(np.arange(N), na)
+    with hydra_b200.GenotypeStore(N, M, na_inds=na, tasks=2, sync_rate=3, n_groups=1, n_mix=4, repr_mode="bed", model="bayesW") as st:
+        st.load_data_from_bed(bed)
+        st.finalize()
+        bw = hydra_b200.BayesW(st, y[keep], fail[keep].astype(float), [[0.001, 0.01, 0.1]], quad_points=11, seed=9)
+        for it in range(4):
+            o = bw.iteration()
+            assert np.array_equal(bw.state()[0], beta[it])
+    line = open(os.path.join(d, "o", "w.csv")).read().split("\n")[3].split(",")
+    assert int(line[0]) == 3 and abs(float(line[1]) - o["mu"]) < 1e-12 and abs(float(line[3]) - o["alpha"]) < 1e-12
