@@ -7,6 +7,7 @@
 #include <memory>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "brr_kernel.cuh"
@@ -143,6 +144,10 @@ struct hb_ctx {
     std::vector<HostRng> task_rng;
     HostRng hyper_rng;
     std::vector<int32_t> perm;  // M: task-local order per local task block
+    std::vector<int32_t> perm_next;   // the next iteration's order, shuffled on a worker thread during the marker loop
+    std::vector<double> zmu_next;
+    std::thread prefetch;
+    bool have_next = false;
     double *pin = nullptr;      // pinned host scratch
     size_t pin_n = 0;
 
@@ -159,6 +164,7 @@ struct hb_ctx {
     std::vector<uint32_t> rec_bytes_h;
 
     ~hb_ctx() {
+        if (prefetch.joinable()) prefetch.join();
         for (int h = 0; h < nranks; h++)
             if (h != rank && peer_inbox[h]) cudaIpcCloseMemHandle(peer_inbox[h]);
         if (inbox) cudaFree(inbox);
@@ -912,13 +918,33 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
     cudaStream_t st = c->stream;
     HB_CUDA(cudaEventRecord(c->ev[0], st));
 
+    // The task streams' draws of an iteration (z for mu :1682, then the shuffle :1692) do not depend on the data, so the
+    // next iteration's draws are produced on a worker thread while the GPU runs the marker loop.
+    if (c->prefetch.joinable()) c->prefetch.join();
+    std::vector<double> zmu(T, 0.0);
+    if (!tape) {
+        if (!c->have_next) {  // first iteration (or after a taped one): draw now
+            for (uint32_t t = 0; t < T; t++) {
+                zmu[t] = c->task_rng[t].normal();
+                if (c->cfg.reserved[0] == 0) {  // reserved[0]: --shuf-mark 0
+                    size_t o = 0;
+                    for (uint32_t tt = 0; tt < t; tt++) o += (size_t)c->blkL[c->t_first + tt];
+                    c->task_rng[t].shuffle(c->perm.data() + o, c->blkL[c->t_first + t]);
+                }
+            }
+        } else {
+            zmu = c->zmu_next;
+            c->perm.swap(c->perm_next);
+        }
+        c->have_next = false;
+    }
     // ---- mu (:1675-1686): eps_r + mu_r is the same vector for every task
     double ssum = 0.0;
     for (uint32_t s = 0; s < c->S; s++) ssum += c->slice_sum_h[s];
     const double epssum = ssum + dN * c->shift + dN * c->mu[0];
     const double mu0_old = c->mu[0];
     for (uint32_t t = 0; t < T; t++) {
-        const double z = tape ? tape->zmu[t] : c->task_rng[t].normal();
+        const double z = tape ? tape->zmu[t] : zmu[t];
         c->mu[t] = epssum / dN + sqrt(c->sigmaE / dN) * z;
     }
     c->shift += mu0_old - c->mu[0];
@@ -932,13 +958,6 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
                 HB_CHECK(tape->perm[o] >= 0 && tape->perm[o] < len, HB_ERR_ARG, "hb_brr_iteration: tape perm[%zu]=%d out of range", o, tape->perm[o]);
                 c->perm[o] = tape->perm[o];
             }
-        }
-    } else {
-        size_t o = 0;
-        for (uint32_t t = 0; t < T; t++) {
-            const int32_t len = c->blkL[c->t_first + t];
-            if (c->cfg.reserved[0] == 0) c->task_rng[t].shuffle(c->perm.data() + o, len);  // reserved[0]: --shuf-mark 0
-            o += (size_t)len;
         }
     }
     HB_CUDA(cudaMemcpyAsync(c->d_perm.p, c->perm.data(), sizeof(int32_t) * M, cudaMemcpyHostToDevice, st));
@@ -982,6 +1001,21 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
     HB_TRY(launch_window_kernel(c, P));
     HB_CUDA(cudaEventRecord(c->ev[2], st));
     c->cur ^= 1;
+    if (!tape) {  // overlap the next iteration's host draws with the marker loop
+        c->perm_next = c->perm;
+        c->zmu_next.assign(T, 0.0);
+        hb_ctx *cc = c;
+        c->prefetch = std::thread([cc, T]() {
+            size_t o = 0;
+            for (uint32_t t = 0; t < T; t++) {
+                cc->zmu_next[t] = cc->task_rng[t].normal();
+                const int32_t len = cc->blkL[cc->t_first + t];
+                if (cc->cfg.reserved[0] == 0) cc->task_rng[t].shuffle(cc->perm_next.data() + o, len);
+                o += (size_t)len;
+            }
+        });
+        c->have_next = true;
+    }
 
     // ---- group statistics (:2496-2521)
     double *d_bsq = c->d_small.p + 1 + 2 * c->S;
