@@ -154,6 +154,82 @@ __global__ void __launch_bounds__(256) k_fill_sparse(const uint8_t *__restrict__
     }
 }
 
+// ---------------------------------------------------------------------------
+// Pass 3 (sparse records): bank-aware order inside every class run of every slice block.
+// The dot product gathers epsilon (8-byte words, 16 distinct bank pairs) from shared memory with one 64-bit word
+// of four indices per lane; the 16 lanes of a half-warp read, for index slot g, the elements at positions
+// 64*chunk + 4*lane + g of the block. The sum over a class does not depend on the order of its indices, so each
+// run is permuted such that those 16 elements have distinct (index mod 16) wherever the residues allow it:
+// elements are ranked by (depth inside their residue list, residue) and dealt to the half-warp groups in that order.
+// Runs longer than kBankMax stay ascending. Exports go through the 2-bit form and are order independent.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kBankMax = 4096;
+
+__global__ void __launch_bounds__(256) k_bank_order(const uint64_t *__restrict__ rec, uint32_t S, uint32_t L) {
+    extern __shared__ uint16_t bank_smem[];
+    __shared__ uint32_t s_cnt[8][16];
+    const uint32_t m = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint64_t r = rec[m];
+    if (r & 1ull) return;
+    uint8_t *base = reinterpret_cast<uint8_t *>(r);
+    const uint32_t *dir = reinterpret_cast<const uint32_t *>(base);
+    uint16_t *payload = reinterpret_cast<uint16_t *>(base + dir_bytes(S));
+    uint16_t *in = bank_smem + (size_t)warp * 2 * kBankMax, *out = in + kBankMax;
+    uint32_t *cnt = s_cnt[warp];
+    const uint32_t lt = (1u << lane) - 1u;
+    for (uint32_t c = warp; c < S; c += nwarps) {
+        const uint32_t st = dir[c * 3], n12 = dir[c * 3 + 1], nmiss = dir[c * 3 + 2];
+        const uint32_t len[3] = {n12 & 0xFFFFu, n12 >> 16, nmiss};
+        uint32_t off = 0;
+        for (int cls = 0; cls < 3; cls++) {
+            const uint32_t n = len[cls];
+            uint16_t *run = payload + (size_t)st * 4 + off;
+            off += ((n + 3) / 4) * 4;
+            if (n <= 16 || n > kBankMax) continue;
+            if (lane < 16) cnt[lane] = 0;
+            __syncwarp();
+            // depth of every element inside its residue list (stable: runs are ascending)
+            for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                const bool ok = i < n;
+                const uint32_t idx = ok ? run[i] : 0u;
+                const uint32_t res = ok ? (idx & 15u) : (16u + lane);  // inactive lanes match nobody
+                const uint32_t peers = __match_any_sync(0xffffffffu, res);
+                uint32_t depth = 0;
+                if (ok) depth = cnt[res] + __popc(peers & lt);
+                __syncwarp();
+                if (ok && (peers >> lane) == 1u) cnt[res] += __popc(peers);  // highest lane of each group updates
+                __syncwarp();
+                if (ok) { in[i] = (uint16_t)idx; out[i] = (uint16_t)depth; }  // out temporarily holds the depth
+            }
+            __syncwarp();
+            const uint32_t nfull = (n / 64u) * 64u;
+            // sequence index s = #elements with smaller (depth, residue); then position of s
+            uint32_t pos_of[kBankMax / 32];
+            for (uint32_t t = 0, i = lane; i < n; i += 32, t++) {
+                const uint32_t idx = in[i], res = idx & 15u, depth = out[i];
+                uint32_t s = 0;
+#pragma unroll
+                for (uint32_t rr = 0; rr < 16; rr++) {
+                    const uint32_t cr = cnt[rr];
+                    s += min(cr, depth) + ((rr < res && cr > depth) ? 1u : 0u);
+                }
+                uint32_t pos = s;
+                if (s < nfull) {
+                    const uint32_t k = s / 16u, l = s % 16u;
+                    pos = 64u * (k / 4u) + 4u * l + (k % 4u);
+                }
+                pos_of[t] = pos;
+            }
+            __syncwarp();
+            for (uint32_t t = 0, i = lane; i < n; i += 32, t++) out[pos_of[t]] = in[i];
+            __syncwarp();
+            for (uint32_t i = lane; i < n; i += 32) run[i] = out[i];
+            __syncwarp();
+        }
+    }
+}
+
 // Pass 2 (BED records): NA-compacted 2-bit codes, pad positions = 11. One thread = 16 individuals.
 __global__ void k_fill_bed(const uint8_t *__restrict__ raw, size_t stride, const uint32_t *__restrict__ rmap,
                            uint32_t N, uint32_t S, uint32_t L, const uint64_t *__restrict__ rec) {

@@ -496,6 +496,16 @@ static int records_from_raw(hb_ctx *c, uint32_t m_first, uint32_t n) {
     k_fill_sparse<<<n, 256, 0, c->stream>>>(c->d_raw.p, stride, c->d_rmap.p, c->N, S, L, c->d_cnt3.p, c->d_start.p, c->d_meta.p,
                                             c->d_rec.p + m_first);
     HB_CUDA(cudaGetLastError());
+    if (!getenv("HB_NO_BANK_ORDER")) {
+        const size_t bsm = (size_t)8 * 2 * kBankMax * sizeof(uint16_t);
+        static bool attr_set = false;
+        if (!attr_set) {
+            HB_CUDA(cudaFuncSetAttribute((const void *)k_bank_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+            attr_set = true;
+        }
+        k_bank_order<<<n, 256, bsm, c->stream>>>(c->d_rec.p + m_first, S, L);
+        HB_CUDA(cudaGetLastError());
+    }
     dim3 g((S * L / 16 + 255) / 256, n);
     k_fill_bed<<<g, 256, 0, c->stream>>>(c->d_raw.p, stride, c->d_rmap.p, c->N, S, L, c->d_rec.p + m_first);
     HB_CUDA(cudaGetLastError());
