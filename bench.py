@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--spectrum", default="B")
     ap.add_argument("--tasks-per-gpu", type=int, default=64)
     ap.add_argument("--sync-rate", type=int, default=10)
-    ap.add_argument("--cpu-sample-markers", type=int, default=16384)
+    ap.add_argument("--cpu-sample-markers", type=int, default=49152)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--n-slices", type=int, default=0)
     return ap.parse_args()
