@@ -831,6 +831,8 @@ int hb_brr_init(hb_ctx *c, const double *y, const int32_t *groups, const double 
     HB_CHECK(c && y && mS, HB_ERR_ARG, "null argument");
     HB_CHECK(c->finalized, HB_ERR_STATE, "hb_brr_init: call hb_stage_finalize first");
     HB_CUDA(cudaSetDevice(c->dev));
+    if (c->prefetch.joinable()) c->prefetch.join();  // draws prefetched for a previous chain are void
+    c->have_next = false;
     const uint32_t N = c->N, K = c->K, G = c->G;
     // groups (global array of m_total; NULL = single group)
     c->MtotGrp.assign(G, 0);

@@ -1,0 +1,109 @@
+"""Properties at BASELINE size (N = 500 000 individuals) that need no CPU oracle run: the oracle would take minutes
+per marker block here, so parity at this size is checked through invariants of the domain."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+N = 500_000
+M = 4096
+
+
+@pytest.fixture(scope="module")
+def store():
+    import hydra_b200
+    from hydra_b200 import synth
+    st = hydra_b200.GenotypeStore(N, M, tasks=32, sync_rate=8, n_groups=1, n_mix=4, repr_mode="sparse")
+    synth.stage_synthetic(st, "B")
+    yield st
+    st.close()
+
+
+def test_layout_uses_the_whole_gpu(store):
+    assert store.n_slices * store.n_cta_groups >= 140 and store.slice_len * store.n_slices >= N
+    assert store.slice_len % 64 == 0 and store.slice_len <= 65472
+
+
+def test_export_then_restage_is_idempotent(store):
+    """records -> reference lists (ascending indices per class) -> records gives the same lists, counts and statistics."""
+    import hydra_b200
+    lists = store.export_sparse(0, 256)
+    for w in range(3):
+        I, S, L = lists[3 * w: 3 * w + 3]
+        for m in (0, 17, 255):
+            run = I[int(S[m]): int(S[m] + L[m])]
+            assert np.all(np.diff(run.astype(np.int64)) > 0) and (len(run) == 0 or run[-1] < N)   # strictly ascending, in range
+    with hydra_b200.GenotypeStore(N, 256, repr_mode="sparse") as st2:
+        st2.load_data_from_sparse(*lists)
+        st2.finalize()
+        again = st2.export_sparse()
+        for a, b in zip(lists, again):
+            assert np.array_equal(a, b)
+        n1, n2, nm = store.marker_counts()
+        m1, m2, mm = st2.marker_counts()
+        assert np.array_equal(n1[:256], m1) and np.array_equal(n2[:256], m2) and np.array_equal(nm[:256], mm)
+        assert np.array_equal(store.marker_stats()[0][:256], st2.marker_stats()[0])
+        # the 2-bit route holds the same genotypes: BED bytes of a marker decode to the same lists
+        with hydra_b200.GenotypeStore(N, 4, repr_mode="bed") as st3:
+            st3.load_data_from_bed(np.stack([store.export_bed(m) for m in range(4)]))
+            st3.finalize()
+            l3 = st3.export_sparse()
+            l0 = store.export_sparse(0, 4)
+            for a, b in zip(l0, l3):
+                assert np.array_equal(a, b)
+
+
+def test_dot_product_is_linear_and_centred(store):
+    rng = np.random.default_rng(0)
+    e1, e2 = rng.normal(size=N), rng.normal(size=N)
+    markers = np.arange(0, M, 7, dtype=np.uint32)
+    store.set_epsilon(e1)
+    d1 = store.sparse_dotprod(markers)
+    store.set_epsilon(e2)
+    d2 = store.sparse_dotprod(markers)
+    store.set_epsilon(2.0 * e1 - 3.0 * e2)
+    d12 = store.sparse_dotprod(markers)
+    scale = np.sqrt(N)
+    np.testing.assert_allclose(d12, 2.0 * d1 - 3.0 * d2, rtol=1e-10, atol=1e-10 * scale)
+    # a constant residual is orthogonal to every centred column (what makes the per-task mu and the scalar base term exact)
+    store.set_epsilon(np.full(N, 3.7))
+    np.testing.assert_allclose(store.sparse_dotprod(markers), 0.0, atol=1e-8)
+
+
+def test_update_then_dot_recovers_the_column_norm(store):
+    """eps = 0; eps += b * x_j  =>  x_j . eps = b * (N - 1) up to the missing genotypes (x_j standardised, :1502-1508, :1855)."""
+    n1, n2, nm = store.marker_counts()
+    markers = np.array([3, 100, 2047], dtype=np.uint32)
+    for m in markers:
+        store.set_epsilon(np.zeros(N))
+        store.sparse_scaadd(np.array([m], np.uint32), np.array([0.25]))
+        got = store.sparse_dotprod(np.array([m], np.uint32))[0]
+        np.testing.assert_allclose(got, 0.25 * (N - 1), rtol=1e-9)
+        eps = store.get_epsilon()
+        assert abs(eps.sum()) < 1e-6      # centred column: the update does not move the mean of epsilon
+
+
+def test_chain_keeps_the_residual_identity_and_is_reproducible(store):
+    """After every iteration eps_task0 = y_scaled - X beta - mu_0 (rebuilt from beta with the update kernel), and two runs with the
+    same seed give bit-identical chains."""
+    import hydra_b200
+    from hydra_b200 import synth
+    y, _, _ = synth.simulate_phenotype(store, n_causal=50)
+    ys = (y - y.mean()) * np.sqrt((N - 1) / ((y - y.mean()) ** 2).sum())
+    runs = []
+    for rep in range(2):
+        brr = hydra_b200.BayesRRm(store, y, [[0.0001, 0.001, 0.01]], seed=99)
+        for it in range(3):
+            o = brr.iteration()
+        beta, comp, acum = brr.state()
+        eps = brr.task_epsilon(0)
+        h = brr.hyper()
+        runs.append((beta.copy(), comp.copy(), eps.copy(), h["sigmaE"]))
+        assert o["n_sync"] > 0 and (beta != 0).sum() > 0
+        # rebuild the residual from scratch
+        store.set_epsilon(ys - h["mu"][0])
+        nz = np.flatnonzero(beta).astype(np.uint32)
+        store.sparse_scaadd(nz, -beta[nz])
+        np.testing.assert_allclose(store.get_epsilon(), eps, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(o["e_sqn"], (eps ** 2).sum(), rtol=1e-10)
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][2], runs[1][2])
+    assert runs[0][3] == runs[1][3]
