@@ -15,8 +15,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 REF = "/root/reference"
 
 
-def parse_lut(path):
-    txt = open(path).read()
+def parse_lut(path=None, txt=None):
+    txt = open(path).read() if txt is None else txt
     out = {}
     for name in ("dotp_lut_a", "dotp_lut_b"):
         m = re.search(name + r"\[1024\][^=]*=\s*\{(.*?)\};", txt, re.S)
@@ -28,7 +28,8 @@ def parse_lut(path):
 
 def main():
     ref = parse_lut(os.path.join(REF, "src/dotp_lut.h"))
-    gen = parse_lut(os.path.join(ROOT, "oracle/_ref/dotp_lut_generated.h"))
+    import subprocess
+    gen = parse_lut(txt=subprocess.run([os.path.join(ROOT, "oracle/_ref/mk_lut")], capture_output=True, text=True, check=True).stdout)
     for k in ref:
         assert np.array_equal(ref[k], gen[k]), k
     np.savez_compressed(os.path.join(ROOT, "tests/golden/lut_ref.npz"), a=ref["dotp_lut_a"].astype(np.int8), b=ref["dotp_lut_b"].astype(np.int8))
