@@ -227,11 +227,15 @@ def main():
     wall_ms, loop_ms, iter_ms = [float(x) for x in t.cpu()]
 
     # ---- end-to-end leg through the host API: per step H2D of the marker order (+hyper tables), D2H of beta/components/acum
+    # the results land in pinned host buffers (what a writer of .bet/.cpn/.acu files would hand to the library)
+    pinned = (torch.empty(store.m_local, dtype=torch.float64, pin_memory=True).numpy(),
+              torch.empty(store.m_local, dtype=torch.int32, pin_memory=True).numpy(),
+              torch.empty(store.m_local, dtype=torch.float64, pin_memory=True).numpy())
     sync_all()
     t_e2e = time.perf_counter()
     for _ in range(a.steps):
         brr.iteration()
-        brr.state()
+        brr.state(out=pinned)
         brr.hyper()
     sync_all()
     e2e_ms = (time.perf_counter() - t_e2e) * 1e3

@@ -221,9 +221,15 @@ class BayesRRm:
         check(self._lib.hb_brr_get_hyper(s._h, ptr(sigmaG), ptr(pi), C.byref(sigmaE), ptr(mu), ptr(bsq), ptr(cass), ptr(m0)))
         return dict(sigmaG=sigmaG, pi=pi, sigmaE=sigmaE.value, mu=mu, bsq=bsq, cass=cass, m0=m0)
 
-    def state(self):
+    def state(self, out=None):
+        """beta, components, Acum of the local markers. `out` = preallocated (beta f64, components i32, acum f64) arrays,
+        e.g. views of pinned host memory, to make the device-to-host copies asynchronous DMA transfers."""
         s = self.store
-        beta, comp, acum = np.zeros(s.m_local), np.zeros(s.m_local, np.int32), np.zeros(s.m_local)
+        if out is None:
+            out = (np.zeros(s.m_local), np.zeros(s.m_local, np.int32), np.zeros(s.m_local))
+        beta, comp, acum = out
+        assert beta.dtype == np.float64 and comp.dtype == np.int32 and acum.dtype == np.float64
+        assert beta.flags.c_contiguous and comp.flags.c_contiguous and acum.flags.c_contiguous and len(beta) == len(comp) == len(acum) == s.m_local
         check(self._lib.hb_brr_get_state(s._h, ptr(beta), ptr(comp), ptr(acum)))
         return beta, comp, acum
 
