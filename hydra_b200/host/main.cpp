@@ -18,7 +18,9 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <fcntl.h>
 #include <sys/stat.h>
+#include <unistd.h>
 #include <vector>
 
 #include "../../include/hydra_b200.h"
@@ -30,7 +32,8 @@ struct Options {  // names follow the reference's Options class (src/options.hpp
         markerBlocksFile;
     bool bedToSparse = false, dryRun = false, readFromBedFile = false, readFromSparseFiles = false;
     uint32_t numberMarkers = 0, numberIndividuals = 0, chainLength = 10000, burnin = 5000, thin = 5, save = 10, syncRate = 1,
-             shuffleMarkers = 1, tasks = 1, device = 0, blocksPerRank = 1;
+             shuffleMarkers = 1, tasks = 1, device = 0, blocksPerRank = 1, rank = 0, world = 1;
+    bool deviceSet = false;
     uint32_t seed = 0;
     bool seedSet = false;
     double thresholdFnz = 0.06;
@@ -99,7 +102,9 @@ Options parse(int argc, const char **argv) {
         }
         // additions of this host (the reference takes the task count from mpirun)
         else if (a == "--tasks") o.tasks = (uint32_t)atoi(need(i));
-        else if (a == "--device") o.device = (uint32_t)atoi(need(i));
+        else if (a == "--device") { o.device = (uint32_t)atoi(need(i)); o.deviceSet = true; }
+        else if (a == "--rank") o.rank = (uint32_t)atoi(need(i));
+        else if (a == "--world") o.world = (uint32_t)atoi(need(i));
         else if (a == "--dry-run") o.dryRun = true;
         // reference options outside the accelerated path: recognised, refused with a clear message
         else if (a == "--restart" || a == "--ignore-xfiles" || a == "--sparse-sync" || a == "--bed-sync" || a == "--covariates" ||
@@ -119,6 +124,22 @@ Options parse(int argc, const char **argv) {
     if (o.numberIndividuals == 0) throw std::runtime_error("--number-individuals has to be set (src/BayesRRm.cpp:3125-3143)");
     if (o.numberMarkers == 0) throw std::runtime_error("--number-markers has to be set (src/BayesRRm.cpp:3125-3143)");
     if (o.tasks == 0) throw std::runtime_error("--tasks must be >= 1");
+    // one process per GPU: rank / world from the launcher's environment (torchrun, mpirun, srun) unless given
+    auto env_u = [](std::initializer_list<const char *> names, uint32_t &dst) {
+        for (const char *n : names)
+            if (const char *v = getenv(n)) { dst = (uint32_t)atoi(v); return true; }
+        return false;
+    };
+    if (o.world == 1) {
+        env_u({"WORLD_SIZE", "OMPI_COMM_WORLD_SIZE", "SLURM_NTASKS"}, o.world);
+        if (o.world > 1) env_u({"RANK", "OMPI_COMM_WORLD_RANK", "SLURM_PROCID"}, o.rank);
+    }
+    if (!o.deviceSet && o.world > 1) {
+        o.device = o.rank;
+        env_u({"LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "SLURM_LOCALID"}, o.device);
+    }
+    if (o.world == 0 || o.rank >= o.world) throw std::runtime_error("bad --rank/--world");
+    if (o.tasks % o.world != 0) throw std::runtime_error("--tasks must be a multiple of the number of GPUs (processes)");
     if (o.thin == 0) o.thin = 1;
     if (o.save % o.thin != 0) o.save = std::max(o.thin, o.save / o.thin * o.thin);  // :1058-1066 save is a multiple of thin
     return o;
@@ -237,6 +258,26 @@ struct OutFile {
     }
 };
 
+// shared output files: every process writes its marker slice at its own offset (the reference uses MPI_File_write_at_all)
+struct SharedFile {
+    int fd = -1;
+    void open_rw(const std::string &path, bool create) {
+        fd = ::open(path.c_str(), create ? (O_RDWR | O_CREAT | O_TRUNC) : O_RDWR, 0644);
+        if (fd < 0) fatal("cannot open output file " + path + ": " + strerror(errno));
+    }
+    void write_at(const void *p, size_t bytes, size_t offset) {
+        const char *c = static_cast<const char *>(p);
+        while (bytes) {
+            const ssize_t w = ::pwrite(fd, c, bytes, (off_t)offset);
+            if (w <= 0) fatal(std::string("pwrite failed: ") + strerror(errno));
+            c += w; bytes -= (size_t)w; offset += (size_t)w;
+        }
+    }
+    ~SharedFile() {
+        if (fd >= 0) ::close(fd);
+    }
+};
+
 template <class T>
 void dump_file(const std::string &path, uint32_t it, uint32_t n, const T *data) {  // .eps/.mrk: u32 it, u32 n, data[n]
     OutFile o;
@@ -308,7 +349,9 @@ int main(int argc, const char **argv) {
         memset(&cfg, 0, sizeof(cfg));
         cfg.device = (int32_t)opt.device;
         cfg.n_ind_raw = Nraw; cfg.n_na = (uint32_t)na.size(); cfg.na_inds = na.data();
-        cfg.m_total = Mtot; cfg.n_tasks_total = opt.tasks; cfg.task_first = 0; cfg.n_tasks_local = opt.tasks;
+        const uint32_t TL = opt.tasks / opt.world;
+        cfg.m_total = Mtot; cfg.n_tasks_total = opt.tasks; cfg.task_first = opt.rank * TL; cfg.n_tasks_local = TL;
+        if (opt.world > 1 && (bayesW || opt.bedToSparse)) throw std::runtime_error("bayesWMPI and --bed-to-sparse run on one GPU (one process) in this version");
         cfg.sync_rate = opt.syncRate; cfg.n_groups = G; cfg.n_mix = K;
         cfg.repr_mode = opt.bedToSparse ? HB_REPR_SPARSE : repr;
         cfg.threshold_fnz = opt.thresholdFnz;
@@ -316,15 +359,15 @@ int main(int argc, const char **argv) {
         cfg.model = bayesW ? 1u : 0u;
         hb_ctx *ctx = nullptr;
         HB(hb_create(&cfg, &ctx));
-        uint32_t N = 0, m_local = 0, lmax = 0;
-        HB(hb_get_layout(ctx, &N, nullptr, &m_local, nullptr, nullptr, nullptr, &lmax));
+        uint32_t N = 0, m_start = 0, m_local = 0, lmax = 0;
+        HB(hb_get_layout(ctx, &N, &m_start, &m_local, nullptr, nullptr, nullptr, &lmax));
 
         // ---- genotypes -> HBM (src/data.cpp:671-739 bed, :742-823 sparse; mixed mode reads the sparse files, :991-996)
         const size_t chunk = std::max<size_t>(1, ((size_t)256 << 20) / std::max<size_t>(1, (Nraw + 3) / 4));
         if (opt.readFromSparseFiles && !opt.bedToSparse) {
             const std::string b = opt.sparseDir + "/" + opt.sparseBsn;
-            for (size_t m0 = 0; m0 < Mtot; m0 += chunk) {
-                const size_t n = std::min(chunk, (size_t)Mtot - m0);
+            for (size_t ml = 0; ml < m_local; ml += chunk) {
+                const size_t n = std::min(chunk, (size_t)m_local - ml), m0 = m_start + ml;
                 std::vector<uint64_t> S[3], Ln[3];
                 std::vector<uint32_t> I[3];
                 const char *ext[3] = {"1", "2", "m"};
@@ -335,16 +378,16 @@ int main(int argc, const char **argv) {
                     I[w] = read_binary<uint32_t>(b + ".si" + ext[w], lo, hi - lo);
                     for (auto &s : S[w]) s -= lo;  // :820-822
                 }
-                HB(hb_stage_sparse(ctx, (uint32_t)m0, (uint32_t)n, I[0].data(), S[0].data(), Ln[0].data(), I[1].data(), S[1].data(),
+                HB(hb_stage_sparse(ctx, (uint32_t)ml, (uint32_t)n, I[0].data(), S[0].data(), Ln[0].data(), I[1].data(), S[1].data(),
                                    Ln[1].data(), I[2].data(), S[2].data(), Ln[2].data()));
             }
         } else {
             const size_t nb = (Nraw + 3) / 4;
-            for (size_t m0 = 0; m0 < Mtot; m0 += chunk) {
-                const size_t n = std::min(chunk, (size_t)Mtot - m0);
+            for (size_t ml = 0; ml < m_local; ml += chunk) {
+                const size_t n = std::min(chunk, (size_t)m_local - ml), m0 = m_start + ml;
                 // 3 magic bytes are skipped, never validated (src/data.cpp:700)
                 auto cols = read_binary<uint8_t>(opt.bedFile + ".bed", 3 + m0 * nb, n * nb);
-                HB(hb_stage_bed(ctx, (uint32_t)m0, (uint32_t)n, cols.data()));
+                HB(hb_stage_bed(ctx, (uint32_t)ml, (uint32_t)n, cols.data()));
             }
         }
         HB(hb_stage_finalize(ctx));
@@ -437,15 +480,58 @@ int main(int argc, const char **argv) {
         if (stat(opt.mcmcOutDir.c_str(), &sb) != 0 && system(("mkdir -p " + opt.mcmcOutDir).c_str()) != 0)
             throw std::runtime_error("could not create output directory --mcmc-out-dir " + opt.mcmcOutDir);
         const std::string out = opt.mcmcOut();
-        OutFile csv, bet, acu, cpn;
-        csv.open(out + ".csv"); bet.open(out + ".bet"); acu.open(out + ".acu"); cpn.open(out + ".cpn");
-        bet.put(&Mtot, 1); acu.put(&Mtot, 1); cpn.put(&Mtot, 1);  // :1304-1308
-        std::vector<OutFile> mus(opt.tasks);
-        for (uint32_t t = 0; t < opt.tasks; t++) mus[t].open(out + ".mus." + std::to_string(t));
+        const bool root = (opt.rank == 0);
+        // rank 0 creates the shared files (old ones are replaced, :1269-1309) before the communicator exists; hb_comm_init
+        // is a barrier, after which the other processes open them
+        SharedFile bet, acu, cpn, xb, xc;
+        OutFile csv;
+        if (root) {
+            csv.open(out + ".csv");
+            bet.open_rw(out + ".bet", true); acu.open_rw(out + ".acu", true); cpn.open_rw(out + ".cpn", true);
+            xb.open_rw(out + ".xbet", true); xc.open_rw(out + ".xcpn", true);
+            bet.write_at(&Mtot, 4, 0); acu.write_at(&Mtot, 4, 0); cpn.write_at(&Mtot, 4, 0);  // :1304-1308
+            xb.write_at(&Mtot, 4, 0); xc.write_at(&Mtot, 4, 0);
+        }
+        if (opt.world > 1) {
+            // NCCL unique id through a file next to the outputs (rank 0 writes, the others wait for it)
+            const char *job = getenv("TORCHELASTIC_RUN_ID") ? getenv("TORCHELASTIC_RUN_ID") : (getenv("SLURM_JOB_ID") ? getenv("SLURM_JOB_ID") : (getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "0"));
+            const std::string idf = out + ".ncclid." + job;
+            uint8_t id[HB_NCCL_ID_BYTES];
+            const time_t t_start = time(nullptr);
+            if (root) {
+                HB(hb_comm_get_unique_id(id));
+                FILE *f = fopen((idf + ".tmp").c_str(), "wb");
+                if (!f || fwrite(id, 1, sizeof(id), f) != sizeof(id)) throw std::runtime_error("cannot write " + idf);
+                fclose(f);
+                if (rename((idf + ".tmp").c_str(), idf.c_str()) != 0) throw std::runtime_error("cannot publish " + idf);
+            } else {
+                bool ok = false;
+                for (int tries = 0; tries < 1200 && !ok; tries++) {
+                    struct stat st;
+                    if (stat(idf.c_str(), &st) == 0 && st.st_size == (off_t)sizeof(id) && st.st_mtime >= t_start - 300) {
+                        FILE *f = fopen(idf.c_str(), "rb");
+                        ok = f && fread(id, 1, sizeof(id), f) == sizeof(id);
+                        if (f) fclose(f);
+                    }
+                    if (!ok) usleep(100000);
+                }
+                if (!ok) throw std::runtime_error("timed out waiting for the NCCL id file " + idf);
+            }
+            HB(hb_comm_init(ctx, id, (int)opt.rank, (int)opt.world));
+            if (root) unlink(idf.c_str());
+        }
+        if (!root) {
+            bet.open_rw(out + ".bet", false); acu.open_rw(out + ".acu", false); cpn.open_rw(out + ".cpn", false);
+            xb.open_rw(out + ".xbet", false); xc.open_rw(out + ".xcpn", false);
+        }
+        const uint32_t t_first = opt.rank * TL;
+        std::vector<OutFile> mus(TL);
+        for (uint32_t t = 0; t < TL; t++) mus[t].open(out + ".mus." + std::to_string(t_first + t));
 
-        std::vector<double> beta(Mtot), acum(Mtot), sigmaG(G), pi((size_t)G * K), mu(opt.tasks), bsq(G), eps(N);
-        std::vector<int32_t> comp(Mtot), cass((size_t)G * K), m0(G), perm;
+        std::vector<double> beta(m_local), acum(m_local), sigmaG(G), pi((size_t)G * K), mu(TL), bsq(G), eps(N);
+        std::vector<int32_t> comp(m_local), cass((size_t)G * K), m0(G), perm;
         double tot_loop_ms = 0.0, tot_iter_ms = 0.0;
+        uint32_t n_saved = 0;
         for (uint32_t it = 0; it < opt.chainLength; it++) {
             hb_brr_iter_out io;
             HB(hb_brr_iteration(ctx, nullptr, &io));
@@ -454,43 +540,49 @@ int main(int argc, const char **argv) {
             HB(hb_brr_get_hyper(ctx, sigmaG.data(), pi.data(), &sigmaE, mu.data(), bsq.data(), cass.data(), m0.data()));
             double sG = 0.0; int m0s = 0;
             for (uint32_t g = 0; g < G; g++) { sG += sigmaG[g]; m0s += m0[g]; }
-            printf("RESULT : it %4u, rank %4d: proc = %9.3f s, sync = %9.3f (%9.3f + %9.3f), n_sync = %8llu (%8llu + %8llu) (%7.3f / %7.3f), sigmaG = %15.10f, sigmaE = %15.10f, betasq = %15.10f, m0 = %10d\n",
-                   it, 0, io.iter_ms * 1e-3, 0.0, 0.0, 0.0, (unsigned long long)io.n_sync, (unsigned long long)io.n_windows, (unsigned long long)io.n_sync,
-                   0.0, 0.0, sG, sigmaE, bsq[0], m0s);  // :2714-2720
+            if (opt.rank % 10 == 0)  // :2713
+                printf("RESULT : it %4u, rank %4d: proc = %9.3f s, sync = %9.3f (%9.3f + %9.3f), n_sync = %8llu (%8llu + %8llu) (%7.3f / %7.3f), sigmaG = %15.10f, sigmaE = %15.10f, betasq = %15.10f, m0 = %10d\n",
+                       it, (int)opt.rank, io.iter_ms * 1e-3, 0.0, 0.0, 0.0, (unsigned long long)io.n_sync, (unsigned long long)io.n_windows, (unsigned long long)io.n_sync,
+                       0.0, 0.0, sG, sigmaE, bsq[0], m0s);  // :2714-2720
             if (it % opt.thin == 0) {
-                char buff[65536];
-                int n = snprintf(buff, sizeof(buff), "%5d, %4d", (int)it, (int)G);  // :2742-2764
-                for (uint32_t g = 0; g < G; g++) n += snprintf(buff + n, sizeof(buff) - n, ", %20.15f", sigmaG[g]);
-                n += snprintf(buff + n, sizeof(buff) - n, ", %20.15f, %20.15f, %7d, %4d, %2d", sigmaE, sG / (sigmaE + sG), m0s, (int)G, (int)K);
-                for (size_t x = 0; x < (size_t)G * K; x++) n += snprintf(buff + n, sizeof(buff) - n, ", %20.15f", pi[x]);
-                n += snprintf(buff + n, sizeof(buff) - n, "\n");
-                csv.put(buff, (size_t)n);
+                if (root) {
+                    char buff[65536];
+                    int n = snprintf(buff, sizeof(buff), "%5d, %4d", (int)it, (int)G);  // :2742-2764
+                    for (uint32_t g = 0; g < G; g++) n += snprintf(buff + n, sizeof(buff) - n, ", %20.15f", sigmaG[g]);
+                    n += snprintf(buff + n, sizeof(buff) - n, ", %20.15f, %20.15f, %7d, %4d, %2d", sigmaE, sG / (sigmaE + sG), m0s, (int)G, (int)K);
+                    for (size_t x = 0; x < (size_t)G * K; x++) n += snprintf(buff + n, sizeof(buff) - n, ", %20.15f", pi[x]);
+                    n += snprintf(buff + n, sizeof(buff) - n, "\n");
+                    csv.put(buff, (size_t)n);
+                    fflush(csv.f);
+                }
                 HB(hb_brr_get_state(ctx, beta.data(), comp.data(), acum.data()));
-                bet.put(&it, 1); bet.put(beta.data(), Mtot);  // records {u32 it; f64[Mtot]} (:2768-2780)
-                acu.put(&it, 1); acu.put(acum.data(), Mtot);
-                cpn.put(&it, 1); cpn.put(comp.data(), Mtot);  // {u32 it; i32[Mtot]} (:2772-2785)
-                for (uint32_t t = 0; t < opt.tasks; t++) { mus[t].put(&it, 1); mus[t].put(&mu[t], 1); }  // :2788-2791
-                fflush(csv.f);
+                // records {u32 it; f64[Mtot]} / {u32 it; i32[Mtot]}; every process writes its slice at MrankS (:2768-2785)
+                const size_t rec8 = 4 + (size_t)n_saved * (4 + (size_t)Mtot * 8), rec4 = 4 + (size_t)n_saved * (4 + (size_t)Mtot * 4);
+                if (root) { bet.write_at(&it, 4, rec8); acu.write_at(&it, 4, rec8); cpn.write_at(&it, 4, rec4); }
+                bet.write_at(beta.data(), (size_t)m_local * 8, rec8 + 4 + (size_t)m_start * 8);
+                acu.write_at(acum.data(), (size_t)m_local * 8, rec8 + 4 + (size_t)m_start * 8);
+                cpn.write_at(comp.data(), (size_t)m_local * 4, rec4 + 4 + (size_t)m_start * 4);
+                for (uint32_t t = 0; t < TL; t++) { mus[t].put(&it, 1); mus[t].put(&mu[t], 1); fflush(mus[t].f); }  // :2788-2791
+                n_saved++;
             }
             if (it > 0 && it % opt.save == 0) {  // :2808-2838, overwritten at every save
-                int32_t starts[4096], lens[4096];
                 std::vector<int32_t> bs(opt.tasks), bl(opt.tasks);
-                (void)starts; (void)lens;
                 HB(hb_get_task_blocks(ctx, bs.data(), bl.data()));
-                for (uint32_t t = 0; t < opt.tasks; t++) {
+                for (uint32_t t = 0; t < TL; t++) {
                     HB(hb_brr_get_task_epsilon(ctx, t, eps.data()));
-                    dump_file(out + ".eps." + std::to_string(t), it, N, eps.data());
-                    perm.resize((size_t)bl[t]);
+                    dump_file(out + ".eps." + std::to_string(t_first + t), it, N, eps.data());
+                    perm.resize((size_t)bl[t_first + t]);
                     HB(hb_brr_get_task_perm(ctx, t, perm.data()));
-                    dump_file(out + ".mrk." + std::to_string(t), it, (uint32_t)bl[t], perm.data());
+                    dump_file(out + ".mrk." + std::to_string(t_first + t), it, (uint32_t)bl[t_first + t], perm.data());
                 }
                 HB(hb_brr_get_state(ctx, beta.data(), comp.data(), nullptr));
-                OutFile xb, xc;
-                xb.open(out + ".xbet"); xc.open(out + ".xcpn");  // u32 Mtot; u32 it; data[Mtot] (:2818-2838)
-                xb.put(&Mtot, 1); xb.put(&it, 1); xb.put(beta.data(), Mtot);
-                xc.put(&Mtot, 1); xc.put(&it, 1); xc.put(comp.data(), Mtot);
+                // u32 Mtot; u32 it; data[Mtot] (:2818-2838)
+                if (root) { xb.write_at(&it, 4, 4); xc.write_at(&it, 4, 4); }
+                xb.write_at(beta.data(), (size_t)m_local * 8, 8 + (size_t)m_start * 8);
+                xc.write_at(comp.data(), (size_t)m_local * 4, 8 + (size_t)m_start * 4);
             }
         }
+        if (root)
         printf("INFO   : time to process the data: %.3f sec (marker loops %.3f sec: %.3f M marker updates/s)\n", tot_iter_ms * 1e-3,
                tot_loop_ms * 1e-3, (double)Mtot * opt.chainLength / (tot_loop_ms * 1e3));
         hb_destroy(ctx);

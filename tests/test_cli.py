@@ -205,3 +205,36 @@ def test_cli_bayesw_run_equals_python_run(tmp_path):
             assert np.array_equal(bw.state()[0], beta[it])
     line = open(os.path.join(d, "o", "w.csv")).read().split("\n")[3].split(",")
     assert int(line[0]) == 3 and abs(float(line[1]) - o["mu"]) < 1e-12 and abs(float(line[3]) - o["alpha"]) < 1e-12
+
+
+@pytest.mark.gpu
+def test_cli_two_processes_two_gpus_equal_one_process(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    d = str(tmp_path)
+    write_dataset(d)
+    common = ["--bfile", os.path.join(d, "t")]
+    a1 = base_args(d, "one", common)
+    a1[a1.index("--tasks") + 1] = "4"
+    r = subprocess.run(a1, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    procs = []
+    for rank in range(2):
+        a2 = base_args(d, "two", common + ["--rank", str(rank), "--world", "2"])
+        a2[a2.index("--tasks") + 1] = "4"
+        procs.append(subprocess.Popen(a2, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                                      env={**os.environ, "MASTER_PORT": "31999", "HB_PEER_TIMEOUT_S": "30"}))
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs[0][-1500:] + outs[1][-1500:]
+    M = 150
+    i1, b1 = read_bet(os.path.join(d, "one", "run.bet"), M)
+    i2, b2 = read_bet(os.path.join(d, "two", "run.bet"), M)
+    assert i1.tolist() == i2.tolist() == [0, 2, 4]
+    np.testing.assert_allclose(b2, b1, rtol=1e-9, atol=1e-14)
+    assert open(os.path.join(d, "one", "run.cpn"), "rb").read() == open(os.path.join(d, "two", "run.cpn"), "rb").read()
+    for t in range(4):
+        assert os.path.exists(os.path.join(d, "two", f"run.mus.{t}")) and os.path.exists(os.path.join(d, "two", f"run.eps.{t}"))
+    e1 = np.fromfile(os.path.join(d, "one", "run.eps.3"), np.float64, offset=8)
+    e2 = np.fromfile(os.path.join(d, "two", "run.eps.3"), np.float64, offset=8)
+    np.testing.assert_allclose(e2, e1, rtol=1e-9, atol=1e-12)
