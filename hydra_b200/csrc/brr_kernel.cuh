@@ -4,18 +4,24 @@
 // (:1757-1809), the mixture draw (:1744-1921), sparse_scaadd (:250-281) / LUT
 // deltaEps (:1976-2010) and the epsilon synchronisation (:2044-2488).
 //
-// Design (DESIGN.md): between two synchronisations hydra's tasks all read a
+// Design (DESIGN.md 2): between two synchronisations hydra's tasks all read a
 // STALE epsilon, so every marker of a sync window (sync_rate steps x T tasks) is
 // independent of the others.  The kernel therefore processes a whole window in
 // parallel:
 //   * individuals are cut in S slices; CTA (r,c) keeps slice c of the residual in
 //     shared memory (r = replica group, R = gridDim/S groups share the window);
-//   * phase A: warps stream the slice block of each marker (u16 local indices or
+//   * dot: warps stream the slice block of each marker (u16 local indices or
 //     2-bit BED bytes, coalesced 64-bit loads) and gather from shared memory;
-//   * the CTA that delivers the last of the S slice partials of a marker sums
-//     them in slice order and draws the mixture component and beta on the device;
-//   * ONE grid barrier per window, after which every CTA applies the window's
-//     non-zero deltaBetas to its slice, in window order (deterministic).
+//   * publish: every slice partial goes out as one 16-byte store carrying the window
+//     tag next to the data, so the consumer needs neither a fence nor a counter;
+//   * draw: marker k of a group is drawn by slice-CTA k % S, one warp per marker
+//     (lanes poll the S slots; lane kk evaluates mixture component kk); changed
+//     markers are appended to a list;
+//   * ONE grid barrier per window; with several GPUs the changed markers (list
+//     entries + genotype records) are then pushed into every peer's inbox over
+//     NVLink and every GPU waits for its peers' arrival counters;
+//   * update: every CTA applies the changed markers of all GPUs to its slice in
+//     global window order (deterministic; all epsilon replicas stay bit-identical).
 #pragma once
 #include "common.cuh"
 
