@@ -269,7 +269,7 @@ def main():
             "e2e": {"value": M_total * a.steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(4 * store.m_local + 8 * 4 * 4 + 1), "d2h_bytes_per_step": int(20 * store.m_local + 8 * (3 + 2 * store.n_slices) + 16 + 128),
                     "ms_per_step": e2e_ms / a.steps, "what": "BayesRRm.iteration() + state() + hyper() through the C ABI: marker order H2D, beta/components/acum D2H every step (thin=1)"},
-            "gpu_launches": 3 * a.steps,
+            "gpu_launches": int(sum(o["n_launches"] for o in outs)),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "kernel": "k_brr_iteration (one cooperative launch per step)",
