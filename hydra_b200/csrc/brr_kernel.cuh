@@ -107,14 +107,18 @@ struct ItemTab {  // the window positions this CTA group works on, with everythi
     const uint64_t *ptr[kTabCap];
     uint64_t rec[kTabCap];
     double mave[kTabCap], mstd[kTabCap], beta[kTabCap], u[kTabCap], z[kTabCap];
-    double part[kTabCap];
     uint32_t nw[kTabCap];   // u64 words of the slice block
     uint32_t b1[kTabCap];   // first word of class 2   (0xFFFFFFFF = BED block)
     uint32_t b2[kTabCap];   // first word of class "missing"
     int32_t m[kTabCap];
     int32_t grp[kTabCap];
+    // dot-phase work units: the slice blocks cut in pieces of (128 << ushift) words (BED: a quarter of that, a BED word
+    // costs 32 gathers), so that the warps of the CTA share the chunk's words evenly whatever the marker sizes are
+    uint16_t ucum[kTabCap + 1];   // exclusive prefix of the units per item
+    uint32_t nunits, ushift;
     uint32_t tag_base, tag_W, tag_k0, tag_valid;  // which window chunk the table describes
 };
+
 
 struct ChgTab {  // changed markers of a window, staged for the epsilon update
     const uint64_t *ptr[kChgCap];
@@ -162,60 +166,78 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 __device__ __forceinline__ double gather4(uint64_t x, const double *__restrict__ E_s) {
     return (E_s[x & 0xFFFFu] + E_s[(x >> 16) & 0xFFFFu]) + (E_s[(x >> 32) & 0xFFFFu] + E_s[x >> 48]);
 }
-__device__ __forceinline__ double dot_sparse_block(const uint64_t *__restrict__ ptr, uint32_t nw, uint32_t b1,
-                                                   uint32_t b2, double mave, const double *__restrict__ E_s,
-                                                   uint32_t lane) {
+// BED word: lane owns 32 consecutive individuals and walks them in a rotated order so that the 16 lanes of a
+// half-warp hit 16 distinct shared-memory banks.
+__device__ __forceinline__ double dot_bed_word(uint64_t bits, uint32_t w, double mave, const double *__restrict__ E_s,
+                                               uint32_t lane) {
     double acc = 0.0;
-    uint32_t w = lane;
-    // four independent 64-bit loads in flight per lane
-    for (; w + 96 < nw; w += 128) {
-        const uint64_t x0 = ld_stream_u64(ptr + w), x1 = ld_stream_u64(ptr + w + 32);
-        const uint64_t x2 = ld_stream_u64(ptr + w + 64), x3 = ld_stream_u64(ptr + w + 96);
-        const double wt0 = (w < b1) ? 1.0 : ((w < b2) ? 2.0 : mave);
-        const double wt1 = (w + 32 < b1) ? 1.0 : ((w + 32 < b2) ? 2.0 : mave);
-        const double wt2 = (w + 64 < b1) ? 1.0 : ((w + 64 < b2) ? 2.0 : mave);
-        const double wt3 = (w + 96 < b1) ? 1.0 : ((w + 96 < b2) ? 2.0 : mave);
-        acc = fma(wt0, gather4(x0, E_s), acc);
-        acc = fma(wt1, gather4(x1, E_s), acc);
-        acc = fma(wt2, gather4(x2, E_s), acc);
-        acc = fma(wt3, gather4(x3, E_s), acc);
-    }
-    // tail: up to four words, loads issued together
-    uint64_t x[4];
-    uint32_t n = 0;
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-        x[t] = 0;
-        if (w + 32u * t < nw) { x[t] = ld_stream_u64(ptr + w + 32u * t); n = t + 1; }
-    }
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-        if ((uint32_t)t < n) {
-            const uint32_t ww = w + 32u * t;
-            const double wt = (ww < b1) ? 1.0 : ((ww < b2) ? 2.0 : mave);
-            acc = fma(wt, gather4(x[t], E_s), acc);
-        }
+    if (bits == ~0ull) return acc;  // 32 x genotype 0
+    const double *e = E_s + 32u * w;
+#pragma unroll 8
+    for (uint32_t t = 0; t < 32; t++) {
+        const uint32_t idx = (t + lane) & 31u;
+        const uint32_t code = (uint32_t)(bits >> (2u * idx)) & 3u;
+        const double v = e[idx];
+        // 00 -> 2, 10 -> 1, 01 -> missing (weight mave), 11 -> 0
+        const double wt = (code == 0u) ? 2.0 : ((code == 2u) ? 1.0 : ((code == 1u) ? mave : 0.0));
+        acc = fma(wt, v, acc);
     }
     return acc;
 }
 
-// BED block: lane owns 32 consecutive individuals per 64-bit word and walks them in a
-// rotated order so that the 16 lanes of a half-warp hit 16 distinct shared-memory banks.
-__device__ __forceinline__ double dot_bed_block(const uint64_t *__restrict__ ptr, uint32_t nw, double mave,
-                                                const double *__restrict__ E_s, uint32_t lane) {
+// Work unit of the dot phase, one 16-byte descriptor in shared memory:
+//   x, y  address of the unit's first 64-bit word
+//   z     number of words | (first word of class "twos", relative, clipped) << 16      (0xFFFF: BED unit)
+//   w     first word of class "missing" (relative, clipped; BED: the unit's first word inside the slice block) | item << 16
+__device__ __forceinline__ uint4 make_unit(const uint64_t *ptr, uint32_t nwords, uint32_t b1rel, uint32_t b2rel, uint32_t k) {
+    const uint64_t a = (uint64_t)(uintptr_t)ptr;
+    return make_uint4((uint32_t)a, (uint32_t)(a >> 32), nwords | (b1rel << 16), b2rel | (k << 16));
+}
+// first (normally only) 128 words of a sparse unit / 32 words of a BED unit; lanes past the end get the pad word,
+// whose four indices point at the dummy slot (always 0.0 during the dot phase)
+__device__ __forceinline__ void load_unit(const uint4 d, uint64_t (&x)[4], uint32_t lane, uint64_t padw) {
+    const uint64_t *ptr = reinterpret_cast<const uint64_t *>(((uint64_t)d.y << 32) | d.x);
+    const uint32_t nwords = d.z & 0xFFFFu;
+#pragma unroll
+    for (uint32_t t = 0; t < 4; t++) {
+        const uint32_t w = lane + 32u * t;
+        x[t] = padw;
+        if (w < nwords) x[t] = ld_stream_u64(ptr + w);
+    }
+}
+__device__ __forceinline__ double dot_words(const uint64_t (&x)[4], uint32_t w0, uint32_t b1, uint32_t b2, double mave,
+                                            const double *__restrict__ E_s, uint32_t lane) {
     double acc = 0.0;
-    for (uint32_t w = lane; w < nw; w += 32) {
-        const uint64_t bits = ld_stream_u64(ptr + w);
-        if (bits == ~0ull) continue;  // 32 x genotype 0
-        const double *e = E_s + 32u * w;
-#pragma unroll 8
-        for (uint32_t t = 0; t < 32; t++) {
-            const uint32_t idx = (t + lane) & 31u;
-            const uint32_t code = (uint32_t)(bits >> (2u * idx)) & 3u;
-            const double v = e[idx];
-            // 00 -> 2, 10 -> 1, 01 -> missing (weight mave), 11 -> 0
-            const double wt = (code == 0u) ? 2.0 : ((code == 2u) ? 1.0 : ((code == 1u) ? mave : 0.0));
-            acc = fma(wt, v, acc);
+#pragma unroll
+    for (uint32_t t = 0; t < 4; t++) {
+        const uint32_t w = w0 + lane + 32u * t;
+        const double wt = (w < b1) ? 1.0 : ((w < b2) ? 2.0 : mave);
+        acc = fma(wt, gather4(x[t], E_s), acc);
+    }
+    return acc;
+}
+// all of a unit: returns the lane's share of sum_w weight(w) * sum_4 E_s[idx]
+__device__ __forceinline__ double dot_unit(const uint4 d, const uint64_t (&x)[4], double mave, const double *__restrict__ E_s,
+                                           uint32_t lane, uint64_t padw) {
+    const uint32_t nwords = d.z & 0xFFFFu, b1 = d.z >> 16, b2 = d.w & 0xFFFFu;
+    if (b1 == 0xFFFFu) {  // BED: b2 = first word of the unit inside the slice block
+        const uint64_t *ptr = reinterpret_cast<const uint64_t *>(((uint64_t)d.y << 32) | d.x);
+        double acc = (lane < nwords) ? dot_bed_word(x[0], b2 + lane, mave, E_s, lane) : 0.0;
+        for (uint32_t w = lane + 32u; w < nwords; w += 32u) acc += dot_bed_word(ld_stream_u64(ptr + w), b2 + w, mave, E_s, lane);
+        return acc;
+    }
+    double acc = dot_words(x, 0u, b1, b2, mave, E_s, lane);
+    if (nwords > 128u) {  // units longer than one step (very heavy chunks only)
+        const uint64_t *ptr = reinterpret_cast<const uint64_t *>(((uint64_t)d.y << 32) | d.x);
+        for (uint32_t w0 = 128u; w0 < nwords; w0 += 128u) {
+            uint64_t y[4];
+#pragma unroll
+            for (uint32_t t = 0; t < 4; t++) {
+                const uint32_t w = w0 + lane + 32u * t;
+                y[t] = padw;
+                if (w < nwords) y[t] = ld_stream_u64(ptr + w);
+            }
+            acc += dot_words(y, w0, b1, b2, mave, E_s, lane);
         }
     }
     return acc;
@@ -382,9 +404,13 @@ __device__ void draw_marker_warp(const BrrParams &P, const ItemTab *tab, uint32_
     }
 }
 
+__device__ __forceinline__ void named_barrier(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // Item table of one window chunk: one thread per window position of this CTA group.
 // Threads [t0, t0+nt) take part; the blocks are prefetched into L2.
-__device__ __forceinline__ void build_table(ItemTab *tab, const BrrParams &P, uint32_t r, uint32_t c, uint32_t base,
+__device__ __forceinline__ void build_table(ItemTab *tab, uint4 *udesc, const BrrParams &P, uint32_t r, uint32_t c, uint32_t base,
                                             uint32_t W, uint32_t k0, uint32_t t0, uint32_t nt, bool prefetch) {
     const uint32_t n_items = (W > r) ? (W - r + P.R - 1) / P.R : 0;
     const uint32_t nk = (n_items > k0) ? min((uint32_t)kTabCap, n_items - k0) : 0;
@@ -409,6 +435,49 @@ __device__ __forceinline__ void build_table(ItemTab *tab, const BrrParams &P, ui
             }
         }
     }
+    // ---- work units of the dot phase: prefix of the units per item, unit -> (item, piece)
+    named_barrier(1, nt);
+    if (tl < 32) {
+        uint32_t cw[4];  // cost of the item's block in sparse-word equivalents
+#pragma unroll
+        for (uint32_t i = 0; i < 4; i++) {
+            const uint32_t k = tl * 4 + i;
+            cw[i] = (k < nk) ? ((tab->b1[k] == 0xFFFFFFFFu) ? tab->nw[k] * 4u : tab->nw[k]) : 0u;
+        }
+        uint32_t sh = 0, un[4], tot;
+        for (;; sh++) {
+            const uint32_t span = 128u << sh;
+            tot = 0;
+#pragma unroll
+            for (uint32_t i = 0; i < 4; i++) { un[i] = (cw[i] + span - 1) / span; tot += un[i]; }
+            uint32_t incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tl >= (uint32_t)o) incl += t;
+            }
+            const uint32_t all = __shfl_sync(0xffffffffu, incl, 31);
+            if (all <= (uint32_t)kUnitCap) {
+                uint32_t a = incl - tot;
+#pragma unroll
+                for (uint32_t i = 0; i < 4; i++) { tab->ucum[tl * 4 + i] = (uint16_t)a; a += un[i]; }
+                if (tl == 31) { tab->ucum[kTabCap] = (uint16_t)all; tab->nunits = all; tab->ushift = sh; }
+                break;
+            }
+        }
+    }
+    named_barrier(1, nt);
+    if (tl < nk) {  // descriptors of the item's units (the unit table is free between two dot phases)
+        const uint32_t u0 = tab->ucum[tl], u1 = tab->ucum[tl + 1], nw = tab->nw[tl], b1 = tab->b1[tl], b2 = tab->b2[tl];
+        const bool bed = (b1 == 0xFFFFFFFFu);
+        const uint32_t span = bed ? (32u << tab->ushift) : (128u << tab->ushift);
+        for (uint32_t u = u0; u < u1; u++) {
+            const uint32_t w0 = (u - u0) * span, n = min(span, nw - w0);
+            const uint32_t b1r = bed ? 0xFFFFu : ((b1 > w0) ? min(b1 - w0, n) : 0u);
+            const uint32_t b2r = bed ? w0 : ((b2 > w0) ? min(b2 - w0, n) : 0u);
+            udesc[u] = make_unit(tab->ptr[tl] + w0, n, b1r, b2r, tl);
+        }
+    }
     if (tl == 0) { tab->tag_base = base; tab->tag_W = W; tab->tag_k0 = k0; tab->tag_valid = 1; }
 }
 
@@ -424,6 +493,7 @@ __device__ __forceinline__ uint32_t find_entry(const uint32_t *cum, uint32_t n, 
 
 constexpr uint32_t kApplyQ = 4;          // 64-bit words staged in registers per thread and round
 constexpr uint32_t kHypSmem = 64;        // G*K up to this: hyper-parameter tables live in shared memory
+constexpr uint32_t kWarps = kThreads / 32;
 constexpr uint32_t kDrawWarps = 8;       // warps that collect partials and draw; the others prebuild the next table
 
 // Epsilon update with the nx markers staged in chg[0..nx) (window order). All threads of the CTA call it.
@@ -431,7 +501,7 @@ constexpr uint32_t kDrawWarps = 8;       // warps that collect partials and draw
 // barrier per marker keeps the order of additions to an individual fixed); BED blocks have length 0 in the
 // flattened space and are applied by the whole CTA in their turn.
 __device__ __forceinline__ void apply_staged(ChgTab *chg, uint32_t nx, double *__restrict__ E_s, uint32_t L, double &added,
-                                             double &off, unsigned long long &nnz_upd) {
+                                             double &off, unsigned long long *nnz_upd) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (warp == 0) {  // exclusive prefix of the block lengths (nx <= 64)
         const uint32_t a0 = (lane < nx && chg->b1[lane] != 0xFFFFFFFFu) ? chg->nw[lane] : 0u;
@@ -488,7 +558,7 @@ __device__ __forceinline__ void apply_staged(ChgTab *chg, uint32_t nx, double *_
     }
     for (uint32_t x = 0; x < nx; x++) {
         off = fma(-chg->mave[x], chg->dbs[x], off);  // base term -mave*mstd*deltaBeta of every individual (:265-267)
-        if (tid == 0 && chg->b1[x] != 0xFFFFFFFFu) nnz_upd += 4ull * chg->nw[x];
+        if (tid == 0 && chg->b1[x] != 0xFFFFFFFFu) *nnz_upd += 4ull * chg->nw[x];
     }
     __syncthreads();
 }
@@ -501,10 +571,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
     ChgTab *chg = reinterpret_cast<ChgTab *>(tabs + 2);
     __shared__ double red[32];
     __shared__ double hyp_s[4 * kHypSmem];
-    __shared__ uint32_t work_ctr;
+    __shared__ uint4 udesc[kUnitCap];                   // work units of the dot phase
+    __shared__ unsigned long long cnt_s[9];             // traffic counters: per warp 0..3 {non-zeros read by the dot, BED blocks}, [8] update
     __shared__ uint32_t chg_n;
     __shared__ uint32_t chg_base[33];
-    __shared__ uint32_t psort[kMaxMerged + 1];
+    __shared__ __align__(8) uint32_t psort[kMaxMerged + 2];
+    double *upart = reinterpret_cast<double *>(psort);  // unit partials of the dot phase (psort is update-phase scratch)
     __shared__ uint32_t pcnt[kMaxRanks];
 
     const uint32_t S = P.S, L = P.L, R = P.R;
@@ -539,13 +611,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
     }
 
     uint32_t bar_target = 0;
-    long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tclk = clock64();
-    unsigned long long gts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    __shared__ long long tph[8];             // phase cycle counters of thread 0 (shared memory: keeps 32 registers free)
+    __shared__ unsigned long long gts[8];
+    if (tid < 8) { tph[tid] = 0; gts[tid] = 0; }
+    long long tclk = clock64();
 #define HB_PHASE(i) do { if (tid == 0) { long long t_ = clock64(); tph[i] += t_ - tclk; tclk = t_; \
         if (P.cta_cycles && win == 10) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); gts[i] = g_; } } } while (0)
     double off = 0.0;
     uint32_t j0 = 0, since = 0, win = 0;
-    unsigned long long nnz_dot = 0, nnz_upd = 0, n_bed = 0, n_sync = 0;
+    uint32_t n_sync = 0;
+    if (tid < 9) cnt_s[tid] = 0;
+    const uint64_t padw = (uint64_t)L * 0x0001000100010001ull;
     const uint32_t SR = (P.SR == 0) ? 1u : P.SR;
 
     while (j0 < P.lmax) {
@@ -562,30 +638,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                 // ---- 1. item table (normally prebuilt during the previous window) -------
                 if (!(tab->tag_valid && tab->tag_base == base && tab->tag_W == W && tab->tag_k0 == k0)) {
                     __syncthreads();
-                    build_table(tab, P, r, c, base, W, k0, 0, blockDim.x, false);
+                    build_table(tab, udesc, P, r, c, base, W, k0, 0, blockDim.x, false);
                 }
-                if (tid == 0) work_ctr = 0;
                 __syncthreads();
                 HB_PHASE(0);
-                // ---- 2. phase A: warps pull items -------------------------------------
-                for (;;) {
-                    uint32_t k = 0;
-                    if (lane == 0) k = atomicAdd(&work_ctr, 1u);
-                    k = __shfl_sync(0xffffffffu, k, 0);
-                    if (k >= nk) break;
-                    const uint32_t nw = tab->nw[k];
-                    double acc = 0.0;
-                    if (tab->m[k] >= 0) {
-                        if (tab->b1[k] == 0xFFFFFFFFu) {
-                            acc = dot_bed_block(tab->ptr[k], nw, tab->mave[k], E_s, lane);
-                            if (lane == 0) n_bed++;
-                        } else {
-                            acc = dot_sparse_block(tab->ptr[k], nw, tab->b1[k], tab->b2[k], tab->mave[k], E_s, lane);
-                            if (lane == 0) nnz_dot += 4ull * nw;
-                        }
+                // ---- 2. dot: warp w takes the units w, w + 16, ...; the words of the next unit are in flight while the
+                //         current one gathers from shared memory (two register sets, no copies)
+                {
+                    const uint32_t nun = tab->nunits;
+                    const uint4 none = make_uint4(0u, 0u, 0u, 0u);
+                    uint32_t u = warp;
+                    uint4 da = (u < nun) ? udesc[u] : none, db;
+                    uint64_t xa[4], xb[4];
+                    load_unit(da, xa, lane, padw);
+                    while (u < nun) {
+                        db = (u + kWarps < nun) ? udesc[u + kWarps] : none;
+                        load_unit(db, xb, lane, padw);
+                        double acc = dot_unit(da, xa, tab->mave[da.w >> 16], E_s, lane, padw);
                         acc = warp_sum(acc);
+                        if (lane == 0) upart[u] = acc;
+                        u += kWarps;
+                        if (u >= nun) break;
+                        da = (u + kWarps < nun) ? udesc[u + kWarps] : none;
+                        load_unit(da, xa, lane, padw);
+                        acc = dot_unit(db, xb, tab->mave[db.w >> 16], E_s, lane, padw);
+                        acc = warp_sum(acc);
+                        if (lane == 0) upart[u] = acc;
+                        u += kWarps;
                     }
-                    if (lane == 0) tab->part[k] = acc;
                 }
                 __syncthreads();
                 HB_PHASE(1);
@@ -597,8 +677,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                         if (P.mode == MODE_CHAIN) P.dB[(size_t)dbuf * P.Wmax + p] = 0.0;  // padded task step (:2029-2034)
                     } else {
                         // partial of num/mstd: sum_1 + 2 sum_2 + mave*sum_M - mave*sum_slice   (:327-339)
-                        st_slot(P.slots + (size_t)p * S + c, fma(-tab->mave[k], slice_sum, tab->part[k]), tag);
+                        double part = 0.0;
+                        for (uint32_t u = tab->ucum[k], u1 = tab->ucum[k + 1]; u < u1; u++) part += upart[u];  // fixed order
+                        st_slot(P.slots + (size_t)p * S + c, fma(-tab->mave[k], slice_sum, part), tag);
                     }
+                }
+                if (tid < kTabCap) {  // traffic counters (warps 0..3 hold the items): one plain add per warp
+                    uint32_t v = 0, vb = 0;
+                    if (tid < nk && tab->m[tid] >= 0) {
+                        if (tab->b1[tid] == 0xFFFFFFFFu) vb = 1u; else v = 4u * tab->nw[tid];
+                    }
+                    v = __reduce_add_sync(0xffffffffu, v);
+                    vb = __reduce_add_sync(0xffffffffu, vb);
+                    if (lane == 0) { cnt_s[2 * warp] += v; cnt_s[2 * warp + 1] += vb; }
                 }
                 // ---- 4. draws: item kk of the group is drawn by slice-CTA kk % S, one warp per item;
                 //         meanwhile the upper warps prepare the next window's table
@@ -611,7 +702,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                     const uint32_t j1 = j0 + n;
                     if (j1 < P.lmax) {
                         const uint32_t n1 = min(SR, P.lmax - j1);
-                        build_table(&tabs[(win + 1u) & 1u], P, r, c, j1 * P.T, n1 * P.T, 0, kDrawWarps * 32, blockDim.x - kDrawWarps * 32, !(P.flags & 1u));
+                        build_table(&tabs[(win + 1u) & 1u], udesc, P, r, c, j1 * P.T, n1 * P.T, 0, kDrawWarps * 32, blockDim.x - kDrawWarps * 32, !(P.flags & 1u));
                     }
                 }
                 __syncthreads();  // table reuse
@@ -745,7 +836,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                         }
                     }
                     __syncthreads();
-                    apply_staged(chg, nx, E_s, L, added, off, nnz_upd);
+                    apply_staged(chg, nx, E_s, L, added, off, &cnt_s[8]);
                 }
                 HB_PHASE(7);
                 any = true;
@@ -790,7 +881,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                         chg->dbs[x] = d; chg->mave[x] = mv;
                     }
                     __syncthreads();
-                    apply_staged(chg, nx, E_s, L, added, off, nnz_upd);
+                    apply_staged(chg, nx, E_s, L, added, off, &cnt_s[8]);
                 }
                 any |= (nchg > 0);
             }
@@ -833,11 +924,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
     if (P.cta_cycles && tid == 0)
         for (int i = 0; i < 8; i++) P.cta_cycles[(size_t)blockIdx.x * 8 + i] = gts[i];
     // traffic counters (lane 0 of every warp holds a share)
-    if (lane == 0) {
-        if (nnz_dot) atomicAdd(&P.stats[2], nnz_dot);
-        if (n_bed && c == 0) atomicAdd(&P.stats[4], n_bed);
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned long long nd = cnt_s[0] + cnt_s[2] + cnt_s[4] + cnt_s[6], nb = cnt_s[1] + cnt_s[3] + cnt_s[5] + cnt_s[7];
+        if (nd) atomicAdd(&P.stats[2], nd);
+        if (nb && c == 0) atomicAdd(&P.stats[4], nb);
+        if (r == 0 && cnt_s[8]) atomicAdd(&P.stats[3], cnt_s[8]);
     }
-    if (tid == 0 && r == 0 && nnz_upd) atomicAdd(&P.stats[3], nnz_upd);
 }
 
 // ---------------------------------------------------------------------------------

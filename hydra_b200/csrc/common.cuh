@@ -58,6 +58,7 @@ __host__ __device__ inline uint32_t dir_bytes(uint32_t S) { return (12u * S + 15
 constexpr int kMaxMix = 16;      // K <= 16 mixture components (incl. zero)
 constexpr int kThreads = 512;    // threads per CTA of the sampler kernel
 constexpr int kTabCap = 128;     // window items staged per table chunk
+constexpr int kUnitCap = 256;    // dot-phase work units per table chunk
 constexpr int kChgCap = 64;      // changed markers staged per epsilon-update round
 
 #ifdef __CUDACC__
