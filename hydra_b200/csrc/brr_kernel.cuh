@@ -328,6 +328,10 @@ __device__ __forceinline__ void st_slot(uint4 *p, double val, uint32_t tag) {
 __device__ void draw_marker_warp(const BrrParams &P, const ItemTab *tab, uint32_t k, const HypTabs &H, uint32_t p, uint32_t q,
                                  uint32_t dbuf, uint32_t buf3, uint32_t tag, uint32_t lane) {
     const uint4 *sl = P.slots + (size_t)p * P.S;
+    // A marker with a non-zero effect will change: its place in the window's list of changed markers is reserved now, so
+    // that the round trip of the atomic overlaps the wait for the partials and the draw.
+    uint32_t idx_early = 0xFFFFFFFFu;
+    if (lane == 0 && P.mode == MODE_CHAIN && tab->beta[k] != 0.0) idx_early = atomicAdd(P.chg_cnt + buf3, 1u);
     double acc = 0.0;
     for (uint32_t c0 = 0; c0 < P.S; c0 += 32) {
         const uint32_t cc = c0 + lane;
@@ -361,6 +365,25 @@ __device__ void draw_marker_warp(const BrrParams &P, const ItemTab *tab, uint32_
             logL = __dadd_rn(__dadd_rn(logL, -H.chalf[g * K + kk]), __dmul_rn(__dmul_rn(muk, num), P.i_2sigE));
         }
         const double prob = tab->u[k];                                               // :1880
+        if (K * K <= 32u) {
+            // All K terms of the cascade at once: lane j*K + i evaluates exp(logL[i] - logL[j]); term[j] = 1 / sum_i (in
+            // component order), or 0 where the reference's 700-test fires (:1884-1890 for j = 0, :1915-1919 for j > 0).
+            const uint32_t j = lane / K, i = lane % K;
+            const double Li = __shfl_sync(0xffffffffu, logL, i), Lj = __shfl_sync(0xffffffffu, logL, j % K);
+            const double e = exp(Li - Lj);
+            const bool bigp = (j < K) && (i >= max(j, 1u)) && (fabs(Li - Lj) > 700.0);
+            const uint32_t bigm = __ballot_sync(0xffffffffu, bigp);
+            double s = 0.0;
+            for (uint32_t i2 = 0; i2 < K; i2++) s += __shfl_sync(0xffffffffu, e, (j * K + i2) & 31u);
+            const bool big = ((bigm >> ((j * K) & 31u)) & ((1u << K) - 1u)) != 0u;
+            const double term = big ? 0.0 : 1.0 / s;
+            double acum = __shfl_sync(0xffffffffu, term, 0);
+            acum0 = acum;                                                            // Acum(marker), :1892
+            for (uint32_t c = 0; c < K; c++) {                                       // :1894-1921
+                if (prob <= acum || c == K - 1) { comp = (int)c; break; }
+                acum += __shfl_sync(0xffffffffu, term, ((c + 1u) * K) & 31u);
+            }
+        } else {
         double ref = __shfl_sync(0xffffffffu, logL, 0);
         bool big = __ballot_sync(0xffffffffu, lane > 0 && lane < K && fabs(logL - ref) > 700.0) != 0u;  // :1884
         double e = exp(logL - ref), s = 0.0;
@@ -376,6 +399,7 @@ __device__ void draw_marker_warp(const BrrParams &P, const ItemTab *tab, uint32_
             for (uint32_t i = 0; i < K; i++) s += __shfl_sync(0xffffffffu, e, i);
             if (!big) acum += 1.0 / s;
         }
+        }
         const double muc = __shfl_sync(0xffffffffu, muk, comp);
         if (comp > 0) beta_new = __dadd_rn(muc, __dmul_rn(H.sdk[g * K + comp], tab->z[k]));  // :1901
     }                                                                                // else :1924-1925
@@ -385,17 +409,18 @@ __device__ void draw_marker_warp(const BrrParams &P, const ItemTab *tab, uint32_
             P.comp[m] = comp;
         }
         const double dbeta = beta_old - beta_new;                                    // :1933
-        if (dbeta != 0.0) {
-            const double dbs = __dmul_rn(dbeta, mstd);
+        if (dbeta != 0.0 || idx_early != 0xFFFFFFFFu) {
+            // (a reserved entry of a marker that drew its old value again carries 0 and does not count as a change)
+            const double dbs = (dbeta != 0.0) ? __dmul_rn(dbeta, mstd) : 0.0;
             P.dMave[slot] = tab->mave[k];
             P.dRec[slot] = tab->rec[k];
             P.dB[slot] = dbs;
-            const uint32_t idx = atomicAdd(P.chg_cnt + buf3, 1u);
+            const uint32_t idx = (idx_early != 0xFFFFFFFFu) ? idx_early : atomicAdd(P.chg_cnt + buf3, 1u);
             ChgEnt en;
             en.p = (P.pc.nranks > 1) ? (p / P.T) * P.pc.T_total + P.pc.t_first + (p % P.T) : p;
             en.m = (uint32_t)m; en.dbs = dbs; en.mave = tab->mave[k]; en.rec = tab->rec[k];
             P.chg_list[(size_t)buf3 * P.Wmax + idx] = en;
-            atomicAdd(&P.stats[5], 1ull);
+            if (dbeta != 0.0) atomicAdd(&P.stats[5], 1ull);
         } else {
             P.dB[slot] = 0.0;
         }
@@ -642,30 +667,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                 }
                 __syncthreads();
                 HB_PHASE(0);
-                // ---- 2. dot: warp w takes the units w, w + 16, ...; the words of the next unit are in flight while the
-                //         current one gathers from shared memory (two register sets, no copies)
+                // ---- 2. dot: warp w takes the units w, w + 16, ...; the words of the next two units are in flight while
+                //         the current one gathers from shared memory (three register sets in rotation, no copies)
                 {
                     const uint32_t nun = tab->nunits;
                     const uint4 none = make_uint4(0u, 0u, 0u, 0u);
                     uint32_t u = warp;
-                    uint4 da = (u < nun) ? udesc[u] : none, db;
-                    uint64_t xa[4], xb[4];
-                    load_unit(da, xa, lane, padw);
+                    uint4 da, db, dc;
+                    uint64_t xa[4], xb[4], xc[4];
+#define HB_FETCH(D, X, UU) do { D = ((UU) < nun) ? udesc[UU] : none; load_unit(D, X, lane, padw); } while (0)
+#define HB_COMPUTE(D, X) do { double acc_ = dot_unit(D, X, tab->mave[D.w >> 16], E_s, lane, padw); acc_ = warp_sum(acc_); \
+                              if (lane == 0) upart[u] = acc_; u += kWarps; } while (0)
+                    HB_FETCH(da, xa, u);
+                    HB_FETCH(db, xb, u + kWarps);
                     while (u < nun) {
-                        db = (u + kWarps < nun) ? udesc[u + kWarps] : none;
-                        load_unit(db, xb, lane, padw);
-                        double acc = dot_unit(da, xa, tab->mave[da.w >> 16], E_s, lane, padw);
-                        acc = warp_sum(acc);
-                        if (lane == 0) upart[u] = acc;
-                        u += kWarps;
+                        HB_FETCH(dc, xc, u + 2 * kWarps);
+                        HB_COMPUTE(da, xa);
                         if (u >= nun) break;
-                        da = (u + kWarps < nun) ? udesc[u + kWarps] : none;
-                        load_unit(da, xa, lane, padw);
-                        acc = dot_unit(db, xb, tab->mave[db.w >> 16], E_s, lane, padw);
-                        acc = warp_sum(acc);
-                        if (lane == 0) upart[u] = acc;
-                        u += kWarps;
+                        HB_FETCH(da, xa, u + 2 * kWarps);
+                        HB_COMPUTE(db, xb);
+                        if (u >= nun) break;
+                        HB_FETCH(db, xb, u + 2 * kWarps);
+                        HB_COMPUTE(dc, xc);
                     }
+#undef HB_FETCH
+#undef HB_COMPUTE
                 }
                 __syncthreads();
                 HB_PHASE(1);
@@ -721,8 +747,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
         uint32_t nlist = 0xFFFFFFFFu;
         if (P.mode == MODE_CHAIN) {
             const uint32_t buf3 = win % 3u, par = win & 1u, NR = P.pc.nranks, me = P.pc.rank;
-            const uint32_t nloc = __ldcg(P.chg_cnt + buf3);
             const ChgEnt *llist = P.chg_list + (size_t)buf3 * P.Wmax;
+            // single GPU: the first entries are read together with the count (one L2 round trip instead of two)
+            constexpr uint32_t kSpec = 64;
+            ChgEnt spec;
+            spec.p = 0xFFFFFFFFu;
+            if (NR == 1 && tid < kSpec) spec = ld_chg_ent(llist + tid);
+            const uint32_t nloc = __ldcg(P.chg_cnt + buf3);
             if (blockIdx.x == 0 && tid == 0) P.chg_cnt[(win + 2u) % 3u] = 0;  // free since the previous grid barrier
             uint32_t ntot = nloc;
             if (NR > 1) {
@@ -807,7 +838,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                         uint32_t h = 0, o = i;
                         if (NR > 1) { while (o >= pcnt[h]) { o -= pcnt[h]; h++; } }
                         if (h == me) {
-                            en[u] = ld_chg_ent(llist + o);
+                            if (NR == 1 && i < kSpec) en[u] = spec; else en[u] = ld_chg_ent(llist + o);
                         } else {
                             const unsigned char *reg = P.pc.inbox_local + ((size_t)par * NR + h) * P.pc.inbox_stride;
                             en[u] = ld_chg_ent(reinterpret_cast<const ChgEnt *>(reg + 16) + o);
@@ -816,7 +847,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                         psort[i] = en[u].p;
                     }
                 }
-                __syncthreads();
+                const bool nonzero = (en[0].p != 0xFFFFFFFFu && en[0].dbs != 0.0) || (en[1].p != 0xFFFFFFFFu && en[1].dbs != 0.0);
+                any = __syncthreads_or(nonzero) != 0;
                 uint32_t rank[2] = {0, 0};
 #pragma unroll
                 for (uint32_t u = 0; u < 2; u++)
@@ -839,7 +871,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                     apply_staged(chg, nx, E_s, L, added, off, &cnt_s[8]);
                 }
                 HB_PHASE(7);
-                any = true;
             }
         }
         if (nlist > kMaxMerged) {  // very many changes on a single GPU (or a unit mode): scan the dense per-position arrays

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) k_fill_sparse(const uint8_t *__restrict__
 // Pass 3 (sparse records): bank-aware order inside every class run of every slice block.
 // The dot product gathers epsilon (8-byte words, 16 distinct bank pairs) from shared memory with one 64-bit word
 // of four indices per lane; the 16 lanes of a half-warp read, for index slot g, the elements at positions
-// 64*chunk + 4*lane + g of the block. The sum over a class does not depend on the order of its indices, so each
+// 64*chunk + 4*lane + g of the block (chunk = 16 consecutive words counted from the start of the slice block). The sum over a class does not depend on the order of its indices, so each
 // run is permuted such that those 16 elements have distinct (index mod 16) wherever the residues allow it:
 // elements are ranked by (depth inside their residue list, residue) and dealt to the half-warp groups in that order.
 // Runs longer than kBankMax stay ascending. Exports go through the 2-bit form and are order independent.
@@ -184,8 +184,10 @@ __global__ void __launch_bounds__(256) k_bank_order(const uint64_t *__restrict__
         for (int cls = 0; cls < 3; cls++) {
             const uint32_t n = len[cls];
             uint16_t *run = payload + (size_t)st * 4 + off;
-            off += ((n + 3) / 4) * 4;
-            if (n <= 16 || n > kBankMax) continue;
+            const uint32_t ws = off / 4u;            // first word of the class inside the slice block
+            const uint32_t nwc = (n + 3u) / 4u;      // its words
+            off += nwc * 4u;
+            if (n <= 16 || 4u * nwc > kBankMax) continue;
             if (lane < 16) cnt[lane] = 0;
             __syncwarp();
             // depth of every element inside its residue list (stable: runs are ascending)
@@ -203,28 +205,37 @@ __global__ void __launch_bounds__(256) k_bank_order(const uint64_t *__restrict__
                 if (ok) { in[i] = (uint16_t)idx; out[i] = (uint16_t)depth; }  // out temporarily holds the depth
             }
             __syncwarp();
-            const uint32_t nfull = (n / 64u) * 64u;
-            // sequence index s = #elements with smaller (depth, residue); then position of s
+            // Sequence index s = #elements with smaller (depth, residue): 16 consecutive elements of the sequence have
+            // distinct residues wherever the residue lists are deep enough. The dot phase reads word w of the block with
+            // lane w % 32, so one gather instruction of a half-warp takes the same lane q of 16 consecutive words
+            // [16g, 16g + 16) of the block: the words of the class are cut at those boundaries and every segment of
+            // `wseg` words is filled column by column (element s' of the segment -> word s' % wseg, lane s' / wseg),
+            // the last, partly filled one included; PAD fills what is left of it.
+            const uint32_t w0 = min(nwc, (16u - (ws & 15u)) & 15u);  // words before the first 16-word boundary
             uint32_t pos_of[kBankMax / 32];
             for (uint32_t t = 0, i = lane; i < n; i += 32, t++) {
                 const uint32_t idx = in[i], res = idx & 15u, depth = out[i];
-                uint32_t s = 0;
+                uint32_t sq = 0;
 #pragma unroll
                 for (uint32_t rr = 0; rr < 16; rr++) {
                     const uint32_t cr = cnt[rr];
-                    s += min(cr, depth) + ((rr < res && cr > depth) ? 1u : 0u);
+                    sq += min(cr, depth) + ((rr < res && cr > depth) ? 1u : 0u);
                 }
-                uint32_t pos = s;
-                if (s < nfull) {
-                    const uint32_t k = s / 16u, l = s % 16u;
-                    pos = 64u * (k / 4u) + 4u * l + (k % 4u);
+                uint32_t segw, wseg, sp;  // first word of the segment (inside the class), its words, index inside it
+                if (sq < 4u * w0) {
+                    segw = 0; wseg = w0; sp = sq;
+                } else {
+                    const uint32_t s2 = sq - 4u * w0, g = s2 / 64u;
+                    segw = w0 + 16u * g; wseg = min(16u, nwc - segw); sp = s2 - 64u * g;
                 }
-                pos_of[t] = pos;
+                pos_of[t] = 4u * (segw + sp % wseg) + sp / wseg;
             }
+            __syncwarp();
+            for (uint32_t i = lane; i < 4u * nwc; i += 32) out[i] = (uint16_t)L;  // PAD
             __syncwarp();
             for (uint32_t t = 0, i = lane; i < n; i += 32, t++) out[pos_of[t]] = in[i];
             __syncwarp();
-            for (uint32_t i = lane; i < n; i += 32) run[i] = out[i];
+            for (uint32_t i = lane; i < 4u * nwc; i += 32) run[i] = out[i];
             __syncwarp();
         }
     }
@@ -271,10 +282,14 @@ __global__ void __launch_bounds__(256) k_record_to_bed(const uint64_t *__restric
     for (uint32_t c = warp; c < S; c += nwarps) {
         const uint32_t st = dir[c * 3], n1 = dir[c * 3 + 1] & 0xFFFFu, n2 = dir[c * 3 + 1] >> 16, nm = dir[c * 3 + 2];
         const uint16_t *blk = payload + (size_t)st * 4;
-        const uint32_t o2 = ((n1 + 3) / 4) * 4, om = o2 + ((n2 + 3) / 4) * 4;
-        for (uint32_t e = lane; e < n1; e += 32) { uint32_t i = c * L + blk[e]; atomicXor(&o32[i >> 4], 1u << (2 * (i & 15))); }
-        for (uint32_t e = lane; e < n2; e += 32) { uint32_t i = c * L + blk[o2 + e]; atomicXor(&o32[i >> 4], 3u << (2 * (i & 15))); }
-        for (uint32_t e = lane; e < nm; e += 32) { uint32_t i = c * L + blk[om + e]; atomicXor(&o32[i >> 4], 2u << (2 * (i & 15))); }
+        // every class is padded to whole words; PAD (= L) entries may sit anywhere inside a class (k_bank_order)
+        const uint32_t o2 = ((n1 + 3) / 4) * 4, om = o2 + ((n2 + 3) / 4) * 4, oe = om + ((nm + 3) / 4) * 4;
+        for (uint32_t e = lane; e < oe; e += 32) {
+            const uint32_t idx = blk[e];
+            if (idx == L) continue;
+            const uint32_t i = c * L + idx, code = (e < o2) ? 1u : ((e < om) ? 3u : 2u);
+            atomicXor(&o32[i >> 4], code << (2 * (i & 15)));
+        }
     }
 }
 
