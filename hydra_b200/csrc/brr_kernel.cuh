@@ -36,6 +36,16 @@ struct ChgEnt {  // 32 bytes
     uint64_t rec;    // record address on the owning GPU / payload offset inside an inbox region
 };
 
+// Per iteration, in window order (q = step * T + task): everything the item table needs about the marker of a position,
+// gathered once by k_window_order so that the table build inside the marker loop is one streaming read without
+// dependent loads (marker -> record -> slice directory used to be three round trips per window).
+struct __align__(16) WinMeta {  // 64 bytes
+    uint64_t rec;
+    double mave, mstd, beta, u, z;
+    int32_t m, grp;
+    uint32_t pad[2];
+};
+
 constexpr uint32_t kMaxRanks = 8;
 constexpr uint32_t kMaxMerged = 1024;        // changed markers of one window over all GPUs (shared-memory sort)
 constexpr size_t kInboxHeader = 16 + (size_t)kMaxMerged * sizeof(ChgEnt);
@@ -80,6 +90,8 @@ struct BrrParams {
     const int32_t *order;  // [lmax*T] local marker or -1
     const double *u;       // [lmax*T]
     const double *z;       // [lmax*T]
+    const WinMeta *meta;   // [lmax*T] chain mode: window-ordered marker data (NULL in the unit modes)
+    const uint4 *dirw;     // [S][lmax*T] chain mode: slice directory entries {word offset, n1 | n2 << 16, nm, -} of the positions
     uint32_t T, SR, lmax, K, G;
     // hyper-parameter tables [G*K]
     const double *logPi, *chalf, *denom, *sdk;
@@ -104,21 +116,18 @@ struct BrrParams {
 };
 
 struct ItemTab {  // the window positions this CTA group works on, with everything the draw needs
+    WinMeta meta[kTabCap];        // chain mode: copied in by cp.async one dot phase ahead (64 bytes per position)
+    uint4 dir[kTabCap];           // chain mode: directory entry of this CTA's slice, same copy
     const uint64_t *ptr[kTabCap];
-    uint64_t rec[kTabCap];
-    double mave[kTabCap], mstd[kTabCap], beta[kTabCap], u[kTabCap], z[kTabCap];
-    uint32_t nw[kTabCap];   // u64 words of the slice block
-    uint32_t b1[kTabCap];   // first word of class 2   (0xFFFFFFFF = BED block)
-    uint32_t b2[kTabCap];   // first word of class "missing"
-    int32_t m[kTabCap];
-    int32_t grp[kTabCap];
+    uint32_t nw[kTabCap];         // u64 words of the slice block
+    uint32_t b1[kTabCap];         // first word of class 2   (0xFFFFFFFF = BED block)
+    uint32_t b2[kTabCap];         // first word of class "missing"
     // dot-phase work units: the slice blocks cut in pieces of (128 << ushift) words (BED: a quarter of that, a BED word
     // costs 32 gathers), so that the warps of the CTA share the chunk's words evenly whatever the marker sizes are
     uint16_t ucum[kTabCap + 1];   // exclusive prefix of the units per item
     uint32_t nunits, ushift;
     uint32_t tag_base, tag_W, tag_k0, tag_valid;  // which window chunk the table describes
 };
-
 
 struct ChgTab {  // changed markers of a window, staged for the epsilon update
     const uint64_t *ptr[kChgCap];
@@ -159,6 +168,11 @@ __device__ __forceinline__ Blk decode_block(uint64_t rr, uint32_t c, uint32_t S,
 
 __device__ __forceinline__ uint64_t ld_l2_u64(const uint64_t *p) {  // coherent at L2 (peer-written inbox data)
     return __ldcg(reinterpret_cast<const unsigned long long *>(p));
+}
+__device__ __forceinline__ uint4 ld_nc_v4(const uint4 *p) {  // read-only for the lifetime of the kernel
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -325,13 +339,13 @@ __device__ __forceinline__ void st_slot(uint4 *p, double val, uint32_t tag) {
 // The warp first collects the S slice partials of table entry k (window position p): every slot carries
 // the window tag next to the data, so no fence or arrival counter is needed. Lane kk < K then evaluates
 // mixture component kk; sums over components are taken in component order (same order as the reference).
-__device__ void draw_marker_warp(const BrrParams &P, const ItemTab *tab, uint32_t k, const HypTabs &H, uint32_t p, uint32_t q,
+__device__ __forceinline__ void draw_marker_warp(const BrrParams &P, const ItemTab *tab, uint32_t k, const HypTabs &H, uint32_t p, uint32_t q,
                                  uint32_t dbuf, uint32_t buf3, uint32_t tag, uint32_t lane) {
     const uint4 *sl = P.slots + (size_t)p * P.S;
     // A marker with a non-zero effect will change: its place in the window's list of changed markers is reserved now, so
     // that the round trip of the atomic overlaps the wait for the partials and the draw.
     uint32_t idx_early = 0xFFFFFFFFu;
-    if (lane == 0 && P.mode == MODE_CHAIN && tab->beta[k] != 0.0) idx_early = atomicAdd(P.chg_cnt + buf3, 1u);
+    if (lane == 0 && P.mode == MODE_CHAIN && tab->meta[k].beta != 0.0) idx_early = atomicAdd(P.chg_cnt + buf3, 1u);
     double acc = 0.0;
     for (uint32_t c0 = 0; c0 < P.S; c0 += 32) {
         const uint32_t cc = c0 + lane;
@@ -342,16 +356,16 @@ __device__ void draw_marker_warp(const BrrParams &P, const ItemTab *tab, uint32_
         }
     }
     const double sum = warp_sum(acc);  // xor tree: fixed order
-    const double mstd = tab->mstd[k];
+    const double mstd = tab->meta[k].mstd;
     const size_t slot = (size_t)dbuf * P.Wmax + p;
     if (P.mode == MODE_DOT) {
         if (lane == 0) P.num_out[q] = __dmul_rn(mstd, sum);
         return;
     }
-    const int32_t m = tab->m[k];
-    const int g = tab->grp[k];
+    const int32_t m = tab->meta[k].m;
+    const int g = tab->meta[k].grp;
     const uint32_t K = P.K;
-    const double beta_old = tab->beta[k];
+    const double beta_old = tab->meta[k].beta;
     double beta_new = 0.0, acum0 = 1.0;
     int comp = -1;
     if (P.grp_active[g]) {
@@ -364,7 +378,7 @@ __device__ void draw_marker_warp(const BrrParams &P, const ItemTab *tab, uint32_
             // log(pi) - 0.5*log(...) + muk*num*i_2sigE, evaluated left to right        (:1874-1876)
             logL = __dadd_rn(__dadd_rn(logL, -H.chalf[g * K + kk]), __dmul_rn(__dmul_rn(muk, num), P.i_2sigE));
         }
-        const double prob = tab->u[k];                                               // :1880
+        const double prob = tab->meta[k].u;                                               // :1880
         if (K * K <= 32u) {
             // All K terms of the cascade at once: lane j*K + i evaluates exp(logL[i] - logL[j]); term[j] = 1 / sum_i (in
             // component order), or 0 where the reference's 700-test fires (:1884-1890 for j = 0, :1915-1919 for j > 0).
@@ -401,7 +415,7 @@ __device__ void draw_marker_warp(const BrrParams &P, const ItemTab *tab, uint32_
         }
         }
         const double muc = __shfl_sync(0xffffffffu, muk, comp);
-        if (comp > 0) beta_new = __dadd_rn(muc, __dmul_rn(H.sdk[g * K + comp], tab->z[k]));  // :1901
+        if (comp > 0) beta_new = __dadd_rn(muc, __dmul_rn(H.sdk[g * K + comp], tab->meta[k].z));  // :1901
     }                                                                                // else :1924-1925
     if (lane == 0) {
         if (comp >= 0) {
@@ -412,13 +426,13 @@ __device__ void draw_marker_warp(const BrrParams &P, const ItemTab *tab, uint32_
         if (dbeta != 0.0 || idx_early != 0xFFFFFFFFu) {
             // (a reserved entry of a marker that drew its old value again carries 0 and does not count as a change)
             const double dbs = (dbeta != 0.0) ? __dmul_rn(dbeta, mstd) : 0.0;
-            P.dMave[slot] = tab->mave[k];
-            P.dRec[slot] = tab->rec[k];
+            P.dMave[slot] = tab->meta[k].mave;
+            P.dRec[slot] = tab->meta[k].rec;
             P.dB[slot] = dbs;
             const uint32_t idx = (idx_early != 0xFFFFFFFFu) ? idx_early : atomicAdd(P.chg_cnt + buf3, 1u);
             ChgEnt en;
             en.p = (P.pc.nranks > 1) ? (p / P.T) * P.pc.T_total + P.pc.t_first + (p % P.T) : p;
-            en.m = (uint32_t)m; en.dbs = dbs; en.mave = tab->mave[k]; en.rec = tab->rec[k];
+            en.m = (uint32_t)m; en.dbs = dbs; en.mave = tab->meta[k].mave; en.rec = tab->meta[k].rec;
             P.chg_list[(size_t)buf3 * P.Wmax + idx] = en;
             if (dbeta != 0.0) atomicAdd(&P.stats[5], 1ull);
         } else {
@@ -433,30 +447,75 @@ __device__ __forceinline__ void named_barrier(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// Item table of one window chunk: one thread per window position of this CTA group.
-// Threads [t0, t0+nt) take part; the blocks are prefetched into L2.
-__device__ __forceinline__ void build_table(ItemTab *tab, uint4 *udesc, const BrrParams &P, uint32_t r, uint32_t c, uint32_t base,
-                                            uint32_t W, uint32_t k0, uint32_t t0, uint32_t nt, bool prefetch) {
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Item table of one window chunk, step 1 (chain mode): asynchronous copy of the window-ordered marker data and of this
+// slice's directory entries into the table; one thread per window position of this CTA group, no registers held.
+__device__ __forceinline__ void stage_items(ItemTab *tab, const BrrParams &P, uint32_t r, uint32_t c, uint32_t base,
+                                            uint32_t W, uint32_t k0, uint32_t tl, uint32_t nt) {
     const uint32_t n_items = (W > r) ? (W - r + P.R - 1) / P.R : 0;
     const uint32_t nk = (n_items > k0) ? min((uint32_t)kTabCap, n_items - k0) : 0;
-    const uint32_t tl = threadIdx.x - t0;
+    const uint32_t Q = P.lmax * P.T;
+    for (uint32_t k = tl; k < nk; k += nt) {
+        const uint32_t q = base + r + P.R * (k0 + k);
+        const uint4 *mp = reinterpret_cast<const uint4 *>(P.meta + q);
+        uint4 *dst = reinterpret_cast<uint4 *>(&tab->meta[k]);
+        cp_async16(dst, mp); cp_async16(dst + 1, mp + 1); cp_async16(dst + 2, mp + 2); cp_async16(dst + 3, mp + 3);
+        cp_async16(&tab->dir[k], P.dirw + (size_t)c * Q + q);
+    }
+}
+// Unit modes (no window-ordered data): gather the marker data of the positions directly.
+__device__ __forceinline__ void fill_items_sync(ItemTab *tab, const BrrParams &P, uint32_t r, uint32_t c, uint32_t base,
+                                                uint32_t W, uint32_t k0, uint32_t tl, uint32_t nt) {
+    const uint32_t n_items = (W > r) ? (W - r + P.R - 1) / P.R : 0;
+    const uint32_t nk = (n_items > k0) ? min((uint32_t)kTabCap, n_items - k0) : 0;
     for (uint32_t k = tl; k < nk; k += nt) {
         const uint32_t p = r + P.R * (k0 + k);
         const int32_t m = P.order[base + p];
-        tab->m[k] = m;
+        WinMeta wm;
+        wm.m = m; wm.rec = 0; wm.mave = 0.0; wm.mstd = 0.0; wm.beta = 0.0; wm.u = 0.0; wm.z = 0.0; wm.grp = 0; wm.pad[0] = wm.pad[1] = 0;
         tab->nw[k] = 0;
         if (m >= 0) {
-            const uint64_t rr = P.rec[m];
-            const Blk b = decode_block(rr, c, P.S, P.L);
-            tab->rec[k] = rr;
-            tab->mave[k] = P.mave[m]; tab->mstd[k] = P.mstd[m]; tab->beta[k] = P.beta[m];
-            tab->grp[k] = P.grp[m];
-            tab->u[k] = P.u[base + p]; tab->z[k] = P.z[base + p];
+            wm.rec = P.rec[m]; wm.mave = P.mave[m]; wm.mstd = P.mstd[m]; wm.beta = P.beta[m]; wm.grp = P.grp[m];
+            wm.u = P.u[base + p]; wm.z = P.z[base + p];
+            const Blk b = decode_block(wm.rec, c, P.S, P.L);
             tab->ptr[k] = b.ptr; tab->nw[k] = b.nw; tab->b1[k] = b.b1; tab->b2[k] = b.b2;
-            if (prefetch) {
-                const char *a = reinterpret_cast<const char *>(b.ptr);
-                const char *e = a + (size_t)b.nw * 8;
-                for (a = reinterpret_cast<const char *>((uintptr_t)a & ~(uintptr_t)127); a < e; a += 128) prefetch_l2(a);
+        }
+        tab->meta[k] = wm;
+    }
+}
+
+// Step 2: slice block of every item from the staged data (prefetched into L2), work units of the dot phase, tags.
+// Threads [t0, t0+nt) take part.
+__device__ __forceinline__ void finish_table(ItemTab *tab, uint4 *udesc, const BrrParams &P, uint32_t r, uint32_t c, uint32_t base,
+                                             uint32_t W, uint32_t k0, uint32_t t0, uint32_t nt, bool prefetch) {
+    const uint32_t n_items = (W > r) ? (W - r + P.R - 1) / P.R : 0;
+    const uint32_t nk = (n_items > k0) ? min((uint32_t)kTabCap, n_items - k0) : 0;
+    const uint32_t tl = threadIdx.x - t0;
+    if (P.meta) {
+        for (uint32_t k = tl; k < nk; k += nt) {
+            tab->nw[k] = 0;
+            if (tab->meta[k].m >= 0) {
+                const uint64_t rr = tab->meta[k].rec;
+                Blk b;
+                if (rr & 1ull) {
+                    b = decode_block(rr, c, P.S, P.L);
+                } else {
+                    const uint4 dv = tab->dir[k];
+                    const uint32_t w1 = ((dv.y & 0xFFFFu) + 3) / 4, w2 = ((dv.y >> 16) + 3) / 4, wm = (dv.z + 3) / 4;
+                    b.ptr = reinterpret_cast<const uint64_t *>(reinterpret_cast<const uint8_t *>(rr) + dir_bytes(P.S)) + dv.x;
+                    b.b1 = w1; b.b2 = w1 + w2; b.nw = w1 + w2 + wm;
+                }
+                tab->ptr[k] = b.ptr; tab->nw[k] = b.nw; tab->b1[k] = b.b1; tab->b2[k] = b.b2;
+                if (prefetch) {
+                    const char *pa = reinterpret_cast<const char *>(b.ptr);
+                    const char *pe = pa + (size_t)b.nw * 8;
+                    for (pa = reinterpret_cast<const char *>((uintptr_t)pa & ~(uintptr_t)127); pa < pe; pa += 128) prefetch_l2(pa);
+                }
             }
         }
     }
@@ -637,11 +696,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
 
     uint32_t bar_target = 0;
     __shared__ long long tph[8];             // phase cycle counters of thread 0 (shared memory: keeps 32 registers free)
-    __shared__ unsigned long long gts[8];
-    if (tid < 8) { tph[tid] = 0; gts[tid] = 0; }
+    __shared__ unsigned long long gts[16];
+    if (tid < 8) tph[tid] = 0;
+    if (tid < 16) gts[tid] = 0;
     long long tclk = clock64();
 #define HB_PHASE(i) do { if (tid == 0) { long long t_ = clock64(); tph[i] += t_ - tclk; tclk = t_; \
         if (P.cta_cycles && win == 10) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); gts[i] = g_; } } } while (0)
+#define HB_STAMP(i, cond) do { if (P.cta_cycles && win == 10 && (cond)) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); gts[i] = g_; } } while (0)
     double off = 0.0;
     uint32_t j0 = 0, since = 0, win = 0;
     uint32_t n_sync = 0;
@@ -663,10 +724,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                 // ---- 1. item table (normally prebuilt during the previous window) -------
                 if (!(tab->tag_valid && tab->tag_base == base && tab->tag_W == W && tab->tag_k0 == k0)) {
                     __syncthreads();
-                    build_table(tab, udesc, P, r, c, base, W, k0, 0, blockDim.x, false);
+                    if (P.meta) { stage_items(tab, P, r, c, base, W, k0, tid, blockDim.x); cp_async_wait_all(); }
+                    else fill_items_sync(tab, P, r, c, base, W, k0, tid, blockDim.x);
+                    __syncthreads();
+                    finish_table(tab, udesc, P, r, c, base, W, k0, 0, blockDim.x, false);
                 }
                 __syncthreads();
                 HB_PHASE(0);
+                // the next window's marker data start their way into the other table now (speculating that this window
+                // ends with a synchronisation: next window = SR steps); they land during the dot phase
+                const bool stage_next = (P.mode == MODE_CHAIN && k0 + kTabCap >= n_items && j0 + n < P.lmax);
+                if (stage_next) stage_items(&tabs[(win + 1u) & 1u], P, r, c, (j0 + n) * P.T, min(SR, P.lmax - (j0 + n)) * P.T, 0, tid, blockDim.x);
                 // ---- 2. dot: warp w takes the units w, w + 16, ...; the words of the next two units are in flight while
                 //         the current one gathers from shared memory (three register sets in rotation, no copies)
                 {
@@ -676,7 +744,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                     uint4 da, db, dc;
                     uint64_t xa[4], xb[4], xc[4];
 #define HB_FETCH(D, X, UU) do { D = ((UU) < nun) ? udesc[UU] : none; load_unit(D, X, lane, padw); } while (0)
-#define HB_COMPUTE(D, X) do { double acc_ = dot_unit(D, X, tab->mave[D.w >> 16], E_s, lane, padw); acc_ = warp_sum(acc_); \
+#define HB_COMPUTE(D, X) do { double acc_ = dot_unit(D, X, tab->meta[D.w >> 16].mave, E_s, lane, padw); acc_ = warp_sum(acc_); \
                               if (lane == 0) upart[u] = acc_; u += kWarps; } while (0)
                     HB_FETCH(da, xa, u);
                     HB_FETCH(db, xb, u + kWarps);
@@ -693,24 +761,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
 #undef HB_FETCH
 #undef HB_COMPUTE
                 }
+                cp_async_wait_all();
                 __syncthreads();
                 HB_PHASE(1);
                 // ---- 3. publish the slice partials (data + tag in one 16-byte store, no fence) ----
                 const uint32_t tag = win + 1u;
                 if (tid < nk) {
                     const uint32_t k = tid, p = r + R * (k0 + k);
-                    if (tab->m[k] < 0) {
+                    if (tab->meta[k].m < 0) {
                         if (P.mode == MODE_CHAIN) P.dB[(size_t)dbuf * P.Wmax + p] = 0.0;  // padded task step (:2029-2034)
                     } else {
                         // partial of num/mstd: sum_1 + 2 sum_2 + mave*sum_M - mave*sum_slice   (:327-339)
                         double part = 0.0;
                         for (uint32_t u = tab->ucum[k], u1 = tab->ucum[k + 1]; u < u1; u++) part += upart[u];  // fixed order
-                        st_slot(P.slots + (size_t)p * S + c, fma(-tab->mave[k], slice_sum, part), tag);
+                        st_slot(P.slots + (size_t)p * S + c, fma(-tab->meta[k].mave, slice_sum, part), tag);
                     }
                 }
+                HB_STAMP(11, tid == 0);
                 if (tid < kTabCap) {  // traffic counters (warps 0..3 hold the items): one plain add per warp
                     uint32_t v = 0, vb = 0;
-                    if (tid < nk && tab->m[tid] >= 0) {
+                    if (tid < nk && tab->meta[tid].m >= 0) {
                         if (tab->b1[tid] == 0xFFFFFFFFu) vb = 1u; else v = 4u * tab->nw[tid];
                     }
                     v = __reduce_add_sync(0xffffffffu, v);
@@ -722,14 +792,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                 if (warp < kDrawWarps) {
                     const uint32_t kf = (c + S - (k0 % S)) % S;  // first table entry owned by this CTA
                     for (uint32_t k = kf + warp * S; k < nk; k += kDrawWarps * S)
-                        if (tab->m[k] >= 0) draw_marker_warp(P, tab, k, H, r + R * (k0 + k), base + r + R * (k0 + k), dbuf, win % 3u, tag, lane);
-                } else if (P.mode == MODE_CHAIN && k0 + kTabCap >= n_items) {
-                    // speculate that this window ends with a synchronisation: next window = SR steps
-                    const uint32_t j1 = j0 + n;
-                    if (j1 < P.lmax) {
-                        const uint32_t n1 = min(SR, P.lmax - j1);
-                        build_table(&tabs[(win + 1u) & 1u], udesc, P, r, c, j1 * P.T, n1 * P.T, 0, kDrawWarps * 32, blockDim.x - kDrawWarps * 32, !(P.flags & 1u));
-                    }
+                        if (tab->meta[k].m >= 0) draw_marker_warp(P, tab, k, H, r + R * (k0 + k), base + r + R * (k0 + k), dbuf, win % 3u, tag, lane);
+                    HB_STAMP(8 + (warp & 1u), lane == 0 && warp < 2);
+                } else if (stage_next) {
+                    const uint32_t j1 = j0 + n, n1 = min(SR, P.lmax - j1);
+                    finish_table(&tabs[(win + 1u) & 1u], udesc, P, r, c, j1 * P.T, n1 * P.T, 0, kDrawWarps * 32, blockDim.x - kDrawWarps * 32, !(P.flags & 1u));
+                    HB_STAMP(10, tid == kDrawWarps * 32);
                 }
                 __syncthreads();  // table reuse
                 HB_PHASE(2);
@@ -953,7 +1021,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
         }
     }
     if (P.cta_cycles && tid == 0)
-        for (int i = 0; i < 8; i++) P.cta_cycles[(size_t)blockIdx.x * 8 + i] = gts[i];
+        for (int i = 0; i < 16; i++) P.cta_cycles[(size_t)blockIdx.x * 16 + i] = gts[i];
     // traffic counters (lane 0 of every warp holds a share)
     __syncthreads();
     if (tid == 0) {
@@ -965,27 +1033,83 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
 }
 
 // ---------------------------------------------------------------------------------
-// Window-ordered inputs of one iteration: order[q], u[q], z[q] with q = j*T + t.
-// perm holds the task-local marker order of every local task block (concatenated);
-// ut/zt != NULL: positional tape values indexed like perm; else RNG spec v1 (Philox).
-__global__ void k_window_order(const int32_t *__restrict__ perm, const double *__restrict__ ut,
+// Window-ordered inputs of one iteration. One block per step j: position q = j*T + slot holds the marker of ONE local
+// task at that step. perm holds the task-local marker order of every local task block (concatenated);
+// ut/zt != NULL: positional tape values indexed like perm; else RNG spec v1 (Philox), keyed by the task, not by the slot.
+// wts != NULL (chain mode, T <= kBalanceMaxT): the tasks of a step are laid out heaviest marker first (ties: lower task
+// first). The marker loop deals the positions of a window round-robin to its CTA groups, so every group gets an equal
+// share of the window's non-zeros; the order of the positions inside a step has no other meaning than the (fixed) order
+// in which the epsilon updates of a window are summed.
+constexpr uint32_t kBalanceMaxT = 1024;
+__global__ void __launch_bounds__(256) k_window_order(const int32_t *__restrict__ perm, const double *__restrict__ ut,
                                const double *__restrict__ zt, const int32_t *__restrict__ task_len,
                                const int32_t *__restrict__ task_off, uint32_t T, uint32_t lmax, uint32_t seed,
                                uint32_t iteration, uint32_t task_first, int32_t *__restrict__ order,
-                               double *__restrict__ u, double *__restrict__ z) {
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= lmax * T) return;
-    const uint32_t t = q % T, j = q / T;
-    if ((int32_t)j >= task_len[t]) { order[q] = -1; u[q] = 0.0; z[q] = 0.0; return; }  // :2029-2034
-    const uint32_t o = (uint32_t)task_off[t] + j;
-    order[q] = task_off[t] + perm[o];
-    if (ut) { u[q] = ut[o]; z[q] = zt[o]; return; }
-    uint32_t w[4];
-    philox4x32(j, iteration, 0x48594452u, 0u, seed, task_first + t, w);
-    u[q] = ((double)(w[0] >> 5) * 67108864.0 + (double)(w[1] >> 6)) * (1.0 / 9007199254740992.0);
-    const double u1 = ((double)w[2] + 0.5) * (1.0 / 4294967296.0);
-    const double u2 = ((double)w[3] + 0.5) * (1.0 / 4294967296.0);
-    z[q] = sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925 * u2);
+                               double *__restrict__ u, double *__restrict__ z,
+                               const uint64_t *__restrict__ rec, const double *__restrict__ mave, const double *__restrict__ mstd,
+                               const double *__restrict__ beta, const int32_t *__restrict__ grp, const uint32_t *__restrict__ wts,
+                               uint32_t S, WinMeta *__restrict__ meta, uint4 *__restrict__ dirw) {
+    __shared__ unsigned long long key[kBalanceMaxT];
+    const uint32_t j = blockIdx.x;
+    const size_t Q = (size_t)lmax * T;
+    const bool balance = (wts != nullptr) && T >= 2 && T <= kBalanceMaxT;
+    if (balance) {
+        uint32_t n = 1;
+        while (n < T) n <<= 1;
+        for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) {
+            unsigned long long k = 0ull;  // padding of the bitonic network sorts last
+            if (t < T) {
+                const unsigned long long w = ((int32_t)j < task_len[t]) ? (unsigned long long)wts[task_off[t] + perm[task_off[t] + j]] + 2ull : 1ull;
+                k = (w << 16) | (unsigned long long)(0xFFFFu - t);
+            }
+            key[t] = k;
+        }
+        __syncthreads();
+        for (uint32_t sz = 2; sz <= n; sz <<= 1) {
+            for (uint32_t st = sz >> 1; st > 0; st >>= 1) {
+                for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+                    const uint32_t l = i ^ st;
+                    if (l > i) {
+                        const bool desc = ((i & sz) == 0);  // overall descending order
+                        const unsigned long long a = key[i], b = key[l];
+                        if ((a < b) == desc) { key[i] = b; key[l] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    for (uint32_t slot = threadIdx.x; slot < T; slot += blockDim.x) {
+        const uint32_t t = balance ? (0xFFFFu - (uint32_t)(key[slot] & 0xFFFFull)) : slot;
+        const size_t q = (size_t)j * T + slot;
+        WinMeta wm;
+        wm.rec = 0; wm.mave = 0.0; wm.mstd = 0.0; wm.beta = 0.0; wm.u = 0.0; wm.z = 0.0; wm.m = -1; wm.grp = 0; wm.pad[0] = wm.pad[1] = 0;
+        if ((int32_t)j >= task_len[t]) {  // :2029-2034
+            order[q] = -1; u[q] = 0.0; z[q] = 0.0;
+        } else {
+            const uint32_t o = (uint32_t)task_off[t] + j;
+            const int32_t m = task_off[t] + perm[o];
+            order[q] = m;
+            if (ut) {
+                wm.u = ut[o]; wm.z = zt[o];
+            } else {
+                uint32_t w[4];
+                philox4x32(j, iteration, 0x48594452u, 0u, seed, task_first + t, w);
+                wm.u = ((double)(w[0] >> 5) * 67108864.0 + (double)(w[1] >> 6)) * (1.0 / 9007199254740992.0);
+                const double u1 = ((double)w[2] + 0.5) * (1.0 / 4294967296.0);
+                const double u2 = ((double)w[3] + 0.5) * (1.0 / 4294967296.0);
+                wm.z = sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925 * u2);
+            }
+            u[q] = wm.u; z[q] = wm.z;
+            if (meta) { wm.m = m; wm.rec = rec[m]; wm.mave = mave[m]; wm.mstd = mstd[m]; wm.beta = beta[m]; wm.grp = grp[m]; }
+        }
+        if (!meta) continue;
+        meta[q] = wm;
+        if (wm.m >= 0 && !(wm.rec & 1ull)) {
+            const uint32_t *dir = reinterpret_cast<const uint32_t *>(wm.rec);
+            for (uint32_t c = 0; c < S; c++) dirw[(size_t)c * Q + q] = make_uint4(dir[c * 3], dir[c * 3 + 1], dir[c * 3 + 2], 0u);
+        }
+    }
 }
 
 // sum of beta^2 per group over the local markers (src/BayesRRm.cpp:2496-2499); block g = group g

@@ -113,6 +113,10 @@ struct hb_ctx {
     DevBuf<int32_t> d_comp, d_cass;
     // per-iteration inputs
     DevBuf<int32_t> d_order, d_perm, d_task_len, d_task_off;
+    DevBuf<uint32_t> d_wts;   // per marker: stored non-zeros (BED: N/2), the weight used to balance the CTA groups
+    bool balance = false;
+    DevBuf<WinMeta> d_wmeta;   // window-ordered marker data of the iteration
+    DevBuf<uint4> d_dirw;     // window-ordered slice directory entries [S][lmax*T]
     DevBuf<double> d_u, d_z, d_ut, d_zt;
     DevBuf<double> d_hyp;
     DevBuf<uint8_t> d_active;
@@ -408,7 +412,7 @@ int hb_create(const hb_config *cfg, hb_ctx **out) {
     HB_CUDA(cudaMemset(c->d_active.p, 0, c->G));
     HB_TRY(c->d_bar.alloc(1)); HB_TRY(c->d_stats.alloc(16));
     c->debug_cycles = getenv("HB_DEBUG_CYCLES") != nullptr;
-    HB_TRY(c->d_ctacyc.alloc((size_t)c->S * c->R * 8));
+    HB_TRY(c->d_ctacyc.alloc((size_t)c->S * c->R * 16));
     HB_CUDA(cudaMemset(c->d_stats.p, 0, 16 * sizeof(unsigned long long)));
     HB_TRY(c->d_order.alloc(1)); HB_TRY(c->d_u.alloc(1)); HB_TRY(c->d_z.alloc(1)); HB_TRY(c->d_num.alloc(1));
     HB_TRY(ensure_scratch(c.get(), 256));
@@ -912,6 +916,14 @@ int hb_brr_init(hb_ctx *c, const double *y, const int32_t *groups, const double 
     HB_CUDA(cudaMemcpy(c->d_task_off.p, to.data(), sizeof(int32_t) * c->T, cudaMemcpyHostToDevice));
     const size_t Q = (size_t)c->lmax * c->T;
     HB_TRY(c->d_order.ensure(Q)); HB_TRY(c->d_u.ensure(Q)); HB_TRY(c->d_z.ensure(Q));
+    HB_TRY(c->d_wmeta.ensure(Q)); HB_TRY(c->d_dirw.ensure((size_t)c->S * Q));
+    c->balance = !getenv("HB_NO_BALANCE");
+    {
+        std::vector<uint32_t> w(c->M);
+        for (uint32_t m = 0; m < c->M; m++) w[m] = c->is_bed[m] ? c->N / 2 : (c->n1[m] + c->n2[m] + c->nm[m]);
+        HB_TRY(c->d_wts.alloc(c->M));
+        HB_CUDA(cudaMemcpy(c->d_wts.p, w.data(), sizeof(uint32_t) * c->M, cudaMemcpyHostToDevice));
+    }
     HB_TRY(c->d_perm.ensure(c->M)); HB_TRY(c->d_ut.ensure(c->M)); HB_TRY(c->d_zt.ensure(c->M));
     HB_TRY(ensure_scratch(c, c->SR * c->T));
     HB_TRY(ensure_pin(c, 8 + 2 * (size_t)c->S + G + (size_t)G * K + 32));
@@ -978,9 +990,11 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
         HB_CUDA(cudaMemcpyAsync(c->d_ut.p, tape->u, sizeof(double) * M, cudaMemcpyHostToDevice, st));
         HB_CUDA(cudaMemcpyAsync(c->d_zt.p, tape->z, sizeof(double) * M, cudaMemcpyHostToDevice, st));
     }
-    k_window_order<<<(Q + 255) / 256, 256, 0, st>>>(c->d_perm.p, tape ? c->d_ut.p : nullptr, tape ? c->d_zt.p : nullptr,
+    k_window_order<<<c->lmax, std::min(256u, (T + 31u) & ~31u), 0, st>>>(c->d_perm.p, tape ? c->d_ut.p : nullptr, tape ? c->d_zt.p : nullptr,
                                                      c->d_task_len.p, c->d_task_off.p, T, c->lmax, c->seed, c->iteration,
-                                                     c->t_first, c->d_order.p, c->d_u.p, c->d_z.p);
+                                                     c->t_first, c->d_order.p, c->d_u.p, c->d_z.p,
+                                                     c->d_rec.p, c->d_mave.p, c->d_mstd.p, c->d_beta.p, c->d_grp.p,
+                                                     c->balance ? c->d_wts.p : nullptr, c->S, c->d_wmeta.p, c->d_dirw.p);
     HB_CUDA(cudaGetLastError());
 
     // ---- hyper-parameter tables (:1721-1723, 1750, 1863-1876, 1901)
@@ -1007,6 +1021,7 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
     BrrParams P;
     fill_params(c, P);
     P.mode = MODE_CHAIN; P.T = T; P.SR = c->SR; P.lmax = c->lmax;
+    P.meta = c->d_wmeta.p; P.dirw = c->d_dirw.p;
     P.shift_in = c->shift;  // fold the accumulated constant into the stored residual
     P.i_2sigE = 1.0 / (2.0 * c->sigmaE);
     HB_CUDA(cudaEventRecord(c->ev[1], st));
@@ -1045,17 +1060,17 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
 
     if (c->debug_cycles) {  // developer aid: spread of the per-CTA phase cycles
         const size_t nc = (size_t)c->S * c->R;
-        std::vector<unsigned long long> cy(nc * 8);
-        cudaMemcpy(cy.data(), c->d_ctacyc.p, sizeof(unsigned long long) * nc * 8, cudaMemcpyDeviceToHost);
+        std::vector<unsigned long long> cy(nc * 16);
+        cudaMemcpy(cy.data(), c->d_ctacyc.p, sizeof(unsigned long long) * nc * 16, cudaMemcpyDeviceToHost);
         // globaltimer stamps (ns) of window 10 at the end of each phase, relative to the earliest "table done"
         unsigned long long t0 = ~0ull;
-        for (size_t b = 0; b < nc; b++) t0 = std::min(t0, cy[b * 8 + 0]);
-        const int ord[7] = {0, 1, 2, 3, 4, 7, 5};
-        const char *nm[7] = {"tab", "dot", "pub", "bar", "upd0", "updA", "sum"};
-        for (int i = 0; i < 7; i++) {
+        for (size_t b = 0; b < nc; b++) t0 = std::min(t0, cy[b * 16 + 0]);
+        const int ord[11] = {0, 1, 11, 8, 9, 10, 2, 3, 4, 7, 5};
+        const char *nm[11] = {"tab", "dot", "publish", "draws of warp 0", "draws of warp 1", "next table", "pub", "bar", "upd0", "updA", "sum"};
+        for (int i = 0; i < 11; i++) {
             double mn = 1e300, mx = 0, sm = 0;
-            for (size_t b = 0; b < nc; b++) { const double v = (double)(cy[b * 8 + ord[i]] - t0); mn = std::min(mn, v); mx = std::max(mx, v); sm += v; }
-            fprintf(stderr, "[hb window 10, ns since first CTA started its dot] end of %-5s min %8.0f mean %8.0f max %8.0f\n", nm[i], mn, sm / (double)nc, mx);
+            for (size_t b = 0; b < nc; b++) { const double v = (double)(cy[b * 16 + ord[i]] - t0); mn = std::min(mn, v); mx = std::max(mx, v); sm += v; }
+            fprintf(stderr, "[hb window 10, ns since first CTA started its dot] end of %-16s min %8.0f mean %8.0f max %8.0f\n", nm[i], mn, sm / (double)nc, mx);
         }
     }
     {
