@@ -43,12 +43,19 @@ struct __align__(16) WinMeta {  // 64 bytes
     uint64_t rec;
     double mave, mstd, beta, u, z;
     int32_t m, grp;
-    uint32_t pad[2];
+    uint32_t rec_bytes;  // size of the record (what a peer GPU needs of it)
+    uint32_t pad;
 };
 
 constexpr uint32_t kMaxRanks = 8;
 constexpr uint32_t kMaxMerged = 1024;        // changed markers of one window over all GPUs (shared-memory sort)
-constexpr size_t kInboxHeader = 16 + (size_t)kMaxMerged * sizeof(ChgEnt);
+// Inbox region of one (window parity, source GPU): 16-byte header {count | window tag << 32}, kMaxMerged list entries and
+// the genotype records behind them. Entries and records travel in the LL form: every 16-byte unit is
+// {data lo, tag, data hi, tag} with tag = the window's sequence number, so that the receiver can tell, unit by unit,
+// whether the data of THIS window have arrived -- no fence and no arrival counter at system scope (a
+// red.release.sys per CTA and window cost 4-5 us on NVLink).
+constexpr size_t kLLEntry = 2 * sizeof(ChgEnt);
+constexpr size_t kInboxHeader = 16 + (size_t)kMaxMerged * kLLEntry;
 
 // Exchange of the changed markers between the GPUs of one node (replaces MPI_Allreduce of deltaEps,
 // src/BayesRRm.cpp:2051, 2456): every GPU pushes (position, deltaBeta*mstd, mave, genotype record) of its
@@ -99,8 +106,9 @@ struct BrrParams {
     double i_2sigE, dNm1;
     // scratch
     uint4 *slots;          // [Wmax*S] slice partials as {lo, tag, hi, tag}: data and flag travel together
-    uint32_t *chg_cnt;     // [3] changed markers of a window (triple buffered)
+    unsigned long long *chg_cnt;  // [3] per window (triple buffered): changed markers | 16-byte units of their records << 32
     ChgEnt *chg_list;      // [3*Wmax] their (position, deltaBeta*mstd, mave, record), in arrival order
+    uint32_t *chg_off;     // [3*Wmax] multi-GPU: place of the record in the peers' inboxes (LL units), same order
     double *dB;            // [2*Wmax] deltaBeta*mstd per window position, double buffered
     double *dMave;         // [2*Wmax] mave of the changed marker
     uint64_t *dRec;        // [2*Wmax] its record
@@ -134,6 +142,7 @@ struct ChgTab {  // changed markers of a window, staged for the epsilon update
     double dbs[kChgCap];
     double mave[kChgCap];
     uint32_t nw[kChgCap], b1[kChgCap], b2[kChgCap];
+    uint32_t ll[kChgCap];       // != 0: the block sits in an inbox in the LL form with this tag (ptr counts 16-byte units)
     uint32_t cum[kChgCap + 1];  // exclusive prefix of nw
 };
 
@@ -166,6 +175,23 @@ __device__ __forceinline__ Blk decode_block(uint64_t rr, uint32_t c, uint32_t S,
     return b;
 }
 
+__device__ __forceinline__ void st_ll(uint4 *dst, uint64_t v, uint32_t tag) {
+    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"((uint32_t)v), "r"(tag), "r"((uint32_t)(v >> 32)), "r"(tag) : "memory");
+}
+// waits for unit `src` of this window; *err is raised if it does not come (dead peer)
+__device__ __forceinline__ uint64_t ld_ll(const uint4 *src, uint32_t tag, uint32_t *err) {
+    uint4 v;
+    for (uint32_t it = 0;; it++) {
+        asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src) : "memory");
+        if (v.y == tag && v.w == tag) break;
+        if (it > (1u << 26)) { atomicExch(err, 2u); break; }
+    }
+    return ((uint64_t)v.z << 32) | v.x;
+}
+__device__ __forceinline__ uint32_t ld_ll_u32(const uint4 *rec, uint32_t byte_off, uint32_t tag, uint32_t *err) {
+    const uint64_t v = ld_ll(rec + byte_off / 8u, tag, err);
+    return (byte_off & 4u) ? (uint32_t)(v >> 32) : (uint32_t)v;
+}
 __device__ __forceinline__ uint64_t ld_l2_u64(const uint64_t *p) {  // coherent at L2 (peer-written inbox data)
     return __ldcg(reinterpret_cast<const unsigned long long *>(p));
 }
@@ -300,6 +326,32 @@ __device__ __forceinline__ double block_sum(double v, double *red /*[32]*/) {
     return s;
 }
 
+// slice block c of a record that sits in an inbox in the LL form; the returned ptr counts 16-byte units
+__device__ __forceinline__ Blk decode_block_ll(const uint4 *rec, bool bed, uint32_t c, uint32_t S, uint32_t L, uint32_t tag, uint32_t *err) {
+    Blk b;
+    if (bed) {
+        b.ptr = reinterpret_cast<const uint64_t *>(rec + (size_t)c * (L / 32));
+        b.nw = L / 32; b.b1 = 0xFFFFFFFFu; b.b2 = 0xFFFFFFFFu;
+    } else {
+        // the 12-byte directory entry lies in one or two 8-byte words: both units are requested together
+        const uint32_t bo = c * 12u, u0 = bo / 8u, u1 = (bo + 8u) / 8u;
+        uint4 a, d;
+        for (uint32_t it = 0;; it++) {
+            asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(rec + u0) : "memory");
+            asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w) : "l"(rec + u1) : "memory");
+            if (a.y == tag && a.w == tag && d.y == tag && d.w == tag) break;
+            if (it > (1u << 26)) { atomicExch(err, 2u); break; }
+        }
+        uint32_t st, n12, nm;
+        if (bo & 4u) { st = a.z; n12 = d.x; nm = d.z; }   // entry starts in the upper half of word u0, rest = word u1 = u0 + 1
+        else { st = a.x; n12 = a.z; nm = d.x; }           // u1 = u0 + 1: third field in its lower half
+        const uint32_t w1 = ((n12 & 0xFFFFu) + 3) / 4, w2 = ((n12 >> 16) + 3) / 4, wm = (nm + 3) / 4;
+        b.ptr = reinterpret_cast<const uint64_t *>(rec + dir_bytes(S) / 8u + st);
+        b.b1 = w1; b.b2 = w1 + w2; b.nw = w1 + w2 + wm;
+    }
+    return b;
+}
+
 struct HypTabs {
     const double *logPi, *chalf, *denom, *sdk;
 };
@@ -344,8 +396,10 @@ __device__ __forceinline__ void draw_marker_warp(const BrrParams &P, const ItemT
     const uint4 *sl = P.slots + (size_t)p * P.S;
     // A marker with a non-zero effect will change: its place in the window's list of changed markers is reserved now, so
     // that the round trip of the atomic overlaps the wait for the partials and the draw.
-    uint32_t idx_early = 0xFFFFFFFFu;
-    if (lane == 0 && P.mode == MODE_CHAIN && tab->meta[k].beta != 0.0) idx_early = atomicAdd(P.chg_cnt + buf3, 1u);
+    // The same atomic reserves the place of its record in the peers' inboxes (multi-GPU).
+    const unsigned long long resv = 1ull | ((P.pc.nranks > 1) ? ((unsigned long long)(tab->meta[k].rec_bytes >> 3) << 32) : 0ull);  // LL units = 8-byte words
+    unsigned long long idx_early = ~0ull;
+    if (lane == 0 && P.mode == MODE_CHAIN && tab->meta[k].beta != 0.0) idx_early = atomicAdd(P.chg_cnt + buf3, resv);
     double acc = 0.0;
     for (uint32_t c0 = 0; c0 < P.S; c0 += 32) {
         const uint32_t cc = c0 + lane;
@@ -423,17 +477,19 @@ __device__ __forceinline__ void draw_marker_warp(const BrrParams &P, const ItemT
             P.comp[m] = comp;
         }
         const double dbeta = beta_old - beta_new;                                    // :1933
-        if (dbeta != 0.0 || idx_early != 0xFFFFFFFFu) {
+        if (dbeta != 0.0 || idx_early != ~0ull) {
             // (a reserved entry of a marker that drew its old value again carries 0 and does not count as a change)
             const double dbs = (dbeta != 0.0) ? __dmul_rn(dbeta, mstd) : 0.0;
             P.dMave[slot] = tab->meta[k].mave;
             P.dRec[slot] = tab->meta[k].rec;
             P.dB[slot] = dbs;
-            const uint32_t idx = (idx_early != 0xFFFFFFFFu) ? idx_early : atomicAdd(P.chg_cnt + buf3, 1u);
+            const unsigned long long got = (idx_early != ~0ull) ? idx_early : atomicAdd(P.chg_cnt + buf3, resv);
+            const uint32_t idx = (uint32_t)got, off_units = (uint32_t)(got >> 32);
             ChgEnt en;
             en.p = (P.pc.nranks > 1) ? (p / P.T) * P.pc.T_total + P.pc.t_first + (p % P.T) : p;
             en.m = (uint32_t)m; en.dbs = dbs; en.mave = tab->meta[k].mave; en.rec = tab->meta[k].rec;
             P.chg_list[(size_t)buf3 * P.Wmax + idx] = en;
+            if (P.pc.nranks > 1) P.chg_off[(size_t)buf3 * P.Wmax + idx] = off_units;  // pushed to the peers after the grid barrier
             if (dbeta != 0.0) atomicAdd(&P.stats[5], 1ull);
         } else {
             P.dB[slot] = 0.0;
@@ -477,10 +533,11 @@ __device__ __forceinline__ void fill_items_sync(ItemTab *tab, const BrrParams &P
         const uint32_t p = r + P.R * (k0 + k);
         const int32_t m = P.order[base + p];
         WinMeta wm;
-        wm.m = m; wm.rec = 0; wm.mave = 0.0; wm.mstd = 0.0; wm.beta = 0.0; wm.u = 0.0; wm.z = 0.0; wm.grp = 0; wm.pad[0] = wm.pad[1] = 0;
+        wm.m = m; wm.rec = 0; wm.mave = 0.0; wm.mstd = 0.0; wm.beta = 0.0; wm.u = 0.0; wm.z = 0.0; wm.grp = 0; wm.rec_bytes = 0; wm.pad = 0;
         tab->nw[k] = 0;
         if (m >= 0) {
             wm.rec = P.rec[m]; wm.mave = P.mave[m]; wm.mstd = P.mstd[m]; wm.beta = P.beta[m]; wm.grp = P.grp[m];
+            if (P.pc.rec_bytes) wm.rec_bytes = P.pc.rec_bytes[m];
             wm.u = P.u[base + p]; wm.z = P.z[base + p];
             const Blk b = decode_block(wm.rec, c, P.S, P.L);
             tab->ptr[k] = b.ptr; tab->nw[k] = b.nw; tab->b1[k] = b.b1; tab->b2[k] = b.b2;
@@ -585,7 +642,7 @@ constexpr uint32_t kDrawWarps = 8;       // warps that collect partials and draw
 // barrier per marker keeps the order of additions to an individual fixed); BED blocks have length 0 in the
 // flattened space and are applied by the whole CTA in their turn.
 __device__ __forceinline__ void apply_staged(ChgTab *chg, uint32_t nx, double *__restrict__ E_s, uint32_t L, double &added,
-                                             double &off, unsigned long long *nnz_upd) {
+                                             double &off, unsigned long long *nnz_upd, uint32_t *llerr) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (warp == 0) {  // exclusive prefix of the block lengths (nx <= 64)
         const uint32_t a0 = (lane < nx && chg->b1[lane] != 0xFFFFFFFFu) ? chg->nw[lane] : 0u;
@@ -616,7 +673,7 @@ __device__ __forceinline__ void apply_staged(ChgTab *chg, uint32_t nx, double *_
                 const uint32_t x = find_entry(chg->cum, nx, f);
                 const uint32_t w = f - chg->cum[x];
                 we[i] = x;
-                wd[i] = ld_l2_u64(chg->ptr[x] + w);
+                wd[i] = chg->ll[x] ? ld_ll(reinterpret_cast<const uint4 *>(chg->ptr[x]) + w, chg->ll[x], llerr) : ld_l2_u64(chg->ptr[x] + w);
                 dd[i] = ((w < chg->b1[x]) ? 1.0 : ((w < chg->b2[x]) ? 2.0 : chg->mave[x])) * chg->dbs[x];
             }
         }
@@ -629,7 +686,8 @@ __device__ __forceinline__ void apply_staged(ChgTab *chg, uint32_t nx, double *_
                 const uint32_t nwb = chg->nw[x];
                 const double dbs = chg->dbs[x], mave = chg->mave[x];
                 for (uint32_t w = tid; w < nwb; w += blockDim.x)
-                    added += apply_bed_word(ld_l2_u64(chg->ptr[x] + w), w, dbs, mave, E_s, lane);
+                    added += apply_bed_word(chg->ll[x] ? ld_ll(reinterpret_cast<const uint4 *>(chg->ptr[x]) + w, chg->ll[x], llerr) : ld_l2_u64(chg->ptr[x] + w),
+                                            w, dbs, mave, E_s, lane);
             } else {
 #pragma unroll
                 for (uint32_t i = 0; i < kApplyQ; i++)
@@ -804,7 +862,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
             }
             if (P.mode == MODE_DOT) break;  // single window, nothing to apply
             // ---- 4. the one grid barrier of the window --------------------------------
-            grid_barrier(P.bar, bar_target, nctas);
+            __syncthreads();
+            bar_target += nctas;
+            if (tid == 0) red_release_add_u32(P.bar, 1u);  // arrive (release: the CTA's results, ordered before by bar.sync)
+            if (tid == 0) { while (ld_acquire_u32(P.bar) < bar_target) { } }
+            __syncthreads();
             HB_PHASE(3);
         }
 
@@ -815,69 +877,75 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
         uint32_t nlist = 0xFFFFFFFFu;
         if (P.mode == MODE_CHAIN) {
             const uint32_t buf3 = win % 3u, par = win & 1u, NR = P.pc.nranks, me = P.pc.rank;
+            const unsigned long long seq_w = P.pc.seq_base + win + 1ull;  // tag of this window's data in the inboxes
             const ChgEnt *llist = P.chg_list + (size_t)buf3 * P.Wmax;
-            // single GPU: the first entries are read together with the count (one L2 round trip instead of two)
+            // the first entries are read together with the count (one L2 round trip instead of two)
             constexpr uint32_t kSpec = 64;
             ChgEnt spec;
             spec.p = 0xFFFFFFFFu;
-            if (NR == 1 && tid < kSpec) spec = ld_chg_ent(llist + tid);
-            const uint32_t nloc = __ldcg(P.chg_cnt + buf3);
-            if (blockIdx.x == 0 && tid == 0) P.chg_cnt[(win + 2u) % 3u] = 0;  // free since the previous grid barrier
+            if (tid < kSpec) spec = ld_chg_ent(llist + tid);
+            const uint32_t nloc = (uint32_t)__ldcg(P.chg_cnt + buf3);
+            if (blockIdx.x == 0 && tid == 0) P.chg_cnt[(win + 2u) % 3u] = 0ull;  // free since the previous grid barrier
             uint32_t ntot = nloc;
             if (NR > 1) {
-                // ---- 5a. push the changed markers (list + genotype records) into every peer's inbox over NVLink
-                const unsigned long long seq = P.pc.seq_base + win + 1ull;
-                uint32_t *sp = psort;  // scratch: exclusive prefix of the record sizes (16-byte units)
-                const bool fits = nloc <= kMaxMerged;
-                if (fits) {
-                    for (uint32_t i = tid; i < nloc; i += blockDim.x) sp[i] = (P.pc.rec_bytes[__ldcg(&llist[i].m)] + 15u) >> 4;
-                    __syncthreads();
-                    if (tid == 0) {
-                        uint32_t a = 0;
-                        for (uint32_t i = 0; i < nloc; i++) { const uint32_t t = sp[i]; sp[i] = a; a += t; }
-                        sp[nloc] = a;
-                    }
-                    __syncthreads();
-                }
-                const uint32_t units = fits ? sp[nloc] : 0u;
-                const bool ok = fits && (kInboxHeader + (size_t)units * 16 <= P.pc.inbox_stride);
-                if (!ok && blockIdx.x == 0 && tid == 0) atomicExch(P.pc.err, 1u);
+                // ---- 5a. this GPU's changed markers for every peer, over NVLink in the LL form (tagged 16-byte stores on
+                // peer-mapped pointers, no fence, no arrival counter): the count (one 8-byte store, tagged), the list
+                // entries (block 0) and the genotype records, whose units all CTAs share evenly -- one SM alone pushes
+                // only ~6 GB/s. The records lie in the inbox in list order: entry i starts at unit off[i] (reserved with
+                // the list slot by the same atomic), so the unit space is contiguous.
+                const unsigned long long seq = seq_w;
                 const size_t region = ((size_t)par * NR + me) * P.pc.inbox_stride;
-                if (ok) {
-                    for (uint32_t f = blockIdx.x * blockDim.x + tid; f < units; f += nctas * blockDim.x) {
-                        const uint32_t e = find_entry(sp, nloc, f);
-                        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(__ldcg(&llist[e].rec) & ~15ull) + (f - sp[e]));
-                        for (uint32_t h = 0; h < NR; h++)
-                            if (h != me) reinterpret_cast<uint4 *>(P.pc.inbox_peer[h] + region + kInboxHeader)[f] = v;
-                    }
-                    if (blockIdx.x == 0) {
-                        for (uint32_t i = tid; i < nloc; i += blockDim.x) {
-                            ChgEnt en = ld_chg_ent(llist + i);
-                            en.rec = (en.rec & 1ull) | ((unsigned long long)sp[i] << 4);  // offset inside the region's payload | BED flag
-                            for (uint32_t h = 0; h < NR; h++)
-                                if (h != me) reinterpret_cast<ChgEnt *>(P.pc.inbox_peer[h] + region + 16)[i] = en;
+                const uint32_t units = (uint32_t)(__ldcg(P.chg_cnt + buf3) >> 32);
+                const bool ok = nloc <= kMaxMerged && kInboxHeader + (size_t)units * 16 <= P.pc.inbox_stride;
+                if (!ok && blockIdx.x == 0 && tid == 0) atomicExch(P.pc.err, 1u);
+                if (blockIdx.x == 0 && tid < NR && tid != me)
+                    *reinterpret_cast<volatile unsigned long long *>(P.pc.inbox_peer[tid] + region) =
+                        (unsigned long long)(ok ? nloc : 0xFFFFFFFFu) | (seq << 32);
+                if (ok && nloc > 0) {
+                    uint32_t *sp = psort;  // scratch: first unit of every entry [nloc + 1], then the record addresses [nloc]
+                    unsigned long long *srec = reinterpret_cast<unsigned long long *>(psort + ((nloc + 2u) & ~1u));
+                    const bool recs_fit = ((nloc + 2u) & ~1u) + 2u * nloc <= kMaxMerged + 2u;
+                    for (uint32_t i = tid; i < nloc; i += blockDim.x) {
+                        const ChgEnt en = (i < kSpec && tid < kSpec) ? spec : ld_chg_ent(llist + i);
+                        const uint32_t o = __ldcg(P.chg_off + (size_t)buf3 * P.Wmax + i);
+                        sp[i] = o;
+                        if (recs_fit) srec[i] = en.rec;
+                        if (blockIdx.x == 0) {  // the list entries first: the peers sort them while the records travel
+                            const uint64_t e0 = (uint64_t)en.p | ((uint64_t)(uint32_t)seq << 32);
+                            const uint64_t e3 = (en.rec & 1ull) | ((unsigned long long)o << 4);  // first LL unit in the payload | BED flag
+                            for (uint32_t h = 0; h < NR; h++) {
+                                if (h == me) continue;
+                                uint4 *d = reinterpret_cast<uint4 *>(P.pc.inbox_peer[h] + region + 16 + (size_t)i * kLLEntry);
+                                st_ll(d, e0, (uint32_t)seq); st_ll(d + 1, (uint64_t)__double_as_longlong(en.dbs), (uint32_t)seq);
+                                st_ll(d + 2, (uint64_t)__double_as_longlong(en.mave), (uint32_t)seq); st_ll(d + 3, e3, (uint32_t)seq);
+                            }
                         }
                     }
+                    if (tid == 0) sp[nloc] = units;
+                    __syncthreads();
+                    for (uint32_t f = blockIdx.x * blockDim.x + tid; f < units; f += nctas * blockDim.x) {
+                        const uint32_t e = find_entry(sp, nloc, f);
+                        const unsigned long long ra = recs_fit ? srec[e] : __ldcg(&llist[e].rec);
+                        const uint64_t v = __ldg(reinterpret_cast<const unsigned long long *>(ra & ~15ull) + (f - sp[e]));
+                        for (uint32_t h = 0; h < NR; h++)
+                            if (h != me) st_ll(reinterpret_cast<uint4 *>(P.pc.inbox_peer[h] + region + kInboxHeader) + f, v, (uint32_t)seq);
+                    }
+                    __syncthreads();  // psort is reused by the merge
                 }
-                // Every CTA signals every peer once per window, after its share of the copy (the release at system scope
-                // orders the signal after the CTA's stores, which bar.sync ordered before it): the receiver waits until the
-                // cumulative arrival counter of a source reaches (sequence number) x (CTAs per GPU). No second grid
-                // barrier and no per-thread system fence.
-                if (blockIdx.x == 0 && tid < NR && tid != me)
-                    *reinterpret_cast<volatile uint32_t *>(P.pc.inbox_peer[tid] + region) = ok ? nloc : 0xFFFFFFFFu;
-                __syncthreads();
-                if (tid < NR && tid != me) red_release_sys_add_u64(P.pc.flags_peer[tid] + me, 1ull);
                 // ---- 5b. wait for every peer's pushes of this window
                 if (tid < NR) {
                     uint32_t nh = ok ? nloc : 0xFFFFFFFFu;
                     if (tid != me) {
                         const long long t0 = clock64();
                         bool late = false;
-                        while (ld_acquire_sys_u64(P.pc.flags_local + tid) < seq * nctas) {
-                            if (clock64() - t0 > P.pc.timeout_cycles) { late = true; break; }
+                        // the peer's count follows its own grid barrier; entries and records are validated unit by unit
+                        const volatile unsigned long long *hdr =
+                            reinterpret_cast<const volatile unsigned long long *>(P.pc.inbox_local + ((size_t)par * NR + tid) * P.pc.inbox_stride);
+                        unsigned long long hv = 0;
+                        while (!late && (uint32_t)((hv = *hdr) >> 32) != (uint32_t)seq) {
+                            if (clock64() - t0 > P.pc.timeout_cycles) late = true;
                         }
-                        nh = late ? 0xFFFFFFFFu
-                                  : __ldcg(reinterpret_cast<const uint32_t *>(P.pc.inbox_local + ((size_t)par * NR + tid) * P.pc.inbox_stride));
+                        nh = late ? 0xFFFFFFFFu : (uint32_t)hv;
                         if (late) atomicExch(P.pc.err, 2u);
                     }
                     pcnt[tid] = nh;
@@ -906,10 +974,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                         uint32_t h = 0, o = i;
                         if (NR > 1) { while (o >= pcnt[h]) { o -= pcnt[h]; h++; } }
                         if (h == me) {
-                            if (NR == 1 && i < kSpec) en[u] = spec; else en[u] = ld_chg_ent(llist + o);
+                            if (o == tid && o < kSpec) en[u] = spec; else en[u] = ld_chg_ent(llist + o);
                         } else {
                             const unsigned char *reg = P.pc.inbox_local + ((size_t)par * NR + h) * P.pc.inbox_stride;
-                            en[u] = ld_chg_ent(reinterpret_cast<const ChgEnt *>(reg + 16) + o);
+                            const uint4 *le = reinterpret_cast<const uint4 *>(reg + 16 + (size_t)o * kLLEntry);
+                            const uint64_t e0 = ld_ll(le, (uint32_t)seq_w, P.pc.err);
+                            en[u].p = (uint32_t)e0; en[u].m = (uint32_t)(e0 >> 32);
+                            en[u].dbs = __longlong_as_double((long long)ld_ll(le + 1, (uint32_t)seq_w, P.pc.err));
+                            en[u].mave = __longlong_as_double((long long)ld_ll(le + 2, (uint32_t)seq_w, P.pc.err));
+                            en[u].rec = ld_ll(le + 3, (uint32_t)seq_w, P.pc.err);
                             rbase[u] = reg + kInboxHeader;
                         }
                         psort[i] = en[u].p;
@@ -928,15 +1001,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
 #pragma unroll
                     for (uint32_t u = 0; u < 2; u++) {
                         if (en[u].p != 0xFFFFFFFFu && rank[u] >= x0 && rank[u] < x0 + nx) {
-                            const uint64_t rr = rbase[u] ? (((uint64_t)(uintptr_t)rbase[u] + (en[u].rec & ~15ull)) | (en[u].rec & 1ull)) : en[u].rec;
-                            const Blk b = decode_block<true>(rr, c, S, L);
+                            const Blk b = rbase[u] ? decode_block_ll(reinterpret_cast<const uint4 *>(rbase[u]) + (en[u].rec >> 4), (en[u].rec & 1ull) != 0,
+                                                                     c, S, L, (uint32_t)seq_w, P.pc.err)
+                                                   : decode_block(en[u].rec, c, S, L);
                             const uint32_t x = rank[u] - x0;
+                            chg->ll[x] = rbase[u] ? (uint32_t)seq_w : 0u;
                             chg->ptr[x] = b.ptr; chg->nw[x] = b.nw; chg->b1[x] = b.b1; chg->b2[x] = b.b2;
                             chg->dbs[x] = en[u].dbs; chg->mave[x] = en[u].mave;
                         }
                     }
                     __syncthreads();
-                    apply_staged(chg, nx, E_s, L, added, off, &cnt_s[8]);
+                    apply_staged(chg, nx, E_s, L, added, off, &cnt_s[8], P.pc.err);
                 }
                 HB_PHASE(7);
             }
@@ -976,11 +1051,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                     const uint32_t nx = min((uint32_t)kChgCap, nchg - x0);
                     if (ch && slot >= x0 && slot < x0 + nx) {
                         const uint32_t x = slot - x0;
-                        chg->ptr[x] = b.ptr; chg->nw[x] = b.nw; chg->b1[x] = b.b1; chg->b2[x] = b.b2;
+                        chg->ptr[x] = b.ptr; chg->nw[x] = b.nw; chg->b1[x] = b.b1; chg->b2[x] = b.b2; chg->ll[x] = 0u;
                         chg->dbs[x] = d; chg->mave[x] = mv;
                     }
                     __syncthreads();
-                    apply_staged(chg, nx, E_s, L, added, off, &cnt_s[8]);
+                    apply_staged(chg, nx, E_s, L, added, off, &cnt_s[8], P.pc.err);
                 }
                 any |= (nchg > 0);
             }
@@ -1047,7 +1122,8 @@ __global__ void __launch_bounds__(256) k_window_order(const int32_t *__restrict_
                                uint32_t iteration, uint32_t task_first, int32_t *__restrict__ order,
                                double *__restrict__ u, double *__restrict__ z,
                                const uint64_t *__restrict__ rec, const double *__restrict__ mave, const double *__restrict__ mstd,
-                               const double *__restrict__ beta, const int32_t *__restrict__ grp, const uint32_t *__restrict__ wts,
+                               const double *__restrict__ beta, const int32_t *__restrict__ grp, const uint32_t *__restrict__ rec_bytes,
+                               const uint32_t *__restrict__ wts,
                                uint32_t S, WinMeta *__restrict__ meta, uint4 *__restrict__ dirw) {
     __shared__ unsigned long long key[kBalanceMaxT];
     const uint32_t j = blockIdx.x;
@@ -1083,7 +1159,7 @@ __global__ void __launch_bounds__(256) k_window_order(const int32_t *__restrict_
         const uint32_t t = balance ? (0xFFFFu - (uint32_t)(key[slot] & 0xFFFFull)) : slot;
         const size_t q = (size_t)j * T + slot;
         WinMeta wm;
-        wm.rec = 0; wm.mave = 0.0; wm.mstd = 0.0; wm.beta = 0.0; wm.u = 0.0; wm.z = 0.0; wm.m = -1; wm.grp = 0; wm.pad[0] = wm.pad[1] = 0;
+        wm.rec = 0; wm.mave = 0.0; wm.mstd = 0.0; wm.beta = 0.0; wm.u = 0.0; wm.z = 0.0; wm.m = -1; wm.grp = 0; wm.rec_bytes = 0; wm.pad = 0;
         if ((int32_t)j >= task_len[t]) {  // :2029-2034
             order[q] = -1; u[q] = 0.0; z[q] = 0.0;
         } else {
@@ -1101,7 +1177,7 @@ __global__ void __launch_bounds__(256) k_window_order(const int32_t *__restrict_
                 wm.z = sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925 * u2);
             }
             u[q] = wm.u; z[q] = wm.z;
-            if (meta) { wm.m = m; wm.rec = rec[m]; wm.mave = mave[m]; wm.mstd = mstd[m]; wm.beta = beta[m]; wm.grp = grp[m]; }
+            if (meta) { wm.m = m; wm.rec = rec[m]; wm.mave = mave[m]; wm.mstd = mstd[m]; wm.beta = beta[m]; wm.grp = grp[m]; wm.rec_bytes = rec_bytes[m]; }
         }
         if (!meta) continue;
         meta[q] = wm;

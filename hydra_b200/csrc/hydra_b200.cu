@@ -125,7 +125,7 @@ struct hb_ctx {
     DevBuf<ChgEnt> d_chg_list;
     DevBuf<double> d_dB, d_dMave, d_num;
     DevBuf<uint64_t> d_dRec;
-    DevBuf<uint32_t> d_chg_cnt, d_bar, d_markers;
+    DevBuf<uint32_t> d_chg_cnt, d_chg_off, d_bar, d_markers;
     DevBuf<unsigned long long> d_stats, d_ctacyc;
     bool debug_cycles = false;
     uint32_t Wmax = 0;
@@ -203,6 +203,7 @@ static int ensure_scratch(hb_ctx *c, uint32_t W) {
     W = (W + 255u) & ~255u;
     HB_TRY(c->d_slots.alloc((size_t)W * c->S));
     HB_TRY(c->d_chg_list.alloc((size_t)3 * W));
+    HB_TRY(c->d_chg_off.alloc((size_t)3 * W));
     HB_TRY(c->d_chg_cnt.alloc(16));
     HB_TRY(c->d_dB.alloc((size_t)2 * W));
     HB_TRY(c->d_dMave.alloc((size_t)2 * W));
@@ -238,7 +239,7 @@ static void fill_params(hb_ctx *c, BrrParams &P) {
     P.logPi = c->d_hyp.p; P.chalf = c->d_hyp.p + gk; P.denom = c->d_hyp.p + 2 * gk; P.sdk = c->d_hyp.p + 3 * gk;
     P.grp_active = c->d_active.p;
     P.dNm1 = (double)(c->N - 1);
-    P.slots = c->d_slots.p; P.chg_cnt = c->d_chg_cnt.p; P.chg_list = c->d_chg_list.p; P.dB = c->d_dB.p; P.dMave = c->d_dMave.p; P.dRec = c->d_dRec.p; P.Wmax = c->Wmax;
+    P.slots = c->d_slots.p; P.chg_cnt = reinterpret_cast<unsigned long long *>(c->d_chg_cnt.p); P.chg_list = c->d_chg_list.p; P.chg_off = c->d_chg_off.p; P.dB = c->d_dB.p; P.dMave = c->d_dMave.p; P.dRec = c->d_dRec.p; P.Wmax = c->Wmax;
     P.bar = c->d_bar.p; P.stats = c->d_stats.p;
     P.mode = MODE_CHAIN;
     P.num_out = c->d_num.p;
@@ -993,7 +994,7 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
     k_window_order<<<c->lmax, std::min(256u, (T + 31u) & ~31u), 0, st>>>(c->d_perm.p, tape ? c->d_ut.p : nullptr, tape ? c->d_zt.p : nullptr,
                                                      c->d_task_len.p, c->d_task_off.p, T, c->lmax, c->seed, c->iteration,
                                                      c->t_first, c->d_order.p, c->d_u.p, c->d_z.p,
-                                                     c->d_rec.p, c->d_mave.p, c->d_mstd.p, c->d_beta.p, c->d_grp.p,
+                                                     c->d_rec.p, c->d_mave.p, c->d_mstd.p, c->d_beta.p, c->d_grp.p, c->d_rec_bytes.p,
                                                      c->balance ? c->d_wts.p : nullptr, c->S, c->d_wmeta.p, c->d_dirw.p);
     HB_CUDA(cudaGetLastError());
 
