@@ -1182,24 +1182,43 @@ __global__ void __launch_bounds__(256) k_window_order(const int32_t *__restrict_
         if (!meta) continue;
         meta[q] = wm;
         if (wm.m >= 0 && !(wm.rec & 1ull)) {
-            const uint32_t *dir = reinterpret_cast<const uint32_t *>(wm.rec);
-            for (uint32_t c = 0; c < S; c++) dirw[(size_t)c * Q + q] = make_uint4(dir[c * 3], dir[c * 3 + 1], dir[c * 3 + 2], 0u);
+            const uint32_t *dir = reinterpret_cast<const uint32_t *>(wm.rec);  // 12 bytes per slice, never written after staging
+            uint32_t c = 0;
+            for (; c + 4 <= S; c += 4) {  // 48 bytes = three 16-byte loads (records are 16-byte aligned)
+                const uint4 a = __ldg(reinterpret_cast<const uint4 *>(dir + c * 3)), b = __ldg(reinterpret_cast<const uint4 *>(dir + c * 3) + 1),
+                            d = __ldg(reinterpret_cast<const uint4 *>(dir + c * 3) + 2);
+                dirw[(size_t)c * Q + q] = make_uint4(a.x, a.y, a.z, 0u);
+                dirw[(size_t)(c + 1) * Q + q] = make_uint4(a.w, b.x, b.y, 0u);
+                dirw[(size_t)(c + 2) * Q + q] = make_uint4(b.z, b.w, d.x, 0u);
+                dirw[(size_t)(c + 3) * Q + q] = make_uint4(d.y, d.z, d.w, 0u);
+            }
+            for (; c < S; c++) dirw[(size_t)c * Q + q] = make_uint4(__ldg(dir + c * 3), __ldg(dir + c * 3 + 1), __ldg(dir + c * 3 + 2), 0u);
         }
     }
 }
 
-// sum of beta^2 per group over the local markers (src/BayesRRm.cpp:2496-2499); block g = group g
-__global__ void __launch_bounds__(1024) k_beta_sqnorm(const double *__restrict__ beta, const int32_t *__restrict__ grp,
-                                                      uint32_t M, double *__restrict__ out) {
+// sum of beta^2 per group over the local markers (src/BayesRRm.cpp:2496-2499): block (b, g) sums the markers of group g
+// inside chunk b, a second small kernel adds the chunk sums in chunk order (fixed order: bit-reproducible)
+constexpr uint32_t kSqChunks = 148;
+__global__ void __launch_bounds__(256) k_beta_sqnorm(const double *__restrict__ beta, const int32_t *__restrict__ grp,
+                                                     uint32_t M, double *__restrict__ part) {
     __shared__ double red[32];
-    const int g = blockIdx.x;
+    const int g = blockIdx.y;
+    const uint32_t per = (M + gridDim.x - 1) / gridDim.x, m0 = blockIdx.x * per, m1 = min(M, m0 + per);
     double v = 0.0;
-    for (uint32_t m = threadIdx.x; m < M; m += blockDim.x) {
+    for (uint32_t m = m0 + threadIdx.x; m < m1; m += blockDim.x) {
         const double b = beta[m];
         if (grp[m] == g) v += b * b;
     }
     const double s = block_sum(v, red);
-    if (threadIdx.x == 0) out[g] = s;
+    if (threadIdx.x == 0) part[(size_t)g * gridDim.x + blockIdx.x] = s;
+}
+__global__ void k_beta_sqnorm_fin(const double *__restrict__ part, uint32_t nchunks, uint32_t G, double *__restrict__ out) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    double s = 0.0;
+    for (uint32_t b = 0; b < nchunks; b++) s += part[(size_t)g * nchunks + b];
+    out[g] = s;
 }
 
 }  // namespace hb

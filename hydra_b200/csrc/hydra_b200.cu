@@ -123,7 +123,7 @@ struct hb_ctx {
     // scratch
     DevBuf<uint4> d_slots;
     DevBuf<ChgEnt> d_chg_list;
-    DevBuf<double> d_dB, d_dMave, d_num;
+    DevBuf<double> d_dB, d_dMave, d_num, d_bsq_part;
     DevBuf<uint64_t> d_dRec;
     DevBuf<uint32_t> d_chg_cnt, d_chg_off, d_bar, d_markers;
     DevBuf<unsigned long long> d_stats, d_ctacyc;
@@ -149,6 +149,7 @@ struct hb_ctx {
     HostRng hyper_rng;
     std::vector<int32_t> perm;  // M: task-local order per local task block
     std::vector<int32_t> perm_next;   // the next iteration's order, shuffled on a worker thread during the marker loop
+    void *pinned_perm[2] = {nullptr, nullptr};  // both buffers are page-locked (cudaHostRegister): the per-iteration H2D copy is a DMA
     std::vector<double> zmu_next;
     std::thread prefetch;
     bool have_next = false;
@@ -169,6 +170,7 @@ struct hb_ctx {
 
     ~hb_ctx() {
         if (prefetch.joinable()) prefetch.join();
+        for (void *q : pinned_perm) if (q) cudaHostUnregister(q);
         for (int h = 0; h < nranks; h++)
             if (h != rank && peer_inbox[h]) cudaIpcCloseMemHandle(peer_inbox[h]);
         if (inbox) cudaFree(inbox);
@@ -904,7 +906,12 @@ int hb_brr_init(hb_ctx *c, const double *y, const int32_t *groups, const double 
     HB_CUDA(cudaMemset(c->d_acum.p, 0, sizeof(double) * c->M));
     HB_CUDA(cudaMemset(c->d_comp.p, 0, sizeof(int32_t) * c->M));
     // identity marker order per task (markerI, :1615-1617)
+    for (void *&q : c->pinned_perm) if (q) { cudaHostUnregister(q); q = nullptr; }
     c->perm.resize(c->M);
+    c->perm_next.resize(c->M);
+    if (cudaHostRegister(c->perm.data(), sizeof(int32_t) * c->M, cudaHostRegisterDefault) == cudaSuccess) c->pinned_perm[0] = c->perm.data();
+    if (cudaHostRegister(c->perm_next.data(), sizeof(int32_t) * c->M, cudaHostRegisterDefault) == cudaSuccess) c->pinned_perm[1] = c->perm_next.data();
+    cudaGetLastError();  // registration is an optimisation only
     {
         size_t o = 0;
         for (uint32_t t = 0; t < c->T; t++)
@@ -1047,7 +1054,9 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
 
     // ---- group statistics (:2496-2521)
     double *d_bsq = c->d_small.p + 1 + 2 * c->S;
-    k_beta_sqnorm<<<G, 1024, 0, st>>>(c->d_beta.p, c->d_grp.p, M, d_bsq);
+    HB_TRY(c->d_bsq_part.ensure((size_t)G * kSqChunks));
+    k_beta_sqnorm<<<dim3(kSqChunks, G), 256, 0, st>>>(c->d_beta.p, c->d_grp.p, M, c->d_bsq_part.p);
+    k_beta_sqnorm_fin<<<(G + 127) / 128, 128, 0, st>>>(c->d_bsq_part.p, kSqChunks, G, d_bsq);
     HB_CUDA(cudaGetLastError());
     const size_t nsmall = 1 + 2 * (size_t)c->S + G;
     double *pin_small = c->pin;
@@ -1145,7 +1154,7 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
         cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); out->loop_ms = ms;
         cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); out->iter_ms = ms;
         out->n_sync = pin_stats[0]; out->n_windows = pin_stats[1];
-        out->n_launches = 3;
+        out->n_launches = 4;
         out->nnz_processed = pin_stats[2]; out->nnz_updated = pin_stats[3];
         out->bed_markers = pin_stats[4]; out->markers_changed = changed_all;
         for (int i = 0; i < 8; i++) out->phase_cycles[i] = pin_stats[8 + i];
