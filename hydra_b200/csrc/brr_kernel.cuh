@@ -10,16 +10,20 @@
 // parallel:
 //   * individuals are cut in S slices; CTA (r,c) keeps slice c of the residual in
 //     shared memory (r = replica group, R = gridDim/S groups share the window);
-//   * dot: warps stream the slice block of each marker (u16 local indices or
-//     2-bit BED bytes, coalesced 64-bit loads) and gather from shared memory;
+//   * item table: k_window_order lays the iteration out in window order (64-byte marker
+//     records + per-slice directory entries); cp.async copies the next window's part
+//     into the second table during the dot phase, the upper warps cut the slice blocks
+//     into work units of <= 128 words during the draw phase;
+//   * dot: warp w streams units w, w+16, ... (u16 local indices or 2-bit BED words,
+//     coalesced 64-bit loads, two units of words in flight) and gathers from shared memory;
 //   * publish: every slice partial goes out as one 16-byte store carrying the window
 //     tag next to the data, so the consumer needs neither a fence nor a counter;
 //   * draw: marker k of a group is drawn by slice-CTA k % S, one warp per marker
-//     (lanes poll the S slots; lane kk evaluates mixture component kk); changed
-//     markers are appended to a list;
+//     (lanes poll the S slots; all terms of the mixture cascade are evaluated at once);
+//     changed markers are appended to a list;
 //   * ONE grid barrier per window; with several GPUs the changed markers (list
-//     entries + genotype records) are then pushed into every peer's inbox over
-//     NVLink and every GPU waits for its peers' arrival counters;
+//     entries + genotype records) are then written into every peer's inbox over
+//     NVLink as tagged 16-byte units (LL form: no fence, no arrival counter);
 //   * update: every CTA applies the changed markers of all GPUs to its slice in
 //     global window order (deterministic; all epsilon replicas stay bit-identical).
 #pragma once

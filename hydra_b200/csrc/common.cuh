@@ -46,9 +46,10 @@ void set_error(const char *fmt, ...);
 //                                n1 | n2 << 16, nm }
 //   payload (starts at align16(12*S)): per slice one block of u64 words, each word =
 //   4 x u16 slice-local indices; first ceil(n1/4) words hold the "ones", then
-//   ceil(n2/4) words the "twos", then ceil(nm/4) words the missing; every class is
-//   in ascending index order (the order of src/data.cpp:1262-1280); unused lanes of
-//   a word hold PAD = L, the index of a dummy slot.
+//   ceil(n2/4) words the "twos", then ceil(nm/4) words the missing. Staging fills every
+//   class in ascending index order (the order of src/data.cpp:1262-1280) and k_bank_order
+//   then permutes the indices inside a class for conflict-free gathers; unused lanes of a
+//   word hold PAD = L, the index of a dummy slot, anywhere inside the class.
 // BED record: S*L/4 bytes, PLINK 2-bit codes at compacted individual positions,
 //   pad positions (>= N) hold 11 (genotype 0); slice c starts at byte c*L/4.
 // rec[m] = device address | 1 if BED.
