@@ -28,6 +28,7 @@ struct BwParams {
     double alpha;
     const double *vec;         // BW_VECSUMS: vector to sum over the classes (failure indicators)
     double *Vpart;             // [S] sum of vi over the slice
+    double *vi;                // [S*L] vi = exp(alpha*eps - EuMasc) itself, refreshed by k_bw_update with the slice sums (K10)
     const int32_t *order;      // window-ordered local marker or -1
     const double *unif;        // window-ordered U(0,1)
     uint32_t base, W, T, t_first, j0;
@@ -67,45 +68,69 @@ struct BwArmsRand {  // RNG spec v1: 31-bit integers from Philox, u = (r + 0.5) 
     }
 };
 
+constexpr uint32_t kBwMaxS = 160;  // slices (<= CTAs of the sampler grid <= SMs)
 __global__ void __launch_bounds__(256) k_bw_window(const BwParams P) {
     __shared__ double red[8];
-    __shared__ double sums[3];
+    __shared__ uint32_t s_cum[kBwMaxS + 1], s_st[kBwMaxS], s_w1[kBwMaxS], s_w12[kBwMaxS];
     const uint32_t p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int32_t m = P.order[P.base + p];
     if (m < 0) return;
     const uint64_t rr = P.rec[m];
     const double shift = *P.shift_in;
     const double bconst = P.alpha * shift - kBwEuMasc;
+    // what is summed over the marker's genotype classes: the chain reads vi as refreshed at the last synchronisation
+    // (same expression, evaluated once per individual instead of once per non-zero); BW_VISUMS evaluates it for its alpha
+    const double *vec = (P.mode == BW_VECSUMS) ? P.vec : ((P.mode == BW_CHAIN) ? P.vi : P.E);
+    const bool take_exp = (P.mode == BW_VISUMS);
     double a1 = 0.0, a2 = 0.0, am = 0.0;
-    for (uint32_t c = 0; c < P.S; c++) {
-        const Blk b = decode_block(rr, c, P.S, P.L);
-        const double *e = (P.mode == BW_VECSUMS ? P.vec : P.E) + (size_t)c * P.L;
-        if (b.b1 == 0xFFFFFFFFu) {
-            for (uint32_t w = tid; w < b.nw; w += blockDim.x) {
-                const uint64_t bits = ld_stream_u64(b.ptr + w);
-                if (bits == ~0ull) continue;
-                for (uint32_t t = 0; t < 32; t++) {
-                    const uint32_t code = (uint32_t)(bits >> (2u * t)) & 3u;
-                    if (code == 3u) continue;
-                    const double x = e[32u * w + t];
-                    const double v = (P.mode == BW_VECSUMS) ? x : exp(P.alpha * x + bconst);
-                    if (code == 2u) a1 += v; else if (code == 0u) a2 += v; else am += v;
-                }
+    if (rr & 1ull) {  // BED record: all slices are one array of S*L/32 words
+        const uint64_t *ptr = reinterpret_cast<const uint64_t *>(rr & ~15ull);
+        const uint32_t nw = P.S * (P.L / 32);
+        for (uint32_t w = tid; w < nw; w += blockDim.x) {
+            const uint64_t bits = ld_stream_u64(ptr + w);
+            if (bits == ~0ull) continue;
+            const double *e = vec + (size_t)32u * w;  // slice c starts at individual c*L = word c*L/32
+            for (uint32_t t = 0; t < 32; t++) {
+                const uint32_t code = (uint32_t)(bits >> (2u * t)) & 3u;
+                if (code == 3u) continue;
+                const double x = e[t];
+                const double v = take_exp ? exp(P.alpha * x + bconst) : x;
+                if (code == 2u) a1 += v; else if (code == 0u) a2 += v; else am += v;
             }
-        } else {
-            for (uint32_t w = tid; w < b.nw; w += blockDim.x) {
-                const uint64_t x4 = ld_stream_u64(b.ptr + w);
-                double s = 0.0;
+        }
+    } else {  // sparse record: the words of all slice blocks as one index space (no slice-by-slice load chains)
+        const uint8_t *bp = reinterpret_cast<const uint8_t *>(rr);
+        const uint32_t *dir = reinterpret_cast<const uint32_t *>(bp);
+        const uint64_t *payload = reinterpret_cast<const uint64_t *>(bp + dir_bytes(P.S));
+        for (uint32_t c = tid; c < P.S; c += blockDim.x) {
+            const uint32_t st = __ldg(dir + c * 3), n12 = __ldg(dir + c * 3 + 1), nm = __ldg(dir + c * 3 + 2);
+            const uint32_t w1 = ((n12 & 0xFFFFu) + 3) / 4, w2 = ((n12 >> 16) + 3) / 4, wm = (nm + 3) / 4;
+            s_st[c] = st; s_w1[c] = w1; s_w12[c] = w1 + w2; s_cum[c + 1] = w1 + w2 + wm;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t a = 0;
+            s_cum[0] = 0;
+            for (uint32_t c = 0; c < P.S; c++) { a += s_cum[c + 1]; s_cum[c + 1] = a; }
+        }
+        __syncthreads();
+        const uint32_t total = s_cum[P.S];
+        for (uint32_t f = tid; f < total; f += blockDim.x) {
+            uint32_t lo = 0, hi = P.S;  // slice c with cum[c] <= f < cum[c+1]
+            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_cum[mid] <= f) lo = mid; else hi = mid; }
+            const uint32_t c = lo, w = f - s_cum[c];
+            const uint64_t x4 = ld_stream_u64(payload + s_st[c] + w);
+            const double *e = vec + (size_t)c * P.L;
+            double sacc = 0.0;
 #pragma unroll
-                for (uint32_t t = 0; t < 4; t++) {
-                    const uint32_t idx = (uint32_t)(x4 >> (16u * t)) & 0xFFFFu;
-                    if (idx != P.L) {
-                        const double x = e[idx];
-                        s += (P.mode == BW_VECSUMS) ? x : exp(P.alpha * x + bconst);
-                    }
+            for (uint32_t t = 0; t < 4; t++) {
+                const uint32_t idx = (uint32_t)(x4 >> (16u * t)) & 0xFFFFu;
+                if (idx != P.L) {
+                    const double x = e[idx];
+                    sacc += take_exp ? exp(P.alpha * x + bconst) : x;
                 }
-                if (w < b.b1) a1 += s; else if (w < b.b2) a2 += s; else am += s;
             }
+            if (w < s_w1[c]) a1 += sacc; else if (w < s_w12[c]) a2 += sacc; else am += sacc;
         }
     }
     const double S1 = bw_block_sum(a1, red), S2 = bw_block_sum(a2, red), SM = bw_block_sum(am, red);
@@ -254,8 +279,13 @@ __global__ void __launch_bounds__(512) k_bw_update(const BwParams P) {
     // refresh the slice's sum of vi (:1832-1834)
     double v = 0.0;
     const double bconst = P.alpha * shift_new - kBwEuMasc;
-    for (uint32_t i = tid; i < L; i += blockDim.x)
-        if ((size_t)c * L + i < P.N) v += exp(P.alpha * __ldcg(E + i) + bconst);
+    for (uint32_t i = tid; i < L; i += blockDim.x) {
+        if ((size_t)c * L + i < P.N) {
+            const double x = exp(P.alpha * __ldcg(E + i) + bconst);
+            P.vi[(size_t)c * L + i] = x;  // gathered by k_bw_window until the next synchronisation
+            v += x;
+        }
+    }
     const double s = bw_block_sum(v, red);
     if (tid == 0) P.Vpart[c] = s;
 }

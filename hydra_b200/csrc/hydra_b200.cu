@@ -135,7 +135,7 @@ struct hb_ctx {
     int bw_rule = -1;
     double bw_alpha = 0.0, bw_mu = 0.0, bw_d = 0.0, bw_sumSigmaG = 0.0;
     uint64_t bw_evals = 0;
-    DevBuf<double> d_sd, d_sumfail, d_fail, d_bwsc;
+    DevBuf<double> d_sd, d_sumfail, d_fail, d_bwsc, d_bw_vi;
     std::vector<double> sd_h, sumfail_h;
 
     // chain (host)

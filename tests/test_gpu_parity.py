@@ -197,6 +197,17 @@ def test_chain_replay_many_tasks_few_ctas():
     _run_chain_case(N=900, M=1000, T=16, SR=8, G=1, K=4, repr_mode="sparse", n_iter=2, seed=3, n_slices=2, max_ctas=8)
 
 
+@pytest.mark.parametrize("K", [2, 7])
+def test_chain_replay_other_mixture_counts(K):
+    # K = 7: more cascade terms than one warp evaluates at once (K*K > 32), the sequential form of :1894-1921 runs
+    _run_chain_case(N=1100, M=260, T=3, SR=4, G=2, K=K, repr_mode="sparse", n_iter=3, seed=40 + K)
+
+
+def test_chain_replay_heavy_blocks_one_group():
+    # common variants on one CTA group: slice blocks of thousands of words, cut in work units longer than one 128-word step
+    _run_chain_case(N=40000, M=48, T=8, SR=4, G=1, K=4, repr_mode="sparse", n_iter=2, seed=11, max_ctas=2)
+
+
 def test_chain_rng_spec_v1_matches_oracle_draws():
     # no hyper-parameter replay: both sides draw sigmaG / pi / sigmaE with RNG spec v1 from the same seed
     _run_chain_case(N=1000, M=200, T=2, SR=3, G=2, K=4, repr_mode="sparse", n_iter=4, seed=2024, replay_hyper=False)
