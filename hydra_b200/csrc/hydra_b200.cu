@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <memory>
 #include <new>
+#include <sstream>
 #include <string>
 #include <thread>
 #include <vector>
@@ -1272,6 +1273,99 @@ int hb_comm_init(hb_ctx *c, const uint8_t id[HB_NCCL_ID_BYTES], int rank, int nr
     HB_CUDA(cudaStreamSynchronize(c->stream));
     HB_CUDA(cudaMemcpy(mx, d_g.p, sizeof(mx), cudaMemcpyDeviceToHost));
     HB_CHECK(mx[0] == -mx[1], HB_ERR_ARG, "hb_comm_init: the GPUs run different grids (%d vs %d CTAs); use the same n_slices / max_ctas", mx[0], -mx[1]);
+    return HB_OK;
+}
+
+}  // extern "C"
+
+
+// ---- restart (hydra's --restart: src/BayesRRm.cpp:842-928 reads .csv/.bet/.cpn/.eps/.mrk/.mus/.rng back).
+// The complete state of the BayesRRm chain of this GPU as one opaque, self-describing blob: hyper-parameters, per-task mu,
+// the residual, marker effects / components / Acum, the host random streams (task streams, hyper-parameter stream, the
+// already drawn order of the next iteration). A run continued from the blob is bit-identical to the uninterrupted run.
+namespace hb {
+struct BlobW {
+    std::vector<unsigned char> b;
+    template <class T> void put(const T *p, size_t n) { const unsigned char *q = reinterpret_cast<const unsigned char *>(p); b.insert(b.end(), q, q + n * sizeof(T)); }
+    template <class T> void one(const T &v) { put(&v, 1); }
+    void str(const std::string &s) { const uint64_t n = s.size(); one(n); put(s.data(), s.size()); }
+};
+struct BlobR {
+    const unsigned char *p, *e;
+    bool ok = true;
+    template <class T> void get(T *d, size_t n) {
+        if (!ok || (size_t)(e - p) < n * sizeof(T)) { ok = false; return; }
+        memcpy(d, p, n * sizeof(T)); p += n * sizeof(T);
+    }
+    template <class T> T one() { T v{}; get(&v, 1); return v; }
+    std::string str() { const uint64_t n = one<uint64_t>(); std::string s; if (ok && (uint64_t)(e - p) >= n) { s.assign(reinterpret_cast<const char *>(p), n); p += n; } else ok = false; return s; }
+};
+static std::string rng_text(const HostRng &r) { std::ostringstream o; o << r.eng; return o.str(); }
+static bool rng_from_text(HostRng &r, const std::string &t) { std::istringstream i(t); i >> r.eng; return !i.fail(); }
+constexpr uint32_t kRestartMagic = 0x31524248u;  // "HBR1"
+}  // namespace hb
+
+extern "C" {
+
+int hb_brr_save_state(hb_ctx *c, void *buf, size_t cap, size_t *need) {
+    HB_CHECK(c && c->brr_ready && need, HB_ERR_STATE, "hb_brr_save_state: call hb_brr_init first");
+    HB_CUDA(cudaSetDevice(c->dev));
+    if (c->prefetch.joinable()) c->prefetch.join();  // the worker thread owns the task streams while it runs
+    const size_t nE = (size_t)c->S * c->L;
+    BlobW w;
+    const uint32_t head[12] = {kRestartMagic, (uint32_t)HB_ABI_VERSION, c->N, c->M, c->T, c->G, c->K, c->S, c->L, c->seed, c->iteration, c->have_next ? 1u : 0u};
+    w.put(head, 12);
+    w.one(c->shift); w.one(c->sigmaE); w.one(c->seq_base);
+    w.put(c->sigmaG.data(), c->G); w.put(c->pi.data(), (size_t)c->G * c->K); w.put(c->mu.data(), c->T); w.put(c->bsq.data(), c->G);
+    w.put(c->cass.data(), (size_t)c->G * c->K); w.put(c->m0.data(), c->G);
+    w.put(c->slice_sum_h.data(), c->S);
+    w.put(c->perm.data(), c->M);
+    if (c->have_next) { w.put(c->perm_next.data(), c->M); w.put(c->zmu_next.data(), c->T); }
+    for (uint32_t t = 0; t < c->T; t++) w.str(rng_text(c->task_rng[t]));
+    w.str(rng_text(c->hyper_rng));
+    std::vector<double> hd(std::max(nE, (size_t)c->M));
+    std::vector<int32_t> hi(c->M);
+    HB_CUDA(cudaMemcpy(hd.data(), c->d_E[c->cur].p, sizeof(double) * nE, cudaMemcpyDeviceToHost)); w.put(hd.data(), nE);
+    HB_CUDA(cudaMemcpy(hd.data(), c->d_beta.p, sizeof(double) * c->M, cudaMemcpyDeviceToHost)); w.put(hd.data(), c->M);
+    HB_CUDA(cudaMemcpy(hd.data(), c->d_acum.p, sizeof(double) * c->M, cudaMemcpyDeviceToHost)); w.put(hd.data(), c->M);
+    HB_CUDA(cudaMemcpy(hi.data(), c->d_comp.p, sizeof(int32_t) * c->M, cudaMemcpyDeviceToHost)); w.put(hi.data(), c->M);
+    *need = w.b.size();
+    if (!buf) return HB_OK;
+    HB_CHECK(cap >= w.b.size(), HB_ERR_ARG, "hb_brr_save_state: buffer of %zu bytes, %zu needed", cap, w.b.size());
+    memcpy(buf, w.b.data(), w.b.size());
+    return HB_OK;
+}
+
+int hb_brr_load_state(hb_ctx *c, const void *buf, size_t n) {
+    HB_CHECK(c && c->brr_ready && buf, HB_ERR_STATE, "hb_brr_load_state: call hb_brr_init (same data, groups, mixtures, tasks) first");
+    HB_CUDA(cudaSetDevice(c->dev));
+    if (c->prefetch.joinable()) c->prefetch.join();
+    BlobR r{static_cast<const unsigned char *>(buf), static_cast<const unsigned char *>(buf) + n};
+    uint32_t head[12] = {0};
+    r.get(head, 12);
+    HB_CHECK(r.ok && head[0] == kRestartMagic, HB_ERR_ARG, "hb_brr_load_state: not a hydra_b200 restart state");
+    HB_CHECK(head[2] == c->N && head[3] == c->M && head[4] == c->T && head[5] == c->G && head[6] == c->K && head[7] == c->S && head[8] == c->L,
+             HB_ERR_ARG, "hb_brr_load_state: the state belongs to another problem (N %u M %u tasks %u groups %u mixtures %u slices %u x %u; here %u %u %u %u %u %u x %u)",
+             head[2], head[3], head[4], head[5], head[6], head[7], head[8], c->N, c->M, c->T, c->G, c->K, c->S, c->L);
+    const size_t nE = (size_t)c->S * c->L;
+    c->seed = head[9]; c->iteration = head[10]; c->have_next = head[11] != 0;
+    c->shift = r.one<double>(); c->sigmaE = r.one<double>(); c->seq_base = r.one<unsigned long long>();
+    r.get(c->sigmaG.data(), c->G); r.get(c->pi.data(), (size_t)c->G * c->K); r.get(c->mu.data(), c->T); r.get(c->bsq.data(), c->G);
+    r.get(c->cass.data(), (size_t)c->G * c->K); r.get(c->m0.data(), c->G);
+    r.get(c->slice_sum_h.data(), c->S);
+    r.get(c->perm.data(), c->M);
+    if (c->have_next) { c->perm_next.resize(c->M); c->zmu_next.assign(c->T, 0.0); r.get(c->perm_next.data(), c->M); r.get(c->zmu_next.data(), c->T); }
+    for (uint32_t t = 0; t < c->T; t++) HB_CHECK(rng_from_text(c->task_rng[t], r.str()), HB_ERR_ARG, "hb_brr_load_state: bad task stream %u", t);
+    HB_CHECK(rng_from_text(c->hyper_rng, r.str()), HB_ERR_ARG, "hb_brr_load_state: bad hyper-parameter stream");
+    std::vector<double> hd(std::max(nE, (size_t)c->M));
+    std::vector<int32_t> hi(c->M);
+    r.get(hd.data(), nE); HB_CHECK(r.ok, HB_ERR_ARG, "hb_brr_load_state: truncated state");
+    HB_CUDA(cudaMemcpy(c->d_E[c->cur].p, hd.data(), sizeof(double) * nE, cudaMemcpyHostToDevice));
+    r.get(hd.data(), c->M); HB_CUDA(cudaMemcpy(c->d_beta.p, hd.data(), sizeof(double) * c->M, cudaMemcpyHostToDevice));
+    r.get(hd.data(), c->M); HB_CUDA(cudaMemcpy(c->d_acum.p, hd.data(), sizeof(double) * c->M, cudaMemcpyHostToDevice));
+    r.get(hi.data(), c->M); HB_CHECK(r.ok, HB_ERR_ARG, "hb_brr_load_state: truncated state");
+    HB_CUDA(cudaMemcpy(c->d_comp.p, hi.data(), sizeof(int32_t) * c->M, cudaMemcpyHostToDevice));
+    c->eps_set = true;
     return HB_OK;
 }
 

@@ -30,7 +30,7 @@ namespace {
 struct Options {  // names follow the reference's Options class (src/options.hpp:20-138)
     std::string bayesType, bedFile, phenotypeFile, failureFile, quad_points, groupIndexFile, groupMixtureFile, mcmcOutDir, mcmcOutNam, sparseDir, sparseBsn,
         markerBlocksFile;
-    bool bedToSparse = false, dryRun = false, readFromBedFile = false, readFromSparseFiles = false;
+    bool bedToSparse = false, dryRun = false, readFromBedFile = false, readFromSparseFiles = false, restart = false;
     uint32_t numberMarkers = 0, numberIndividuals = 0, chainLength = 10000, burnin = 5000, thin = 5, save = 10, syncRate = 1,
              shuffleMarkers = 1, tasks = 1, device = 0, blocksPerRank = 1, rank = 0, world = 1;
     bool deviceSet = false;
@@ -107,7 +107,8 @@ Options parse(int argc, const char **argv) {
         else if (a == "--world") o.world = (uint32_t)atoi(need(i));
         else if (a == "--dry-run") o.dryRun = true;
         // reference options outside the accelerated path: recognised, refused with a clear message
-        else if (a == "--restart" || a == "--ignore-xfiles" || a == "--sparse-sync" || a == "--bed-sync" || a == "--covariates" ||
+        else if (a == "--restart") o.restart = true;
+        else if (a == "--ignore-xfiles" || a == "--sparse-sync" || a == "--bed-sync" || a == "--covariates" ||
                  a == "--check-RAM" || a == "--groupPriorsFile" || a == "--dPriorsFile")
             throw std::runtime_error("option \"" + a + "\" of hydra is not supported by hydra_b200 yet (see DESIGN.md, out of scope)");
         else
@@ -249,6 +250,10 @@ struct OutFile {
         f = fopen(path.c_str(), "wb");  // the reference deletes old files and creates new ones (:1269-1309)
         if (!f) fatal("cannot create output file " + path + ": " + strerror(errno));
     }
+    void open_append(const std::string &path) {  // --restart: the file of the interrupted run is continued
+        f = fopen(path.c_str(), "ab");
+        if (!f) fatal("cannot open output file " + path + ": " + strerror(errno));
+    }
     template <class T>
     void put(const T *p, size_t n) {
         if (fwrite(p, sizeof(T), n, f) != n) fatal("write failed");
@@ -277,6 +282,51 @@ struct SharedFile {
         if (fd >= 0) ::close(fd);
     }
 };
+
+// --restart (src/BayesRRm.cpp:842-928). The reference reads its text / binary outputs back (15 digits of the .csv, the Boost
+// text state of .rng); here every process keeps one state file <out>.rst.<rank>, written at every --save point:
+// u32 'HBRS', u32 iteration, u32 records written to .bet/.cpn/.acu/.mus so far, then the library's opaque chain state.
+constexpr uint32_t kRstMagic = 0x53524248u;
+void write_restart_file(const std::string &path, hb_ctx *ctx, uint32_t it, uint32_t n_saved) {
+    size_t need = 0;
+    HB(hb_brr_save_state(ctx, nullptr, 0, &need));
+    std::vector<unsigned char> blob(need);
+    HB(hb_brr_save_state(ctx, blob.data(), blob.size(), &need));
+    {
+        OutFile o;
+        o.open(path + ".tmp");
+        const uint32_t head[3] = {kRstMagic, it, n_saved};
+        o.put(head, 3);
+        o.put(blob.data(), blob.size());
+    }
+    if (rename((path + ".tmp").c_str(), path.c_str()) != 0) fatal("cannot publish " + path);
+}
+void read_restart_file(const std::string &path, hb_ctx *ctx, uint32_t &it, uint32_t &n_saved) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) fatal("--restart: cannot open " + path + " (it is written at every --save point of a run with the same options)");
+    uint32_t head[3] = {0, 0, 0};
+    if (fread(head, 4, 3, f) != 3 || head[0] != kRstMagic) fatal("--restart: " + path + " is not a hydra_b200 restart file");
+    std::vector<unsigned char> blob;
+    unsigned char buf[1 << 16];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof(buf), f)) > 0) blob.insert(blob.end(), buf, buf + n);
+    fclose(f);
+    HB(hb_brr_load_state(ctx, blob.data(), blob.size()));
+    it = head[1]; n_saved = head[2];
+}
+// keep the .csv lines of the iterations up to `it` (first field of every line)
+void truncate_csv(const std::string &path, uint32_t it) {
+    std::ifstream in(path);
+    if (!in) fatal("--restart: cannot open " + path);
+    std::string line, keep;
+    while (std::getline(in, line)) {
+        if (line.empty() || (uint32_t)atoi(line.c_str()) > it) break;
+        keep += line + "\n";
+    }
+    in.close();
+    std::ofstream o(path, std::ios::trunc);
+    o << keep;
+}
 
 template <class T>
 void dump_file(const std::string &path, uint32_t it, uint32_t n, const T *data) {  // .eps/.mrk: u32 it, u32 n, data[n]
@@ -432,6 +482,7 @@ int main(int argc, const char **argv) {
             for (uint32_t k = 1; k < K; k++) mSflat[g * K + k] = mS[g][k - 1];
         const uint32_t seed = opt.seedSet ? opt.seed : (uint32_t)time(nullptr);
         if (bayesW) {
+            if (opt.restart) throw std::runtime_error("option \"--restart\" is not supported for bayesWMPI by hydra_b200 yet");
             HB(hb_bw_init(ctx, y.data(), fail.data(), groups.empty() ? nullptr : groups.data(), mSflat.data(), (uint32_t)atoi(opt.quad_points.c_str()), seed));
             struct stat sbw;
             if (stat(opt.mcmcOutDir.c_str(), &sbw) != 0 && system(("mkdir -p " + opt.mcmcOutDir).c_str()) != 0)
@@ -485,7 +536,7 @@ int main(int argc, const char **argv) {
         // is a barrier, after which the other processes open them
         SharedFile bet, acu, cpn, xb, xc;
         OutFile csv;
-        if (root) {
+        if (root && !opt.restart) {
             csv.open(out + ".csv");
             bet.open_rw(out + ".bet", true); acu.open_rw(out + ".acu", true); cpn.open_rw(out + ".cpn", true);
             xb.open_rw(out + ".xbet", true); xc.open_rw(out + ".xcpn", true);
@@ -520,19 +571,41 @@ int main(int argc, const char **argv) {
             HB(hb_comm_init(ctx, id, (int)opt.rank, (int)opt.world));
             if (root) unlink(idf.c_str());
         }
-        if (!root) {
+        if (!root || opt.restart) {
             bet.open_rw(out + ".bet", false); acu.open_rw(out + ".acu", false); cpn.open_rw(out + ".cpn", false);
             xb.open_rw(out + ".xbet", false); xc.open_rw(out + ".xcpn", false);
         }
         const uint32_t t_first = opt.rank * TL;
         std::vector<OutFile> mus(TL);
-        for (uint32_t t = 0; t < TL; t++) mus[t].open(out + ".mus." + std::to_string(t_first + t));
+        uint32_t it_first = 0, n_saved = 0;
+        if (opt.restart) {
+            // continue the chain after the last --save point of the interrupted run: state back into the library, output
+            // files cut back to that iteration (the reference does the same from its own files, :842-928)
+            uint32_t it_saved = 0;
+            read_restart_file(out + ".rst." + std::to_string(opt.rank), ctx, it_saved, n_saved);
+            it_first = it_saved + 1;
+            if (root) {
+                truncate_csv(out + ".csv", it_saved);
+                csv.open_append(out + ".csv");
+                if (truncate((out + ".bet").c_str(), 4 + (off_t)n_saved * (4 + (off_t)Mtot * 8)) != 0 ||
+                    truncate((out + ".acu").c_str(), 4 + (off_t)n_saved * (4 + (off_t)Mtot * 8)) != 0 ||
+                    truncate((out + ".cpn").c_str(), 4 + (off_t)n_saved * (4 + (off_t)Mtot * 4)) != 0)
+                    fatal("--restart: cannot cut the .bet/.acu/.cpn files back to the restart point");
+            }
+            for (uint32_t t = 0; t < TL; t++) {
+                const std::string mf = out + ".mus." + std::to_string(t_first + t);
+                if (truncate(mf.c_str(), (off_t)n_saved * 12) != 0) fatal("--restart: cannot cut " + mf + " back to the restart point");
+                mus[t].open_append(mf);
+            }
+            printf("INFO   : restarting after iteration %u (%u records in .bet/.cpn/.acu)\n", it_saved, n_saved);
+        } else {
+            for (uint32_t t = 0; t < TL; t++) mus[t].open(out + ".mus." + std::to_string(t_first + t));
+        }
 
         std::vector<double> beta(m_local), acum(m_local), sigmaG(G), pi((size_t)G * K), mu(TL), bsq(G), eps(N);
         std::vector<int32_t> comp(m_local), cass((size_t)G * K), m0(G), perm;
         double tot_loop_ms = 0.0, tot_iter_ms = 0.0;
-        uint32_t n_saved = 0;
-        for (uint32_t it = 0; it < opt.chainLength; it++) {
+        for (uint32_t it = it_first; it < opt.chainLength; it++) {
             hb_brr_iter_out io;
             HB(hb_brr_iteration(ctx, nullptr, &io));
             tot_loop_ms += io.loop_ms; tot_iter_ms += io.iter_ms;
@@ -580,11 +653,12 @@ int main(int argc, const char **argv) {
                 if (root) { xb.write_at(&it, 4, 4); xc.write_at(&it, 4, 4); }
                 xb.write_at(beta.data(), (size_t)m_local * 8, 8 + (size_t)m_start * 8);
                 xc.write_at(comp.data(), (size_t)m_local * 4, 8 + (size_t)m_start * 4);
+                write_restart_file(out + ".rst." + std::to_string(opt.rank), ctx, it, n_saved);
             }
         }
         if (root)
         printf("INFO   : time to process the data: %.3f sec (marker loops %.3f sec: %.3f M marker updates/s)\n", tot_iter_ms * 1e-3,
-               tot_loop_ms * 1e-3, (double)Mtot * opt.chainLength / (tot_loop_ms * 1e3));
+               tot_loop_ms * 1e-3, (double)Mtot * (opt.chainLength - it_first) / (tot_loop_ms * 1e3));
         hb_destroy(ctx);
     } catch (const std::exception &e) {
         fatal(e.what());

@@ -236,6 +236,18 @@ class BayesRRm:
     def set_state(self, beta=None, components=None):
         check(self._lib.hb_brr_set_state(self.store._h, ptr(arr(beta, np.float64)), ptr(arr(components, np.int32))))
 
+    def save_state(self):
+        """The complete chain state of this GPU (hydra --restart); bytes for load_state of a BayesRRm built on the same inputs."""
+        need = C.c_size_t(0)
+        check(self._lib.hb_brr_save_state(self.store._h, None, C.c_size_t(0), C.byref(need)))
+        buf = (C.c_ubyte * need.value)()
+        check(self._lib.hb_brr_save_state(self.store._h, buf, C.c_size_t(need.value), C.byref(need)))
+        return bytes(buf)
+
+    def load_state(self, blob):
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        check(self._lib.hb_brr_load_state(self.store._h, buf, C.c_size_t(len(blob))))
+
     def task_epsilon(self, task_local=0):
         e = np.zeros(self.store.n_ind)
         check(self._lib.hb_brr_get_task_epsilon(self.store._h, C.c_uint32(task_local), ptr(e)))

@@ -160,6 +160,31 @@ def test_cli_bed_vs_sparse_vs_python_runs_are_identical(tmp_path):
     assert struct.unpack("<II", raw[:8]) == (4, N - len(na)) and len(raw) == 8 + 8 * (N - len(na))
 
 
+@pytest.mark.gpu
+def test_cli_restart_continues_the_chain_bit_for_bit(tmp_path):
+    """hydra's --restart (src/BayesRRm.cpp:842-928): a run interrupted after a --save point and continued with --restart
+    writes the same files, byte for byte, as the uninterrupted run (the chain state file keeps exact doubles and the
+    random streams, where the reference re-reads 15 digits of its .csv)."""
+    d = str(tmp_path)
+    write_dataset(d)
+    chain = ["--chain-length", "9", "--thin", "1", "--save", "4"]
+    r = subprocess.run(base_args(d, "full", ["--bfile", os.path.join(d, "t")] + chain), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    cut = ["--chain-length", "6", "--thin", "1", "--save", "4"]   # stops after iteration 5, last save point = iteration 4
+    r = subprocess.run(base_args(d, "part", ["--bfile", os.path.join(d, "t")] + cut), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    r = subprocess.run(base_args(d, "part", ["--bfile", os.path.join(d, "t"), "--restart"] + chain), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "restarting after iteration 4" in r.stdout
+    for ext in ("csv", "bet", "cpn", "acu", "xbet", "xcpn", "eps.0", "eps.2", "mrk.1", "mus.0", "mus.2", "rst.0"):
+        a = open(os.path.join(d, "full", "run." + ext), "rb").read()
+        b = open(os.path.join(d, "part", "run." + ext), "rb").read()
+        assert a == b, ext
+    # a state file of another problem is refused
+    r = subprocess.run(base_args(d, "part", ["--bfile", os.path.join(d, "t"), "--restart", "--tasks", "2"] + chain), capture_output=True, text=True)
+    assert r.returncode != 0 and "FATAL" in r.stdout
+
+
 def test_cli_reads_the_weibull_example_files():
     ex = "/root/reference/example"
     if not os.path.isdir(ex):
