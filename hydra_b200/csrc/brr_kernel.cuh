@@ -63,14 +63,12 @@ constexpr size_t kInboxHeader = 16 + (size_t)kMaxMerged * kLLEntry;
 
 // Exchange of the changed markers between the GPUs of one node (replaces MPI_Allreduce of deltaEps,
 // src/BayesRRm.cpp:2051, 2456): every GPU pushes (position, deltaBeta*mstd, mave, genotype record) of its
-// changed markers into every peer's inbox over NVLink, then raises a flag in the peer's memory.
+// changed markers into every peer's inbox over NVLink as tagged units; the receiver validates count, entries and records by their tags.
 struct PeerComm {
     uint32_t nranks, rank;
     uint32_t T_total, t_first;
     unsigned char *inbox_local;               // [2 parities][nranks sources] regions of inbox_stride bytes
     unsigned char *inbox_peer[kMaxRanks];     // peer-mapped inbox of rank h (unused for self)
-    unsigned long long *flags_local;          // [nranks] sequence numbers raised by the peers
-    unsigned long long *flags_peer[kMaxRanks];
     size_t inbox_stride;
     unsigned long long seq_base;              // sequence number of this launch's window 0, minus 1
     const uint32_t *rec_bytes;                // [M] bytes of each local record
@@ -369,17 +367,6 @@ __device__ __forceinline__ ChgEnt ld_chg_ent(const ChgEnt *e) {
     en.mave = __longlong_as_double((long long)(((unsigned long long)b.y << 32) | b.x));
     en.rec = ((unsigned long long)b.w << 32) | b.z;
     return en;
-}
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ void red_release_sys_add_u64(unsigned long long *p, unsigned long long v) {
-    asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
 }
 __device__ __forceinline__ uint4 ld_slot(const uint4 *p) {
     uint4 v;

@@ -250,11 +250,8 @@ static void fill_params(hb_ctx *c, BrrParams &P) {
     P.flags = getenv("HB_NO_PREFETCH") ? 1u : 0u;
     P.pc.nranks = (uint32_t)c->nranks; P.pc.rank = (uint32_t)c->rank;
     P.pc.T_total = c->Ttot; P.pc.t_first = c->t_first;
-    P.pc.inbox_local = c->inbox; P.pc.flags_local = c->flags;
-    for (int h = 0; h < c->nranks; h++) {
-        P.pc.inbox_peer[h] = c->peer_inbox[h];
-        P.pc.flags_peer[h] = c->peer_inbox[h] ? reinterpret_cast<unsigned long long *>(c->peer_inbox[h] + c->comm_bytes - 256) : nullptr;
-    }
+    P.pc.inbox_local = c->inbox;
+    for (int h = 0; h < c->nranks; h++) P.pc.inbox_peer[h] = c->peer_inbox[h];
     P.pc.inbox_stride = c->inbox_stride; P.pc.seq_base = c->seq_base;
     P.pc.rec_bytes = c->d_rec_bytes.p; P.pc.err = c->d_err.p;
     {
