@@ -38,6 +38,7 @@ struct Options {  // names follow the reference's Options class (src/options.hpp
     bool seedSet = false;
     double thresholdFnz = 0.06;
     std::vector<double> S{0.01, 0.001, 0.0001};  // src/options.hpp:102-110
+    std::vector<std::string> ignored;            // reference options that have no effect here
     std::string mcmcOut() const { return mcmcOutDir + "/" + mcmcOutNam; }
 };
 
@@ -108,8 +109,11 @@ Options parse(int argc, const char **argv) {
         else if (a == "--dry-run") o.dryRun = true;
         // reference options outside the accelerated path: recognised, refused with a clear message
         else if (a == "--restart") o.restart = true;
-        else if (a == "--ignore-xfiles" || a == "--sparse-sync" || a == "--bed-sync" || a == "--covariates" ||
-                 a == "--check-RAM" || a == "--groupPriorsFile" || a == "--dPriorsFile")
+        // --sparse-sync / --bed-sync pick the reference's MPI algorithm for the epsilon synchronisation (:2080-2453); the result is
+        // the same sum. Here the GPUs always exchange the changed markers themselves over NVLink, so both are accepted as
+        // no-ops; --ignore-xfiles concerns the reference's restart files, which this host does not read (state file instead).
+        else if (a == "--sparse-sync" || a == "--bed-sync" || a == "--ignore-xfiles") o.ignored.push_back(a);
+        else if (a == "--covariates" || a == "--check-RAM" || a == "--groupPriorsFile" || a == "--dPriorsFile")
             throw std::runtime_error("option \"" + a + "\" of hydra is not supported by hydra_b200 yet (see DESIGN.md, out of scope)");
         else
             throw std::runtime_error("\nError: invalid option \"" + a + "\".\n");  // src/options.cpp:292-296
@@ -386,6 +390,8 @@ int main(int argc, const char **argv) {
         printf("INFO   : hydra_b200: %s, N = %u (%zu NA phenotypes), M = %u, %u task(s), sync rate %u, %u group(s) x %u mixtures, input %s\n",
                opt.bedToSparse ? "bed-to-sparse" : opt.bayesType.c_str(), Nraw, na.size(), Mtot, opt.tasks, opt.syncRate, G, K - 1,
                repr == HB_REPR_MIXED ? "mixed" : (repr == HB_REPR_BED ? "bed" : "sparse"));
+        for (auto &ig : opt.ignored)
+            printf("INFO   : option %s has no effect here (the GPUs always exchange the changed markers themselves; restart uses <out>.rst.<rank>)\n", ig.c_str());
         if (opt.dryRun) {
             printf("INFO   : dry run: options and input files parsed, nothing computed\n");
             return 0;

@@ -91,6 +91,17 @@ def test_cli_dry_run_reads_reference_formats(tmp_path):
     assert r.returncode != 0 and ".bim file has 150 markers" in r.stdout
 
 
+def test_cli_accepts_the_reference_sync_options_and_refuses_unsupported_ones(tmp_path):
+    d = str(tmp_path)
+    write_dataset(d)
+    r = subprocess.run(base_args(d, "o", ["--bfile", os.path.join(d, "t"), "--dry-run", "--sparse-sync", "--bed-sync", "--ignore-xfiles"]),
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("has no effect here") == 3
+    r = subprocess.run(base_args(d, "o", ["--bfile", os.path.join(d, "t"), "--dry-run", "--covariates", "x.cov"]), capture_output=True, text=True)
+    assert r.returncode != 0 and "not supported by hydra_b200" in r.stdout + r.stderr
+
+
 def test_cli_reads_the_reference_example_files():
     # parser fixtures shipped with the reference (SURVEY 8c iv): copied line counts only, no reference file is read at GPU time
     ex = "/root/reference/example"
