@@ -247,14 +247,18 @@ __device__ __forceinline__ void load_unit(const uint4 d, uint64_t (&x)[4], uint3
         if (w < nwords) x[t] = ld_stream_u64(ptr + w);
     }
 }
-__device__ __forceinline__ double dot_words(const uint64_t (&x)[4], uint32_t w0, uint32_t b1, uint32_t b2, double mave,
+__device__ __forceinline__ double dot_words(const uint64_t (&x)[4], uint32_t w0, uint32_t nwords, uint32_t b1, uint32_t b2, double mave,
                                             const double *__restrict__ E_s, uint32_t lane) {
     double acc = 0.0;
 #pragma unroll
     for (uint32_t t = 0; t < 4; t++) {
-        const uint32_t w = w0 + lane + 32u * t;
-        const double wt = (w < b1) ? 1.0 : ((w < b2) ? 2.0 : mave);
-        acc = fma(wt, gather4(x[t], E_s), acc);
+        // most slice blocks are short (rare variants): a group of 32 words that lies entirely past the end is skipped
+        // (warp-uniform test) instead of gathering the pad slot 4 x 32 times
+        if (w0 + 32u * t < nwords) {
+            const uint32_t w = w0 + lane + 32u * t;
+            const double wt = (w < b1) ? 1.0 : ((w < b2) ? 2.0 : mave);
+            acc = fma(wt, gather4(x[t], E_s), acc);
+        }
     }
     return acc;
 }
@@ -268,7 +272,7 @@ __device__ __forceinline__ double dot_unit(const uint4 d, const uint64_t (&x)[4]
         for (uint32_t w = lane + 32u; w < nwords; w += 32u) acc += dot_bed_word(ld_stream_u64(ptr + w), b2 + w, mave, E_s, lane);
         return acc;
     }
-    double acc = dot_words(x, 0u, b1, b2, mave, E_s, lane);
+    double acc = dot_words(x, 0u, nwords, b1, b2, mave, E_s, lane);
     if (nwords > 128u) {  // units longer than one step (very heavy chunks only)
         const uint64_t *ptr = reinterpret_cast<const uint64_t *>(((uint64_t)d.y << 32) | d.x);
         for (uint32_t w0 = 128u; w0 < nwords; w0 += 128u) {
@@ -279,7 +283,7 @@ __device__ __forceinline__ double dot_unit(const uint4 d, const uint64_t (&x)[4]
                 y[t] = padw;
                 if (w < nwords) y[t] = ld_stream_u64(ptr + w);
             }
-            acc += dot_words(y, w0, b1, b2, mave, E_s, lane);
+            acc += dot_words(y, w0, nwords, b1, b2, mave, E_s, lane);
         }
     }
     return acc;
@@ -784,31 +788,45 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                 // ends with a synchronisation: next window = SR steps); they land during the dot phase
                 const bool stage_next = (P.mode == MODE_CHAIN && k0 + kTabCap >= n_items && j0 + n < P.lmax);
                 if (stage_next) stage_items(&tabs[(win + 1u) & 1u], P, r, c, (j0 + n) * P.T, min(SR, P.lmax - (j0 + n)) * P.T, 0, tid, blockDim.x);
-                // ---- 2. dot: warp w takes the units w, w + 16, ...; the words of the next two units are in flight while
-                //         the current one gathers from shared memory (three register sets in rotation, no copies)
+                // ---- 2. dot: warp w takes the units w, w + 16, ... two at a time (their gathers and the two warp reductions
+                //         interleave: twice the independent work per warp), while the words of the next two units are in flight
+                //         (four register sets in rotation, no copies)
                 {
                     const uint32_t nun = tab->nunits;
                     const uint4 none = make_uint4(0u, 0u, 0u, 0u);
                     uint32_t u = warp;
-                    uint4 da, db, dc;
-                    uint64_t xa[4], xb[4], xc[4];
+                    uint4 da, db, dc, dd;
+                    uint64_t xa[4], xb[4], xc[4], xd[4];
 #define HB_FETCH(D, X, UU) do { D = ((UU) < nun) ? udesc[UU] : none; load_unit(D, X, lane, padw); } while (0)
-#define HB_COMPUTE(D, X) do { double acc_ = dot_unit(D, X, tab->meta[D.w >> 16].mave, E_s, lane, padw); acc_ = warp_sum(acc_); \
-                              if (lane == 0) upart[u] = acc_; u += kWarps; } while (0)
+#define HB_COMPUTE2(D0, X0, D1, X1) do { \
+                        const double m0_ = tab->meta[D0.w >> 16].mave, m1_ = tab->meta[D1.w >> 16].mave; \
+                        double a0_, a1_; \
+                        if ((D0.z >> 16) != 0xFFFFu && (D1.z >> 16) != 0xFFFFu && (D0.z & 0xFFFFu) <= 128u && (D1.z & 0xFFFFu) <= 128u) { \
+                            a0_ = dot_words(X0, 0u, D0.z & 0xFFFFu, D0.z >> 16, D0.w & 0xFFFFu, m0_, E_s, lane); \
+                            a1_ = dot_words(X1, 0u, D1.z & 0xFFFFu, D1.z >> 16, D1.w & 0xFFFFu, m1_, E_s, lane); \
+                        } else { \
+                            a0_ = dot_unit(D0, X0, m0_, E_s, lane, padw); \
+                            a1_ = dot_unit(D1, X1, m1_, E_s, lane, padw); \
+                        } \
+                        _Pragma("unroll") for (int o_ = 16; o_ > 0; o_ >>= 1) { \
+                            const double t0_ = __shfl_xor_sync(0xffffffffu, a0_, o_), t1_ = __shfl_xor_sync(0xffffffffu, a1_, o_); \
+                            a0_ += t0_; a1_ += t1_; \
+                        } \
+                        if (lane == 0) { upart[u] = a0_; if (u + kWarps < nun) upart[u + kWarps] = a1_; } \
+                        u += 2 * kWarps; } while (0)
                     HB_FETCH(da, xa, u);
                     HB_FETCH(db, xb, u + kWarps);
                     while (u < nun) {
                         HB_FETCH(dc, xc, u + 2 * kWarps);
-                        HB_COMPUTE(da, xa);
+                        HB_FETCH(dd, xd, u + 3 * kWarps);
+                        HB_COMPUTE2(da, xa, db, xb);
                         if (u >= nun) break;
                         HB_FETCH(da, xa, u + 2 * kWarps);
-                        HB_COMPUTE(db, xb);
-                        if (u >= nun) break;
-                        HB_FETCH(db, xb, u + 2 * kWarps);
-                        HB_COMPUTE(dc, xc);
+                        HB_FETCH(db, xb, u + 3 * kWarps);
+                        HB_COMPUTE2(dc, xc, dd, xd);
                     }
 #undef HB_FETCH
-#undef HB_COMPUTE
+#undef HB_COMPUTE2
                 }
                 cp_async_wait_all();
                 __syncthreads();
