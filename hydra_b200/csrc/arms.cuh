@@ -102,6 +102,10 @@ HB_HD inline void arms_cumulate(ArmsEnvelope &e) {
     }
 }
 
+struct ArmsSerialCumulate {  // default integration of the envelope: the reference's serial loops
+    HB_HD void operator()(ArmsEnvelope &e) const { arms_cumulate(e); }
+};
+
 struct ArmsPoint {
     double x, y, ey;
     int pl, pr;
@@ -138,9 +142,11 @@ HB_HD inline void arms_invert(const ArmsEnvelope &e, double prob, ArmsPoint &p) 
 
 // One sample from the density exp(logdens(x)) on [xl, xr], starting abscissae xinit[0..ninit) ascending.
 // logdens: double(double); urand: double() in (0,1). Returns ARMS_OK or an error code; *xsamp holds the sample.
-template <class LogDens, class URand>
+// cumulate: how the envelope is exponentiated and integrated after every change (the device passes a warp-cooperative
+// functor that computes the same numbers, one envelope point per lane).
+template <class LogDens, class URand, class Cumulate = ArmsSerialCumulate>
 HB_HD inline int arms_sample(const double *xinit, int ninit, double xl, double xr, LogDens &logdens, URand &urand, double *xsamp,
-                             ArmsEnvelope &e) {
+                             ArmsEnvelope &e, Cumulate cumulate = Cumulate()) {
     // ---- initial envelope (:247-354)
     if (ninit < 3) return ARMS_FEW_INIT;
     const int mpoint = 2 * ninit + 1;
@@ -166,7 +172,7 @@ HB_HD inline int arms_sample(const double *xinit, int ninit, double xl, double x
         const int rc = arms_meet(e, j);
         if (rc) return rc;
     }
-    arms_cumulate(e);
+    cumulate(e);
     e.cpoint = mpoint;
     // ---- adaptive rejection (:207-225): sample (:358-368), test (:449-548), update (:552-655)
     for (;;) {
@@ -222,7 +228,7 @@ HB_HD inline int arms_sample(const double *xinit, int ninit, double xl, double x
                 rc = arms_meet(e, e.pr[e.pr[e.pr[q]]]);
                 if (rc) return rc;
             }
-            arms_cumulate(e);
+            cumulate(e);
         }
         if (!(y >= ynew)) { *xsamp = p.x; return ARMS_OK; }  // accepted at the rejection step
     }

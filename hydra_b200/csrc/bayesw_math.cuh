@@ -86,13 +86,13 @@ struct BwBetaDens {
 
 // ARMS draw of beta around the previous value (:1562-1582): xinit = b - L/10, b, b + L/20, b + L/10; bounds b -+ L,
 // L = 2*sqrt(sumSigmaG * C_k)
-template <class URand>
+template <class URand, class Cumulate = ArmsSerialCumulate>
 HB_HD inline int bw_sample_beta(const BwMarker &m, double C_k, double sum_sigmaG, double beta_old, URand &urand, double *beta_new,
-                                ArmsEnvelope &env) {
+                                ArmsEnvelope &env, Cumulate cumulate = Cumulate()) {
     const double safe_limit = 2 * sqrt(sum_sigmaG * C_k);
     const double xinit[4] = {beta_old - safe_limit / 10, beta_old, beta_old + safe_limit / 20, beta_old + safe_limit / 10};
     BwBetaDens d{m, C_k};
-    return arms_sample(xinit, 4, beta_old - safe_limit, beta_old + safe_limit, d, urand, beta_new, env);
+    return arms_sample(xinit, 4, beta_old - safe_limit, beta_old + safe_limit, d, urand, beta_new, env, cumulate);
 }
 
 }  // namespace hb

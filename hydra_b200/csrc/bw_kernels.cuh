@@ -68,10 +68,70 @@ struct BwArmsRand {  // RNG spec v1: 31-bit integers from Philox, u = (r + 0.5) 
     }
 };
 
+// Warp-cooperative integration of the ARMS envelope. The draw itself is serial (lane 0), but after every new point the
+// reference re-exponentiates and re-integrates the whole envelope (its maximum moves): one exp and one divide per point, the
+// bulk of the draw's time on a single thread. Lane 0 lists the points in order and wakes the other lanes of its warp, which
+// wait in bw_arms_helpers(); every lane evaluates the reference's expressions for its points; lane 0 adds the areas up in order.
+struct BwArmsShared {
+    ArmsEnvelope env;
+    double area[kArmsPoints];
+    int ord[kArmsPoints];
+    int n, cmd;
+};
+__device__ __forceinline__ void bw_coop_ey(BwArmsShared &sh, uint32_t lane) {
+    ArmsEnvelope &e = sh.env;
+    for (int i = (int)lane; i < sh.n; i += 32) { const int q = sh.ord[i]; e.ey[q] = arms_expshift(e.y[q], e.ymax); }
+}
+__device__ __forceinline__ void bw_coop_area(BwArmsShared &sh, uint32_t lane) {
+    ArmsEnvelope &e = sh.env;
+    for (int i = (int)lane + 1; i < sh.n; i += 32) {
+        const int q = sh.ord[i], l = sh.ord[i - 1];
+        double a;
+        if (e.x[l] == e.x[q]) a = 0.0;
+        else if (fabs(e.y[q] - e.y[l]) < kArmsYEPS) a = 0.5 * (e.ey[q] + e.ey[l]) * (e.x[q] - e.x[l]);
+        else a = ((e.ey[q] - e.ey[l]) / (e.y[q] - e.y[l])) * (e.x[q] - e.x[l]);
+        sh.area[q] = a;
+    }
+}
+struct BwCoopCumulate {  // called by lane 0 only
+    BwArmsShared *sh;
+    __device__ void operator()(ArmsEnvelope &e) const {
+        int lm = 0;
+        while (e.pl[lm] >= 0) lm = e.pl[lm];
+        int n = 0;
+        double ymax = e.y[lm];
+        for (int q = lm; q >= 0; q = e.pr[q]) { sh->ord[n++] = q; if (e.y[q] > ymax) ymax = e.y[q]; }
+        e.ymax = ymax;
+        sh->n = n; sh->cmd = 1;
+        __syncwarp();
+        bw_coop_ey(*sh, 0);
+        __syncwarp();
+        bw_coop_area(*sh, 0);
+        __syncwarp();
+        e.cum[lm] = 0.0;
+        for (int i = 1; i < n; i++) e.cum[sh->ord[i]] = e.cum[sh->ord[i - 1]] + sh->area[sh->ord[i]];
+    }
+};
+__device__ __forceinline__ void bw_arms_helpers(BwArmsShared &sh, uint32_t lane) {  // lanes 1..31 of the drawing warp
+    for (;;) {
+        __syncwarp();
+        if (sh.cmd == 0) break;
+        bw_coop_ey(sh, lane);
+        __syncwarp();
+        bw_coop_area(sh, lane);
+        __syncwarp();
+    }
+}
+__device__ __forceinline__ void bw_arms_release(BwArmsShared &sh) {  // lane 0, when it needs no (more) help
+    sh.cmd = 0;
+    __syncwarp();
+}
+
 constexpr uint32_t kBwMaxS = 160;  // slices (<= CTAs of the sampler grid <= SMs)
 __global__ void __launch_bounds__(256) k_bw_window(const BwParams P) {
     __shared__ double red[8];
     __shared__ uint32_t s_cum[kBwMaxS + 1], s_st[kBwMaxS], s_w1[kBwMaxS], s_w12[kBwMaxS];
+    __shared__ BwArmsShared s_arms;
     const uint32_t p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int32_t m = P.order[P.base + p];
     if (m < 0) return;
@@ -188,15 +248,15 @@ __global__ void __launch_bounds__(256) k_bw_window(const BwParams P) {
         if ((k + 1) == km1) acum = 1;                                             // :1592-1593
         else acum += ML[k + 1] / MLsum;
     }
-    if (lane != 0) return;
+    if (lane != 0) { bw_arms_helpers(s_arms, lane); return; }  // the other lanes serve lane 0's envelope integrations
     double beta_new = beta_old;  // the cascade can fall through without a draw (as in the reference)
     if (comp == 0) beta_new = 0.0;
     else if (comp > 0) {
-        ArmsEnvelope env;
         BwArmsRand ur{P.seed, P.t_first + (p % P.T), P.iteration, P.j0 + p / P.T, 0u};
-        const int rc = bw_sample_beta(bm, P.cVa[g * km1 + comp - 1], P.sumSigmaG, beta_old, ur, &beta_new, env);
-        if (rc != ARMS_OK) { atomicExch(P.err, (uint32_t)rc); return; }
+        const int rc = bw_sample_beta(bm, P.cVa[g * km1 + comp - 1], P.sumSigmaG, beta_old, ur, &beta_new, s_arms.env, BwCoopCumulate{&s_arms});
+        if (rc != ARMS_OK) { atomicExch(P.err, (uint32_t)rc); bw_arms_release(s_arms); return; }
     }
+    bw_arms_release(s_arms);
     if (comp >= 0) {
         atomicAdd(&P.cass[g * K + comp], 1);
         P.comp[m] = comp;
@@ -312,12 +372,14 @@ __global__ void k_bw_unit_marginal(BwMarker m, int rule, const double *prior, co
     bw_marginal_likelihoods(rule, prior, cVa, km1, m, post);
 }
 __global__ void k_bw_unit_arms(BwMarker m, double Ck, double sumSigmaG, double beta_old, uint32_t seed, uint32_t task, uint32_t iteration,
-                               uint32_t j, double *out) {
-    ArmsEnvelope env;
+                               uint32_t j, double *out) {  // one warp: lane 0 draws, the others help (as in k_bw_window)
+    __shared__ BwArmsShared sh;
+    if (threadIdx.x != 0) { bw_arms_helpers(sh, threadIdx.x); return; }
     BwArmsRand ur{seed, task, iteration, j, 0u};
     double bn = 0.0;
-    const int rc = bw_sample_beta(m, Ck, sumSigmaG, beta_old, ur, &bn, env);
-    out[0] = bn; out[1] = (double)rc; out[2] = (double)env.neval; out[3] = (double)ur.idx;
+    const int rc = bw_sample_beta(m, Ck, sumSigmaG, beta_old, ur, &bn, sh.env, BwCoopCumulate{&sh});
+    bw_arms_release(sh);
+    out[0] = bn; out[1] = (double)rc; out[2] = (double)sh.env.neval; out[3] = (double)ur.idx;
 }
 
 }  // namespace hb
