@@ -323,10 +323,17 @@ __global__ void __launch_bounds__(512) k_bw_update(const BwParams P) {
                         }
                     } else {
                         const double d = ((w < s_b1[x]) ? 1.0 : ((w < s_b2[x]) ? 2.0 : mave)) * dbs;
+                        // the four individuals of a word are distinct: their loads go out together, then the stores
+                        uint32_t idx[4];
+                        double v[4];
+#pragma unroll
                         for (uint32_t t = 0; t < 4; t++) {
-                            const uint32_t idx = (uint32_t)(bits >> (16u * t)) & 0xFFFFu;
-                            if (idx != L) __stcg(E + idx, __ldcg(E + idx) + d);
+                            idx[t] = (uint32_t)(bits >> (16u * t)) & 0xFFFFu;
+                            v[t] = (idx[t] != L) ? __ldcg(E + idx[t]) : 0.0;
                         }
+#pragma unroll
+                        for (uint32_t t = 0; t < 4; t++)
+                            if (idx[t] != L) __stcg(E + idx[t], v[t] + d);
                     }
                 }
                 off = fma(-mave, dbs, off);
