@@ -35,15 +35,21 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="hydra_b200", choices=["hydra_b200", "reference"])
+    ap.add_argument("--model", default="bayesrr", choices=["bayesrr", "bayesw"],
+                    help="bayesrr = the headline workload (BASELINE config 4); bayesw = the same genotypes under the Weibull model "
+                         "(BASELINE config 3 at scale; 1 GPU, 131072 markers unless --m-per-gpu is given)")
     ap.add_argument("--n", type=int, default=500_000, help="individuals")
-    ap.add_argument("--m-per-gpu", type=int, default=1_000_000, help="markers per GPU (M = this x gpus)")
+    ap.add_argument("--m-per-gpu", type=int, default=None, help="markers per GPU (M = this x gpus); default 1 000 000 (bayesw: 131 072)")
     ap.add_argument("--spectrum", default="B")
     ap.add_argument("--tasks-per-gpu", type=int, default=64)
     ap.add_argument("--sync-rate", type=int, default=10)
     ap.add_argument("--cpu-sample-markers", type=int, default=49152)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--n-slices", type=int, default=0)
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.m_per_gpu is None:
+        a.m_per_gpu = 1_000_000 if a.model == "bayesrr" else 131_072
+    return a
 
 
 def workload_config(a, world):
@@ -155,6 +161,105 @@ def cpu_reference_run(a, n_ind, n_markers, m_total, steps, warmup):
             "ms_per_step_sample": float(loop.mean() * 1e3), "compile": "gcc -Ofast -march=native -fopenmp (reference src/Makefile_G flags)"}
 
 
+# ----------------------------------------------------------------------------- BayesW line (not the headline)
+def weibull_phenotype(n, g, seed=3):
+    """log t = mu + g + w / alpha with mu = 4.1, alpha = 10, var(g) = 0.01675 (example/Weibull.h2), 10 % censored."""
+    rng = np.random.default_rng(seed)
+    g = (g - g.mean()) / g.std() * np.sqrt(0.01675)
+    y = 4.1 + g + np.log(rng.exponential(size=n)) / 10.0 + 0.577215664901532 / 10.0
+    fail = (rng.random(n) > 0.1).astype(np.float64)
+    return y, fail
+
+
+def bayesw_cpu_run(a, n_markers, m_total, n_iter=2):
+    """The CPU restatement of the reference's BayesW loop (oracle/hydra_oracle_bw.c + the reference's own ARMS object code),
+    one thread simulating 16 tasks, on the first n_markers markers of the workload."""
+    import oracle
+    sp = cpu_sample_lists(a, n_markers, m_total)
+    rng = np.random.default_rng(11)
+    y, fail = weibull_phenotype(a.n, rng.normal(size=a.n))
+    T = 16
+    tm = oracle.TapeMaker(5, T, n_markers).make(n_iter)
+    tape = dict(perm=tm["perm"], p=tm["u"])
+    t0 = time.time()
+    oracle.bw_chain(a.n, n_markers, T, 4, 1, a.sync_rate, n_iter, 25, sp, y, fail, np.zeros(n_markers, np.int32),
+                    np.array([[0.0, 0.001, 0.01, 0.1]]), tape, 5, hyper_seed=7)
+    wall = time.time() - t0
+    return {"value": n_markers * n_iter / wall, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{n_markers} markers of the same workload (N={a.n}), {T} tasks simulated by one thread, sync_rate {a.sync_rate}, "
+                      f"{n_iter} iterations incl. the mu / alpha ARMS steps; {wall:.1f} s",
+            "compile": "gcc -O2 (oracle) + the reference's src/BayesW_arms.cpp object code"}
+
+
+def bayesw_main(a, local_rank):
+    import torch
+    import hydra_b200
+    from hydra_b200 import synth
+    M = a.m_per_gpu
+    store = hydra_b200.GenotypeStore(a.n, M, tasks=a.tasks_per_gpu, sync_rate=a.sync_rate, n_groups=1, n_mix=4, repr_mode="sparse",
+                                     device=local_rank, model="bayesW")
+    t0 = time.time()
+    synth.stage_synthetic(store, a.spectrum)
+    stage_s = time.time() - t0
+    g, _, _ = synth.simulate_phenotype(store, n_causal=max(10, M // 200))
+    y, fail = weibull_phenotype(a.n, g)
+    bw = hydra_b200.BayesW(store, y, fail, [[0.001, 0.01, 0.1]], quad_points=25, seed=5)
+    n1, n2, nm = store.marker_counts()
+    nnz_total = int((n1.astype(np.int64) + n2 + nm).sum())
+    for _ in range(a.warmup):
+        bw.iteration()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter()
+    outs = [bw.iteration() for _ in range(a.steps)]
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    loop_ms = float(sum(o["loop_ms"] for o in outs))
+    t_e2e = time.perf_counter()
+    for _ in range(a.steps):
+        bw.iteration()
+        bw.state()
+        bw.hyper()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t_e2e) * 1e3
+    clocks = sampler.stop()
+    # algorithmic bytes: 12 B per stored non-zero visited (index + vi), per synchronisation 16*N (epsilon read, vi written)
+    alg = [12.0 * nnz_total + 16.0 * store.n_ind * o["n_sync"] for o in outs]
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
+    peak = float(peaks["hbm_gbs"]) if peaks else 6650.0
+    achieved = float(np.sum(alg)) / (loop_ms * 1e-3) / 1e9
+    cfg = workload_config(a, 1)
+    cfg["workload"] = (f"BayesW (Weibull, 25 quadrature points) sparse, synthetic N={a.n} M={M} (spectrum {a.spectrum}), 1 group, "
+                       f"S=0.001,0.01,0.1, {a.tasks_per_gpu} tasks x sync_rate {a.sync_rate}, 10 % censored")
+    cfg["m_markers"] = M
+    res = {"metric": METRIC, "model": "bayesW", "value": M * a.steps / (wall_ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": a.steps,
+           "warmup": a.warmup, "ms_per_step": wall_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic (device-generated genotypes, simulated Weibull phenotype)", "config": cfg,
+           "marker_loop": {"ms_per_step": loop_ms / a.steps, "marker_updates_per_sec": M * a.steps / (loop_ms * 1e-3),
+                           "windows_per_step": outs[-1]["n_windows"], "us_per_window": loop_ms * 1e3 / sum(o["n_windows"] for o in outs),
+                           "markers_changed_last_step": outs[-1]["markers_changed"]},
+           "e2e": {"value": M * a.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(4 * M), "d2h_bytes_per_step": int(12 * M + 256),
+                   "ms_per_step": e2e_ms / a.steps, "what": "BayesW.iteration() + state() + hyper() through the C ABI"},
+           "gpu_launches": int(sum(o["n_launches"] for o in outs)),
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                        "kernel": "k_bw_window + k_bw_update (one launch pair per synchronisation window)",
+                        "algorithmic_bytes_per_launch": float(np.mean(alg)),
+                        "note": "latency-bound: the window waits for the serial ARMS draws of its few changing markers (DESIGN.md 6)"},
+           "clocks": clocks,
+           "layout": {"slices": store.n_slices, "genotype_bytes_per_gpu": store.genotype_bytes, "mean_nnz_per_marker": nnz_total / M,
+                      "stage_seconds": stage_s}}
+    if not a.no_cpu_baseline:
+        try:
+            res["cpu_baseline"] = bayesw_cpu_run(a, min(2048, M), M)
+        except Exception as e:
+            res["cpu_baseline"] = {"error": repr(e)}
+    print(json.dumps(res), flush=True)
+    store.close()
+    return 0
+
+
 # ----------------------------------------------------------------------------- main
 def main():
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep NCCL's version banner off stdout (one JSON line only)
@@ -169,6 +274,10 @@ def main():
         if rank != 0:
             return 0
         return reference_arm(a, world)
+    if a.model == "bayesw":
+        if world > 1:
+            raise SystemExit("bench.py --model bayesw: BayesW runs on one GPU in this version")
+        return bayesw_main(a, local_rank)
 
     import torch
     import hydra_b200
