@@ -212,19 +212,35 @@ __device__ __forceinline__ double gather4(uint64_t x, const double *__restrict__
 // half-warp hit 16 distinct shared-memory banks.
 __device__ __forceinline__ double dot_bed_word(uint64_t bits, uint32_t w, double mave, const double *__restrict__ E_s,
                                                uint32_t lane) {
-    double acc = 0.0;
-    if (bits == ~0ull) return acc;  // 32 x genotype 0
+    // PLINK codes (b1 b0): 00 -> 2, 10 -> 1, 11 -> 0, 01 -> missing (weight mave). Only the non-zero genotypes are
+    // visited: A = individuals with b0 == 0 (genotype 1 or 2), of which those with b1 == 0 as well count twice; the
+    // missing ones (b0 == 1, b1 == 0) are rare. The trip count is the lane's number of non-zeros, not 32.
+    if (bits == ~0ull) return 0.0;  // 32 x genotype 0
     const double *e = E_s + 32u * w;
-#pragma unroll 8
-    for (uint32_t t = 0; t < 32; t++) {
-        const uint32_t idx = (t + lane) & 31u;
-        const uint32_t code = (uint32_t)(bits >> (2u * idx)) & 3u;
-        const double v = e[idx];
-        // 00 -> 2, 10 -> 1, 01 -> missing (weight mave), 11 -> 0
-        const double wt = (code == 0u) ? 2.0 : ((code == 2u) ? 1.0 : ((code == 1u) ? mave : 0.0));
-        acc = fma(wt, v, acc);
+    double acc = 0.0, acc2 = 0.0;
+#pragma unroll
+    for (uint32_t h = 0; h < 2; h++) {  // 16 individuals per 32-bit half
+        const uint32_t v = (uint32_t)(bits >> (32u * h));
+        const uint32_t b0 = v & 0x55555555u, b1 = (v >> 1) & 0x55555555u;
+        uint32_t a = ~b0 & 0x55555555u;          // genotype 1 or 2
+        const uint32_t two = a & ~b1;            // genotype 2
+        uint32_t miss = b0 & ~b1;
+        const double *eh = e + 16u * h;
+        while (a) {
+            const uint32_t pos = __ffs((int)a) - 1u;  // even bit position = 2 x individual
+            a &= a - 1u;
+            const double x = eh[pos >> 1];
+            acc += x;
+            if ((two >> pos) & 1u) acc2 += x;
+        }
+        while (miss) {
+            const uint32_t pos = __ffs((int)miss) - 1u;
+            miss &= miss - 1u;
+            acc = fma(mave, eh[pos >> 1], acc);
+        }
     }
-    return acc;
+    (void)lane;
+    return acc + acc2;
 }
 
 // Work unit of the dot phase, one 16-byte descriptor in shared memory:
@@ -298,16 +314,22 @@ __device__ __forceinline__ double apply_bed_word(uint64_t x, uint32_t w, double 
     double *e = E_s + 32u * w;
     const double d1 = dbs, d2 = 2.0 * dbs, dm = mave * dbs;
     double added = 0.0;
-#pragma unroll 8
-    for (uint32_t t = 0; t < 32; t++) {
-        const uint32_t idx = (t + lane) & 31u;
-        const uint32_t code = (uint32_t)(x >> (2u * idx)) & 3u;
-        if (code != 3u) {
-            const double d = (code == 0u) ? d2 : ((code == 2u) ? d1 : dm);
-            e[idx] += d;
+#pragma unroll
+    for (uint32_t h = 0; h < 2; h++) {  // only the non-zero genotypes are visited (codes as in dot_bed_word)
+        const uint32_t v = (uint32_t)(x >> (32u * h));
+        const uint32_t b0 = v & 0x55555555u, b1 = (v >> 1) & 0x55555555u;
+        uint32_t a = (~b0 & 0x55555555u) | (b0 & ~b1);  // genotype 1, 2 or missing
+        const uint32_t two = ~b0 & ~b1 & 0x55555555u, miss = b0 & ~b1;
+        double *eh = e + 16u * h;
+        while (a) {
+            const uint32_t pos = __ffs((int)a) - 1u;
+            a &= a - 1u;
+            const double d = ((miss >> pos) & 1u) ? dm : (((two >> pos) & 1u) ? d2 : d1);
+            eh[pos >> 1] += d;
             added += d;
         }
     }
+    (void)lane;
     return added;
 }
 // sparse: four u16 indices, unique inside a marker; unused lanes of a word point at the dummy slot L
