@@ -284,8 +284,11 @@ __device__ __forceinline__ double dot_unit(const uint4 d, const uint64_t (&x)[4]
     const uint32_t nwords = d.z & 0xFFFFu, b1 = d.z >> 16, b2 = d.w & 0xFFFFu;
     if (b1 == 0xFFFFu) {  // BED: b2 = first word of the unit inside the slice block
         const uint64_t *ptr = reinterpret_cast<const uint64_t *>(((uint64_t)d.y << 32) | d.x);
-        double acc = (lane < nwords) ? dot_bed_word(x[0], b2 + lane, mave, E_s, lane) : 0.0;
-        for (uint32_t w = lane + 32u; w < nwords; w += 32u) acc += dot_bed_word(ld_stream_u64(ptr + w), b2 + w, mave, E_s, lane);
+        double acc = 0.0;
+#pragma unroll
+        for (uint32_t t = 0; t < 4; t++)  // load_unit has fetched up to four words per lane
+            if (lane + 32u * t < nwords) acc += dot_bed_word(x[t], b2 + lane + 32u * t, mave, E_s, lane);
+        for (uint32_t w = lane + 128u; w < nwords; w += 32u) acc += dot_bed_word(ld_stream_u64(ptr + w), b2 + w, mave, E_s, lane);
         return acc;
     }
     double acc = dot_words(x, 0u, nwords, b1, b2, mave, E_s, lane);
