@@ -1299,7 +1299,7 @@ struct BlobR {
 };
 static std::string rng_text(const HostRng &r) { std::ostringstream o; o << r.eng; return o.str(); }
 static bool rng_from_text(HostRng &r, const std::string &t) { std::istringstream i(t); i >> r.eng; return !i.fail(); }
-constexpr uint32_t kRestartMagic = 0x31524248u;  // "HBR1"
+constexpr uint32_t kRestartMagic = 0x32524248u;  // "HBR2"
 }  // namespace hb
 
 extern "C" {
@@ -1313,6 +1313,8 @@ int hb_brr_save_state(hb_ctx *c, void *buf, size_t cap, size_t *need) {
     const uint32_t head[12] = {kRestartMagic, (uint32_t)HB_ABI_VERSION, c->N, c->M, c->T, c->G, c->K, c->S, c->L, c->seed, c->iteration, c->have_next ? 1u : 0u};
     w.put(head, 12);
     w.one(c->shift); w.one(c->sigmaE); w.one(c->seq_base);
+    const double bwv[4] = {c->bw_mu, c->bw_alpha, c->bw_sumSigmaG, c->bw_ready ? 1.0 : 0.0};  // BayesW scalars (the same blob serves both models)
+    w.put(bwv, 4);
     w.put(c->sigmaG.data(), c->G); w.put(c->pi.data(), (size_t)c->G * c->K); w.put(c->mu.data(), c->T); w.put(c->bsq.data(), c->G);
     w.put(c->cass.data(), (size_t)c->G * c->K); w.put(c->m0.data(), c->G);
     w.put(c->slice_sum_h.data(), c->S);
@@ -1322,7 +1324,7 @@ int hb_brr_save_state(hb_ctx *c, void *buf, size_t cap, size_t *need) {
     w.str(rng_text(c->hyper_rng));
     std::vector<double> hd(std::max(nE, (size_t)c->M));
     std::vector<int32_t> hi(c->M);
-    HB_CUDA(cudaMemcpy(hd.data(), c->d_E[c->cur].p, sizeof(double) * nE, cudaMemcpyDeviceToHost)); w.put(hd.data(), nE);
+    HB_CUDA(cudaMemcpy(hd.data(), c->d_E[c->bw_ready ? 0 : c->cur].p, sizeof(double) * nE, cudaMemcpyDeviceToHost)); w.put(hd.data(), nE);
     HB_CUDA(cudaMemcpy(hd.data(), c->d_beta.p, sizeof(double) * c->M, cudaMemcpyDeviceToHost)); w.put(hd.data(), c->M);
     HB_CUDA(cudaMemcpy(hd.data(), c->d_acum.p, sizeof(double) * c->M, cudaMemcpyDeviceToHost)); w.put(hd.data(), c->M);
     HB_CUDA(cudaMemcpy(hi.data(), c->d_comp.p, sizeof(int32_t) * c->M, cudaMemcpyDeviceToHost)); w.put(hi.data(), c->M);
@@ -1347,6 +1349,10 @@ int hb_brr_load_state(hb_ctx *c, const void *buf, size_t n) {
     const size_t nE = (size_t)c->S * c->L;
     c->seed = head[9]; c->iteration = head[10]; c->have_next = head[11] != 0;
     c->shift = r.one<double>(); c->sigmaE = r.one<double>(); c->seq_base = r.one<unsigned long long>();
+    double bwv[4] = {0, 0, 0, 0};
+    r.get(bwv, 4);
+    HB_CHECK(r.ok && (bwv[3] != 0.0) == c->bw_ready, HB_ERR_ARG, "hb_brr_load_state: the state belongs to the other model (BayesRRm / BayesW)");
+    if (c->bw_ready) { c->bw_mu = bwv[0]; c->bw_alpha = bwv[1]; c->bw_sumSigmaG = bwv[2]; }
     r.get(c->sigmaG.data(), c->G); r.get(c->pi.data(), (size_t)c->G * c->K); r.get(c->mu.data(), c->T); r.get(c->bsq.data(), c->G);
     r.get(c->cass.data(), (size_t)c->G * c->K); r.get(c->m0.data(), c->G);
     r.get(c->slice_sum_h.data(), c->S);
@@ -1357,7 +1363,7 @@ int hb_brr_load_state(hb_ctx *c, const void *buf, size_t n) {
     std::vector<double> hd(std::max(nE, (size_t)c->M));
     std::vector<int32_t> hi(c->M);
     r.get(hd.data(), nE); HB_CHECK(r.ok, HB_ERR_ARG, "hb_brr_load_state: truncated state");
-    HB_CUDA(cudaMemcpy(c->d_E[c->cur].p, hd.data(), sizeof(double) * nE, cudaMemcpyHostToDevice));
+    HB_CUDA(cudaMemcpy(c->d_E[c->bw_ready ? 0 : c->cur].p, hd.data(), sizeof(double) * nE, cudaMemcpyHostToDevice));
     r.get(hd.data(), c->M); HB_CUDA(cudaMemcpy(c->d_beta.p, hd.data(), sizeof(double) * c->M, cudaMemcpyHostToDevice));
     r.get(hd.data(), c->M); HB_CUDA(cudaMemcpy(c->d_acum.p, hd.data(), sizeof(double) * c->M, cudaMemcpyHostToDevice));
     r.get(hi.data(), c->M); HB_CHECK(r.ok, HB_ERR_ARG, "hb_brr_load_state: truncated state");

@@ -488,19 +488,31 @@ int main(int argc, const char **argv) {
             for (uint32_t k = 1; k < K; k++) mSflat[g * K + k] = mS[g][k - 1];
         const uint32_t seed = opt.seedSet ? opt.seed : (uint32_t)time(nullptr);
         if (bayesW) {
-            if (opt.restart) throw std::runtime_error("option \"--restart\" is not supported for bayesWMPI by hydra_b200 yet");
             HB(hb_bw_init(ctx, y.data(), fail.data(), groups.empty() ? nullptr : groups.data(), mSflat.data(), (uint32_t)atoi(opt.quad_points.c_str()), seed));
             struct stat sbw;
             if (stat(opt.mcmcOutDir.c_str(), &sbw) != 0 && system(("mkdir -p " + opt.mcmcOutDir).c_str()) != 0)
                 throw std::runtime_error("could not create output directory --mcmc-out-dir " + opt.mcmcOutDir);
             const std::string out = opt.mcmcOut();
             OutFile csv, bet, cpn;
-            csv.open(out + ".csv"); bet.open(out + ".bet"); cpn.open(out + ".cpn");
-            bet.put(&Mtot, 1); cpn.put(&Mtot, 1);
+            uint32_t it_first = 0, n_saved = 0;
+            if (opt.restart) {  // as for BayesRRm: state file of the last --save point, outputs cut back to it
+                uint32_t it_saved = 0;
+                read_restart_file(out + ".rst.0", ctx, it_saved, n_saved);
+                it_first = it_saved + 1;
+                truncate_csv(out + ".csv", it_saved);
+                if (truncate((out + ".bet").c_str(), 4 + (off_t)n_saved * (4 + (off_t)Mtot * 8)) != 0 ||
+                    truncate((out + ".cpn").c_str(), 4 + (off_t)n_saved * (4 + (off_t)Mtot * 4)) != 0)
+                    fatal("--restart: cannot cut the .bet/.cpn files back to the restart point");
+                csv.open_append(out + ".csv"); bet.open_append(out + ".bet"); cpn.open_append(out + ".cpn");
+                printf("INFO   : restarting after iteration %u (%u records in .bet/.cpn)\n", it_saved, n_saved);
+            } else {
+                csv.open(out + ".csv"); bet.open(out + ".bet"); cpn.open(out + ".cpn");
+                bet.put(&Mtot, 1); cpn.put(&Mtot, 1);
+            }
             std::vector<double> beta(Mtot), sigmaG(G), pi((size_t)G * K), bsq(G), eps(N);
             std::vector<int32_t> comp(Mtot), cass((size_t)G * K), m0(G);
             double tot_ms = 0.0;
-            for (uint32_t it = 0; it < opt.chainLength; it++) {
+            for (uint32_t it = it_first; it < opt.chainLength; it++) {
                 hb_bw_iter_out io;
                 HB(hb_bw_iteration(ctx, nullptr, &io));
                 tot_ms += io.iter_ms;
@@ -520,11 +532,13 @@ int main(int argc, const char **argv) {
                     HB(hb_brr_get_state(ctx, beta.data(), comp.data(), nullptr));
                     bet.put(&it, 1); bet.put(beta.data(), Mtot);
                     cpn.put(&it, 1); cpn.put(comp.data(), Mtot);
-                    fflush(csv.f);
+                    fflush(csv.f); fflush(bet.f); fflush(cpn.f);
+                    n_saved++;
                 }
                 if (it > 0 && it % opt.save == 0) {
                     HB(hb_get_epsilon(ctx, eps.data()));
                     dump_file(out + ".eps.0", it, N, eps.data());
+                    write_restart_file(out + ".rst.0", ctx, it, n_saved);
                 }
             }
             printf("INFO   : time to process the data: %.3f sec\n", tot_ms * 1e-3);

@@ -165,8 +165,8 @@ int hb_brr_get_state(hb_ctx *ctx, double *beta, int32_t *components, double *acu
 int hb_brr_set_state(hb_ctx *ctx, const double *beta, const int32_t *components); /* --restart */
 /* --restart (src/BayesRRm.cpp:842-928: the reference reads .csv .bet .cpn .eps .mrk .mus .rng back). The complete chain
  * state of this GPU as one opaque blob: hyper-parameters, per-task mu, residual, effects / components / Acum and the host
- * random streams. `buf == NULL`: only *need is set. After hb_brr_init with the same inputs and layout, hb_brr_load_state
- * continues the chain bit-identically to the uninterrupted run. */
+ * random streams. `buf == NULL`: only *need is set. After hb_brr_init (or hb_bw_init: the pair serves both models) with the
+ * same inputs and layout, hb_brr_load_state continues the chain bit-identically to the uninterrupted run. */
 int hb_brr_save_state(hb_ctx *ctx, void *buf, size_t cap, size_t *need);
 int hb_brr_load_state(hb_ctx *ctx, const void *buf, size_t n);
 /* epsilon of local task t as the reference dumps it to .eps.<rank> (:2827) */

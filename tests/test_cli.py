@@ -241,6 +241,17 @@ def test_cli_bayesw_run_equals_python_run(tmp_path):
             assert np.array_equal(bw.state()[0], beta[it])
     line = open(os.path.join(d, "o", "w.csv")).read().split("\n")[3].split(",")
     assert int(line[0]) == 3 and abs(float(line[1]) - o["mu"]) < 1e-12 and abs(float(line[3]) - o["alpha"]) < 1e-12
+    # --restart: stop after iteration 2 (its --save point), continue to 4 iterations: the same files byte for byte
+    base = [_exe(), "--mpibayes", "bayesWMPI", "--bfile", os.path.join(d, "w"), "--pheno", os.path.join(d, "w.phen"),
+            "--failure", os.path.join(d, "w.fail"), "--quad_points", "11", "--number-individuals", str(N), "--number-markers", str(M),
+            "--S", "0.001,0.01,0.1", "--thin", "1", "--save", "2", "--seed", "9", "--sync-rate", "3", "--tasks", "2",
+            "--mcmc-out-dir", os.path.join(d, "p"), "--mcmc-out-name", "w"]
+    r = subprocess.run(base + ["--chain-length", "3"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    r = subprocess.run(base + ["--chain-length", "4", "--restart"], capture_output=True, text=True)
+    assert r.returncode == 0 and "restarting after iteration 2" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    for ext in ("csv", "bet", "cpn", "eps.0"):
+        assert open(os.path.join(d, "o", "w." + ext), "rb").read() == open(os.path.join(d, "p", "w." + ext), "rb").read(), ext
 
 
 @pytest.mark.gpu
