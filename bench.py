@@ -403,6 +403,18 @@ def main():
 
 def reference_arm(a, world):
     """CPU leg as its own arm: same metric/config, bounded sample per step, all host threads."""
+    if a.model == "bayesw":
+        n_markers = min(2048, a.m_per_gpu)
+        r = bayesw_cpu_run(a, n_markers, a.m_per_gpu, n_iter=max(2, min(a.steps, 4)))
+        cfg = workload_config(a, 1)
+        cfg["workload"] = f"BayesW (Weibull, 25 quadrature points) sparse, synthetic N={a.n} M={a.m_per_gpu} (spectrum {a.spectrum}), 64 tasks x sync_rate {a.sync_rate}"
+        cfg["m_markers"] = a.m_per_gpu
+        print(json.dumps({"impl": "reference", "metric": METRIC, "model": "bayesW", "value": r["value"], "unit": UNIT, "n_gpus": 1, "steps": a.steps,
+                          "warmup": a.warmup, "ms_per_step": a.m_per_gpu / r["value"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f64", "data": "synthetic", "config": cfg, "cpu_baseline": r,
+                          "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "note": "ms_per_step extrapolated linearly from the sample; CPU restatement of the reference's BayesW loop with the reference's own ARMS object code"}), flush=True)
+        return 0
     n_markers = min(a.cpu_sample_markers, a.m_per_gpu * world)
     r = cpu_reference_run(a, a.n, n_markers, a.m_per_gpu * world, a.steps, a.warmup)
     res = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
