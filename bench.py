@@ -46,9 +46,19 @@ def parse():
     ap.add_argument("--cpu-sample-markers", type=int, default=49152)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--n-slices", type=int, default=0)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --m-per-gpu markers on every GPU (the driver's default); strong: --m-total markers shared by the GPUs "
+                         "(BASELINE config 5: M = 8 000 000 over 1/2/4/8 GPUs, spectrum C so that the 1-GPU point is resident)")
+    ap.add_argument("--m-total", type=int, default=8_000_000, help="total markers of a --scaling strong run")
+    ap.add_argument("--no-extras", action="store_true", help="skip parity_check / latency_floor / bayesw sub-runs (profiling runs)")
     a = ap.parse_args()
     if a.m_per_gpu is None:
         a.m_per_gpu = 1_000_000 if a.model == "bayesrr" else 131_072
+    if a.scaling == "strong":
+        world = int(os.environ.get("WORLD_SIZE", str(a.gpus)))
+        if a.m_total % world:
+            raise SystemExit("--m-total must be a multiple of the number of GPUs")
+        a.m_per_gpu = a.m_total // world
     return a
 
 
@@ -57,7 +67,8 @@ def workload_config(a, world):
         "workload": f"BayesRRm sparse, synthetic N={a.n} M={a.m_per_gpu * world} (spectrum {a.spectrum}: log-uniform MAF, "
                     f"0.1% missing), 1 group, S=0.0001,0.001,0.01, {a.tasks_per_gpu * world} tasks x sync_rate {a.sync_rate}",
         "n_individuals": a.n, "m_markers": a.m_per_gpu * world, "spectrum": a.spectrum,
-        "tasks": a.tasks_per_gpu * world, "sync_rate": a.sync_rate, "partition": f"markers/tasks over {world} GPU(s)",
+        "tasks": a.tasks_per_gpu * world, "sync_rate": a.sync_rate,
+        "partition": f"markers/tasks over {world} GPU(s)" + (f" (strong scaling: M fixed at {a.m_per_gpu * world})" if a.scaling == "strong" else ""),
         "l2_policy": "inputs larger than L2 (genotype records >> 126 MB, each read once per step)",
     }
 
@@ -138,7 +149,12 @@ def cpu_sample_lists(a, n_markers, m_total):
 def cpu_reference_run(a, n_ind, n_markers, m_total, steps, warmup):
     """Times the CPU restatement of the reference loop on the first n_markers markers (same spectrum, same N).
     Layout: T = host cores tasks x 1 thread each (the reference's '12 tasks x 1 thread' MPI layout as OpenMP threads)."""
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the CPU leg must use the host's cores regardless
+    # (libgomp reads the variable when the oracle library is loaded, so it is set before the first import)
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(ncpu)
     import oracle
+    oracle.set_num_threads(ncpu)
     cores = oracle.num_threads(True)
     t_prep = time.time()
     sp = cpu_sample_lists(a, n_markers, m_total)
@@ -155,7 +171,7 @@ def cpu_reference_run(a, n_ind, n_markers, m_total, steps, warmup):
     wall = time.time() - t0
     loop = out["loop_seconds"][warmup:]
     rate = n_markers * len(loop) / float(loop.sum())
-    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "tasks": T, "threads_per_task": 1,
             "sample": f"{n_markers} markers of the same workload (N={n_ind}), {T} tasks x 1 OpenMP thread, sync_rate {a.sync_rate}, "
                       f"{len(loop)} timed iteration(s) after {warmup} warm-up; marker loop only; chain {wall:.1f} s + data generation {t_prep:.1f} s",
             "ms_per_step_sample": float(loop.mean() * 1e3), "compile": "gcc -Ofast -march=native -fopenmp (reference src/Makefile_G flags)"}
@@ -191,7 +207,7 @@ def bayesw_cpu_run(a, n_markers, m_total, n_iter=2):
             "compile": "gcc -O2 (oracle) + the reference's src/BayesW_arms.cpp object code"}
 
 
-def bayesw_main(a, local_rank):
+def bayesw_line(a, local_rank, with_cpu=True):
     import torch
     import hydra_b200
     from hydra_b200 import synth
@@ -250,14 +266,93 @@ def bayesw_main(a, local_rank):
            "clocks": clocks,
            "layout": {"slices": store.n_slices, "genotype_bytes_per_gpu": store.genotype_bytes, "mean_nnz_per_marker": nnz_total / M,
                       "stage_seconds": stage_s}}
-    if not a.no_cpu_baseline:
+    if with_cpu and not a.no_cpu_baseline:
         try:
             res["cpu_baseline"] = bayesw_cpu_run(a, min(2048, M), M)
         except Exception as e:
             res["cpu_baseline"] = {"error": repr(e)}
-    print(json.dumps(res), flush=True)
     store.close()
+    return res
+
+
+def bayesw_main(a, local_rank):
+    print(json.dumps(bayesw_line(a, local_rank)), flush=True)
     return 0
+
+
+# ----------------------------------------------------------------------------- extras of the headline line
+def parity_check(rank, world, local_rank, dist):
+    """A small deterministic replay against the CPU oracle ON THE RANKS OF THIS RUN, before the timed region: world GPUs x 4
+    tasks each must reproduce the oracle run with 4*world tasks (mixed BED/sparse records, sync_rate 5, 3 iterations).
+    The oracle is the checker here, nothing of it is timed or shipped."""
+    import hydra_b200
+    import oracle
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import bed_from_lists, random_bed, reference_lists, simulate_y
+    N, M, TL, SR, G, K, n_iter, seed = 3000, 1536, 4, 5, 2, 4, 3, 77
+    T = TL * world
+    rng = np.random.default_rng(seed)
+    bed, g = random_bed(rng, M, N, pmiss=0.01)
+    sp = reference_lists(bed, N)
+    y = simulate_y(rng, g, n_causal=60)
+    groups = (np.arange(M) % G).astype(np.int32)
+    mS = np.tile(np.array([0.0, 0.001, 0.01, 0.1]), (G, 1))
+    sigmaG0 = np.array([0.4, 0.6])
+    tape = oracle.TapeMaker(seed, T, M).make(n_iter)
+    fnz = (sp.N1L + sp.N2L + sp.NML).astype(np.float64) / N
+    usebed = (fnz > 0.35).astype(np.uint8)
+    ref = oracle.brr_chain(N, M, T, K, G, SR, n_iter, sp, y, groups, mS, tape, sigmaG0, usebed=usebed, bed=bed_from_lists(sp, N))
+    st = hydra_b200.GenotypeStore(N, M, tasks=T, task_first=rank * TL, tasks_local=TL, sync_rate=SR, n_groups=G, n_mix=K,
+                                  repr_mode="mixed", threshold_fnz=0.35, device=local_rank)
+    ms, ml = st.m_start, st.m_local
+    st.load_data_from_bed(bed[ms:ms + ml])
+    st.finalize()
+    if world > 1:
+        st.comm_init(dist)
+    brr = hydra_b200.BayesRRm(st, y, mS, groups=groups, sigmaG0=sigmaG0, seed=seed)
+    comp_ok, nsync_ok, beta_err, eps_err, n_changed = True, True, 0.0, 0.0, 0
+    for it in range(n_iter):
+        tp = dict(zmu=tape["zmu"][it][rank * TL:(rank + 1) * TL], perm=tape["perm"][it][ms:ms + ml], u=tape["u"][it][ms:ms + ml],
+                  z=tape["z"][it][ms:ms + ml], sigmaG=ref["sigmaG"][it], pi=ref["pi"][it], sigmaE=ref["sigmaE"][it:it + 1])
+        o = brr.iteration(tp)
+        beta, comp, _ = brr.state()
+        rb = ref["beta"][it][ms:ms + ml]
+        comp_ok &= bool(np.array_equal(comp, ref["comp"][it][ms:ms + ml])) and bool(np.array_equal(brr.hyper()["cass"], ref["cass"][it]))
+        nsync_ok &= int(o["n_sync"]) == int(ref["nsync"][it])
+        beta_err = max(beta_err, float(np.max(np.abs(beta - rb) / np.maximum(np.abs(rb), 1e-5))))   # |beta| of a non-zero effect >> 1e-5
+        for t in range(TL):
+            re_ = ref["eps"][it, rank * TL + t]
+            eps_err = max(eps_err, float(np.max(np.abs(brr.task_epsilon(t) - re_) / np.maximum(np.abs(re_), 1e-2))))
+        n_changed += int(o["markers_changed"])
+    st.close()
+    v = np.array([beta_err, eps_err, 0.0 if comp_ok else 1.0, 0.0 if nsync_ok else 1.0])
+    if world > 1:
+        import torch
+        t = torch.from_numpy(v).cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        v = t.cpu().numpy()
+    return {"n_gpus": world, "what": f"oracle replay on the ranks of this run: N={N} M={M} mixed records, {T} tasks x sync_rate {SR}, {G} groups, {n_iter} iterations",
+            "max_rel_err": float(max(v[0], v[1])), "beta_max_rel_err": float(v[0]), "eps_max_rel_err": float(v[1]),
+            "components_equal": bool(v[2] == 0.0), "n_sync_equal": bool(v[3] == 0.0), "markers_changed": n_changed,
+            "ok": bool(v[2] == 0.0 and v[3] == 0.0 and max(v[0], v[1]) < 1e-10)}
+
+
+def latency_floor(a, local_rank):
+    """Per-marker latency floor: 1 task, sync after every marker (the reference's 1-rank configuration, BASELINE config 1
+    at N = 500 000): every window is ONE marker, so the time per window is the serial latency of a marker update."""
+    import hydra_b200
+    from hydra_b200 import synth
+    M = 4096
+    st = hydra_b200.GenotypeStore(a.n, M, tasks=1, sync_rate=1, n_groups=1, n_mix=4, repr_mode="sparse", device=local_rank)
+    synth.stage_synthetic(st, a.spectrum)
+    y, _, _ = synth.simulate_phenotype(st, n_causal=20)
+    brr = hydra_b200.BayesRRm(st, y, [[0.0001, 0.001, 0.01]], seed=1222)
+    for _ in range(2):
+        brr.iteration()
+    outs = [brr.iteration() for _ in range(3)]
+    st.close()
+    return {"us_per_marker": float(sum(o["loop_ms"] for o in outs)) * 1e3 / (3 * M),
+            "config": f"N={a.n}, {M} markers of spectrum {a.spectrum}, 1 task x sync_rate 1 (one marker per synchronisation window)"}
 
 
 # ----------------------------------------------------------------------------- main
@@ -290,6 +385,14 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- driver-visible parity proof at THIS rank count (VERDICT r1 #1c), before anything is timed
+    pc = None
+    if not a.no_extras:
+        try:
+            pc = parity_check(rank, world, local_rank, dist)
+        except Exception as e:  # the bench line must still print; a failed check is reported, not hidden
+            pc = {"n_gpus": world, "ok": False, "error": repr(e)}
 
     T_total = a.tasks_per_gpu * world
     M_total = a.m_per_gpu * world
@@ -361,17 +464,39 @@ def main():
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
     peak = float(peaks["hbm_gbs"]) if peaks else 6650.0
     achieved = float(np.sum(alg_bytes)) / (loop_ms * 1e-3) / 1e9  # per-rank bytes / max-over-ranks kernel time
+    # measured DRAM traffic of one launch (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum): only valid for the
+    # 1-GPU default workload it was captured on; null elsewhere
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and world == 1 and a.m_per_gpu == 1_000_000 and a.spectrum == "B" and a.n == 500_000:
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    # second and third roofline from the kernel's own counters: what the launch really moves.
+    #   DRAM: genotype words are read once (8 B per 64-bit word of four u16 indices = 2 B per stored non-zero incl. padding),
+    #         the window-ordered marker data (64 B) and slice directory entries (16 B x slices) once, beta/components/Acum
+    #         written (20 B), epsilon read + written once; BED records: slices*slice_len/4 B each.
+    #   SMEM: every gathered word costs one LDS.64 per index lane group; the LSU moves one 128-B wavefront per clock and SM,
+    #         a 64-bit gather of a full warp needs >= 2.
+    Q = store.lmax * a.tasks_per_gpu
+    nnz_pad = float(np.mean([o["nnz_processed"] for o in outs]))
+    bed_m = float(np.mean([o["bed_markers"] for o in outs]))
+    dram_bytes = (2.0 * nnz_pad + Q * (64.0 + 16.0 * store.n_slices) + 20.0 * store.m_local + 16.0 * store.n_slices * store.slice_len
+                  + bed_m * store.n_slices * store.slice_len / 4.0)
+    upd_pad = float(np.mean([o["nnz_updated"] for o in outs])) * store.n_cta_groups   # every CTA group applies every change
+    sm_clock_hz = 1e6 * (clocks["sm_mhz"] if clocks and clocks.get("sm_mhz") else 1965.0)
+    n_sms = store.n_slices * store.n_cta_groups
+    lsu_wavefronts = 2.0 * (nnz_pad + 2.0 * upd_pad) / 32.0       # ideal: 2 wavefronts per 32-lane 64-bit access (update = load + store)
+    t_loop = loop_ms / a.steps * 1e-3
+    roof_dram = {"bytes_per_launch": dram_bytes, "gbps": dram_bytes / t_loop / 1e9, "frac_of_hbm": dram_bytes / t_loop / 1e9 / peak,
+                 "source": "kernel counters (2 B x stored non-zeros + window tables + state)"}
+    roof_smem = {"wavefronts_per_launch": lsu_wavefronts, "frac_of_lsu_peak": lsu_wavefronts / (t_loop * sm_clock_hz * n_sms),
+                 "source": "kernel counters, ideal 2 wavefronts per 64-bit warp gather; peak = 1 wavefront/clock/SM on the CTAs' SMs"}
 
     if rank == 0:
         res = {
             "metric": METRIC, "value": M_total * a.steps / (wall_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": wall_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": a.warmup, "ms_per_step": wall_ms / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic (device-generated genotypes, simulated phenotype)", "config": workload_config(a, world),
-            "sec_per_iteration": wall_ms / a.steps * 1e-3,
+            "sec_per_iteration": wall_ms / a.steps * 1e-3, "parity_check": pc,
             "marker_loop": {"ms_per_step": loop_ms / a.steps, "marker_updates_per_sec": M_total * a.steps / (loop_ms * 1e-3),
                             "windows_per_step": outs[-1]["n_windows"], "syncs_per_step": outs[-1]["n_sync"],
                             "markers_changed_last_step": outs[-1]["markers_changed"], "us_per_window": loop_ms * 1e3 / sum(o["n_windows"] for o in outs)},
@@ -380,15 +505,34 @@ def main():
                     "ms_per_step": e2e_ms / a.steps, "what": "BayesRRm.iteration() + state() + hyper() through the C ABI: marker order H2D, beta/components/acum D2H every step (thin=1)"},
             "gpu_launches": int(sum(o["n_launches"] for o in outs)),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "dram": roof_dram, "smem": roof_smem,
+                         "real_bound": "smem-lsu" if roof_smem["frac_of_lsu_peak"] > roof_dram["frac_of_hbm"] else "hbm",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "kernel": "k_brr_iteration (one cooperative launch per step)",
                          "algorithmic_bytes_per_launch": float(np.mean(alg_bytes)),
-                         "note": "epsilon lives in shared memory and indices are 16-bit, so real DRAM traffic is ~2 B per stored non-zero; "
-                                 "achieved counts the reference's algorithmic 12/16 B per non-zero"},
+                         "note": "`frac` uses SURVEY 8(d)'s algorithmic bytes (12/16 B per non-zero + 24*N per sync), a model of the REFERENCE's "
+                                 "traffic; the kernel keeps epsilon in shared memory and indices in 16 bits, so its real DRAM traffic is "
+                                 "`dram` (~2 B per stored non-zero) and its real ceiling is the shared-memory gather rate (`smem`) plus the "
+                                 "per-window latency chain (marker_loop.us_per_window)"},
             "clocks": clocks,
             "layout": {"slices": store.n_slices, "slice_len": store.slice_len, "cta_groups": store.n_cta_groups,
                        "genotype_bytes_per_gpu": store.genotype_bytes, "mean_nnz_per_marker": nnz_total / store.m_local, "stage_seconds": stage_s},
         }
+        store.close()
+        if world == 1 and not a.no_extras:
+            try:
+                res["latency_floor"] = latency_floor(a, local_rank)
+            except Exception as e:
+                res["latency_floor"] = {"error": repr(e)}
+            try:  # BayesW (BASELINE config 3 at scale): a driver-visible number next to the headline
+                import copy
+                b = copy.copy(a)
+                b.m_per_gpu, b.steps, b.warmup = 131_072, 4, 2
+                bl = bayesw_line(b, local_rank, with_cpu=False)
+                res["bayesw"] = {k: bl[k] for k in ("value", "unit", "ms_per_step", "marker_loop", "roofline", "gpu_launches")}
+                res["bayesw"]["workload"] = bl["config"]["workload"]
+            except Exception as e:
+                res["bayesw"] = {"error": repr(e)}
         if not a.no_cpu_baseline and world == 1:
             try:
                 res["cpu_baseline"] = cpu_reference_run(a, a.n, min(a.cpu_sample_markers, M_total), M_total, 1, 1)
@@ -421,6 +565,9 @@ def reference_arm(a, world):
            "ms_per_step": r["ms_per_step_sample"] * (a.m_per_gpu * world / n_markers), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(a, world),
            "cpu_baseline": r, "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "reference_layout": {"tasks_run": r["tasks"], "threads_per_task": 1, "host_cores": r["cores"],
+                                "why": "the CPU leg runs one hydra task per host core (the reference's '12 tasks x 1 thread per node' MPI layout); "
+                                       "config.tasks is the GPU arm's task count"},
            "note": "ms_per_step extrapolated linearly from the sample to the full M; the reference binary needs MPI+Eigen+Boost (absent), "
                    "so this is the CPU restatement of its loop (oracle/hydra_oracle.c)"}
     print(json.dumps(res), flush=True)

@@ -740,13 +740,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
     __shared__ __align__(8) uint32_t psort[kMaxMerged + 2];
     double *upart = reinterpret_cast<double *>(psort);  // unit partials of the dot phase (psort is update-phase scratch)
     __shared__ uint32_t pcnt[kMaxRanks];
+    __shared__ uint32_t abort_s;                        // != 0: the exchange failed somewhere, leave the window loop
 
     const uint32_t S = P.S, L = P.L, R = P.R;
     const uint32_t c = blockIdx.x % S, r = blockIdx.x / S;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t nctas = gridDim.x;
 
-    if (tid == 0) { tabs[0].tag_valid = 0; tabs[1].tag_valid = 0; }
+    if (tid == 0) { tabs[0].tag_valid = 0; tabs[1].tag_valid = 0; abort_s = 0u; }
     HypTabs H{P.logPi, P.chalf, P.denom, P.sdk};
     {
         const uint32_t gk = P.G * P.K;
@@ -899,8 +900,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
             __syncthreads();
             bar_target += nctas;
             if (tid == 0) red_release_add_u32(P.bar, 1u);  // arrive (release: the CTA's results, ordered before by bar.sync)
-            if (tid == 0) { while (ld_acquire_u32(P.bar) < bar_target) { } }
+            if (tid == 0) {
+                // A CTA that gave up on the exchange (dead peer, capacity) never arrives here again: everybody else finds
+                // the sticky error word while spinning and leaves the window loop as well (no hang on a partial failure).
+                uint32_t spin = 0;
+                while (ld_acquire_u32(P.bar) < bar_target) {
+                    if (P.pc.nranks > 1 && (++spin & 0x3FFu) == 0u && *reinterpret_cast<volatile uint32_t *>(P.pc.err) != 0u) { abort_s = 1u; break; }
+                }
+            }
             __syncthreads();
+            if (abort_s) break;
             HB_PHASE(3);
         }
 
@@ -976,8 +985,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                         const volatile unsigned long long *hdr =
                             reinterpret_cast<const volatile unsigned long long *>(P.pc.inbox_local + ((size_t)par * NR + tid) * P.pc.inbox_stride);
                         unsigned long long hv = 0;
+                        uint32_t spin = 0;
                         while (!late && (uint32_t)((hv = *hdr) >> 32) != (uint32_t)seq) {
                             if (clock64() - t0 > P.pc.timeout_cycles) late = true;
+                            if ((++spin & 0xFFu) == 0u && *reinterpret_cast<volatile uint32_t *>(P.pc.err) != 0u) late = true;  // somebody already gave up
                         }
                         nh = late ? 0xFFFFFFFFu : (uint32_t)hv;
                         if (late) atomicExch(P.pc.err, 2u);

@@ -260,6 +260,24 @@ static void fill_params(hb_ctx *c, BrrParams &P) {
     }
 }
 
+// All GPUs of a run must agree on a few scalars (the seed: hyper-parameters are drawn on every GPU from the same stream
+// instead of the reference's MPI_Bcast from rank 0, src/BayesRRm.cpp:2585, 2705, 2731; the restart point). min == max over the ranks.
+static int check_equal_over_ranks(hb_ctx *c, const uint64_t *vals, uint32_t n, const char *what) {
+    if (c->nranks <= 1 || !c->nccl) return HB_OK;
+    DevBuf<int64_t> d;
+    HB_TRY(d.alloc(2 * (size_t)n));
+    std::vector<int64_t> h(2 * (size_t)n);
+    for (uint32_t i = 0; i < n; i++) { h[i] = (int64_t)vals[i]; h[n + i] = -(int64_t)vals[i]; }
+    HB_CUDA(cudaMemcpyAsync(d.p, h.data(), sizeof(int64_t) * 2 * n, cudaMemcpyHostToDevice, c->stream));
+    HB_NCCL(ncclAllReduce(d.p, d.p, 2 * (size_t)n, ncclInt64, ncclMax, c->nccl, c->stream));
+    HB_CUDA(cudaMemcpyAsync(h.data(), d.p, sizeof(int64_t) * 2 * n, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    for (uint32_t i = 0; i < n; i++)
+        HB_CHECK(h[i] == -h[n + i], HB_ERR_ARG, "%s differs between the GPUs of this run (value %u: min %lld, max %lld, here %llu)", what, i,
+                 (long long)-h[n + i], (long long)h[i], (unsigned long long)vals[i]);
+    return HB_OK;
+}
+
 static int launch_window_kernel(hb_ctx *c, BrrParams &P) {
     HB_CUDA(cudaMemsetAsync(c->d_bar.p, 0, sizeof(uint32_t), c->stream));
     HB_CUDA(cudaMemsetAsync(c->d_chg_cnt.p, 0, 16 * sizeof(uint32_t), c->stream));
@@ -932,9 +950,10 @@ int hb_brr_init(hb_ctx *c, const double *y, const int32_t *groups, const double 
     }
     HB_TRY(c->d_perm.ensure(c->M)); HB_TRY(c->d_ut.ensure(c->M)); HB_TRY(c->d_zt.ensure(c->M));
     HB_TRY(ensure_scratch(c, c->SR * c->T));
-    HB_TRY(ensure_pin(c, 8 + 2 * (size_t)c->S + G + (size_t)G * K + 32));
+    HB_TRY(ensure_pin(c, std::max<size_t>(4 * (size_t)G * K, 8 + 2 * (size_t)c->S + G + (size_t)G * K + 32)));  // hyp tables (4*G*K) and the per-iteration read-back share it
     c->iteration = 0;
     c->brr_ready = true;
+    { const uint64_t sv = seed; HB_TRY(check_equal_over_ranks(c, &sv, 1, "the seed (give every process the same --seed)")); }
     return HB_OK;
 }
 
@@ -1270,7 +1289,14 @@ int hb_comm_init(hb_ctx *c, const uint8_t id[HB_NCCL_ID_BYTES], int rank, int nr
     HB_CUDA(cudaStreamSynchronize(c->stream));
     HB_CUDA(cudaMemcpy(mx, d_g.p, sizeof(mx), cudaMemcpyDeviceToHost));
     HB_CHECK(mx[0] == -mx[1], HB_ERR_ARG, "hb_comm_init: the GPUs run different grids (%d vs %d CTAs); use the same n_slices / max_ctas", mx[0], -mx[1]);
+    if (c->brr_ready) { const uint64_t sv = c->seed; HB_TRY(check_equal_over_ranks(c, &sv, 1, "the seed (give every process the same --seed)")); }
     return HB_OK;
+}
+
+int hb_comm_check_equal(hb_ctx *c, const uint64_t *vals, uint32_t n, const char *what) {
+    HB_CHECK(c && vals && n > 0 && n <= 64, HB_ERR_ARG, "hb_comm_check_equal: bad argument");
+    HB_CUDA(cudaSetDevice(c->dev));
+    return check_equal_over_ranks(c, vals, n, what ? what : "a value");
 }
 
 }  // extern "C"
@@ -1355,6 +1381,7 @@ int hb_brr_load_state(hb_ctx *c, const void *buf, size_t n) {
     if (c->bw_ready) { c->bw_mu = bwv[0]; c->bw_alpha = bwv[1]; c->bw_sumSigmaG = bwv[2]; }
     r.get(c->sigmaG.data(), c->G); r.get(c->pi.data(), (size_t)c->G * c->K); r.get(c->mu.data(), c->T); r.get(c->bsq.data(), c->G);
     r.get(c->cass.data(), (size_t)c->G * c->K); r.get(c->m0.data(), c->G);
+    for (uint32_t g = 0; g < c->G && g < c->active.size(); g++) c->active[g] = (c->sigmaG[g] != 0.0) ? 1 : 0;  // adaV follows the restored sigmaG (:1592-1597)
     r.get(c->slice_sum_h.data(), c->S);
     r.get(c->perm.data(), c->M);
     if (c->have_next) { c->perm_next.resize(c->M); c->zmu_next.assign(c->T, 0.0); r.get(c->perm_next.data(), c->M); r.get(c->zmu_next.data(), c->T); }

@@ -486,7 +486,7 @@ int main(int argc, const char **argv) {
         std::vector<double> mSflat((size_t)G * K, 0.0);
         for (uint32_t g = 0; g < G; g++)
             for (uint32_t k = 1; k < K; k++) mSflat[g * K + k] = mS[g][k - 1];
-        const uint32_t seed = opt.seedSet ? opt.seed : (uint32_t)time(nullptr);
+        uint32_t seed = opt.seedSet ? opt.seed : (uint32_t)time(nullptr);  // multi-GPU: rank 0's value is shipped with the NCCL id (below)
         if (bayesW) {
             HB(hb_bw_init(ctx, y.data(), fail.data(), groups.empty() ? nullptr : groups.data(), mSflat.data(), (uint32_t)atoi(opt.quad_points.c_str()), seed));
             struct stat sbw;
@@ -545,8 +545,6 @@ int main(int argc, const char **argv) {
             hb_destroy(ctx);
             return 0;
         }
-        HB(hb_brr_init(ctx, y.data(), groups.empty() ? nullptr : groups.data(), mSflat.data(), nullptr, seed));
-
         struct stat sb;
         if (stat(opt.mcmcOutDir.c_str(), &sb) != 0 && system(("mkdir -p " + opt.mcmcOutDir).c_str()) != 0)
             throw std::runtime_error("could not create output directory --mcmc-out-dir " + opt.mcmcOutDir);
@@ -567,10 +565,14 @@ int main(int argc, const char **argv) {
             // NCCL unique id through a file next to the outputs (rank 0 writes, the others wait for it)
             const char *job = getenv("TORCHELASTIC_RUN_ID") ? getenv("TORCHELASTIC_RUN_ID") : (getenv("SLURM_JOB_ID") ? getenv("SLURM_JOB_ID") : (getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "0"));
             const std::string idf = out + ".ncclid." + job;
-            uint8_t id[HB_NCCL_ID_BYTES];
+            // the file carries the NCCL id and rank 0's seed: without --seed every process would otherwise take its own
+            // time(0), and the hyper-parameter streams (drawn on every GPU instead of MPI_Bcast, :2585, 2705, 2731) would differ
+            uint8_t id[HB_NCCL_ID_BYTES + 4];
             const time_t t_start = time(nullptr);
             if (root) {
+                unlink(idf.c_str());  // a file left by a crashed run must not be picked up by the other ranks
                 HB(hb_comm_get_unique_id(id));
+                memcpy(id + HB_NCCL_ID_BYTES, &seed, 4);
                 FILE *f = fopen((idf + ".tmp").c_str(), "wb");
                 if (!f || fwrite(id, 1, sizeof(id), f) != sizeof(id)) throw std::runtime_error("cannot write " + idf);
                 fclose(f);
@@ -579,7 +581,7 @@ int main(int argc, const char **argv) {
                 bool ok = false;
                 for (int tries = 0; tries < 1200 && !ok; tries++) {
                     struct stat st;
-                    if (stat(idf.c_str(), &st) == 0 && st.st_size == (off_t)sizeof(id) && st.st_mtime >= t_start - 300) {
+                    if (stat(idf.c_str(), &st) == 0 && st.st_size == (off_t)sizeof(id) && st.st_mtime >= t_start - 30) {  // the launcher starts the ranks together
                         FILE *f = fopen(idf.c_str(), "rb");
                         ok = f && fread(id, 1, sizeof(id), f) == sizeof(id);
                         if (f) fclose(f);
@@ -590,7 +592,9 @@ int main(int argc, const char **argv) {
             }
             HB(hb_comm_init(ctx, id, (int)opt.rank, (int)opt.world));
             if (root) unlink(idf.c_str());
+            if (!opt.seedSet) memcpy(&seed, id + HB_NCCL_ID_BYTES, 4);
         }
+        HB(hb_brr_init(ctx, y.data(), groups.empty() ? nullptr : groups.data(), mSflat.data(), nullptr, seed));  // multi-GPU: also checks that the seed is common
         if (!root || opt.restart) {
             bet.open_rw(out + ".bet", false); acu.open_rw(out + ".acu", false); cpn.open_rw(out + ".cpn", false);
             xb.open_rw(out + ".xbet", false); xc.open_rw(out + ".xcpn", false);
@@ -603,6 +607,10 @@ int main(int argc, const char **argv) {
             // files cut back to that iteration (the reference does the same from its own files, :842-928)
             uint32_t it_saved = 0;
             read_restart_file(out + ".rst." + std::to_string(opt.rank), ctx, it_saved, n_saved);
+            {   // the per-process state files are written independently: all must stem from the same --save point
+                const uint64_t v[2] = {it_saved, n_saved};
+                HB(hb_comm_check_equal(ctx, v, 2, "--restart: the restart point (iteration, records) of the <out>.rst.<rank> files"));
+            }
             it_first = it_saved + 1;
             if (root) {
                 truncate_csv(out + ".csv", it_saved);

@@ -217,6 +217,10 @@ int hb_bw_arms_beta(hb_ctx *ctx, const double *pars, double C_k, double sum_sigm
 #define HB_NCCL_ID_BYTES 128
 int hb_comm_get_unique_id(uint8_t id[HB_NCCL_ID_BYTES]);
 int hb_comm_init(hb_ctx *ctx, const uint8_t id[HB_NCCL_ID_BYTES], int rank, int nranks);
+/* Fails (HB_ERR_ARG, message names `what`) unless every GPU of the run passes the same n <= 64 values: the seed (the
+ * reference broadcasts rank 0's hyper-parameter draws, src/BayesRRm.cpp:2585, 2705, 2731; here every GPU draws them from
+ * the same stream, so the seed must be common) and the restart point of --restart (:842-928). No-op on one GPU. */
+int hb_comm_check_equal(hb_ctx *ctx, const uint64_t *vals, uint32_t n, const char *what);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -325,6 +325,11 @@ def num_threads(fast=True):
     return lib(fast).ho_num_threads()
 
 
+def set_num_threads(n, fast=True):
+    """OpenMP threads of the timing build (torchrun exports OMP_NUM_THREADS=1; the CPU baseline must not inherit that)."""
+    lib(fast).ho_set_num_threads(C.c_int(int(n)))
+
+
 # --------------------------------------------------------------------------- BayesW
 _ARMS = None
 
@@ -416,4 +421,79 @@ def bw_chain(N, Mtot, T, K, G, sync_rate, n_iter, quad_points, sp: SparseLists, 
     rc = lib().ho_bw_chain(C.byref(a))
     if rc != 0:
         raise RuntimeError(f"ho_bw_chain: ARMS error code {rc}")
+    return out
+
+
+# --------------------------------------------------------------------------- reference object code (pins)
+_REFK = None
+
+
+def ref_kernels():
+    """Function bodies of the reference (src/BayesRRm.cpp:60-413, 1757-1849, 1976-2019; src/data.cpp:826-865, 1112-1290)
+    compiled from where they lie by oracle/build_ref.sh into oracle/_ref/libref_kernels.so. None if it was never built."""
+    global _REFK
+    if _REFK is None:
+        p = os.path.join(_HERE, "_ref", "libref_kernels.so")
+        if not os.path.exists(p):
+            return None
+        _REFK = C.CDLL(p)
+        for n in ("rk_sum_vector_elements_f64", "rk_sparse_dotprod", "rk_loop_num_bed"):
+            getattr(_REFK, n).restype = C.c_double
+    return _REFK
+
+
+def ref_sparse_fill_indices(bed: np.ndarray, nind: int) -> SparseLists:
+    """The reference's own Data::sparse_data_get_sizes_from_raw + sparse_data_fill_indices (object code)."""
+    bed = _c(bed, np.uint8)
+    M, NB = bed.shape
+    R = ref_kernels()
+    n1, n2, nm = c_sz(), c_sz(), c_sz()
+    R.rk_sparse_get_sizes_from_raw(_p(bed), C.c_uint(M), C.c_uint(NB), C.c_uint(nind), C.byref(n1), C.byref(n2), C.byref(nm))
+    I1, I2, IM = (np.empty(max(n.value, 1), np.uint32) for n in (n1, n2, nm))
+    S = [np.zeros(M, np.uint64) for _ in range(6)]
+    R.rk_sparse_fill_indices(_p(bed), C.c_uint(M), C.c_uint(NB), C.c_uint(nind), _p(S[0]), _p(S[1]), _p(I1), _p(S[2]), _p(S[3]), _p(I2),
+                             _p(S[4]), _p(S[5]), _p(IM))
+    return SparseLists(I1[: n1.value], S[0], S[1], I2[: n2.value], S[2], S[3], IM[: nm.value], S[4], S[5])
+
+
+def ref_correct_for_missing_phenotype(sp: SparseLists, na_inds) -> None:
+    na = _c(na_inds, np.uint32)
+    M = len(sp.N1S)
+    R = ref_kernels()
+    for (S, Ln, I) in ((sp.N1S, sp.N1L, sp.I1), (sp.N2S, sp.N2L, sp.I2), (sp.NMS, sp.NML, sp.IM)):
+        R.rk_sparse_correct_for_missing_phenotype(_p(S), _p(Ln), _p(I), C.c_int(M), None, _p(na), C.c_int(len(na)))
+
+
+def ref_sparse_dotprod(eps, sp: SparseLists, m: int, mave: float, mstd: float) -> float:
+    eps = _c(eps, np.float64)
+    return ref_kernels().rk_sparse_dotprod(
+        _p(eps), _p(sp.I1), c_sz(int(sp.N1S[m])), c_sz(int(sp.N1L[m])), _p(sp.I2), c_sz(int(sp.N2S[m])), c_sz(int(sp.N2L[m])),
+        _p(sp.IM), c_sz(int(sp.NMS[m])), c_sz(int(sp.NML[m])), C.c_double(mave), C.c_double(mstd), C.c_int(len(eps)))
+
+
+def ref_sparse_scaadd(N: int, dmult: float, sp: SparseLists, m: int, mave: float, mstd: float):
+    out = np.empty(N)
+    ref_kernels().rk_sparse_scaadd(
+        _p(out), C.c_double(dmult), _p(sp.I1), c_sz(int(sp.N1S[m])), c_sz(int(sp.N1L[m])), _p(sp.I2), c_sz(int(sp.N2S[m])),
+        c_sz(int(sp.N2L[m])), _p(sp.IM), c_sz(int(sp.NMS[m])), c_sz(int(sp.NML[m])), C.c_double(mave), C.c_double(mstd), C.c_int(N))
+    return out
+
+
+def ref_lut_dotprod(raw, eps, mave: float, mstd: float) -> float:
+    """The `if (USEBED[marker])` branch of the marker loop, src/BayesRRm.cpp:1757-1840 (object code)."""
+    raw, eps = _c(raw, np.uint8), _c(eps, np.float64)
+    return ref_kernels().rk_loop_num_bed(_p(raw), _p(eps), C.c_int(len(eps)), C.c_double(mave), C.c_double(mstd))
+
+
+def ref_lut_scaadd(N: int, raw, dbeta: float, mave: float, mstd: float):
+    raw = _c(raw, np.uint8)
+    out = np.zeros(N)
+    ref_kernels().rk_loop_deltaeps_bed(_p(raw), _p(out), C.c_double(dbeta), C.c_int(N), C.c_double(mave), C.c_double(mstd))
+    return out
+
+
+def ref_bed_marker_from_sparse(Ntot: int, i1, i2, im) -> np.ndarray:
+    out = np.empty(snp_len_byt(Ntot), np.uint8)
+    i1, i2, im = _c(i1, np.uint32), _c(i2, np.uint32), _c(im, np.uint32)
+    ref_kernels().rk_get_bed_marker_from_sparse(_p(out), C.c_int(Ntot), _p(i1), c_sz(len(i1)), _p(i2), c_sz(len(i2)), _p(im), c_sz(len(im)))
     return out

@@ -13,7 +13,7 @@
  * PARITY STATUS
  *   - LUT tables: pinned against the reference's own src/dotp_lut.h and the
  *     reference's generator src/mk_lut.cpp (see oracle/build_ref.sh and
- *     tests/golden/lut_sha256.txt).
+ *     tests/golden/lut_ref.npz, made by tests/golden/make_golden.py).
  *   - BED decode / sparse conversion / NA compaction: integer, restated 1:1.
  *   - Chain arithmetic: restated 1:1 from src/BayesRRm.cpp; the reference
  *     cannot be built here (needs MPI, Eigen, Boost -- none installed) and it
@@ -796,6 +796,13 @@ HO_API void ho_tape_iteration(ho_mt *streams, uint32_t seed, int T, int Mtot, ui
 }
 
 HO_API int ho_sizeof_mt(void) { return (int)sizeof(ho_mt); }
+HO_API void ho_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 HO_API int ho_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -169,6 +169,39 @@ def test_cli_bed_vs_sparse_vs_python_runs_are_identical(tmp_path):
     assert len(lines[0].split(",")) == 2 + 2 + 5 + 8
     raw = open(os.path.join(d, "bed", "run.eps.0"), "rb").read()
     assert struct.unpack("<II", raw[:8]) == (4, N - len(na)) and len(raw) == 8 + 8 * (N - len(na))
+    _check_with_reference_converters(os.path.join(d, "bed", "run"), M, N - len(na), its, beta, comp)
+
+
+def _check_with_reference_converters(base, M, Nc, its, beta, comp):
+    """The reference's OWN readers of its output files (postproc/beta_converter.cpp:33-52, components_converter.cpp:33-52,
+    epsilon_converter.cpp:30-43), compiled from where they lie by oracle/build_ref.sh, must read the files this host writes:
+    record offsets, iteration headers and every value (format oracles). Skipped only where oracle/_ref was
+    never built (no /root/reference)."""
+    import re
+    conv = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(conv, "beta_converter")):
+        pytest.skip("oracle/_ref converters not built")
+    n_rec = len(its)
+    out = subprocess.run([os.path.join(conv, "beta_converter"), base + ".bet", str(n_rec - 1)], capture_output=True, text=True).stdout
+    assert f"{M} markers were processed." in out
+    heads = [int(x) for x in re.findall(r"read iteration number (\d+) \(iter=", out)]
+    assert heads == list(its)
+    vals = re.findall(r"^\s*(\d+)/\s*(\d+) =\s*(\S+)$", out, re.M)
+    assert len(vals) == n_rec * M
+    got = np.array([float(v[2]) for v in vals]).reshape(n_rec, M)
+    assert [int(v[0]) for v in vals[::M]] == list(its) and [int(v[1]) for v in vals[:M]] == list(range(M))
+    np.testing.assert_allclose(got, beta, rtol=0, atol=0.6e-12)     # the converter prints %20.12f
+    out = subprocess.run([os.path.join(conv, "components_converter"), base + ".cpn", str(n_rec - 1)], capture_output=True, text=True).stdout
+    assert f"{M} markers were processed." in out
+    # (the reference's components converter passes a double to %2d, so only its record headers are meaningful)
+    assert [int(x) for x in re.findall(r"read iteration number (\d+) \(iter=", out)] == list(its)
+    assert len(re.findall(r"^\s*\d+/\s*\d+ =", out, re.M)) == n_rec * M and comp.shape == (n_rec, M)
+    out = subprocess.run([os.path.join(conv, "epsilon_converter"), base + ".eps.0"], capture_output=True, text=True).stdout
+    assert "iteration 4 was last logged into epsilon file." in out and f"{Nc} individuals were processed." in out
+    ev = np.array([float(x) for x in re.findall(r"^\s*4/\s*\d+ =\s*(\S+)$", out, re.M)])
+    eps = np.frombuffer(open(base + ".eps.0", "rb").read()[8:], np.float64)
+    assert len(ev) == Nc
+    np.testing.assert_allclose(ev, eps, rtol=0, atol=0.6e-11)       # %20.11f
 
 
 @pytest.mark.gpu

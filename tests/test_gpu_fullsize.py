@@ -107,3 +107,67 @@ def test_chain_keeps_the_residual_identity_and_is_reproducible(store):
         np.testing.assert_allclose(o["e_sqn"], (eps ** 2).sum(), rtol=1e-10)
     assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][2], runs[1][2])
     assert runs[0][3] == runs[1][3]
+
+
+# ------------------------------------------------------------------------------------ oracle replay at the benchmarked layout
+def _synthetic_problem(M, spectrum="B", n_causal=24, seed=20240902):
+    """The bench's own genotype recipe (hydra_b200.synth, regenerated bit-for-bit by the CPU oracle) + a phenotype with signal."""
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    from hydra_b200 import synth
+    p = synth.maf_spectrum(M, *synth.SPECTRA[spectrum])
+    thr = synth.thresholds(p)
+    with ThreadPoolExecutor(8) as ex:
+        bed = np.concatenate(list(ex.map(lambda o: oracle.synth_bed(synth.SEED_GENO, N, thr[o:o + 64], None, j0=o, fast=True), range(0, M, 64))))
+    sp = oracle.sparse_fill_indices(bed, N)
+    mave, mstd = oracle.marker_stats_brr(N, sp.N1L, sp.N2L, sp.NML)
+    rng = np.random.default_rng(seed)
+    g = np.zeros(N)
+    for m in rng.choice(M, size=n_causal, replace=False):
+        g += oracle.sparse_scaadd(N, rng.normal(), sp, int(m), mave[m], mstd[m])
+    y = g * np.sqrt(0.5 / g.var()) + rng.normal(0.0, np.sqrt(0.5), size=N)
+    return thr, bed, sp, y
+
+
+@pytest.mark.parametrize("repr_mode", ["sparse", "mixed"])
+def test_chain_replay_at_bench_layout(repr_mode):
+    """VERDICT r1 #1a: the BENCHMARKED configuration against the oracle -- N = 500 000, 64 tasks x sync_rate 10, the default
+    layout (21 slices x 7 CTA groups on 148 SMs), spectrum-B genotypes, 3 iterations, sparse records and the mixed
+    representation (threshold_fnz 0.06: the reference's default, src/options.hpp:86); beta, epsilon of every task, Acum,
+    statistics at 1e-10, components / cass / n_sync equal."""
+    import hydra_b200
+    import oracle
+    from hydra_b200 import synth
+    from helpers import bed_from_lists
+    M, T, SR, K, n_iter, seed = 1920, 64, 10, 4, 3, 1222
+    thr, bed, sp, y = _synthetic_problem(M)
+    fnz = (sp.N1L + sp.N2L + sp.NML).astype(np.float64) / N
+    usebed = (fnz > 0.06).astype(np.uint8) if repr_mode == "mixed" else np.zeros(M, np.uint8)
+    if repr_mode == "mixed":
+        assert 0 < usebed.sum() < M
+    mS = np.array([[0.0, 0.0001, 0.001, 0.01]])
+    tape = oracle.TapeMaker(seed, T, M).make(n_iter)
+    ref = oracle.brr_chain(N, M, T, K, 1, SR, n_iter, sp, y, np.zeros(M, np.int32), mS, tape, np.array([0.5]),
+                           usebed=usebed, bed=bed if repr_mode == "mixed" else None, hyper_seed=(seed ^ 0x5bd1e995) & 0xFFFFFFFF)
+    with hydra_b200.GenotypeStore(N, M, tasks=T, sync_rate=SR, n_groups=1, n_mix=K, repr_mode=repr_mode, threshold_fnz=0.06) as st:
+        import torch
+        if torch.cuda.get_device_properties(0).multi_processor_count == 148:
+            assert (st.n_slices, st.n_cta_groups) == (21, 7)      # the layout bench.py reports
+        st.load_synthetic(synth.SEED_GENO, thr)
+        st.finalize()
+        assert np.array_equal(st.marker_is_bed(), usebed)
+        brr = hydra_b200.BayesRRm(st, y, mS, sigmaG0=np.array([0.5]), seed=seed)
+        for it in range(n_iter):
+            o = brr.iteration()       # RNG spec v1 on the device == the oracle's tape; hyper-parameters drawn on both sides
+            beta, comp, acum = brr.state()
+            h = brr.hyper()
+            assert np.array_equal(comp, ref["comp"][it]), f"components differ at iteration {it}"
+            assert np.array_equal(h["cass"], ref["cass"][it]) and o["n_sync"] == ref["nsync"][it]
+            np.testing.assert_allclose(beta, ref["beta"][it], rtol=1e-10, atol=1e-15, err_msg=f"beta it {it}")
+            np.testing.assert_allclose(acum, ref["acum"][it], rtol=1e-9, atol=1e-300)
+            np.testing.assert_allclose(h["mu"], ref["mu"][it], rtol=1e-10, atol=1e-13)
+            np.testing.assert_allclose(o["e_sqn"], ref["esqn"][it], rtol=1e-10)
+            np.testing.assert_allclose([h["sigmaE"], h["sigmaG"][0]], [ref["sigmaE"][it], ref["sigmaG"][it][0]], rtol=1e-10)
+            for t in (0, 1, T // 2, T - 1):
+                np.testing.assert_allclose(brr.task_epsilon(t), ref["eps"][it, t], rtol=1e-10, atol=1e-12, err_msg=f"eps it {it} task {t}")
+        assert (beta != 0).sum() > 0 and o["n_sync"] > 0

@@ -247,3 +247,87 @@ def test_errors_are_loud():
     with hydra_b200.GenotypeStore(100, 10) as st:
         with pytest.raises(hydra_b200.HydraError):
             st.finalize()  # nothing staged
+
+
+# ------------------------------------------------------------------------------------ BASELINE configs 1 and 2 at their real size
+def _example_scale_case(T, SR, G, repr_mode, seed, n_iter=3):
+    """N = 5 000, M = 10 000 (the size of example/t_M10K_N_5K, whose .bed is missing from the reference checkout):
+    common-variant stand-in with the example's .mS rows (0.001,0.01,0.1), 200 causal markers, h2 ~ 0.5."""
+    import hydra_b200
+    N, M, K = 5000, 10000, 4
+    rng = np.random.default_rng(seed)
+    bed, g = random_bed(rng, M, N, maf_lo=0.01, maf_hi=0.5, pmiss=0.002)
+    sp = reference_lists(bed, N)
+    causal = rng.choice(M, size=200, replace=False)
+    x = np.where(g[causal] < 0, 0, g[causal]).astype(np.float64)
+    x = (x - x.mean(1, keepdims=True)) / x.std(1, keepdims=True)
+    y = x.T @ rng.normal(0, np.sqrt(0.5 / 200), size=200) + rng.normal(0, np.sqrt(0.5), size=N)
+    groups = (np.arange(M) >= M // 2).astype(np.int32) if G == 2 else np.zeros(M, np.int32)   # example/normal.group: two blocks of 5000
+    mS = np.tile(np.array([0.0, 0.001, 0.01, 0.1]), (G, 1))
+    sigmaG0 = rng.uniform(0.2, 0.8, size=G)
+    tape = oracle.TapeMaker(seed, T, M).make(n_iter)
+    usebed = np.ones(M, np.uint8) if repr_mode == "bed" else np.zeros(M, np.uint8)
+    ref = oracle.brr_chain(N, M, T, K, G, SR, n_iter, sp, y, groups, mS, tape, sigmaG0, usebed=usebed,
+                           bed=bed_from_lists(sp, N) if repr_mode == "bed" else None, hyper_seed=(seed ^ 0x5bd1e995) & 0xFFFFFFFF)
+    with hydra_b200.GenotypeStore(N, M, tasks=T, sync_rate=SR, n_groups=G, n_mix=K, repr_mode=repr_mode) as st:
+        st.load_data_from_bed(bed)
+        st.finalize()
+        brr = hydra_b200.BayesRRm(st, y, mS, groups=groups, sigmaG0=sigmaG0, seed=seed)
+        for it in range(n_iter):
+            o = brr.iteration()
+            beta, comp, acum = brr.state()
+            h = brr.hyper()
+            assert np.array_equal(comp, ref["comp"][it]), f"components differ at iteration {it}"
+            assert np.array_equal(h["cass"], ref["cass"][it]) and o["n_sync"] == ref["nsync"][it]
+            np.testing.assert_allclose(beta, ref["beta"][it], rtol=RTOL, atol=1e-15, err_msg=f"beta it {it}")
+            np.testing.assert_allclose(h["bsq"], ref["bsq"][it], rtol=RTOL)
+            np.testing.assert_allclose(o["e_sqn"], ref["esqn"][it], rtol=RTOL)
+            np.testing.assert_allclose(h["sigmaG"], ref["sigmaG"][it], rtol=RTOL)
+            np.testing.assert_allclose(h["pi"], ref["pi"][it], rtol=RTOL)
+            for t in range(T):
+                np.testing.assert_allclose(brr.task_epsilon(t), ref["eps"][it, t], rtol=RTOL, atol=1e-12, err_msg=f"eps it {it} task {t}")
+        assert (beta != 0).sum() > 10
+
+
+def test_chain_replay_config1_full_size():
+    # BASELINE config 1 as written: BED input, M = 10 000, N = 5 000, 1 task, sync after every marker
+    _example_scale_case(T=1, SR=1, G=1, repr_mode="bed", seed=1222)
+
+
+def test_chain_replay_config2_full_size():
+    # BASELINE config 2 as written: grouped mixtures (2 groups), 4 tasks, sync_rate 10
+    _example_scale_case(T=4, SR=10, G=2, repr_mode="sparse", seed=1223)
+
+
+def test_restart_keeps_a_switched_off_group_off():
+    """a group whose sigmaG was set to 0 (m0 == 0, src/BayesRRm.cpp:2534-2542) stays switched off after
+    load_state (adaV re-derived from the restored sigmaG, :1592-1597): continued and uninterrupted runs are identical."""
+    import hydra_b200
+    N, M, T, SR, G, K = 700, 60, 2, 3, 2, 3
+    rng = np.random.default_rng(8)
+    bed, g = random_bed(rng, M, N)
+    y = simulate_y(rng, g, n_causal=5)
+    groups = np.zeros(M, np.int32)
+    groups[7] = 1                              # group 1 = one null marker: it draws component 0 sooner or later
+    mS = np.tile(np.array([0.0, 0.001, 0.01]), (G, 1))
+    with hydra_b200.GenotypeStore(N, M, tasks=T, sync_rate=SR, n_groups=G, n_mix=K) as st:
+        st.load_data_from_bed(bed)
+        st.finalize()
+        brr = hydra_b200.BayesRRm(st, y, mS, groups=groups, sigmaG0=np.array([0.5, 0.5]), seed=3)
+        for it in range(60):
+            brr.iteration()
+            if brr.hyper()["sigmaG"][1] == 0.0:
+                break
+        assert brr.hyper()["sigmaG"][1] == 0.0, "group 1 was never switched off"
+        blob = brr.save_state()
+        straight = []
+        for _ in range(4):
+            brr.iteration()
+            straight.append((brr.state()[0].copy(), brr.hyper()["cass"].copy(), brr.hyper()["sigmaG"].copy()))
+        brr2 = hydra_b200.BayesRRm(st, y, mS, groups=groups, sigmaG0=np.array([0.5, 0.5]), seed=3)
+        brr2.load_state(blob)
+        for k in range(4):
+            brr2.iteration()
+            h = brr2.hyper()
+            assert np.array_equal(brr2.state()[0], straight[k][0]) and np.array_equal(h["cass"], straight[k][1])
+            assert np.array_equal(h["sigmaG"], straight[k][2]) and h["sigmaG"][1] == 0.0
