@@ -24,14 +24,25 @@
 //   * ONE grid barrier per window; with several GPUs the changed markers (list
 //     entries + genotype records) are then written into every peer's inbox over
 //     NVLink as tagged 16-byte units (LL form: no fence, no arrival counter);
-//   * update: every CTA applies the changed markers of all GPUs to its slice in
-//     global window order (deterministic; all epsilon replicas stay bit-identical).
+//   * update: every CTA applies the changed markers of all GPUs to its slice. The slice is held as 64-bit FIXED POINT
+//     (56-bit biased value, grid 2^-sh chosen per launch from sum|eps|; top byte free): integer adds are associative, so
+//     every sum of the kernel -- dot products, slice sums, updates -- is exact and ORDER-INDEPENDENT. The changed markers
+//     of a window are therefore applied without any ordering (no per-marker barrier, no merge sort by window position,
+//     peers' markers as they arrive, any number of them): the words of all changed markers of a chunk are loaded
+//     together and applied marker by marker (one CTA barrier per marker keeps two threads from updating the same
+//     individual at once); all epsilon replicas on all GPUs stay bit-identical and a run is bit-reproducible.
 #pragma once
 #include "common.cuh"
 
 namespace hb {
 
 enum : int { MODE_CHAIN = 0, MODE_DOT = 1, MODE_SCAADD = 2 };
+
+// epsilon in shared memory: llrint(eps * 2^sh) as a 64-bit two's complement integer
+typedef unsigned long long u64;
+// The scalar base term of a launch is summed on its own, finer grid: an error in it is an error of every individual
+// (N times in the sum of the residual), so it gets the resolution of a double at magnitude 1; |sum| stays far below 2^10.
+constexpr int kOffShift = 52;
 
 struct ChgEnt {  // 32 bytes
     uint32_t p;      // GLOBAL window position: step * T_total + global task (the order hydra's ranks are summed in)
@@ -52,7 +63,7 @@ struct __align__(16) WinMeta {  // 64 bytes
 };
 
 constexpr uint32_t kMaxRanks = 8;
-constexpr uint32_t kMaxMerged = 1024;        // changed markers of one window over all GPUs (shared-memory sort)
+constexpr uint32_t kMaxMerged = 4096;        // changed markers of one window that one GPU can ship to its peers (inbox entry region)
 // Inbox region of one (window parity, source GPU): 16-byte header {count | window tag << 32}, kMaxMerged list entries and
 // the genotype records behind them. Entries and records travel in the LL form: every 16-byte unit is
 // {data lo, tag, data hi, tag} with tag = the window's sequence number, so that the receiver can tell, unit by unit,
@@ -87,9 +98,12 @@ struct BrrParams {
     const double *E_in;    // [S*L] common residual without base terms
     double *E_out;         // [S*L]
     double shift_in;       // folded into E at load (base terms of the previous launch)
+    double q_scale, q_inv; // 2^sh and 2^-sh of the launch's fixed-point grid
     double *off_out;       // base-term accumulator of this launch (scalar)
     double *slice_sum_out; // [S]  sum of E over the slice (i < N)
     double *slice_sq_out;  // [S]  sum of E^2
+    double *slice_abs_out; // [S]  sum of |E|  -> the next launch's grid
+    double *slice_max_out; // [S]  max |E|
     // marker state
     double *beta;          // [M]
     int32_t *comp;         // [M]
@@ -111,6 +125,7 @@ struct BrrParams {
     unsigned long long *chg_cnt;  // [3] per window (triple buffered): changed markers | 16-byte units of their records << 32
     ChgEnt *chg_list;      // [3*Wmax] their (position, deltaBeta*mstd, mave, record), in arrival order
     uint32_t *chg_off;     // [3*Wmax] multi-GPU: place of the record in the peers' inboxes (LL units), same order
+    uint4 *chg_dir;        // [3*Wmax][S] the changed markers' slice directory entries, same order (every CTA finds its own next to the entry)
     double *dB;            // [2*Wmax] deltaBeta*mstd per window position, double buffered
     double *dMave;         // [2*Wmax] mave of the changed marker
     uint64_t *dRec;        // [2*Wmax] its record
@@ -139,18 +154,10 @@ struct ItemTab {  // the window positions this CTA group works on, with everythi
     uint32_t tag_base, tag_W, tag_k0, tag_valid;  // which window chunk the table describes
 };
 
-struct ChgTab {  // changed markers of a window, staged for the epsilon update
-    const uint64_t *ptr[kChgCap];
-    double dbs[kChgCap];
-    double mave[kChgCap];
-    uint32_t nw[kChgCap], b1[kChgCap], b2[kChgCap];
-    uint32_t ll[kChgCap];       // != 0: the block sits in an inbox in the LL form with this tag (ptr counts 16-byte units)
-    uint32_t cum[kChgCap + 1];  // exclusive prefix of nw
-};
-
 struct Blk {
     const uint64_t *ptr;
     uint32_t nw, b1, b2;
+    uint32_t n1, n2, nm;        // genotype counts of the slice block (sparse records; BED: 0)
 };
 
 // slice block c of a marker record (common.cuh "record layout")
@@ -162,6 +169,7 @@ __device__ __forceinline__ Blk decode_block(uint64_t rr, uint32_t c, uint32_t S,
         b.nw = L / 32;
         b.b1 = 0xFFFFFFFFu;
         b.b2 = 0xFFFFFFFFu;
+        b.n1 = 0; b.n2 = 0; b.nm = 0;
     } else {
         const uint8_t *bp = reinterpret_cast<const uint8_t *>(rr);
         const uint32_t *dir = reinterpret_cast<const uint32_t *>(bp) + c * 3;
@@ -173,10 +181,25 @@ __device__ __forceinline__ Blk decode_block(uint64_t rr, uint32_t c, uint32_t S,
         b.b1 = w1;
         b.b2 = w1 + w2;
         b.nw = w1 + w2 + wm;
+        b.n1 = n12 & 0xFFFFu; b.n2 = n12 >> 16; b.nm = nm;
     }
     return b;
 }
 
+// the same from a directory entry that is already at hand ({word offset, n1 | n2 << 16, nm, -})
+__device__ __forceinline__ Blk block_from_dir(uint64_t rr, const uint4 dv, uint32_t c, uint32_t S, uint32_t L) {
+    Blk b;
+    if (rr & 1ull) {
+        b.ptr = reinterpret_cast<const uint64_t *>(rr & ~15ull) + (size_t)c * (L / 32);
+        b.nw = L / 32; b.b1 = 0xFFFFFFFFu; b.b2 = 0xFFFFFFFFu; b.n1 = 0; b.n2 = 0; b.nm = 0;
+    } else {
+        const uint32_t w1 = ((dv.y & 0xFFFFu) + 3) / 4, w2 = ((dv.y >> 16) + 3) / 4, wm = (dv.z + 3) / 4;
+        b.ptr = reinterpret_cast<const uint64_t *>(reinterpret_cast<const uint8_t *>(rr) + dir_bytes(S)) + dv.x;
+        b.b1 = w1; b.b2 = w1 + w2; b.nw = w1 + w2 + wm;
+        b.n1 = dv.y & 0xFFFFu; b.n2 = dv.y >> 16; b.nm = dv.z;
+    }
+    return b;
+}
 __device__ __forceinline__ void st_ll(uint4 *dst, uint64_t v, uint32_t tag) {
     asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"((uint32_t)v), "r"(tag), "r"((uint32_t)(v >> 32)), "r"(tag) : "memory");
 }
@@ -204,20 +227,18 @@ __device__ __forceinline__ uint4 ld_nc_v4(const uint4 *p) {  // read-only for th
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// ---- slice block dot product: sum_w weight(w) * sum_4 E_s[idx] ------------------
-__device__ __forceinline__ double gather4(uint64_t x, const double *__restrict__ E_s) {
-    return (E_s[x & 0xFFFFu] + E_s[(x >> 16) & 0xFFFFu]) + (E_s[(x >> 32) & 0xFFFFu] + E_s[x >> 48]);
+// ---- slice block dot product on the fixed-point slice. Integer sums are exact: the lanes', warps' and units' shares can
+//      be added in any order. Two accumulators per marker: a12 = sum_1 + 2 sum_2, am = sum_missing.
+__device__ __forceinline__ u64 gather4(uint64_t x, const u64 *__restrict__ Eq) {
+    return (Eq[x & 0xFFFFu] + Eq[(x >> 16) & 0xFFFFu]) + (Eq[(x >> 32) & 0xFFFFu] + Eq[x >> 48]);
 }
-// BED word: lane owns 32 consecutive individuals and walks them in a rotated order so that the 16 lanes of a
-// half-warp hit 16 distinct shared-memory banks.
-__device__ __forceinline__ double dot_bed_word(uint64_t bits, uint32_t w, double mave, const double *__restrict__ E_s,
-                                               uint32_t lane) {
-    // PLINK codes (b1 b0): 00 -> 2, 10 -> 1, 11 -> 0, 01 -> missing (weight mave). Only the non-zero genotypes are
+// BED word: the lane owns 32 consecutive individuals (word w of the slice block).
+__device__ __forceinline__ void dot_bed_word(uint64_t bits, uint32_t w, const u64 *__restrict__ Eq, u64 &a12, u64 &am) {
+    // PLINK codes (b1 b0): 00 -> 2, 10 -> 1, 11 -> 0, 01 -> missing. Only the non-zero genotypes are
     // visited: A = individuals with b0 == 0 (genotype 1 or 2), of which those with b1 == 0 as well count twice; the
     // missing ones (b0 == 1, b1 == 0) are rare. The trip count is the lane's number of non-zeros, not 32.
-    if (bits == ~0ull) return 0.0;  // 32 x genotype 0
-    const double *e = E_s + 32u * w;
-    double acc = 0.0, acc2 = 0.0;
+    if (bits == ~0ull) return;  // 32 x genotype 0
+    const u64 *e = Eq + 32u * w;
 #pragma unroll
     for (uint32_t h = 0; h < 2; h++) {  // 16 individuals per 32-bit half
         const uint32_t v = (uint32_t)(bits >> (32u * h));
@@ -225,22 +246,20 @@ __device__ __forceinline__ double dot_bed_word(uint64_t bits, uint32_t w, double
         uint32_t a = ~b0 & 0x55555555u;          // genotype 1 or 2
         const uint32_t two = a & ~b1;            // genotype 2
         uint32_t miss = b0 & ~b1;
-        const double *eh = e + 16u * h;
+        const u64 *eh = e + 16u * h;
         while (a) {
             const uint32_t pos = __ffs((int)a) - 1u;  // even bit position = 2 x individual
             a &= a - 1u;
-            const double x = eh[pos >> 1];
-            acc += x;
-            if ((two >> pos) & 1u) acc2 += x;
+            const u64 x = eh[pos >> 1];
+            a12 += x;
+            if ((two >> pos) & 1u) a12 += x;
         }
         while (miss) {
             const uint32_t pos = __ffs((int)miss) - 1u;
             miss &= miss - 1u;
-            acc = fma(mave, eh[pos >> 1], acc);
+            am += eh[pos >> 1];
         }
     }
-    (void)lane;
-    return acc + acc2;
 }
 
 // Work unit of the dot phase, one 16-byte descriptor in shared memory:
@@ -252,7 +271,7 @@ __device__ __forceinline__ uint4 make_unit(const uint64_t *ptr, uint32_t nwords,
     return make_uint4((uint32_t)a, (uint32_t)(a >> 32), nwords | (b1rel << 16), b2rel | (k << 16));
 }
 // first (normally only) 128 words of a sparse unit / 32 words of a BED unit; lanes past the end get the pad word,
-// whose four indices point at the dummy slot (always 0.0 during the dot phase)
+// whose four indices point at the dummy slot (always 0 during the dot phase)
 __device__ __forceinline__ void load_unit(const uint4 d, uint64_t (&x)[4], uint32_t lane, uint64_t padw) {
     const uint64_t *ptr = reinterpret_cast<const uint64_t *>(((uint64_t)d.y << 32) | d.x);
     const uint32_t nwords = d.z & 0xFFFFu;
@@ -263,37 +282,44 @@ __device__ __forceinline__ void load_unit(const uint4 d, uint64_t (&x)[4], uint3
         if (w < nwords) x[t] = ld_stream_u64(ptr + w);
     }
 }
-__device__ __forceinline__ double dot_words(const uint64_t (&x)[4], uint32_t w0, uint32_t nwords, uint32_t b1, uint32_t b2, double mave,
-                                            const double *__restrict__ E_s, uint32_t lane) {
-    double acc = 0.0;
+__device__ __forceinline__ void dot_words(const uint64_t (&x)[4], uint32_t w0, uint32_t nwords, uint32_t b1, uint32_t b2,
+                                          const u64 *__restrict__ Eq, uint32_t lane, u64 &a12, u64 &am) {
+    u64 a1 = 0, a2 = 0;
 #pragma unroll
     for (uint32_t t = 0; t < 4; t++) {
         // most slice blocks are short (rare variants): a group of 32 words that lies entirely past the end is skipped
         // (warp-uniform test) instead of gathering the pad slot 4 x 32 times
-        if (w0 + 32u * t < nwords) {
-            const uint32_t w = w0 + lane + 32u * t;
-            const double wt = (w < b1) ? 1.0 : ((w < b2) ? 2.0 : mave);
-            acc = fma(wt, gather4(x[t], E_s), acc);
+        const uint32_t wb = w0 + 32u * t;
+        if (wb < nwords) {
+            const u64 g = gather4(x[t], Eq);      // pad lanes: 4 x the dummy slot = 0
+            // a group of 32 words mostly lies inside one class: warp-uniform tests, the lane-wise form only at the two borders
+            if (wb + 32u <= b1) a1 += g;
+            else if (wb >= b1 && wb + 32u <= b2) a2 += g;
+            else if (wb >= b2) am += g;
+            else {
+                const uint32_t w = wb + lane;
+                if (w < b1) a1 += g;
+                else if (w < b2) a2 += g;
+                else am += g;
+            }
         }
     }
-    return acc;
+    a12 += a1 + a2 + a2;
 }
-// all of a unit: returns the lane's share of sum_w weight(w) * sum_4 E_s[idx]
-__device__ __forceinline__ double dot_unit(const uint4 d, const uint64_t (&x)[4], double mave, const double *__restrict__ E_s,
-                                           uint32_t lane, uint64_t padw) {
+// all of a unit: the lane's share of (a12, am)
+__device__ __forceinline__ void dot_unit(const uint4 d, const uint64_t (&x)[4], const u64 *__restrict__ Eq,
+                                         uint32_t lane, uint64_t padw, u64 &a12, u64 &am) {
     const uint32_t nwords = d.z & 0xFFFFu, b1 = d.z >> 16, b2 = d.w & 0xFFFFu;
+    const uint64_t *ptr = reinterpret_cast<const uint64_t *>(((uint64_t)d.y << 32) | d.x);
     if (b1 == 0xFFFFu) {  // BED: b2 = first word of the unit inside the slice block
-        const uint64_t *ptr = reinterpret_cast<const uint64_t *>(((uint64_t)d.y << 32) | d.x);
-        double acc = 0.0;
 #pragma unroll
         for (uint32_t t = 0; t < 4; t++)  // load_unit has fetched up to four words per lane
-            if (lane + 32u * t < nwords) acc += dot_bed_word(x[t], b2 + lane + 32u * t, mave, E_s, lane);
-        for (uint32_t w = lane + 128u; w < nwords; w += 32u) acc += dot_bed_word(ld_stream_u64(ptr + w), b2 + w, mave, E_s, lane);
-        return acc;
+            if (lane + 32u * t < nwords) dot_bed_word(x[t], b2 + lane + 32u * t, Eq, a12, am);
+        for (uint32_t w = lane + 128u; w < nwords; w += 32u) dot_bed_word(ld_stream_u64(ptr + w), b2 + w, Eq, a12, am);
+        return;
     }
-    double acc = dot_words(x, 0u, nwords, b1, b2, mave, E_s, lane);
+    dot_words(x, 0u, nwords, b1, b2, Eq, lane, a12, am);
     if (nwords > 128u) {  // units longer than one step (very heavy chunks only)
-        const uint64_t *ptr = reinterpret_cast<const uint64_t *>(((uint64_t)d.y << 32) | d.x);
         for (uint32_t w0 = 128u; w0 < nwords; w0 += 128u) {
             uint64_t y[4];
 #pragma unroll
@@ -302,49 +328,16 @@ __device__ __forceinline__ double dot_unit(const uint4 d, const uint64_t (&x)[4]
                 y[t] = padw;
                 if (w < nwords) y[t] = ld_stream_u64(ptr + w);
             }
-            acc += dot_words(y, w0, nwords, b1, b2, mave, E_s, lane);
+            dot_words(y, w0, nwords, b1, b2, Eq, lane, a12, am);
         }
     }
-    return acc;
 }
 
-// ---- epsilon update with one 64-bit word of a marker's slice block; both return the sum of
-//      what was added to real individuals (keeps the slice sum current without a rescan)
-// BED: word w covers individuals 32w .. 32w+31
-__device__ __forceinline__ double apply_bed_word(uint64_t x, uint32_t w, double dbs, double mave, double *__restrict__ E_s,
-                                                 uint32_t lane) {
-    if (x == ~0ull) return 0.0;
-    double *e = E_s + 32u * w;
-    const double d1 = dbs, d2 = 2.0 * dbs, dm = mave * dbs;
-    double added = 0.0;
+__device__ __forceinline__ u64 warp_sum_u64(u64 v) {
 #pragma unroll
-    for (uint32_t h = 0; h < 2; h++) {  // only the non-zero genotypes are visited (codes as in dot_bed_word)
-        const uint32_t v = (uint32_t)(x >> (32u * h));
-        const uint32_t b0 = v & 0x55555555u, b1 = (v >> 1) & 0x55555555u;
-        uint32_t a = (~b0 & 0x55555555u) | (b0 & ~b1);  // genotype 1, 2 or missing
-        const uint32_t two = ~b0 & ~b1 & 0x55555555u, miss = b0 & ~b1;
-        double *eh = e + 16u * h;
-        while (a) {
-            const uint32_t pos = __ffs((int)a) - 1u;
-            a &= a - 1u;
-            const double d = ((miss >> pos) & 1u) ? dm : (((two >> pos) & 1u) ? d2 : d1);
-            eh[pos >> 1] += d;
-            added += d;
-        }
-    }
-    (void)lane;
-    return added;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
 }
-// sparse: four u16 indices, unique inside a marker; unused lanes of a word point at the dummy slot L
-__device__ __forceinline__ double apply_word(uint64_t x, double d, double *__restrict__ E_s, uint32_t L) {
-    const uint32_t i0 = (uint32_t)(x & 0xFFFFu), i1 = (uint32_t)((x >> 16) & 0xFFFFu);
-    const uint32_t i2 = (uint32_t)((x >> 32) & 0xFFFFu), i3 = (uint32_t)(x >> 48);
-    const double e0 = E_s[i0], e1 = E_s[i1], e2 = E_s[i2], e3 = E_s[i3];  // independent loads
-    E_s[i0] = e0 + d; E_s[i1] = e1 + d; E_s[i2] = e2 + d; E_s[i3] = e3 + d;
-    const uint32_t real = (i0 != L) + (i1 != L) + (i2 != L) + (i3 != L);
-    return d * (double)real;
-}
-
 __device__ __forceinline__ double block_sum(double v, double *red /*[32]*/) {
     v = warp_sum(v);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -356,6 +349,30 @@ __device__ __forceinline__ double block_sum(double v, double *red /*[32]*/) {
     for (uint32_t w = 0; w < nw; w++) s += red[w];  // fixed order: identical in every CTA
     return s;
 }
+__device__ __forceinline__ u64 block_sum_u64(u64 v, double *red /*[32]*/) {
+    v = warp_sum_u64(v);
+    u64 *r = reinterpret_cast<u64 *>(red);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) r[warp] = v;
+    __syncthreads();
+    u64 s = 0;
+    const uint32_t nw = blockDim.x >> 5;
+    for (uint32_t w = 0; w < nw; w++) s += r[w];
+    return s;
+}
+__device__ __forceinline__ double block_max(double v, double *red /*[32]*/) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double s = 0.0;
+    const uint32_t nw = blockDim.x >> 5;
+    for (uint32_t w = 0; w < nw; w++) s = fmax(s, red[w]);
+    return s;
+}
 
 // slice block c of a record that sits in an inbox in the LL form; the returned ptr counts 16-byte units
 __device__ __forceinline__ Blk decode_block_ll(const uint4 *rec, bool bed, uint32_t c, uint32_t S, uint32_t L, uint32_t tag, uint32_t *err) {
@@ -363,6 +380,7 @@ __device__ __forceinline__ Blk decode_block_ll(const uint4 *rec, bool bed, uint3
     if (bed) {
         b.ptr = reinterpret_cast<const uint64_t *>(rec + (size_t)c * (L / 32));
         b.nw = L / 32; b.b1 = 0xFFFFFFFFu; b.b2 = 0xFFFFFFFFu;
+        b.n1 = 0; b.n2 = 0; b.nm = 0;
     } else {
         // the 12-byte directory entry lies in one or two 8-byte words: both units are requested together
         const uint32_t bo = c * 12u, u0 = bo / 8u, u1 = (bo + 8u) / 8u;
@@ -379,6 +397,7 @@ __device__ __forceinline__ Blk decode_block_ll(const uint4 *rec, bool bed, uint3
         const uint32_t w1 = ((n12 & 0xFFFFu) + 3) / 4, w2 = ((n12 >> 16) + 3) / 4, wm = (nm + 3) / 4;
         b.ptr = reinterpret_cast<const uint64_t *>(rec + dir_bytes(S) / 8u + st);
         b.b1 = w1; b.b2 = w1 + w2; b.nw = w1 + w2 + wm;
+        b.n1 = n12 & 0xFFFFu; b.n2 = n12 >> 16; b.nm = nm;
     }
     return b;
 }
@@ -412,14 +431,20 @@ __device__ __forceinline__ void st_slot(uint4 *p, double val, uint32_t tag) {
 // the window tag next to the data, so no fence or arrival counter is needed. Lane kk < K then evaluates
 // mixture component kk; sums over components are taken in component order (same order as the reference).
 __device__ __forceinline__ void draw_marker_warp(const BrrParams &P, const ItemTab *tab, uint32_t k, const HypTabs &H, uint32_t p, uint32_t q,
-                                 uint32_t dbuf, uint32_t buf3, uint32_t tag, uint32_t lane) {
+                                 uint32_t dbuf, uint32_t buf3, uint32_t tag, uint32_t lane, long long *tp) {
+    long long t0_ = tp ? clock64() : 0ll;
     const uint4 *sl = P.slots + (size_t)p * P.S;
     // A marker with a non-zero effect will change: its place in the window's list of changed markers is reserved now, so
     // that the round trip of the atomic overlaps the wait for the partials and the draw.
     // The same atomic reserves the place of its record in the peers' inboxes (multi-GPU).
     const unsigned long long resv = 1ull | ((P.pc.nranks > 1) ? ((unsigned long long)(tab->meta[k].rec_bytes >> 3) << 32) : 0ull);  // LL units = 8-byte words
-    unsigned long long idx_early = ~0ull;
+    unsigned long long idx_early = ~0ull;   // (meaningful in lane 0)
     if (lane == 0 && P.mode == MODE_CHAIN && tab->meta[k].beta != 0.0) idx_early = atomicAdd(P.chg_cnt + buf3, resv);
+    // The marker's slice directory entries (one per lane) are requested now, for every marker: if it changes, they are
+    // stored next to its list entry so that the update needs no dependent read (the load is hidden by the wait below).
+    uint4 mydir = make_uint4(0u, 0u, 0u, 0u);
+    const size_t Qn = (size_t)P.lmax * P.T;
+    if (P.mode == MODE_CHAIN && P.dirw && lane < P.S) mydir = ld_nc_v4(P.dirw + (size_t)lane * Qn + q);
     double acc = 0.0;
     for (uint32_t c0 = 0; c0 < P.S; c0 += 32) {
         const uint32_t cc = c0 + lane;
@@ -430,8 +455,9 @@ __device__ __forceinline__ void draw_marker_warp(const BrrParams &P, const ItemT
         }
     }
     const double sum = warp_sum(acc);  // xor tree: fixed order
+    if (tp && lane == 0) { const long long t_ = clock64(); tp[0] += t_ - t0_; t0_ = t_; }
     const double mstd = tab->meta[k].mstd;
-    const size_t slot = (size_t)dbuf * P.Wmax + p;
+    (void)dbuf;
     if (P.mode == MODE_DOT) {
         if (lane == 0) P.num_out[q] = __dmul_rn(mstd, sum);
         return;
@@ -491,6 +517,21 @@ __device__ __forceinline__ void draw_marker_warp(const BrrParams &P, const ItemT
         const double muc = __shfl_sync(0xffffffffu, muk, comp);
         if (comp > 0) beta_new = __dadd_rn(muc, __dmul_rn(H.sdk[g * K + comp], tab->meta[k].z));  // :1901
     }                                                                                // else :1924-1925
+    if (tp && lane == 0) { const long long t_ = clock64(); tp[1] += t_ - t0_; t0_ = t_; }
+    {   // changed marker: the directory entries go next to the list entry (all lanes), then lane 0 writes the entry
+        const double dbeta_w = beta_old - beta_new;
+        const bool chg_w = (dbeta_w != 0.0 || idx_early != ~0ull);   // lane 0's view decides
+        if (__shfl_sync(0xffffffffu, (int)chg_w, 0)) {
+            unsigned long long got_w = 0ull;
+            if (lane == 0) got_w = (idx_early != ~0ull) ? idx_early : atomicAdd(P.chg_cnt + buf3, resv);
+            got_w = __shfl_sync(0xffffffffu, got_w, 0);
+            idx_early = got_w;   // lane 0 uses it below
+            uint4 *dd = P.chg_dir + ((size_t)buf3 * P.Wmax + (uint32_t)got_w) * P.S;
+            if (lane < P.S) dd[lane] = mydir;
+            for (uint32_t cc = lane + 32u; cc < P.S; cc += 32u) dd[cc] = ld_nc_v4(P.dirw + (size_t)cc * Qn + q);
+            __syncwarp();
+        }
+    }
     if (lane == 0) {
         if (comp >= 0) {
             atomicAdd(&P.cass[g * K + comp], 1);                                     // :1904
@@ -500,9 +541,6 @@ __device__ __forceinline__ void draw_marker_warp(const BrrParams &P, const ItemT
         if (dbeta != 0.0 || idx_early != ~0ull) {
             // (a reserved entry of a marker that drew its old value again carries 0 and does not count as a change)
             const double dbs = (dbeta != 0.0) ? __dmul_rn(dbeta, mstd) : 0.0;
-            P.dMave[slot] = tab->meta[k].mave;
-            P.dRec[slot] = tab->meta[k].rec;
-            P.dB[slot] = dbs;
             const unsigned long long got = (idx_early != ~0ull) ? idx_early : atomicAdd(P.chg_cnt + buf3, resv);
             const uint32_t idx = (uint32_t)got, off_units = (uint32_t)(got >> 32);
             ChgEnt en;
@@ -511,11 +549,10 @@ __device__ __forceinline__ void draw_marker_warp(const BrrParams &P, const ItemT
             P.chg_list[(size_t)buf3 * P.Wmax + idx] = en;
             if (P.pc.nranks > 1) P.chg_off[(size_t)buf3 * P.Wmax + idx] = off_units;  // pushed to the peers after the grid barrier
             if (dbeta != 0.0) atomicAdd(&P.stats[5], 1ull);
-        } else {
-            P.dB[slot] = 0.0;
         }
         P.beta[m] = beta_new;
         P.acum[m] = acum0;
+        if (tp) { const long long t_ = clock64(); tp[2] += t_ - t0_; }
     }
 }
 
@@ -561,6 +598,7 @@ __device__ __forceinline__ void fill_items_sync(ItemTab *tab, const BrrParams &P
             wm.u = P.u[base + p]; wm.z = P.z[base + p];
             const Blk b = decode_block(wm.rec, c, P.S, P.L);
             tab->ptr[k] = b.ptr; tab->nw[k] = b.nw; tab->b1[k] = b.b1; tab->b2[k] = b.b2;
+            tab->dir[k] = make_uint4(0u, b.n1 | (b.n2 << 16), b.nm, 0u);   // genotype counts of the block: bias of the dot product
         }
         tab->meta[k] = wm;
     }
@@ -657,90 +695,243 @@ constexpr uint32_t kHypSmem = 64;        // G*K up to this: hyper-parameter tabl
 constexpr uint32_t kWarps = kThreads / 32;
 constexpr uint32_t kDrawWarps = 8;       // warps that collect partials and draw; the others prebuild the next table
 
-// Epsilon update with the nx markers staged in chg[0..nx) (window order). All threads of the CTA call it.
-// Sparse words of all staged markers are flattened, loaded together and applied marker by marker (one CTA
-// barrier per marker keeps the order of additions to an individual fixed); BED blocks have length 0 in the
-// flattened space and are applied by the whole CTA in their turn.
-__device__ __forceinline__ void apply_staged(ChgTab *chg, uint32_t nx, double *__restrict__ E_s, uint32_t L, double &added,
-                                             double &off, unsigned long long *nnz_upd, uint32_t *llerr) {
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (warp == 0) {  // exclusive prefix of the block lengths (nx <= 64)
-        const uint32_t a0 = (lane < nx && chg->b1[lane] != 0xFFFFFFFFu) ? chg->nw[lane] : 0u;
-        const uint32_t a1 = (lane + 32 < nx && chg->b1[lane + 32] != 0xFFFFFFFFu) ? chg->nw[lane + 32] : 0u;
-        uint32_t s0 = a0, s1 = a1;
+// clock read that cannot be scheduled before `dep` is available (developer timing of phases that end with loads in flight)
+__device__ __forceinline__ long long clock_after(uint32_t dep) {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64; // %1" : "=l"(t) : "r"(dep) : "memory");
+    return t;
+}
+// ---- epsilon update -------------------------------------------------------------------------------------------------
+struct ChgTab {  // changed markers of a window, staged for the epsilon update. Packed in 16-byte fields (three stores per entry)
+    uint4 a[kChgCap];           // x,y: address of the slice block; z,w: q1 = fixed-point deltaBeta*mstd (genotype 1; genotype 2: twice that)
+    uint4 b[kChgCap];           // x,y: qm = fixed-point mave*deltaBeta*mstd (missing genotype); z: words (0: nothing to apply); w: first word of class 2 (0xFFFFFFFF: BED)
+    uint4 c[kChgCap];           // x: first word of class "missing"; y: != 0: block in an inbox in the LL form with this tag (address counts 16-byte units);
+                                // z: exclusive prefix of the words of the sparse entries (BED entries count 0)
+    uint32_t total, n_sparse, n_bed, any;   // (16-byte aligned: written with one store)
+    long long delta_sum;        // what the chunk's sparse entries add to the slice sum (from the genotype counts of their directory entries)
+    long long bed_delta;        // same for its BED entries (counted while they are applied)
+    long long qm_sum;           // sum of mave*mstd*deltaBeta on the grid 2^-kOffShift: the base term -mave*mstd*deltaBeta of every
+                                // individual (:265-267) is kept as ONE scalar per launch
+    long long pad_;
+};
+static_assert(sizeof(ChgTab) % 16 == 0, "ChgTab");
+
+// Fixed-point deltas of one changed marker: q1 (genotype 1), qm (missing), its share dl of the slice sum, its base term qo
+// on the finer grid of the launch's scalar.
+__device__ __forceinline__ void entry_deltas(const Blk &b, double dbs, double mave, double q_scale, long long &q1, long long &qm,
+                                             long long &dl, long long &qo) {
+    q1 = __double2ll_rn(dbs * q_scale);
+    qm = __double2ll_rn(mave * dbs * q_scale);
+    const double base = mave * dbs;
+    // what the entry adds to the slice sum (exact): n1*q1 + n2*2*q1 + nm*qm; BED blocks are counted while they are applied
+    dl = (b.b1 == 0xFFFFFFFFu) ? 0ll : ((long long)b.n1 + 2ll * (long long)b.n2) * q1 + (long long)b.nm * qm;
+    qo = (fabs(base) < 512.0) ? __double2ll_rn(base * 4503599627370496.0 /* 2^kOffShift */) : (long long)(1ull << 62);   // absurd value: caught by the caller
+}
+__device__ __forceinline__ void store_entry(ChgTab *chg, uint32_t x, const Blk &b, uint32_t ll, long long q1, long long qm, uint32_t nw_eff, uint32_t cum) {
+    const uint64_t pa = (uint64_t)(uintptr_t)b.ptr;
+    chg->a[x] = make_uint4((uint32_t)pa, (uint32_t)(pa >> 32), (uint32_t)(u64)q1, (uint32_t)((u64)q1 >> 32));
+    chg->b[x] = make_uint4((uint32_t)(u64)qm, (uint32_t)((u64)qm >> 32), nw_eff, b.b1);
+    chg->c[x] = make_uint4(b.b2, ll, cum, 0u);
+}
+// Warps 0 and 1 stage a chunk of <= 64 entries (one entry per thread): deltas, prefix of the block lengths, counters.
+// Warp 1's prefix needs warp 0's total, which it computes itself from the lengths (both warps see all 64 lengths through
+// one shared array written before a named barrier of the two warps).
+__device__ __forceinline__ void stage_chunk(ChgTab *chg, uint32_t *scr /*[64]*/, uint32_t nx, const Blk &b, double dbs, double mave, uint32_t ll,
+                                            double q_scale, uint32_t tid /* < 64 */) {
+    const uint32_t lane = tid & 31u, wrp = tid >> 5;
+    const bool valid = tid < nx;
+    long long q1 = 0, qm = 0, dl = 0, qo = 0;
+    if (valid) entry_deltas(b, dbs, mave, q_scale, q1, qm, dl, qo);
+    const uint32_t nwe = (valid && dbs != 0.0) ? b.nw : 0u;
+    const bool live = nwe != 0u, bed = live && b.b1 == 0xFFFFFFFFu;
+    const uint32_t a = (live && !bed) ? nwe : 0u;
+    uint32_t s0 = a;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t0 = __shfl_up_sync(0xffffffffu, s0, o), t1 = __shfl_up_sync(0xffffffffu, s1, o);
-            if (lane >= (uint32_t)o) { s0 += t0; s1 += t1; }
-        }
-        const uint32_t tot0 = __shfl_sync(0xffffffffu, s0, 31);
-        chg->cum[lane + 1] = s0;
-        chg->cum[lane + 33] = tot0 + s1;
-        if (lane == 0) chg->cum[0] = 0;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t0 = __shfl_up_sync(0xffffffffu, s0, o);
+        if (lane >= (uint32_t)o) s0 += t0;
     }
-    __syncthreads();
-    const uint32_t total = chg->cum[nx];
-    uint32_t xdone = 0;  // entries [0, xdone) are complete
-    for (uint32_t f0 = 0; f0 < total || xdone < nx; f0 += kApplyQ * kThreads) {
+    const uint32_t tot = __shfl_sync(0xffffffffu, s0, 31);
+    dl = (long long)warp_sum_u64((u64)dl);
+    qo = (long long)warp_sum_u64((u64)qo);
+    const uint32_t nsp = __popc(__ballot_sync(0xffffffffu, live && !bed)), nbd = __popc(__ballot_sync(0xffffffffu, bed));
+    if (lane == 0) {   // this warp's totals for the other one
+        scr[wrp * 8 + 0] = tot; scr[wrp * 8 + 1] = nsp; scr[wrp * 8 + 2] = nbd;
+        *reinterpret_cast<long long *>(scr + wrp * 8 + 4) = dl; *reinterpret_cast<long long *>(scr + wrp * 8 + 6) = qo;
+    }
+    named_barrier(2, 64);
+    const uint32_t base = wrp ? scr[0] : 0u;
+    if (valid) store_entry(chg, tid, b, ll, q1, qm, nwe, base + s0 - a);
+    if (tid == 0) {
+        *reinterpret_cast<uint4 *>(&chg->total) = make_uint4(scr[0] + scr[8], scr[1] + scr[9], scr[2] + scr[10], (scr[1] + scr[9] + scr[2] + scr[10]) ? 1u : 0u);
+        chg->delta_sum = *reinterpret_cast<long long *>(scr + 4) + *reinterpret_cast<long long *>(scr + 12);
+        chg->qm_sum = *reinterpret_cast<long long *>(scr + 6) + *reinterpret_cast<long long *>(scr + 14);
+        chg->bed_delta = 0ll;
+    }
+}
+// Unit mode (one entry per thread, any thread): the entry, its sums through shared-memory atomics; finish_chunk adds the prefix.
+__device__ __forceinline__ void stage_entry_any(ChgTab *chg, uint32_t x, const Blk &b, double dbs, double mave, double q_scale) {
+    long long q1, qm, dl, qo;
+    entry_deltas(b, dbs, mave, q_scale, q1, qm, dl, qo);
+    store_entry(chg, x, b, 0u, q1, qm, (dbs != 0.0) ? b.nw : 0u, 0u);
+    atomicAdd(reinterpret_cast<unsigned long long *>(&chg->delta_sum), (unsigned long long)dl);
+    atomicAdd(reinterpret_cast<unsigned long long *>(&chg->qm_sum), (unsigned long long)qo);
+}
+__device__ __forceinline__ void finish_chunk(ChgTab *chg, uint32_t nx, uint32_t lane) {   // warp 0, after a CTA barrier
+    const uint4 b0 = (lane < nx) ? chg->b[lane] : make_uint4(0u, 0u, 0u, 0u), b1 = (lane + 32u < nx) ? chg->b[lane + 32u] : make_uint4(0u, 0u, 0u, 0u);
+    const bool v0 = b0.z != 0u, v1 = b1.z != 0u, bed0 = v0 && b0.w == 0xFFFFFFFFu, bed1 = v1 && b1.w == 0xFFFFFFFFu;
+    const uint32_t a0 = (v0 && !bed0) ? b0.z : 0u, a1 = (v1 && !bed1) ? b1.z : 0u;
+    uint32_t s0 = a0, s1 = a1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t0 = __shfl_up_sync(0xffffffffu, s0, o), t1 = __shfl_up_sync(0xffffffffu, s1, o);
+        if (lane >= (uint32_t)o) { s0 += t0; s1 += t1; }
+    }
+    const uint32_t tot0 = __shfl_sync(0xffffffffu, s0, 31), tot1 = __shfl_sync(0xffffffffu, s1, 31);
+    if (lane < nx) chg->c[lane].z = s0 - a0;
+    if (lane + 32u < nx) chg->c[lane + 32u].z = tot0 + s1 - a1;
+    const uint32_t nsp = __popc(__ballot_sync(0xffffffffu, v0 && !bed0)) + __popc(__ballot_sync(0xffffffffu, v1 && !bed1));
+    const uint32_t nbd = __popc(__ballot_sync(0xffffffffu, bed0)) + __popc(__ballot_sync(0xffffffffu, bed1));
+    if (lane == 0) { chg->bed_delta = 0ll; chg->total = tot0 + tot1; chg->n_sparse = nsp; chg->n_bed = nbd; chg->any = (nsp + nbd) ? 1u : 0u; }
+}
+// last entry x < nx whose prefix is <= f
+__device__ __forceinline__ uint32_t find_chunk_entry(const ChgTab *chg, uint32_t nx, uint32_t f) {
+    uint32_t lo = 0, hi = nx;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (chg->c[mid].z <= f) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+// sparse word: four u16 indices, all different inside one marker; unused lanes of a word point at the dummy slot L (skipped)
+__device__ __forceinline__ void apply_word(uint64_t x, long long q, u64 *__restrict__ Eq, uint32_t L) {
+    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    const uint32_t i0 = lo & 0xFFFFu, i1 = lo >> 16, i2 = hi & 0xFFFFu, i3 = hi >> 16;
+    const u64 v0 = Eq[i0], v1 = Eq[i1], v2 = Eq[i2], v3 = Eq[i3];   // independent loads (the indices differ, or are the dummy slot)
+    if (i0 != L) Eq[i0] = v0 + (u64)q;
+    if (i1 != L) Eq[i1] = v1 + (u64)q;
+    if (i2 != L) Eq[i2] = v2 + (u64)q;
+    if (i3 != L) Eq[i3] = v3 + (u64)q;
+}
+// BED word w: individuals 32w .. 32w+31; returns what was added (a BED block has no genotype counts in a directory)
+__device__ __forceinline__ long long apply_bed_word(uint64_t bits, uint32_t w, long long q1, long long q2, long long qm, u64 *__restrict__ Eq) {
+    long long added = 0;
+    if (bits == ~0ull) return added;
+#pragma unroll
+    for (uint32_t h = 0; h < 2; h++) {  // only the non-zero genotypes are visited (codes as in dot_bed_word)
+        const uint32_t v = (uint32_t)(bits >> (32u * h));
+        const uint32_t b0 = v & 0x55555555u, b1 = (v >> 1) & 0x55555555u;
+        uint32_t a = (~b0 & 0x55555555u) | (b0 & ~b1);  // genotype 1, 2 or missing
+        const uint32_t two = ~b0 & ~b1 & 0x55555555u, miss = b0 & ~b1;
+        u64 *eh = Eq + 32u * w + 16u * h;
+        while (a) {
+            const uint32_t pos = __ffs((int)a) - 1u;
+            a &= a - 1u;
+            const long long d = ((miss >> pos) & 1u) ? qm : (((two >> pos) & 1u) ? q2 : q1);
+            eh[pos >> 1] += (u64)d;
+            added += d;
+        }
+    }
+    return added;
+}
+
+// Epsilon update with the nx entries staged in chg (CTA barrier passed). All threads of the CTA call it.
+// The slice is fixed point: the order in which the entries are added does not matter, and the slice sum follows from the
+// genotype counts (no reduction). The sparse words of all entries are flattened and loaded together (`ll` is the same for
+// the whole chunk: two separate load paths, because a value that is selected between two loads is moved behind the join
+// and every load would be waited for before the next one is issued); they are then applied entry by entry, one CTA
+// barrier per entry, so that two threads never update the same individual at once. BED blocks follow, one at a time.
+// Returns (in every thread) what was added to the slice sum. Ends with a CTA barrier.
+__device__ __forceinline__ long long apply_chunk(ChgTab *chg, uint32_t nx, bool ll_chunk, u64 *__restrict__ Eq, uint32_t L,
+                                                 unsigned long long *nnz_upd, uint32_t *err) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t total = chg->total, nbed = chg->n_bed;
+    long long added = chg->delta_sum;
+    bool synced = true;   // nothing written since the last barrier
+    for (uint32_t f0 = 0; f0 < total; f0 += kApplyQ * kThreads) {
         uint64_t wd[kApplyQ];
+        long long qv[kApplyQ];
         uint32_t we[kApplyQ];
-        double dd[kApplyQ];
+        uint32_t xlo = 0xFFFFFFFFu, xhi = 0u;
 #pragma unroll
         for (uint32_t i = 0; i < kApplyQ; i++) {
             const uint32_t f = f0 + tid + i * kThreads;
-            we[i] = 0xFFFFFFFFu; wd[i] = 0; dd[i] = 0.0;
+            we[i] = 0xFFFFFFFFu; wd[i] = 0ull; qv[i] = 0;
             if (f < total) {
-                const uint32_t x = find_entry(chg->cum, nx, f);
-                const uint32_t w = f - chg->cum[x];
-                we[i] = x;
-                wd[i] = chg->ll[x] ? ld_ll(reinterpret_cast<const uint4 *>(chg->ptr[x]) + w, chg->ll[x], llerr) : ld_l2_u64(chg->ptr[x] + w);
-                dd[i] = ((w < chg->b1[x]) ? 1.0 : ((w < chg->b2[x]) ? 2.0 : chg->mave[x])) * chg->dbs[x];
+                const uint32_t x = find_chunk_entry(chg, nx, f);
+                const uint4 ea = chg->a[x], eb = chg->b[x], ec = chg->c[x];
+                const uint32_t w = f - ec.z;
+                const uint64_t pa = ((uint64_t)ea.y << 32) | ea.x;
+                we[i] = x; xlo = min(xlo, x); xhi = max(xhi, x);
+                const long long q1 = (long long)(((u64)ea.w << 32) | ea.z);
+                qv[i] = (w < eb.w) ? q1 : ((w < ec.x) ? 2ll * q1 : (long long)(((u64)eb.y << 32) | eb.x));
+                if (!ll_chunk) wd[i] = __ldcg(reinterpret_cast<const unsigned long long *>(pa) + w);
+                else wd[i] = ld_ll(reinterpret_cast<const uint4 *>(pa) + w, ec.y, err);
             }
         }
+        // entries touched by this round: [x_first, x_last]; trailing entries without flattened words are skipped
         const uint32_t fend = min(total, f0 + kApplyQ * kThreads);
-        // last entry touched by this round; trailing entries without flattened words (BED, empty) follow it
-        uint32_t xhi = (f0 < total) ? find_entry(chg->cum, nx, fend - 1u) : xdone;
-        if (fend == total) xhi = nx - 1u;
-        for (uint32_t x = xdone; x <= xhi; x++) {
-            if (chg->b1[x] == 0xFFFFFFFFu) {
-                const uint32_t nwb = chg->nw[x];
-                const double dbs = chg->dbs[x], mave = chg->mave[x];
-                for (uint32_t w = tid; w < nwb; w += blockDim.x)
-                    added += apply_bed_word(chg->ll[x] ? ld_ll(reinterpret_cast<const uint4 *>(chg->ptr[x]) + w, chg->ll[x], llerr) : ld_l2_u64(chg->ptr[x] + w),
-                                            w, dbs, mave, E_s, lane);
-            } else {
+        const uint32_t x_first = find_chunk_entry(chg, nx, f0), x_last = find_chunk_entry(chg, nx, fend - 1u);
+        for (uint32_t x = x_first; x <= x_last; x++) {
+            if (chg->b[x].z == 0u || chg->b[x].w == 0xFFFFFFFFu) continue;   // nothing to apply / BED (below)
+            if (!synced) __syncthreads();
+            if (x >= xlo && x <= xhi) {
 #pragma unroll
                 for (uint32_t i = 0; i < kApplyQ; i++)
-                    if (we[i] == x) added += apply_word(wd[i], dd[i], E_s, L);
+                    if (we[i] == x) apply_word(wd[i], qv[i], Eq, L);
             }
-            __syncthreads();
+            synced = false;
         }
-        // an entry cut by the round boundary continues in the next round
-        xdone = (fend < total && chg->cum[xhi + 1] > fend) ? xhi : xhi + 1u;
     }
-    for (uint32_t x = 0; x < nx; x++) {
-        off = fma(-chg->mave[x], chg->dbs[x], off);  // base term -mave*mstd*deltaBeta of every individual (:265-267)
-        if (tid == 0 && chg->b1[x] != 0xFFFFFFFFu) *nnz_upd += 4ull * chg->nw[x];
+    if (nbed) {
+        long long dl = 0;
+        for (uint32_t x = 0; x < nx; x++) {
+            const uint4 eb = chg->b[x];
+            if (eb.w != 0xFFFFFFFFu || eb.z == 0u) continue;
+            if (!synced) __syncthreads();   // the previous entry (or the sparse pass) is complete
+            synced = false;
+            const uint4 ea = chg->a[x], ec = chg->c[x];
+            const uint32_t nwb = eb.z, ll = ec.y;
+            const uint64_t pa = ((uint64_t)ea.y << 32) | ea.x;
+            const long long q1 = (long long)(((u64)ea.w << 32) | ea.z), q2 = 2ll * q1, qm = (long long)(((u64)eb.y << 32) | eb.x);
+            if (!ll_chunk) {
+                for (uint32_t w = tid; w < nwb; w += blockDim.x) dl += apply_bed_word(__ldcg(reinterpret_cast<const unsigned long long *>(pa) + w), w, q1, q2, qm, Eq);
+            } else {
+                for (uint32_t w = tid; w < nwb; w += blockDim.x) dl += apply_bed_word(ld_ll(reinterpret_cast<const uint4 *>(pa) + w, ll, err), w, q1, q2, qm, Eq);
+            }
+        }
+        dl = (long long)warp_sum_u64((u64)dl);
+        if ((tid & 31u) == 0u && dl != 0) atomicAdd(reinterpret_cast<unsigned long long *>(&chg->bed_delta), (unsigned long long)dl);
+        __syncthreads();
+        added += chg->bed_delta;
+        synced = false;   // (chg was read after the barrier: one more before it is restaged)
     }
-    __syncthreads();
+    if (tid == 0 && nnz_upd)
+        for (uint32_t x = 0; x < nx; x++) {
+            const uint4 eb = chg->b[x];
+            if (eb.w != 0xFFFFFFFFu) *nnz_upd += 4ull * eb.z;
+        }
+    __syncthreads();   // the slice is complete; chg may be restaged
+    return added;
 }
 
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *E_s = reinterpret_cast<double *>(smem_raw);                 // [L+1], slot L = dummy for PAD
+    u64 *Eq = reinterpret_cast<u64 *>(smem_raw);                        // [L+1] fixed point, slot L = dummy for PAD (always 0)
     ItemTab *tabs = reinterpret_cast<ItemTab *>(smem_raw + (((size_t)P.L + 2) * 8 + 15) / 16 * 16);
     ChgTab *chg = reinterpret_cast<ChgTab *>(tabs + 2);
     __shared__ double red[32];
     __shared__ double hyp_s[4 * kHypSmem];
     __shared__ uint4 udesc[kUnitCap];                   // work units of the dot phase
-    __shared__ unsigned long long cnt_s[9];             // traffic counters: per warp 0..3 {non-zeros read by the dot, BED blocks}, [8] update
+    __shared__ unsigned long long cnt_s[10];             // traffic counters: per warp 0..3 {non-zeros read by the dot, BED blocks}, [8] update
     __shared__ uint32_t chg_n;
     __shared__ uint32_t chg_base[33];
-    __shared__ __align__(8) uint32_t psort[kMaxMerged + 2];
-    double *upart = reinterpret_cast<double *>(psort);  // unit partials of the dot phase (psort is update-phase scratch)
+    __shared__ __align__(16) uint32_t psort[4 * kUnitCap];   // scratch of the exchange (unit offsets of the entries)
+    u64 *upart = reinterpret_cast<u64 *>(psort);        // unit partials of the dot phase: {a12, am} per unit
     __shared__ uint32_t pcnt[kMaxRanks];
     __shared__ uint32_t abort_s;                        // != 0: the exchange failed somewhere, leave the window loop
+    __shared__ __align__(8) uint32_t stg_scr[16];       // the two staging warps' totals
 
     const uint32_t S = P.S, L = P.L, R = P.R;
     const uint32_t c = blockIdx.x % S, r = blockIdx.x / S;
@@ -759,33 +950,37 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
             H = HypTabs{hyp_s, hyp_s + kHypSmem, hyp_s + 2 * kHypSmem, hyp_s + 3 * kHypSmem};
         }
     }
-    // ---- load the slice (fold the base terms of the previous launch) -------------
-    for (uint32_t i = tid; i < L; i += blockDim.x) {
-        const uint32_t gi = c * L + i;
-        E_s[i] = (gi < P.N) ? (P.E_in[gi] + P.shift_in) : 0.0;
-    }
-    if (tid == 0) E_s[L] = 0.0;
-    __syncthreads();
-    double slice_sum;
+    // ---- load the slice: fixed point on the launch's grid (the base terms of the previous launch are folded in) ----
+    long long slice_sum_q;   // sum of the slice's values (exact), the same in every thread
     {
-        double v = 0.0;
-        for (uint32_t i = tid; i < L; i += blockDim.x) v += E_s[i];
-        slice_sum = block_sum(v, red);
+        u64 v = 0;
+        bool bad = false;
+        for (uint32_t i = tid; i < L; i += blockDim.x) {
+            const uint32_t gi = c * L + i;
+            const long long q = (gi < P.N) ? __double2ll_rn((P.E_in[gi] + P.shift_in) * P.q_scale) : 0ll;
+            bad |= (q > (1ll << 61)) || (q < -(1ll << 61));
+            Eq[i] = (u64)q;
+            v += (u64)q;
+        }
+        if (tid == 0) Eq[L] = 0ull;
+        if (bad) atomicExch(P.pc.err, 5u);
+        slice_sum_q = (long long)block_sum_u64(v, red);
     }
 
     uint32_t bar_target = 0;
-    __shared__ long long tph[8];             // phase cycle counters of thread 0 (shared memory: keeps 32 registers free)
+    __shared__ long long tph[16];            // phase cycle counters of thread 0 (shared memory: keeps 32 registers free); 8..15: developer detail
     __shared__ unsigned long long gts[16];
-    if (tid < 8) tph[tid] = 0;
+    if (tid < 16) tph[tid] = 0;
     if (tid < 16) gts[tid] = 0;
-    long long tclk = clock64();
+    long long tclk = clock64(), tsub = tclk;
 #define HB_PHASE(i) do { if (tid == 0) { long long t_ = clock64(); tph[i] += t_ - tclk; tclk = t_; \
         if (P.cta_cycles && win == 10) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); gts[i] = g_; } } } while (0)
+#define HB_SUB(i) do { if (tid == 0) { long long t_ = clock64(); tph[i] += t_ - tsub; tsub = t_; } } while (0)
 #define HB_STAMP(i, cond) do { if (P.cta_cycles && win == 10 && (cond)) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); gts[i] = g_; } } while (0)
-    double off = 0.0;
+    long long off_q = 0;     // base terms of this launch, fixed point (every thread keeps the same value)
     uint32_t j0 = 0, since = 0, win = 0;
     uint32_t n_sync = 0;
-    if (tid < 9) cnt_s[tid] = 0;
+    if (tid < 10) cnt_s[tid] = 0;
     const uint64_t padw = (uint64_t)L * 0x0001000100010001ull;
     const uint32_t SR = (P.SR == 0) ? 1u : P.SR;
 
@@ -825,20 +1020,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                     uint64_t xa[4], xb[4], xc[4], xd[4];
 #define HB_FETCH(D, X, UU) do { D = ((UU) < nun) ? udesc[UU] : none; load_unit(D, X, lane, padw); } while (0)
 #define HB_COMPUTE2(D0, X0, D1, X1) do { \
-                        const double m0_ = tab->meta[D0.w >> 16].mave, m1_ = tab->meta[D1.w >> 16].mave; \
-                        double a0_, a1_; \
+                        u64 a0_ = 0, a1_ = 0, m0_ = 0, m1_ = 0; \
                         if ((D0.z >> 16) != 0xFFFFu && (D1.z >> 16) != 0xFFFFu && (D0.z & 0xFFFFu) <= 128u && (D1.z & 0xFFFFu) <= 128u) { \
-                            a0_ = dot_words(X0, 0u, D0.z & 0xFFFFu, D0.z >> 16, D0.w & 0xFFFFu, m0_, E_s, lane); \
-                            a1_ = dot_words(X1, 0u, D1.z & 0xFFFFu, D1.z >> 16, D1.w & 0xFFFFu, m1_, E_s, lane); \
+                            dot_words(X0, 0u, D0.z & 0xFFFFu, D0.z >> 16, D0.w & 0xFFFFu, Eq, lane, a0_, m0_); \
+                            dot_words(X1, 0u, D1.z & 0xFFFFu, D1.z >> 16, D1.w & 0xFFFFu, Eq, lane, a1_, m1_); \
                         } else { \
-                            a0_ = dot_unit(D0, X0, m0_, E_s, lane, padw); \
-                            a1_ = dot_unit(D1, X1, m1_, E_s, lane, padw); \
+                            dot_unit(D0, X0, Eq, lane, padw, a0_, m0_); \
+                            dot_unit(D1, X1, Eq, lane, padw, a1_, m1_); \
                         } \
                         _Pragma("unroll") for (int o_ = 16; o_ > 0; o_ >>= 1) { \
-                            const double t0_ = __shfl_xor_sync(0xffffffffu, a0_, o_), t1_ = __shfl_xor_sync(0xffffffffu, a1_, o_); \
+                            const u64 t0_ = __shfl_xor_sync(0xffffffffu, a0_, o_), t1_ = __shfl_xor_sync(0xffffffffu, a1_, o_); \
                             a0_ += t0_; a1_ += t1_; \
                         } \
-                        if (lane == 0) { upart[u] = a0_; if (u + kWarps < nun) upart[u + kWarps] = a1_; } \
+                        /* missing genotypes are rare: most units have no word of that class (warp-uniform test) */ \
+                        const bool hm0_ = (D0.z >> 16) == 0xFFFFu || (D0.w & 0xFFFFu) < (D0.z & 0xFFFFu); \
+                        const bool hm1_ = (D1.z >> 16) == 0xFFFFu || (D1.w & 0xFFFFu) < (D1.z & 0xFFFFu); \
+                        if (hm0_) m0_ = warp_sum_u64(m0_); \
+                        if (hm1_) m1_ = warp_sum_u64(m1_); \
+                        if (lane == 0) { \
+                            upart[2u * u] = a0_; upart[2u * u + 1u] = hm0_ ? m0_ : 0ull; \
+                            if (u + kWarps < nun) { upart[2u * (u + kWarps)] = a1_; upart[2u * (u + kWarps) + 1u] = hm1_ ? m1_ : 0ull; } \
+                        } \
                         u += 2 * kWarps; } while (0)
                     HB_FETCH(da, xa, u);
                     HB_FETCH(db, xb, u + kWarps);
@@ -861,13 +1063,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                 const uint32_t tag = win + 1u;
                 if (tid < nk) {
                     const uint32_t k = tid, p = r + R * (k0 + k);
-                    if (tab->meta[k].m < 0) {
-                        if (P.mode == MODE_CHAIN) P.dB[(size_t)dbuf * P.Wmax + p] = 0.0;  // padded task step (:2029-2034)
-                    } else {
+                    if (tab->meta[k].m >= 0) {   // (a padded task step contributes nothing, :2029-2034)
                         // partial of num/mstd: sum_1 + 2 sum_2 + mave*sum_M - mave*sum_slice   (:327-339)
-                        double part = 0.0;
-                        for (uint32_t u = tab->ucum[k], u1 = tab->ucum[k + 1]; u < u1; u++) part += upart[u];  // fixed order
-                        st_slot(P.slots + (size_t)p * S + c, fma(-tab->meta[k].mave, slice_sum, part), tag);
+                        u64 s12 = 0, sm = 0;
+                        for (uint32_t u = tab->ucum[k], u1 = tab->ucum[k + 1]; u < u1; u++) { s12 += upart[2u * u]; sm += upart[2u * u + 1u]; }
+                        const double d12 = (double)(long long)s12 * P.q_inv, dm = (double)(long long)(sm - (u64)slice_sum_q) * P.q_inv;
+                        st_slot(P.slots + (size_t)p * S + c, fma(tab->meta[k].mave, dm, d12), tag);
                     }
                 }
                 HB_STAMP(11, tid == 0);
@@ -885,7 +1086,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                 if (warp < kDrawWarps) {
                     const uint32_t kf = (c + S - (k0 % S)) % S;  // first table entry owned by this CTA
                     for (uint32_t k = kf + warp * S; k < nk; k += kDrawWarps * S)
-                        if (tab->meta[k].m >= 0) draw_marker_warp(P, tab, k, H, r + R * (k0 + k), base + r + R * (k0 + k), dbuf, win % 3u, tag, lane);
+                        if (tab->meta[k].m >= 0) draw_marker_warp(P, tab, k, H, r + R * (k0 + k), base + r + R * (k0 + k), dbuf, win % 3u, tag, lane, (warp == 0) ? &tph[13] : nullptr);
                     HB_STAMP(8 + (warp & 1u), lane == 0 && warp < 2);
                 } else if (stage_next) {
                     const uint32_t j1 = j0 + n, n1 = min(SR, P.lmax - j1);
@@ -913,23 +1114,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
             HB_PHASE(3);
         }
 
-        // ---- 5. apply the window's non-zero deltaBetas in window order ---------------
+        // ---- 5. apply the window's non-zero deltaBetas (in any order: the slice is fixed point) ---------------
         bool any = false;
-        double added = 0.0;
         const size_t dslot = (size_t)dbuf * P.Wmax;
-        uint32_t nlist = 0xFFFFFFFFu;
         if (P.mode == MODE_CHAIN) {
             const uint32_t buf3 = win % 3u, par = win & 1u, NR = P.pc.nranks, me = P.pc.rank;
             const unsigned long long seq_w = P.pc.seq_base + win + 1ull;  // tag of this window's data in the inboxes
             const ChgEnt *llist = P.chg_list + (size_t)buf3 * P.Wmax;
-            // the first entries are read together with the count (one L2 round trip instead of two)
-            constexpr uint32_t kSpec = 64;
+            const uint4 *ldir = P.chg_dir + (size_t)buf3 * P.Wmax * S;   // [entry][slice] directory entries of the changed markers
+            if (tid == 0) tsub = clock64();
+            // the first 64 entries and their directory entries are requested together with the count (one L2 round trip)
             ChgEnt spec;
-            spec.p = 0xFFFFFFFFu;
-            if (tid < kSpec) spec = ld_chg_ent(llist + tid);
-            const uint32_t nloc = (uint32_t)__ldcg(P.chg_cnt + buf3);
+            spec.p = 0xFFFFFFFFu; spec.m = 0; spec.dbs = 0.0; spec.mave = 0.0; spec.rec = 0;
+            uint4 sdir = make_uint4(0u, 0u, 0u, 0u);
+            if (tid < kChgCap) { spec = ld_chg_ent(llist + tid); sdir = __ldcg(ldir + (size_t)tid * S + c); }
+            const unsigned long long cntv = __ldcg(P.chg_cnt + buf3);
+            const uint32_t nloc = (uint32_t)cntv;
             if (blockIdx.x == 0 && tid == 0) P.chg_cnt[(win + 2u) % 3u] = 0ull;  // free since the previous grid barrier
-            uint32_t ntot = nloc;
+            bool ok = true;
             if (NR > 1) {
                 // ---- 5a. this GPU's changed markers for every peer, over NVLink in the LL form (tagged 16-byte stores on
                 // peer-mapped pointers, no fence, no arrival counter): the count (one 8-byte store, tagged), the list
@@ -938,22 +1140,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                 // the list slot by the same atomic), so the unit space is contiguous.
                 const unsigned long long seq = seq_w;
                 const size_t region = ((size_t)par * NR + me) * P.pc.inbox_stride;
-                const uint32_t units = (uint32_t)(__ldcg(P.chg_cnt + buf3) >> 32);
-                const bool ok = nloc <= kMaxMerged && kInboxHeader + (size_t)units * 16 <= P.pc.inbox_stride;
+                const uint32_t units = (uint32_t)(cntv >> 32);
+                ok = nloc <= kMaxMerged && kInboxHeader + (size_t)units * 16 <= P.pc.inbox_stride;
                 if (!ok && blockIdx.x == 0 && tid == 0) atomicExch(P.pc.err, 1u);
                 if (blockIdx.x == 0 && tid < NR && tid != me)
                     *reinterpret_cast<volatile unsigned long long *>(P.pc.inbox_peer[tid] + region) =
                         (unsigned long long)(ok ? nloc : 0xFFFFFFFFu) | (seq << 32);
                 if (ok && nloc > 0) {
-                    uint32_t *sp = psort;  // scratch: first unit of every entry [nloc + 1], then the record addresses [nloc]
+                    // scratch: first unit of every entry [nloc + 1], then the record addresses [nloc]; very long lists
+                    // are searched in global memory instead
+                    constexpr uint32_t kScr = 4 * kUnitCap;
+                    const bool sp_fit = nloc + 2u <= kScr;
+                    uint32_t *sp = psort;
                     unsigned long long *srec = reinterpret_cast<unsigned long long *>(psort + ((nloc + 2u) & ~1u));
-                    const bool recs_fit = ((nloc + 2u) & ~1u) + 2u * nloc <= kMaxMerged + 2u;
+                    const bool recs_fit = ((nloc + 2u) & ~1u) + 2u * nloc <= kScr;
+                    const uint32_t *goff = P.chg_off + (size_t)buf3 * P.Wmax;
                     for (uint32_t i = tid; i < nloc; i += blockDim.x) {
-                        const ChgEnt en = (i < kSpec && tid < kSpec) ? spec : ld_chg_ent(llist + i);
-                        const uint32_t o = __ldcg(P.chg_off + (size_t)buf3 * P.Wmax + i);
-                        sp[i] = o;
+                        const ChgEnt en = ld_chg_ent(llist + i);
+                        const uint32_t o = __ldcg(goff + i);
+                        if (sp_fit) sp[i] = o;
                         if (recs_fit) srec[i] = en.rec;
-                        if (blockIdx.x == 0) {  // the list entries first: the peers sort them while the records travel
+                        if (blockIdx.x == 0) {  // the list entries first: the peers stage them while the records travel
                             const uint64_t e0 = (uint64_t)en.p | ((uint64_t)(uint32_t)seq << 32);
                             const uint64_t e3 = (en.rec & 1ull) | ((unsigned long long)o << 4);  // first LL unit in the payload | BED flag
                             for (uint32_t h = 0; h < NR; h++) {
@@ -964,24 +1171,60 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                             }
                         }
                     }
-                    if (tid == 0) sp[nloc] = units;
+                    if (tid == 0 && sp_fit) sp[nloc] = units;
                     __syncthreads();
                     for (uint32_t f = blockIdx.x * blockDim.x + tid; f < units; f += nctas * blockDim.x) {
-                        const uint32_t e = find_entry(sp, nloc, f);
+                        uint32_t e, e_first;
+                        if (sp_fit) { e = find_entry(sp, nloc, f); e_first = sp[e]; }
+                        else {  // offsets ascend with the list index (one atomic reserves both)
+                            uint32_t lo = 0, hi = nloc;
+                            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldcg(goff + mid) <= f) lo = mid; else hi = mid; }
+                            e = lo; e_first = __ldcg(goff + lo);
+                        }
                         const unsigned long long ra = recs_fit ? srec[e] : __ldcg(&llist[e].rec);
-                        const uint64_t v = __ldg(reinterpret_cast<const unsigned long long *>(ra & ~15ull) + (f - sp[e]));
+                        const uint64_t v = __ldg(reinterpret_cast<const unsigned long long *>(ra & ~15ull) + (f - e_first));
                         for (uint32_t h = 0; h < NR; h++)
                             if (h != me) st_ll(reinterpret_cast<uint4 *>(P.pc.inbox_peer[h] + region + kInboxHeader) + f, v, (uint32_t)seq);
                     }
-                    __syncthreads();  // psort is reused by the merge
+                    __syncthreads();  // the scratch is free again
                 }
-                // ---- 5b. wait for every peer's pushes of this window
+            }
+            // ---- 5b. this GPU's own changed markers (the peers' are still on their way). Warps 0 and 1 stage a chunk (one entry
+            //          per thread); the slice directory entry travels with the list entry (written by the drawing warp), and
+            //          the first 64 entries were requested together with the count: one L2 round trip up to here.
+            if (ok) {
+                for (uint32_t x0 = 0; x0 < nloc; x0 += kChgCap) {
+                    const uint32_t nx = min((uint32_t)kChgCap, nloc - x0);
+                    if (tid < kChgCap) {
+                        Blk bk;
+                        bk.ptr = nullptr; bk.nw = 0; bk.b1 = 0; bk.b2 = 0; bk.n1 = 0; bk.n2 = 0; bk.nm = 0;
+                        double dbs = 0.0, mv = 0.0;
+                        if (tid < nx) {
+                            const ChgEnt en = (x0 == 0) ? spec : ld_chg_ent(llist + x0 + tid);
+                            const uint4 dv = (x0 == 0) ? sdir : __ldcg(ldir + (size_t)(x0 + tid) * S + c);
+                            bk = block_from_dir(en.rec, dv, c, S, L);
+                            dbs = en.dbs; mv = en.mave;
+                        }
+                        stage_chunk(chg, stg_scr, nx, bk, dbs, mv, 0u, P.q_scale, tid);
+                    }
+                    __syncthreads();
+                    HB_SUB(9);
+                    any |= chg->any != 0u;
+                    off_q -= chg->qm_sum;
+                    slice_sum_q += apply_chunk(chg, nx, false, Eq, L, (r == 0) ? &cnt_s[8] : nullptr, P.pc.err);
+                    HB_SUB(10);
+                }
+            }
+            HB_PHASE(4);
+            if (NR > 1) {
+                // ---- 5c. wait for every peer's count of this window (it follows the peer's own grid barrier); entries and
+                //          records are validated unit by unit when they are read
+                const unsigned long long seq = seq_w;
                 if (tid < NR) {
                     uint32_t nh = ok ? nloc : 0xFFFFFFFFu;
                     if (tid != me) {
                         const long long t0 = clock64();
                         bool late = false;
-                        // the peer's count follows its own grid barrier; entries and records are validated unit by unit
                         const volatile unsigned long long *hdr =
                             reinterpret_cast<const volatile unsigned long long *>(P.pc.inbox_local + ((size_t)par * NR + tid) * P.pc.inbox_stride);
                         unsigned long long hv = 0;
@@ -996,90 +1239,54 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                     pcnt[tid] = nh;
                 }
                 __syncthreads();
-                ntot = 0;
                 bool bad = false;
-                for (uint32_t h = 0; h < NR; h++) { bad |= (pcnt[h] == 0xFFFFFFFFu); ntot += bad ? 0u : pcnt[h]; }
-                if (bad || ntot > kMaxMerged) {  // give up: the host reports the failure after the launch
-                    if (blockIdx.x == 0 && tid == 0) atomicExch(P.pc.err, bad ? 3u : 4u);
+                for (uint32_t h = 0; h < NR; h++) bad |= (pcnt[h] == 0xFFFFFFFFu);
+                if (bad) {  // give up: the host reports the failure after the launch
+                    if (blockIdx.x == 0 && tid == 0) atomicExch(P.pc.err, 3u);
                     break;
                 }
-            } else if (tid == 0) {
-                pcnt[0] = nloc;
-            }
-            nlist = ntot;
-            if (ntot > 0 && ntot <= kMaxMerged) {
-                // ---- 5c. merge: sort the changed markers of all GPUs by global window position
-                ChgEnt en[2];
-                const unsigned char *rbase[2] = {nullptr, nullptr};
-#pragma unroll
-                for (uint32_t u = 0; u < 2; u++) {
-                    const uint32_t i = tid + u * kThreads;
-                    en[u].p = 0xFFFFFFFFu;
-                    if (i < ntot) {
-                        uint32_t h = 0, o = i;
-                        if (NR > 1) { while (o >= pcnt[h]) { o -= pcnt[h]; h++; } }
-                        if (h == me) {
-                            if (o == tid && o < kSpec) en[u] = spec; else en[u] = ld_chg_ent(llist + o);
-                        } else {
-                            const unsigned char *reg = P.pc.inbox_local + ((size_t)par * NR + h) * P.pc.inbox_stride;
-                            const uint4 *le = reinterpret_cast<const uint4 *>(reg + 16 + (size_t)o * kLLEntry);
-                            const uint64_t e0 = ld_ll(le, (uint32_t)seq_w, P.pc.err);
-                            en[u].p = (uint32_t)e0; en[u].m = (uint32_t)(e0 >> 32);
-                            en[u].dbs = __longlong_as_double((long long)ld_ll(le + 1, (uint32_t)seq_w, P.pc.err));
-                            en[u].mave = __longlong_as_double((long long)ld_ll(le + 2, (uint32_t)seq_w, P.pc.err));
-                            en[u].rec = ld_ll(le + 3, (uint32_t)seq_w, P.pc.err);
-                            rbase[u] = reg + kInboxHeader;
+                // ---- 5d. the peers' changed markers, straight from the inboxes (no merge: any order gives the same slice)
+                for (uint32_t hh = 1; hh < NR; hh++) {
+                    const uint32_t h = (me + hh) % NR, n_h = pcnt[h];
+                    const unsigned char *reg = P.pc.inbox_local + ((size_t)par * NR + h) * P.pc.inbox_stride;
+                    for (uint32_t x0 = 0; x0 < n_h; x0 += kChgCap) {
+                        const uint32_t nx = min((uint32_t)kChgCap, n_h - x0);
+                        if (tid < kChgCap) {
+                            Blk bk;
+                            bk.ptr = nullptr; bk.nw = 0; bk.b1 = 0; bk.b2 = 0; bk.n1 = 0; bk.n2 = 0; bk.nm = 0;
+                            double dbs = 0.0, mv = 0.0;
+                            if (tid < nx) {
+                                const uint4 *le = reinterpret_cast<const uint4 *>(reg + 16 + (size_t)(x0 + tid) * kLLEntry);
+                                dbs = __longlong_as_double((long long)ld_ll(le + 1, (uint32_t)seq, P.pc.err));
+                                mv = __longlong_as_double((long long)ld_ll(le + 2, (uint32_t)seq, P.pc.err));
+                                const uint64_t rr = ld_ll(le + 3, (uint32_t)seq, P.pc.err);
+                                bk = decode_block_ll(reinterpret_cast<const uint4 *>(reg + kInboxHeader) + (rr >> 4), (rr & 1ull) != 0,
+                                                     c, S, L, (uint32_t)seq, P.pc.err);
+                            }
+                            stage_chunk(chg, stg_scr, nx, bk, dbs, mv, (uint32_t)seq, P.q_scale, tid);
                         }
-                        psort[i] = en[u].p;
+                        __syncthreads();
+                        any |= chg->any != 0u;
+                        off_q -= chg->qm_sum;
+                        slice_sum_q += apply_chunk(chg, nx, true, Eq, L, (r == 0) ? &cnt_s[8] : nullptr, P.pc.err);
                     }
                 }
-                const bool nonzero = (en[0].p != 0xFFFFFFFFu && en[0].dbs != 0.0) || (en[1].p != 0xFFFFFFFFu && en[1].dbs != 0.0);
-                any = __syncthreads_or(nonzero) != 0;
-                uint32_t rank[2] = {0, 0};
-#pragma unroll
-                for (uint32_t u = 0; u < 2; u++)
-                    if (en[u].p != 0xFFFFFFFFu)
-                        for (uint32_t i = 0; i < ntot; i++) rank[u] += (psort[i] < en[u].p) ? 1u : 0u;
-                HB_PHASE(4);
-                for (uint32_t x0 = 0; x0 < ntot; x0 += kChgCap) {
-                    const uint32_t nx = min((uint32_t)kChgCap, ntot - x0);
-#pragma unroll
-                    for (uint32_t u = 0; u < 2; u++) {
-                        if (en[u].p != 0xFFFFFFFFu && rank[u] >= x0 && rank[u] < x0 + nx) {
-                            const Blk b = rbase[u] ? decode_block_ll(reinterpret_cast<const uint4 *>(rbase[u]) + (en[u].rec >> 4), (en[u].rec & 1ull) != 0,
-                                                                     c, S, L, (uint32_t)seq_w, P.pc.err)
-                                                   : decode_block(en[u].rec, c, S, L);
-                            const uint32_t x = rank[u] - x0;
-                            chg->ll[x] = rbase[u] ? (uint32_t)seq_w : 0u;
-                            chg->ptr[x] = b.ptr; chg->nw[x] = b.nw; chg->b1[x] = b.b1; chg->b2[x] = b.b2;
-                            chg->dbs[x] = en[u].dbs; chg->mave[x] = en[u].mave;
-                        }
-                    }
-                    __syncthreads();
-                    apply_staged(chg, nx, E_s, L, added, off, &cnt_s[8], P.pc.err);
-                }
-                HB_PHASE(7);
             }
-        }
-        if (nlist > kMaxMerged) {  // very many changes on a single GPU (or a unit mode): scan the dense per-position arrays
+            if (off_q > (1ll << 61) || off_q < -(1ll << 61)) atomicExch(P.pc.err, 5u);
+            HB_PHASE(7);
+        } else if (P.mode == MODE_SCAADD) {  // unit mode: the caller's dense deltaBeta array, one entry per position
             for (uint32_t p0 = 0; p0 < W; p0 += blockDim.x) {
                 const uint32_t p = p0 + tid;
                 const double d = (p < W) ? __ldcg(P.dB + dslot + p) : 0.0;
                 const bool ch = (d != 0.0);
                 // every changed position decodes its own record: one dependent-load chain for all of them
                 Blk b;
+                b.ptr = nullptr; b.nw = 0; b.b1 = 0; b.b2 = 0; b.n1 = 0; b.n2 = 0; b.nm = 0;
                 double mv = 0.0;
                 if (ch) {
-                    uint64_t rr;
-                    if (P.mode == MODE_SCAADD) {
-                        const int32_t m = P.order[base + p];
-                        rr = P.rec[m];
-                        mv = P.mave[m];
-                    } else {
-                        rr = __ldcg(P.dRec + dslot + p);
-                        mv = __ldcg(P.dMave + dslot + p);
-                    }
-                    b = decode_block(rr, c, S, L);
+                    const int32_t m = P.order[base + p];
+                    mv = P.mave[m];
+                    b = decode_block(P.rec[m], c, S, L);
                 }
                 const uint32_t bal = __ballot_sync(0xffffffffu, ch);
                 if (lane == 0) chg_base[warp] = __popc(bal);
@@ -1094,21 +1301,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                 const uint32_t slot = chg_base[warp] + __popc(bal & ((1u << lane) - 1u));
                 for (uint32_t x0 = 0; x0 < nchg; x0 += kChgCap) {
                     const uint32_t nx = min((uint32_t)kChgCap, nchg - x0);
-                    if (ch && slot >= x0 && slot < x0 + nx) {
-                        const uint32_t x = slot - x0;
-                        chg->ptr[x] = b.ptr; chg->nw[x] = b.nw; chg->b1[x] = b.b1; chg->b2[x] = b.b2; chg->ll[x] = 0u;
-                        chg->dbs[x] = d; chg->mave[x] = mv;
-                    }
+                    if (tid == 0) { chg->delta_sum = 0ll; chg->qm_sum = 0ll; }
                     __syncthreads();
-                    apply_staged(chg, nx, E_s, L, added, off, &cnt_s[8], P.pc.err);
+                    if (ch && slot >= x0 && slot < x0 + nx) stage_entry_any(chg, slot - x0, b, d, mv, P.q_scale);
+                    __syncthreads();
+                    if (warp == 0) finish_chunk(chg, nx, lane);
+                    __syncthreads();
+                    any |= chg->any != 0u;
+                    off_q -= chg->qm_sum;
+                    slice_sum_q += apply_chunk(chg, nx, false, Eq, L, (r == 0) ? &cnt_s[8] : nullptr, P.pc.err);
                 }
-                any |= (nchg > 0);
             }
+            if (off_q > (1ll << 61) || off_q < -(1ll << 61)) atomicExch(P.pc.err, 5u);
             HB_PHASE(4);
         }
         if (any) {
-            if (tid == 0) E_s[L] = 0.0;  // the dummy slot collected the PAD lanes
-            slice_sum += block_sum(added, red);
             since = 0;
             n_sync++;
         } else {
@@ -1119,25 +1326,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
         HB_PHASE(5);
     }
 
-    // ---- epilogue: group 0 stores the slices and their sums ----------------------------
+    // ---- epilogue: group 0 stores the slices (back in double) and their sums ------------------
     if (P.mode != MODE_DOT) {
         if (r == 0) {
-            double v = 0.0, v2 = 0.0;
+            double v = 0.0, v2 = 0.0, va = 0.0, vm = 0.0;
             for (uint32_t i = tid; i < L; i += blockDim.x) {
                 const uint32_t gi = c * L + i;
-                const double e = E_s[i];
+                const long long qe = (long long)Eq[i];
+                if (qe > (1ll << 62) || qe < -(1ll << 62)) atomicExch(P.pc.err, 5u);   // left the range the grid was chosen for
+                const double e = (double)qe * P.q_inv;
                 P.E_out[gi] = e;
-                if (gi < P.N) { v += e; v2 += e * e; }
+                if (gi < P.N) { v += e; v2 += e * e; va += fabs(e); vm = fmax(vm, fabs(e)); }
             }
             const double s1 = block_sum(v, red);
             const double s2 = block_sum(v2, red);
-            if (tid == 0) { P.slice_sum_out[c] = s1; P.slice_sq_out[c] = s2; }
+            const double sa = block_sum(va, red);
+            const double sx = block_max(vm, red);
+            if (tid == 0) { P.slice_sum_out[c] = s1; P.slice_sq_out[c] = s2; P.slice_abs_out[c] = sa; P.slice_max_out[c] = sx; }
         }
         if (blockIdx.x == 0 && tid == 0) {
-            *P.off_out = off;
+            *P.off_out = ldexp((double)off_q, -kOffShift);
             P.stats[0] = n_sync;
             P.stats[1] = win;
-            for (int i = 0; i < 8; i++) P.stats[8 + i] = (unsigned long long)tph[i];
+            for (int i = 0; i < 16; i++) P.stats[8 + i] = (unsigned long long)tph[i];
         }
     }
     if (P.cta_cycles && tid == 0)
@@ -1149,6 +1360,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
         if (nd) atomicAdd(&P.stats[2], nd);
         if (nb && c == 0) atomicAdd(&P.stats[4], nb);
         if (r == 0 && cnt_s[8]) atomicAdd(&P.stats[3], cnt_s[8]);
+        if (blockIdx.x == 0) P.stats[6] = cnt_s[9];   // arbitration rounds of the update (CTA 0)
     }
 }
 

@@ -108,6 +108,10 @@ struct hb_ctx {
     DevBuf<double> d_small;  // [0]=off, [1..S]=slice_sum, [1+S..2S]=slice_sq, then bsq[G]
     std::vector<double> slice_sum_h;
     bool eps_set = false;
+    // fixed-point grid of the marker kernel: the largest sum of |eps| over one slice and the largest |eps| (of the stored
+    // residual, before the scalar `shift` is folded in); refreshed by every launch, set by hb_set_epsilon / load_state
+    double eps_slice_abs = 0.0, eps_abs_max = 0.0;
+    int last_sh = 0;
 
     // marker state
     DevBuf<double> d_beta, d_acum;
@@ -124,6 +128,7 @@ struct hb_ctx {
     // scratch
     DevBuf<uint4> d_slots;
     DevBuf<ChgEnt> d_chg_list;
+    DevBuf<uint4> d_chg_dir;
     DevBuf<double> d_dB, d_dMave, d_num, d_bsq_part;
     DevBuf<uint64_t> d_dRec;
     DevBuf<uint32_t> d_chg_cnt, d_chg_off, d_bar, d_markers;
@@ -207,6 +212,7 @@ static int ensure_scratch(hb_ctx *c, uint32_t W) {
     HB_TRY(c->d_slots.alloc((size_t)W * c->S));
     HB_TRY(c->d_chg_list.alloc((size_t)3 * W));
     HB_TRY(c->d_chg_off.alloc((size_t)3 * W));
+    HB_TRY(c->d_chg_dir.alloc((size_t)3 * W * c->S));
     HB_TRY(c->d_chg_cnt.alloc(16));
     HB_TRY(c->d_dB.alloc((size_t)2 * W));
     HB_TRY(c->d_dMave.alloc((size_t)2 * W));
@@ -235,6 +241,8 @@ static void fill_params(hb_ctx *c, BrrParams &P) {
     P.off_out = c->d_small.p;
     P.slice_sum_out = c->d_small.p + 1;
     P.slice_sq_out = c->d_small.p + 1 + c->S;
+    P.slice_abs_out = c->d_small.p + 1 + 2 * c->S + c->G;
+    P.slice_max_out = c->d_small.p + 1 + 3 * c->S + c->G;
     P.beta = c->d_beta.p; P.comp = c->d_comp.p; P.acum = c->d_acum.p; P.cass = c->d_cass.p;
     P.order = c->d_order.p; P.u = c->d_u.p; P.z = c->d_z.p;
     P.T = 1; P.SR = 1; P.lmax = 0; P.K = c->K; P.G = c->G;
@@ -242,12 +250,12 @@ static void fill_params(hb_ctx *c, BrrParams &P) {
     P.logPi = c->d_hyp.p; P.chalf = c->d_hyp.p + gk; P.denom = c->d_hyp.p + 2 * gk; P.sdk = c->d_hyp.p + 3 * gk;
     P.grp_active = c->d_active.p;
     P.dNm1 = (double)(c->N - 1);
-    P.slots = c->d_slots.p; P.chg_cnt = reinterpret_cast<unsigned long long *>(c->d_chg_cnt.p); P.chg_list = c->d_chg_list.p; P.chg_off = c->d_chg_off.p; P.dB = c->d_dB.p; P.dMave = c->d_dMave.p; P.dRec = c->d_dRec.p; P.Wmax = c->Wmax;
+    P.slots = c->d_slots.p; P.chg_cnt = reinterpret_cast<unsigned long long *>(c->d_chg_cnt.p); P.chg_list = c->d_chg_list.p; P.chg_off = c->d_chg_off.p; P.chg_dir = c->d_chg_dir.p; P.dB = c->d_dB.p; P.dMave = c->d_dMave.p; P.dRec = c->d_dRec.p; P.Wmax = c->Wmax;
     P.bar = c->d_bar.p; P.stats = c->d_stats.p;
     P.mode = MODE_CHAIN;
     P.num_out = c->d_num.p;
     P.cta_cycles = c->debug_cycles ? c->d_ctacyc.p : nullptr;
-    P.flags = getenv("HB_NO_PREFETCH") ? 1u : 0u;
+    P.flags = (getenv("HB_NO_PREFETCH") ? 1u : 0u) | (getenv("HB_DBG_FLAGS") ? (uint32_t)atoi(getenv("HB_DBG_FLAGS")) : 0u);   // developer knobs
     P.pc.nranks = (uint32_t)c->nranks; P.pc.rank = (uint32_t)c->rank;
     P.pc.T_total = c->Ttot; P.pc.t_first = c->t_first;
     P.pc.inbox_local = c->inbox;
@@ -278,7 +286,23 @@ static int check_equal_over_ranks(hb_ctx *c, const uint64_t *vals, uint32_t n, c
     return HB_OK;
 }
 
+// Fixed-point grid 2^-sh of one launch (brr_kernel.cuh): every partial sum of a dot product over one slice,
+// S1 + 2 S2 <= 2 sum|eps|, must fit 63 bits, and every value 55 bits (the top byte of a slot is the update's tag). Both
+// with a margin for what the residual can do during the launch (x2 on the sums, whose bound is already the worst case of
+// an all-same-sign subset, x4 on single values); the kernel raises error 5 if a value leaves the range nevertheless.
+static void pick_grid(hb_ctx *c, double shift_in, BrrParams &P) {
+    const double a = c->eps_slice_abs + fabs(shift_in) * (double)c->L + 1.0;
+    const double m = c->eps_abs_max + fabs(shift_in) + 1e-300;
+    int sh = (int)floor(std::min(log2(ldexp(1.0, 61) / (2.0 * a)), log2(ldexp(1.0, 53) / m)));
+    sh = std::max(8, std::min(sh, 60));
+    if (const char *f = getenv("HB_FIXED_SHIFT")) sh = atoi(f);   // developer knob
+    c->last_sh = sh;
+    P.q_scale = ldexp(1.0, sh);
+    P.q_inv = ldexp(1.0, -sh);
+}
+
 static int launch_window_kernel(hb_ctx *c, BrrParams &P) {
+    pick_grid(c, P.shift_in, P);
     HB_CUDA(cudaMemsetAsync(c->d_bar.p, 0, sizeof(uint32_t), c->stream));
     HB_CUDA(cudaMemsetAsync(c->d_chg_cnt.p, 0, 16 * sizeof(uint32_t), c->stream));
     // the slots carry window tags starting at 1: clear what this launch can touch
@@ -287,6 +311,21 @@ static int launch_window_kernel(hb_ctx *c, BrrParams &P) {
     void *args[] = {(void *)&P};
     dim3 grid(c->S * c->R), block(kThreads);
     HB_CUDA(cudaLaunchCooperativeKernel((const void *)k_brr_iteration, grid, block, args, c->smem_bytes, c->stream));
+    return HB_OK;
+}
+
+static int check_kernel_error(hb_ctx *c, const char *who) {
+    uint32_t err = 0;
+    HB_CUDA(cudaMemcpy(&err, c->d_err.p, sizeof(err), cudaMemcpyDeviceToHost));
+    if (err != 0) {
+        uint32_t zero = 0;
+        cudaMemcpy(c->d_err.p, &zero, sizeof(zero), cudaMemcpyHostToDevice);
+    }
+    HB_CHECK(err != 5, HB_ERR_STATE, "%s: a residual left the fixed-point range of the marker kernel (grid 2^-%d): epsilon grew more than "
+             "4x within one launch", who, c->last_sh);
+    HB_CHECK(err == 0, HB_ERR_NCCL, "%s: exchange between the GPUs failed (code %u: 1 = inbox too small for the window's changed markers "
+             "(HB_INBOX_MB) or more than %u of them on one GPU, 2 = a peer did not answer in time (HB_PEER_TIMEOUT_S), 3 = a peer reported a failure)",
+             who, err, kMaxMerged);
     return HB_OK;
 }
 
@@ -417,7 +456,7 @@ int hb_create(const hb_config *cfg, hb_ctx **out) {
     HB_TRY(c->d_E[0].alloc((size_t)c->S * c->L)); HB_TRY(c->d_E[1].alloc((size_t)c->S * c->L));
     HB_CUDA(cudaMemset(c->d_E[0].p, 0, sizeof(double) * c->S * c->L));
     HB_CUDA(cudaMemset(c->d_E[1].p, 0, sizeof(double) * c->S * c->L));
-    HB_TRY(c->d_small.alloc(1 + 2 * (size_t)c->S + c->G));
+    HB_TRY(c->d_small.alloc(1 + 4 * (size_t)c->S + c->G));
     HB_CUDA(cudaMemset(c->d_small.p, 0, sizeof(double) * c->d_small.n));
     c->slice_sum_h.assign(c->S, 0.0);
     HB_TRY(c->d_beta.alloc(M)); HB_TRY(c->d_acum.alloc(M)); HB_TRY(c->d_comp.alloc(M));
@@ -429,10 +468,10 @@ int hb_create(const hb_config *cfg, hb_ctx **out) {
     HB_CUDA(cudaMemset(c->d_cass.p, 0, sizeof(int32_t) * gk));
     HB_CUDA(cudaMemset(c->d_hyp.p, 0, sizeof(double) * 4 * gk));
     HB_CUDA(cudaMemset(c->d_active.p, 0, c->G));
-    HB_TRY(c->d_bar.alloc(1)); HB_TRY(c->d_stats.alloc(16));
+    HB_TRY(c->d_bar.alloc(1)); HB_TRY(c->d_stats.alloc(32));
     c->debug_cycles = getenv("HB_DEBUG_CYCLES") != nullptr;
     HB_TRY(c->d_ctacyc.alloc((size_t)c->S * c->R * 16));
-    HB_CUDA(cudaMemset(c->d_stats.p, 0, 16 * sizeof(unsigned long long)));
+    HB_CUDA(cudaMemset(c->d_stats.p, 0, 32 * sizeof(unsigned long long)));
     HB_TRY(c->d_order.alloc(1)); HB_TRY(c->d_u.alloc(1)); HB_TRY(c->d_z.alloc(1)); HB_TRY(c->d_num.alloc(1));
     HB_TRY(ensure_scratch(c.get(), 256));
     HB_TRY(ensure_pin(c.get(), 4096));
@@ -782,6 +821,12 @@ int hb_set_epsilon(hb_ctx *c, const double *eps) {
     HB_CUDA(cudaStreamSynchronize(c->stream));
     c->shift = 0.0;
     c->eps_set = true;
+    c->eps_slice_abs = 0.0; c->eps_abs_max = 0.0;
+    for (uint32_t s0 = 0; s0 < c->N; s0 += c->L) {
+        double a = 0.0;
+        for (uint32_t i = s0; i < std::min(c->N, s0 + c->L); i++) { a += fabs(eps[i]); c->eps_abs_max = std::max(c->eps_abs_max, fabs(eps[i])); }
+        c->eps_slice_abs = std::max(c->eps_slice_abs, a);
+    }
     return HB_OK;
 }
 
@@ -838,10 +883,25 @@ int hb_scaadd_markers(hb_ctx *c, const uint32_t *markers, const double *dbeta, u
     fill_params(c, P);
     P.mode = MODE_SCAADD; P.T = 1; P.lmax = n; P.SR = 1;
     P.shift_in = 0.0;
+    {   // the fixed-point grid must hold the updated residual: bound it by the L1 norm / twice the sum of the updates
+        double add_abs = 0.0, add_max = 0.0;
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t m = markers[i];
+            add_abs += fabs(dbs[i]) * ((double)c->n1[m] + 2.0 * (double)c->n2[m] + fabs(c->mave_h[m]) * (double)c->nm[m]);
+            add_max += 2.0 * fabs(dbs[i]);
+        }
+        c->eps_slice_abs += add_abs;
+        c->eps_abs_max += add_max;
+    }
     HB_TRY(launch_window_kernel(c, P));
     double off = 0.0;
+    std::vector<double> am(2 * (size_t)c->S);
     HB_CUDA(cudaMemcpyAsync(&off, c->d_small.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaMemcpyAsync(am.data(), c->d_small.p + 1 + 2 * c->S + c->G, sizeof(double) * 2 * c->S, cudaMemcpyDeviceToHost, c->stream));
     HB_CUDA(cudaStreamSynchronize(c->stream));
+    HB_TRY(check_kernel_error(c, "hb_scaadd_markers"));
+    c->eps_slice_abs = *std::max_element(am.begin(), am.begin() + c->S);
+    c->eps_abs_max = *std::max_element(am.begin() + c->S, am.end());
     c->cur ^= 1;
     c->shift += off;
     return HB_OK;
@@ -950,7 +1010,7 @@ int hb_brr_init(hb_ctx *c, const double *y, const int32_t *groups, const double 
     }
     HB_TRY(c->d_perm.ensure(c->M)); HB_TRY(c->d_ut.ensure(c->M)); HB_TRY(c->d_zt.ensure(c->M));
     HB_TRY(ensure_scratch(c, c->SR * c->T));
-    HB_TRY(ensure_pin(c, std::max<size_t>(4 * (size_t)G * K, 8 + 2 * (size_t)c->S + G + (size_t)G * K + 32)));  // hyp tables (4*G*K) and the per-iteration read-back share it
+    HB_TRY(ensure_pin(c, std::max<size_t>(4 * (size_t)G * K, 8 + 4 * (size_t)c->S + G + (size_t)G * K + 32)));  // hyp tables (4*G*K) and the per-iteration read-back share it
     c->iteration = 0;
     c->brr_ready = true;
     { const uint64_t sv = seed; HB_TRY(check_equal_over_ranks(c, &sv, 1, "the seed (give every process the same --seed)")); }
@@ -1040,7 +1100,7 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
     HB_CUDA(cudaMemcpyAsync(c->d_hyp.p, c->pin, sizeof(double) * 4 * gk, cudaMemcpyHostToDevice, st));
     HB_CUDA(cudaMemcpyAsync(c->d_active.p, c->active.data(), G, cudaMemcpyHostToDevice, st));
     HB_CUDA(cudaMemsetAsync(c->d_cass.p, 0, sizeof(int32_t) * gk, st));  // :1697
-    HB_CUDA(cudaMemsetAsync(c->d_stats.p, 0, sizeof(unsigned long long) * 16, st));
+    HB_CUDA(cudaMemsetAsync(c->d_stats.p, 0, sizeof(unsigned long long) * 32, st));
 
     // ---- marker loop
     BrrParams P;
@@ -1075,17 +1135,25 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
     k_beta_sqnorm<<<dim3(kSqChunks, G), 256, 0, st>>>(c->d_beta.p, c->d_grp.p, M, c->d_bsq_part.p);
     k_beta_sqnorm_fin<<<(G + 127) / 128, 128, 0, st>>>(c->d_bsq_part.p, kSqChunks, G, d_bsq);
     HB_CUDA(cudaGetLastError());
-    const size_t nsmall = 1 + 2 * (size_t)c->S + G;
+    const size_t nsmall = 1 + 4 * (size_t)c->S + G;
     double *pin_small = c->pin;
     int32_t *pin_cass = reinterpret_cast<int32_t *>(c->pin + nsmall);
     unsigned long long *pin_stats = reinterpret_cast<unsigned long long *>(c->pin + nsmall + (gk + 1) / 2 + 1);
     HB_CUDA(cudaMemcpyAsync(pin_small, c->d_small.p, sizeof(double) * nsmall, cudaMemcpyDeviceToHost, st));
     HB_CUDA(cudaMemcpyAsync(pin_cass, c->d_cass.p, sizeof(int32_t) * gk, cudaMemcpyDeviceToHost, st));
-    HB_CUDA(cudaMemcpyAsync(pin_stats, c->d_stats.p, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost, st));
+    HB_CUDA(cudaMemcpyAsync(pin_stats, c->d_stats.p, sizeof(unsigned long long) * 32, cudaMemcpyDeviceToHost, st));
     HB_CUDA(cudaEventRecord(c->ev[3], st));
     HB_CUDA(cudaStreamSynchronize(st));
 
     if (c->debug_cycles) {  // developer aid: spread of the per-CTA phase cycles
+        fprintf(stderr, "[hb] fixed-point grid 2^-%d\n", c->last_sh);
+        {
+            const double nwin = (double)std::max<unsigned long long>(1, pin_stats[1]);
+            const char *nm8[8] = {"upd:count", "upd:stage", "upd:apply", "-", "-", "draw:poll", "draw:math", "draw:store"};
+            fprintf(stderr, "[hb] CTA 0 thread 0 cycles per window:");
+            for (int i = 0; i < 8; i++) fprintf(stderr, " %s=%.0f", nm8[i], (double)pin_stats[16 + i] / nwin);
+            fprintf(stderr, "\n");
+        }
         const size_t nc = (size_t)c->S * c->R;
         std::vector<unsigned long long> cy(nc * 16);
         cudaMemcpy(cy.data(), c->d_ctacyc.p, sizeof(unsigned long long) * nc * 16, cudaMemcpyDeviceToHost);
@@ -1100,18 +1168,17 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
             fprintf(stderr, "[hb window 10, ns since first CTA started its dot] end of %-16s min %8.0f mean %8.0f max %8.0f\n", nm[i], mn, sm / (double)nc, mx);
         }
     }
-    {
-        uint32_t err = 0;
-        HB_CUDA(cudaMemcpy(&err, c->d_err.p, sizeof(err), cudaMemcpyDeviceToHost));
-        HB_CHECK(err == 0, HB_ERR_NCCL, "hb_brr_iteration: exchange between the GPUs failed (code %u: 1 = inbox too small (HB_INBOX_MB), "
-                 "2 = a peer did not answer in time (HB_PEER_TIMEOUT_S), 3 = a peer reported a failure, 4 = more than %u changed markers in one window)",
-                 err, kMaxMerged);
-        c->seq_base += pin_stats[1];
-    }
+    HB_TRY(check_kernel_error(c, "hb_brr_iteration"));
+    c->seq_base += pin_stats[1];
     const double off = pin_small[0];
     c->shift = off;  // the launch folded the old shift into E; the new constant is this launch's base terms
     double s1 = 0.0, s2 = 0.0;
     for (uint32_t s = 0; s < c->S; s++) { c->slice_sum_h[s] = pin_small[1 + s]; s1 += pin_small[1 + s]; s2 += pin_small[1 + c->S + s]; }
+    c->eps_slice_abs = 0.0; c->eps_abs_max = 0.0;   // the next launch's fixed-point grid
+    for (uint32_t s = 0; s < c->S; s++) {
+        c->eps_slice_abs = std::max(c->eps_slice_abs, pin_small[1 + 2 * c->S + G + s]);
+        c->eps_abs_max = std::max(c->eps_abs_max, pin_small[1 + 3 * c->S + G + s]);
+    }
     // sum (E+off)^2 over the N individuals
     const double e_sqn = s2 + 2.0 * off * s1 + dN * off * off;
     for (uint32_t g = 0; g < G; g++) c->bsq[g] = pin_small[1 + 2 * c->S + g];
@@ -1391,6 +1458,12 @@ int hb_brr_load_state(hb_ctx *c, const void *buf, size_t n) {
     std::vector<int32_t> hi(c->M);
     r.get(hd.data(), nE); HB_CHECK(r.ok, HB_ERR_ARG, "hb_brr_load_state: truncated state");
     HB_CUDA(cudaMemcpy(c->d_E[c->bw_ready ? 0 : c->cur].p, hd.data(), sizeof(double) * nE, cudaMemcpyHostToDevice));
+    c->eps_slice_abs = 0.0; c->eps_abs_max = 0.0;
+    for (uint32_t s0 = 0; s0 < c->N; s0 += c->L) {
+        double a = 0.0;
+        for (uint32_t i = s0; i < std::min(c->N, s0 + c->L); i++) { a += fabs(hd[i]); c->eps_abs_max = std::max(c->eps_abs_max, fabs(hd[i])); }
+        c->eps_slice_abs = std::max(c->eps_slice_abs, a);
+    }
     r.get(hd.data(), c->M); HB_CUDA(cudaMemcpy(c->d_beta.p, hd.data(), sizeof(double) * c->M, cudaMemcpyHostToDevice));
     r.get(hd.data(), c->M); HB_CUDA(cudaMemcpy(c->d_acum.p, hd.data(), sizeof(double) * c->M, cudaMemcpyHostToDevice));
     r.get(hi.data(), c->M); HB_CHECK(r.ok, HB_ERR_ARG, "hb_brr_load_state: truncated state");

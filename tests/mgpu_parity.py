@@ -23,14 +23,19 @@ def main():
         (1500, 403, 2, 10, 2, 4, "sparse", 4, 7),
         (1200, 300, 1, 1, 1, 4, "bed", 3, 1222),
         (2000, 1000, 8, 8, 1, 3, "mixed", 2, 5),
+        # dense trait, 64 tasks per GPU x sync rate 10: most of the 640 markers per GPU and window change, i.e. more than
+        # 1024 changed markers per window from 2 GPUs on (the old merge gave up there with error 4)
+        (600, 4096, 64, 10, 1, 4, "sparse", 3, 31),
     ]):
         T = TL * world
         rng = np.random.default_rng(seed)
         bed, g = random_bed(rng, M, N, pmiss=0.01)
         sp = reference_lists(bed, N)
-        y = simulate_y(rng, g, n_causal=max(3, M // 10))
+        y = simulate_y(rng, g, n_causal=M if case == 3 else max(3, M // 10), h2=0.9 if case == 3 else 0.5)
         groups = (np.arange(M) % G).astype(np.int32)
         mS = np.tile(np.array([0.0] + [10.0 ** (-(K - 1 - k)) for k in range(1, K)]), (G, 1))
+        if case == 3:
+            mS = np.array([[0.0, 1e-6, 1e-5, 1e-4]])   # tiny slab variances: about half of the markers take a non-zero effect at every draw
         sigmaG0 = rng.uniform(0.2, 0.8, size=G)
         tape = oracle.TapeMaker(seed, T, M).make(n_iter)
         fnz = (sp.N1L + sp.N2L + sp.NML).astype(np.float64) / N
@@ -55,6 +60,10 @@ def main():
             np.testing.assert_allclose(h["bsq"], ref["bsq"][it], rtol=1e-10)
             np.testing.assert_allclose(o["e_sqn"], ref["esqn"][it], rtol=1e-10)
             assert o["n_sync"] == ref["nsync"][it]
+            if case == 3 and it == n_iter - 1 and rank == 0:
+                per_window = o["markers_changed"] / max(1, o["n_windows"])
+                print(f"case 3: {per_window:.0f} changed markers per window over all GPUs", flush=True)
+                assert per_window > 0.4 * 640 * world, per_window   # > 1024 from 4 GPUs on
             for t in range(TL):
                 np.testing.assert_allclose(brr.task_epsilon(t), ref["eps"][it, rank * TL + t], rtol=1e-10, atol=1e-12)
         st.close()

@@ -118,7 +118,7 @@ def test_dot_and_scaadd(repr_mode, N, M, n_slices):
                 ref += oracle.lut_scaadd(N, bed[m], d, mave[m], mstd[m])
             else:
                 ref += oracle.sparse_scaadd(N, d, sp, int(m), mave[m], mstd[m])
-        np.testing.assert_allclose(got, ref, rtol=RTOL, atol=1e-14)
+        np.testing.assert_allclose(got, ref, rtol=RTOL, atol=1e-12)   # epsilon lives on a fixed-point grid of 2^-45 .. 2^-51
         # the dot product sees the updated residual
         num2 = st.sparse_dotprod(markers[:5])
         want3 = np.array([oracle.sparse_dotprod(ref, sp, int(m), mave[m], mstd[m]) for m in markers[:5]])
