@@ -284,27 +284,21 @@ __device__ __forceinline__ void load_unit(const uint4 d, uint64_t (&x)[4], uint3
 }
 __device__ __forceinline__ void dot_words(const uint64_t (&x)[4], uint32_t w0, uint32_t nwords, uint32_t b1, uint32_t b2,
                                           const u64 *__restrict__ Eq, uint32_t lane, u64 &a12, u64 &am) {
-    u64 a1 = 0, a2 = 0;
 #pragma unroll
     for (uint32_t t = 0; t < 4; t++) {
         // most slice blocks are short (rare variants): a group of 32 words that lies entirely past the end is skipped
         // (warp-uniform test) instead of gathering the pad slot 4 x 32 times
         const uint32_t wb = w0 + 32u * t;
         if (wb < nwords) {
+            const uint32_t w = wb + lane;
             const u64 g = gather4(x[t], Eq);      // pad lanes: 4 x the dummy slot = 0
-            // a group of 32 words mostly lies inside one class: warp-uniform tests, the lane-wise form only at the two borders
-            if (wb + 32u <= b1) a1 += g;
-            else if (wb >= b1 && wb + 32u <= b2) a2 += g;
-            else if (wb >= b2) am += g;
-            else {
-                const uint32_t w = wb + lane;
-                if (w < b1) a1 += g;
-                else if (w < b2) a2 += g;
-                else am += g;
-            }
+            // class weights as small integer factors (two multiply-adds per accumulator, no branches, no selects of 64-bit
+            // values): genotype 1 -> a12 += g, genotype 2 -> a12 += 2g, missing -> am += g
+            const uint32_t wt = (w < b1) ? 1u : ((w < b2) ? 2u : 0u), wm = (w < b2) ? 0u : 1u;
+            a12 += g * (u64)wt;
+            am += g * (u64)wm;
         }
     }
-    a12 += a1 + a2 + a2;
 }
 // all of a unit: the lane's share of (a12, am)
 __device__ __forceinline__ void dot_unit(const uint4 d, const uint64_t (&x)[4], const u64 *__restrict__ Eq,

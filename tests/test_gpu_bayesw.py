@@ -79,7 +79,7 @@ def test_bayesw_marginal_likelihoods_match_oracle(quad):
             prior, cVa = [0.9, 0.05, 0.03, 0.02], [0.001, 0.01, 0.1]
             got = sampler.bw_marginal_likelihoods(st, quad, pars, prior, cVa)
             want = oracle.bw_marginal_likelihoods(quad, pars, prior, cVa)
-            np.testing.assert_allclose(got, want, rtol=1e-9)
+            np.testing.assert_allclose(got, want, rtol=1e-11)   # measured max 9.1e-13 over 200 cases (scripts/bw_error_probe.py)
 
 
 def test_bayesw_device_arms_matches_reference_arms():
@@ -103,7 +103,12 @@ def test_bayesw_device_arms_matches_reference_arms():
             if got["nrand"] == want["nrand"] and got["neval"] == want["neval"]:
                 same += 1
                 np.testing.assert_allclose(got["beta"], want["beta"], rtol=1e-9, atol=1e-15)
-    assert same >= 58   # an ulp difference of device exp/log may flip an accept/reject decision in rare cases
+    # same uniforms, same control flow in ALL cases (400/400 in scripts/bw_error_probe.py): the accept/reject decisions of the
+    # device ARMS are those of the reference's object code. The sample itself is the inverse of the piecewise-exponential
+    # envelope's cumulative, x = xl + log(1 + slope * area_needed * exp(-yl)) / slope (src/BayesW_arms.cpp:390-415): a 1-ulp
+    # difference between CUDA's and glibc's exp/log is amplified by 1 / (slope * dx) ~ 1e5-1e7 there, hence 1e-9 (measured
+    # max 2.2e-9 over 400 cases) on the SAMPLE although every log-density agrees to 1e-13.
+    assert same == 60
 
 
 @pytest.mark.parametrize("T,SR,G,repr_mode,replay_hyper", [(1, 1, 1, "sparse", True), (3, 4, 2, "sparse", True), (2, 3, 1, "bed", False)])
@@ -133,12 +138,14 @@ def test_bayesw_chain_replay(T, SR, G, repr_mode, replay_hyper):
             o = bw.iteration(tp)
             beta, comp = bw.state()
             h = bw.hyper()
-            np.testing.assert_allclose(o["mu"], ref["mu"][it], rtol=1e-9, err_msg=f"mu it {it}")
-            np.testing.assert_allclose(o["alpha"], ref["alpha"][it], rtol=1e-9, err_msg=f"alpha it {it}")
+            # tolerances = north_star's 1e-10 where the measured difference allows it (scripts/bw_error_probe.py: mu 1.7e-14,
+            # alpha 5.7e-13, beta 2.8e-11, epsilon 2.9e-13 absolute, sigmaG 1.8e-13, pi 0 on these chains)
+            np.testing.assert_allclose(o["mu"], ref["mu"][it], rtol=1e-11, err_msg=f"mu it {it}")
+            np.testing.assert_allclose(o["alpha"], ref["alpha"][it], rtol=1e-11, err_msg=f"alpha it {it}")
             assert np.array_equal(comp, ref["comp"][it]), f"components differ at iteration {it}"
-            np.testing.assert_allclose(beta, ref["beta"][it], rtol=1e-8, atol=1e-14, err_msg=f"beta it {it}")
+            np.testing.assert_allclose(beta, ref["beta"][it], rtol=1e-10, atol=1e-14, err_msg=f"beta it {it}")
             assert np.array_equal(h["cass"], ref["cass"][it])
             assert o["n_sync"] == ref["nsync"][it]
-            np.testing.assert_allclose(bw.epsilon(), ref["eps"][it], rtol=1e-8, atol=1e-11, err_msg=f"eps it {it}")
-            np.testing.assert_allclose(h["sigmaG"], ref["sigmaG"][it], rtol=1e-7)
-            np.testing.assert_allclose(h["pi"], ref["pi"][it], rtol=1e-7)
+            np.testing.assert_allclose(bw.epsilon(), ref["eps"][it], rtol=1e-10, atol=1e-12, err_msg=f"eps it {it}")
+            np.testing.assert_allclose(h["sigmaG"], ref["sigmaG"][it], rtol=1e-10)
+            np.testing.assert_allclose(h["pi"], ref["pi"][it], rtol=1e-10)
