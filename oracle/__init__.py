@@ -270,11 +270,12 @@ class _BrrArgs(C.Structure):
         + [("hyper_seed", C.c_uint32)]
         + [(n, C.c_void_p) for n in ("out_beta", "out_comp", "out_acum", "out_mu", "out_eps", "out_sigmaG", "out_sigmaE",
                                      "out_pi", "out_bsq", "out_cass", "out_esqn", "out_epssum", "out_nsync", "out_loop_seconds")]
+        + [("X", C.c_void_p), ("F", C.c_int32), ("tape_xI", C.c_void_p), ("tape_zcov", C.c_void_p), ("out_gamma", C.c_void_p)]
     )
 
 
 def brr_chain(N, Mtot, T, K, G, sync_rate, n_iter, sp: SparseLists, y_raw, groups, mS, tape, sigmaG0,
-              usebed=None, bed=None, hyper=None, hyper_seed=0, want_eps=True, fast=False, want_marker_out=True):
+              usebed=None, bed=None, hyper=None, hyper_seed=0, want_eps=True, fast=False, want_marker_out=True, covariates=None):
     """Run the BayesRRm oracle chain. `tape` = dict(zmu, perm, u, z); `hyper` =
     dict(sigmaG, sigmaE, pi) to replay hyper-parameter VALUES, or None to draw
     them with mt19937(hyper_seed) (RNG spec v1).  Returns dict of per-iteration outputs."""
@@ -312,6 +313,13 @@ def brr_chain(N, Mtot, T, K, G, sync_rate, n_iter, sp: SparseLists, y_raw, group
     if hyper is not None:
         a.tape_sigmaG, a.tape_sigmaE, a.tape_pi = k(hyper["sigmaG"], np.float64), k(hyper["sigmaE"], np.float64), k(hyper["pi"], np.float64)
     a.hyper_seed = hyper_seed & 0xFFFFFFFF
+    if covariates is not None:   # fixed effects (src/BayesRRm.cpp:2648-2681): X (N, F); tape may carry xI (n_iter, F) and zcov (n_iter, F)
+        Xc = np.ascontiguousarray(covariates, dtype=np.float64)
+        assert Xc.shape[0] == N
+        a.X, a.F = k(Xc, np.float64), Xc.shape[1]
+        a.tape_xI, a.tape_zcov = k(tape.get("xI"), np.int32), k(tape.get("zcov"), np.float64)
+        out["gamma"] = np.zeros((n_iter, Xc.shape[1]))
+        a.out_gamma = out["gamma"].ctypes.data
     for name in ("beta", "comp", "acum", "mu", "eps", "sigmaG", "sigmaE", "pi", "bsq", "cass", "esqn", "epssum", "nsync", "loop_seconds"):
         v = out[name]
         setattr(a, "out_" + name, None if v is None else v.ctypes.data)

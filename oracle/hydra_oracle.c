@@ -517,6 +517,12 @@ typedef struct {
     double *out_epssum; /* n_iter*T */
     int64_t *out_nsync; /* n_iter: number of epsilon synchronisations */
     double *out_loop_seconds; /* n_iter: wall time of the marker loop only */
+    /* fixed effects (--covariates, src/BayesRRm.cpp:2648-2681); F == 0: none */
+    const double *X;          /* N x F row-major, used as read (src/data.cpp:1615-1672: no centring or scaling) */
+    int32_t F;
+    const int32_t *tape_xI;   /* n_iter*F: order of the covariates per iteration, or NULL -> Fisher-Yates of the running order with mt_hyper */
+    const double *tape_zcov;  /* n_iter*F: standard normals, or NULL -> mt_hyper */
+    double *out_gamma;        /* n_iter*F */
 } ho_brr_args;
 
 static double now_s(void) {
@@ -557,6 +563,9 @@ HO_API int ho_brr_chain(const ho_brr_args *a) {
     for (int g = 0; g < G; g++) if (MtotGrp[g] == 0) sigmaG[g] = 0.0; /* :1239-1240 */
 
     ho_mt mt_hyper; ho_mt_seed(&mt_hyper, a->hyper_seed);
+    int *xI = (int *)malloc(sizeof(int) * (size_t)(a->F > 0 ? a->F : 1));
+    double *gam = (double *)calloc((size_t)(a->F > 0 ? a->F : 1), sizeof(double));   /* gamma.setZero() :1092 */
+    for (int i = 0; i < a->F; i++) xI[i] = i;                                         /* :1113-1117 */
 
     /* mave/mstd :1502-1508 (global arrays) */
     double *mave = (double *)malloc(sizeof(double) * Mtot), *mstd = (double *)malloc(sizeof(double) * Mtot);
@@ -745,6 +754,27 @@ HO_API int ho_brr_chain(const ho_brr_args *a) {
                 for (int k = 0; k < K; k++) estPi[g * K + k] /= s;
             }
         }
+        /* :2648-2681 fixed effects. The reference draws gamma on every rank from the rank's own stream without a broadcast
+         * (the ranks' epsilon then diverge); here, as for the other hyper-parameters, ONE value per covariate
+         * (rank 0's view: its epsilon, the hyper-parameter stream) is applied to every task. sigmaF = s02F = 1 (:1605, :2680). */
+        if (a->F > 0) {
+            const int F = a->F;
+            const double sigE_sigF = sigmaE / 1.0;
+            if (a->tape_xI) for (int i = 0; i < F; i++) xI[i] = a->tape_xI[(size_t)itx * F + i];
+            else ho_shuffle(&mt_hyper, xI, F);                   /* :2653 std::shuffle(xI) */
+            for (int i = 0; i < F; i++) {
+                const int f = xI[i];
+                const double gamma_old = gam[f];
+                double num_f = 0.0;
+                for (int k = 0; k < N; k++) num_f += a->X[(size_t)k * F + f] * (eps[0][k] + gamma_old * a->X[(size_t)k * F + f]);   /* :2666-2668 */
+                const double denom_f = dNm1 + sigE_sigF;                                                                     /* :2670 */
+                const double z = a->tape_zcov ? a->tape_zcov[(size_t)itx * F + i] : ho_mt_normal(&mt_hyper);
+                gam[f] = num_f / denom_f + sqrt(sigmaE / denom_f) * z;                                                       /* :2671 */
+                for (int r = 0; r < T; r++)
+                    for (int k = 0; k < N; k++) eps[r][k] = eps[r][k] + (gamma_old - gam[f]) * a->X[(size_t)k * F + f];     /* :2673-2676 */
+            }
+            if (a->out_gamma) memcpy(a->out_gamma + (size_t)itx * F, gam, sizeof(double) * F);
+        }
         /* :2685-2690 (rank 0's epsilon; its sigmaE is broadcast :2705) */
         double e_sqn = 0.0;
         for (int i = 0; i < N; ++i) e_sqn += eps[0][i] * eps[0][i];
@@ -770,7 +800,7 @@ HO_API int ho_brr_chain(const ho_brr_args *a) {
     free(Beta); free(components); free(Acum); free(adaV); free(mu); free(cass); free(sum_cass);
     free(bsq); free(m0); free(tsad);
     free(mave); free(mstd); free(sigmaG); free(MtotGrp); free(cVa); free(cVaI); free(estPi);
-    free(MrankS); free(MrankL);
+    free(MrankS); free(MrankL); free(xI); free(gam);
     return 0;
 }
 
