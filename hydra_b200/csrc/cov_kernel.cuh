@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) k_cov_gibbs(const CovParams P) {
     const uint32_t nb = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
     const size_t n_all = (size_t)P.S * P.L;
     const size_t per = ((n_all + nb - 1) / nb + 255) & ~(size_t)255;
-    const size_t i0 = std::min<size_t>(n_all, (size_t)b * per), i1 = std::min<size_t>(n_all, i0 + per);
+    const size_t i0 = ((size_t)b * per < n_all) ? (size_t)b * per : n_all, i1 = (i0 + per < n_all) ? i0 + per : n_all;
     uint32_t bar_target = 0;
     for (uint32_t i = 0; i < P.F; i++) {
         const int32_t f = P.xI[i];

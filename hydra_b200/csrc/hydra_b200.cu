@@ -15,6 +15,7 @@
 #include "bw_kernels.cuh"
 #include "common.cuh"
 #include "convert.cuh"
+#include "cov_kernel.cuh"
 #include "host_rng.hpp"
 
 #include <nccl.h>
@@ -153,6 +154,13 @@ struct hb_ctx {
     double sigmaE = 0.0;
     std::vector<HostRng> task_rng;
     HostRng hyper_rng;
+    // fixed effects (--covariates)
+    uint32_t F = 0;
+    DevBuf<double> d_X, d_gamma, d_zcov, d_covpart;
+    DevBuf<int32_t> d_xI;
+    DevBuf<uint32_t> d_covbar;
+    std::vector<double> gamma;
+    std::vector<int32_t> xI;
     std::vector<int32_t> perm;  // M: task-local order per local task block
     std::vector<int32_t> perm_next;   // the next iteration's order, shuffled on a worker thread during the marker loop
     void *pinned_perm[2] = {nullptr, nullptr};  // both buffers are page-locked (cudaHostRegister): the per-iteration H2D copy is a DMA
@@ -452,7 +460,7 @@ int hb_create(const hb_config *cfg, hb_ctx **out) {
     c->is_bed.assign(M, 0); c->staged.assign(M, 0); c->rec_h.assign(M, 0); c->rec_bytes_h.assign(M, 0);
     HB_TRY(c->d_rec_bytes.alloc(M)); HB_TRY(c->d_err.alloc(1));
     HB_CUDA(cudaMemset(c->d_err.p, 0, sizeof(uint32_t)));
-    HB_TRY(c->d_red.alloc(2 * ((size_t)cfg->n_groups * (1 + cfg->n_mix) + 4)));
+    HB_TRY(c->d_red.alloc(2 * ((size_t)cfg->n_groups * (1 + cfg->n_mix) + 8)));
     HB_TRY(c->d_E[0].alloc((size_t)c->S * c->L)); HB_TRY(c->d_E[1].alloc((size_t)c->S * c->L));
     HB_CUDA(cudaMemset(c->d_E[0].p, 0, sizeof(double) * c->S * c->L));
     HB_CUDA(cudaMemset(c->d_E[1].p, 0, sizeof(double) * c->S * c->L));
@@ -1013,6 +1021,7 @@ int hb_brr_init(hb_ctx *c, const double *y, const int32_t *groups, const double 
     HB_TRY(ensure_pin(c, std::max<size_t>(4 * (size_t)G * K, 8 + 4 * (size_t)c->S + G + (size_t)G * K + 32)));  // hyp tables (4*G*K) and the per-iteration read-back share it
     c->iteration = 0;
     c->brr_ready = true;
+    c->F = 0; c->gamma.clear(); c->xI.clear();   // fixed effects are attached after the init (hb_brr_set_covariates)
     { const uint64_t sv = seed; HB_TRY(check_equal_over_ranks(c, &sv, 1, "the seed (give every process the same --seed)")); }
     return HB_OK;
 }
@@ -1184,16 +1193,18 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
     for (uint32_t g = 0; g < G; g++) c->bsq[g] = pin_small[1 + 2 * c->S + g];
     for (size_t x = 0; x < gk; x++) c->cass[x] = pin_cass[x];
     double e_sqn_g = e_sqn;
+    double mu_g0 = c->mu[0];
     unsigned long long changed_all = pin_stats[5];
     if (c->nranks > 1) {
         // group statistics summed over the GPUs (MPI_Allreduce of beta_squaredNorm and cass, :2517-2518); e_sqn is that
         // of global task 0, whose sigmaE draw the reference broadcasts (:2705)
-        const size_t nr = G + gk + 2;
+        const size_t nr = G + gk + 3;
         std::vector<double> red(nr, 0.0);
         for (uint32_t g = 0; g < G; g++) red[g] = c->bsq[g];
         for (size_t x = 0; x < gk; x++) red[G + x] = (double)c->cass[x];
         red[G + gk] = (c->t_first == 0) ? e_sqn : 0.0;
         red[G + gk + 1] = (double)pin_stats[5];
+        red[G + gk + 2] = (c->t_first == 0) ? c->mu[0] : 0.0;   // mu of global task 0 (the fixed effects use its residual)
         HB_CUDA(cudaMemcpyAsync(c->d_red.p, red.data(), sizeof(double) * nr, cudaMemcpyHostToDevice, st));
         HB_NCCL(ncclAllReduce(c->d_red.p, c->d_red.p + nr, nr, ncclDouble, ncclSum, c->nccl, st));
         HB_CUDA(cudaMemcpyAsync(red.data(), c->d_red.p + nr, sizeof(double) * nr, cudaMemcpyDeviceToHost, st));
@@ -1202,6 +1213,7 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
         for (size_t x = 0; x < gk; x++) c->cass[x] = (int32_t)llround(red[G + x]);
         e_sqn_g = red[G + gk];
         changed_all = (unsigned long long)llround(red[G + gk + 1]);
+        mu_g0 = red[G + gk + 2];
     }
 
     // ---- hyper-parameters (:2525-2578, 2685-2731)
@@ -1227,6 +1239,44 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
             for (uint32_t k = 0; k < K; k++) c->pi[g * K + k] /= s;  // dirichlet(cass+1), :2577
         }
     }
+    // ---- fixed effects (:2648-2681): gamma and epsilon, then the residual's statistics again
+    int cov_launches = 0;
+    if (c->F > 0) {
+        const uint32_t F = c->F;
+        std::vector<double> zc(F);
+        if (tape && tape->xI) { for (uint32_t i = 0; i < F; i++) { HB_CHECK(tape->xI[i] >= 0 && (uint32_t)tape->xI[i] < F, HB_ERR_ARG, "hb_brr_iteration: tape xI out of range"); c->xI[i] = tape->xI[i]; } }
+        else c->hyper_rng.shuffle(c->xI.data(), (int)F);                                  // :2653
+        for (uint32_t i = 0; i < F; i++) zc[i] = (tape && tape->zcov) ? tape->zcov[i] : c->hyper_rng.normal();
+        HB_CUDA(cudaMemcpyAsync(c->d_xI.p, c->xI.data(), sizeof(int32_t) * F, cudaMemcpyHostToDevice, st));
+        HB_CUDA(cudaMemcpyAsync(c->d_zcov.p, zc.data(), sizeof(double) * F, cudaMemcpyHostToDevice, st));
+        HB_CUDA(cudaMemsetAsync(c->d_covbar.p, 0, sizeof(uint32_t), st));
+        CovParams Q;
+        Q.N = N; Q.S = c->S; Q.L = c->L; Q.F = F;
+        Q.E = c->d_E[c->cur].p;
+        Q.shift = c->shift + (c->mu[0] - mu_g0);      // residual of GLOBAL task 0 (on one GPU: of task 0)
+        Q.X = c->d_X.p; Q.xI = c->d_xI.p; Q.z = c->d_zcov.p; Q.gamma = c->d_gamma.p;
+        Q.sigmaE = c->sigmaE; Q.denom = dNm1 + c->sigmaE / 1.0;                            // sigmaF = s02F = 1 (:1605, :2656, :2670)
+        Q.part = c->d_covpart.p; Q.bar = c->d_covbar.p;
+        Q.slice_sum = c->d_small.p + 1; Q.slice_sq = c->d_small.p + 1 + c->S;
+        Q.slice_abs = c->d_small.p + 1 + 2 * c->S + G; Q.slice_max = c->d_small.p + 1 + 3 * c->S + G;
+        void *args[] = {(void *)&Q};
+        const unsigned nb = (unsigned)std::min<uint32_t>((uint32_t)c->n_sms, 148u);
+        HB_CUDA(cudaLaunchCooperativeKernel((const void *)k_cov_gibbs, dim3(nb), dim3(256), args, 0, st));
+        cov_launches = 1;
+        HB_CUDA(cudaMemcpyAsync(pin_small, c->d_small.p, sizeof(double) * nsmall, cudaMemcpyDeviceToHost, st));
+        HB_CUDA(cudaMemcpyAsync(c->gamma.data(), c->d_gamma.p, sizeof(double) * F, cudaMemcpyDeviceToHost, st));
+        HB_CUDA(cudaStreamSynchronize(st));
+        double t1 = 0.0, t2 = 0.0;
+        c->eps_slice_abs = 0.0; c->eps_abs_max = 0.0;
+        for (uint32_t s = 0; s < c->S; s++) {
+            c->slice_sum_h[s] = pin_small[1 + s]; t1 += pin_small[1 + s]; t2 += pin_small[1 + c->S + s];
+            c->eps_slice_abs = std::max(c->eps_slice_abs, pin_small[1 + 2 * c->S + G + s]);
+            c->eps_abs_max = std::max(c->eps_abs_max, pin_small[1 + 3 * c->S + G + s]);
+        }
+        // sum (E + shift_g0)^2 with the residual of global task 0 (identical on every GPU: the replicas are bit-identical)
+        const double sh0 = Q.shift;
+        e_sqn_g = t2 + 2.0 * sh0 * t1 + dN * sh0 * sh0;
+    }
     if (tape && tape->sigmaE) c->sigmaE = tape->sigmaE[0];
     else c->sigmaE = c->hyper_rng.inv_scaled_chisq(v0E + dN, (e_sqn_g + v0E * s02E) / (v0E + dN));  // :2690
     c->iteration++;
@@ -1238,7 +1288,7 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
         cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); out->loop_ms = ms;
         cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); out->iter_ms = ms;
         out->n_sync = pin_stats[0]; out->n_windows = pin_stats[1];
-        out->n_launches = 4;
+        out->n_launches = 4 + (uint64_t)cov_launches;
         out->nnz_processed = pin_stats[2]; out->nnz_updated = pin_stats[3];
         out->bed_markers = pin_stats[4]; out->markers_changed = changed_all;
         for (int i = 0; i < 8; i++) out->phase_cycles[i] = pin_stats[8 + i];
@@ -1294,6 +1344,35 @@ int hb_brr_get_task_perm(hb_ctx *c, uint32_t task_local, int32_t *perm) {
     size_t o = 0;
     for (uint32_t t = 0; t < task_local; t++) o += (size_t)c->blkL[c->t_first + t];
     std::copy(c->perm.begin() + o, c->perm.begin() + o + c->blkL[c->t_first + task_local], perm);
+    return HB_OK;
+}
+
+int hb_brr_set_covariates(hb_ctx *c, const double *X, uint32_t n_cov) {
+    HB_CHECK(c && c->brr_ready, HB_ERR_STATE, "hb_brr_set_covariates: call hb_brr_init first");
+    HB_CHECK(n_cov == 0 || X, HB_ERR_ARG, "hb_brr_set_covariates: null matrix");
+    HB_CHECK(c->cfg.model == 0, HB_ERR_ARG, "hb_brr_set_covariates: fixed effects are available for BayesRRm only");
+    HB_CUDA(cudaSetDevice(c->dev));
+    c->F = n_cov;
+    c->gamma.assign(n_cov, 0.0);                      // gamma.setZero(), :1092
+    c->xI.resize(n_cov);
+    for (uint32_t i = 0; i < n_cov; i++) c->xI[i] = (int32_t)i;   // :1113-1117
+    if (n_cov == 0) return HB_OK;
+    const size_t n_all = (size_t)c->S * c->L;
+    std::vector<double> col(n_all * n_cov, 0.0);      // column-major on the slice layout, padded individuals 0
+    for (uint32_t k = 0; k < c->N; k++)
+        for (uint32_t f = 0; f < n_cov; f++) col[(size_t)f * n_all + k] = X[(size_t)k * n_cov + f];
+    HB_TRY(c->d_X.alloc(n_all * n_cov));
+    HB_CUDA(cudaMemcpy(c->d_X.p, col.data(), sizeof(double) * n_all * n_cov, cudaMemcpyHostToDevice));
+    HB_TRY(c->d_gamma.alloc(n_cov)); HB_TRY(c->d_zcov.alloc(n_cov)); HB_TRY(c->d_xI.alloc(n_cov));
+    HB_TRY(c->d_covpart.alloc(2 * 148)); HB_TRY(c->d_covbar.alloc(1));
+    HB_CUDA(cudaMemset(c->d_gamma.p, 0, sizeof(double) * n_cov));
+    return HB_OK;
+}
+
+int hb_brr_get_gamma(hb_ctx *c, double *gamma, int32_t *xI) {
+    HB_CHECK(c && c->brr_ready, HB_ERR_STATE, "hb_brr_get_gamma: call hb_brr_init first");
+    if (gamma) std::copy(c->gamma.begin(), c->gamma.end(), gamma);
+    if (xI) std::copy(c->xI.begin(), c->xI.end(), xI);
     return HB_OK;
 }
 
@@ -1421,6 +1500,7 @@ int hb_brr_save_state(hb_ctx *c, void *buf, size_t cap, size_t *need) {
     HB_CUDA(cudaMemcpy(hd.data(), c->d_beta.p, sizeof(double) * c->M, cudaMemcpyDeviceToHost)); w.put(hd.data(), c->M);
     HB_CUDA(cudaMemcpy(hd.data(), c->d_acum.p, sizeof(double) * c->M, cudaMemcpyDeviceToHost)); w.put(hd.data(), c->M);
     HB_CUDA(cudaMemcpy(hi.data(), c->d_comp.p, sizeof(int32_t) * c->M, cudaMemcpyDeviceToHost)); w.put(hi.data(), c->M);
+    { const uint32_t F = c->F; w.one(F); w.put(c->gamma.data(), F); w.put(c->xI.data(), F); }   // fixed effects (.gam / .xiv of the reference)
     *need = w.b.size();
     if (!buf) return HB_OK;
     HB_CHECK(cap >= w.b.size(), HB_ERR_ARG, "hb_brr_save_state: buffer of %zu bytes, %zu needed", cap, w.b.size());
@@ -1468,6 +1548,13 @@ int hb_brr_load_state(hb_ctx *c, const void *buf, size_t n) {
     r.get(hd.data(), c->M); HB_CUDA(cudaMemcpy(c->d_acum.p, hd.data(), sizeof(double) * c->M, cudaMemcpyHostToDevice));
     r.get(hi.data(), c->M); HB_CHECK(r.ok, HB_ERR_ARG, "hb_brr_load_state: truncated state");
     HB_CUDA(cudaMemcpy(c->d_comp.p, hi.data(), sizeof(int32_t) * c->M, cudaMemcpyHostToDevice));
+    {
+        const uint32_t F = r.one<uint32_t>();
+        HB_CHECK(r.ok && F == c->F, HB_ERR_ARG, "hb_brr_load_state: the state has %u fixed effects, this chain %u (call hb_brr_set_covariates first)", F, c->F);
+        r.get(c->gamma.data(), F); r.get(c->xI.data(), F);
+        HB_CHECK(r.ok, HB_ERR_ARG, "hb_brr_load_state: truncated state");
+        if (F) HB_CUDA(cudaMemcpy(c->d_gamma.p, c->gamma.data(), sizeof(double) * F, cudaMemcpyHostToDevice));
+    }
     c->eps_set = true;
     return HB_OK;
 }

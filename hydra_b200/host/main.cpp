@@ -29,7 +29,7 @@ namespace {
 
 struct Options {  // names follow the reference's Options class (src/options.hpp:20-138)
     std::string bayesType, bedFile, phenotypeFile, failureFile, quad_points, groupIndexFile, groupMixtureFile, mcmcOutDir, mcmcOutNam, sparseDir, sparseBsn,
-        markerBlocksFile;
+        markerBlocksFile, covariatesFile;
     bool bedToSparse = false, dryRun = false, readFromBedFile = false, readFromSparseFiles = false, restart = false;
     uint32_t numberMarkers = 0, numberIndividuals = 0, chainLength = 10000, burnin = 5000, thin = 5, save = 10, syncRate = 1,
              shuffleMarkers = 1, tasks = 1, device = 0, blocksPerRank = 1, rank = 0, world = 1;
@@ -113,7 +113,8 @@ Options parse(int argc, const char **argv) {
         // the same sum. Here the GPUs always exchange the changed markers themselves over NVLink, so both are accepted as
         // no-ops; --ignore-xfiles concerns the reference's restart files, which this host does not read (state file instead).
         else if (a == "--sparse-sync" || a == "--bed-sync" || a == "--ignore-xfiles") o.ignored.push_back(a);
-        else if (a == "--covariates" || a == "--check-RAM" || a == "--groupPriorsFile" || a == "--dPriorsFile")
+        else if (a == "--covariates") o.covariatesFile = need(i);   // src/options.cpp:286-290
+        else if (a == "--check-RAM" || a == "--groupPriorsFile" || a == "--dPriorsFile")
             throw std::runtime_error("option \"" + a + "\" of hydra is not supported by hydra_b200 yet (see DESIGN.md, out of scope)");
         else
             throw std::runtime_error("\nError: invalid option \"" + a + "\".\n");  // src/options.cpp:292-296
@@ -175,6 +176,37 @@ void read_phen(const std::string &path, uint32_t n_ind, std::vector<double> &y, 
         line++;
     }
     if (line != n_ind) throw std::runtime_error("phenotype file [" + path + "] has " + std::to_string(line) + " lines, --number-individuals is " + std::to_string(n_ind));
+}
+
+// src/data.cpp:1615-1672: phenotype and covariate files read together; "FID IID c1 c2 ..." per line; an NA phenotype or an NA in
+// any covariate drops the individual; X is kept as read (row-major, individuals x covariates)
+void read_phen_cov(const std::string &phen, const std::string &covf, uint32_t n_ind, std::vector<double> &y, std::vector<double> &X,
+                   uint32_t &n_cov, std::vector<uint32_t> &na) {
+    std::ifstream inp(phen), inc(covf);
+    if (!inp) throw std::runtime_error("Error: can not open the phenotype file [" + phen + "] to read.");
+    if (!inc) throw std::runtime_error("Error: can not open the covariates file [" + covf + "] to read.");
+    std::string lp, lc;
+    uint32_t line = 0;
+    n_cov = 0;
+    while (std::getline(inp, lp)) {
+        auto tp = split(lp, " \t\r");
+        if (tp.empty()) continue;
+        if (!std::getline(inc, lc)) throw std::runtime_error("covariates file [" + covf + "] is shorter than the phenotype file");
+        auto tc = split(lc, " \t\r");
+        if (tp.size() < 3 || tc.size() < 3) throw std::runtime_error("phenotype / covariates files: malformed line " + std::to_string(line + 1));
+        bool naC = false;
+        for (size_t i = 2; i < tc.size(); i++) naC |= (tc[i] == "NA");
+        if (tp[2] != "NA" && !naC) {
+            if (n_cov == 0) n_cov = (uint32_t)tc.size() - 2;
+            if (tc.size() - 2 != n_cov) throw std::runtime_error("covariates file [" + covf + "]: line " + std::to_string(line + 1) + " has a different number of columns");
+            y.push_back(atof(tp[2].c_str()));
+            for (size_t i = 2; i < tc.size(); i++) X.push_back(std::stod(tc[i]));
+        } else {
+            na.push_back(line);
+        }
+        line++;
+    }
+    if (line != n_ind) throw std::runtime_error("phenotype file [" + phen + "] has " + std::to_string(line) + " lines, --number-individuals is " + std::to_string(n_ind));
 }
 
 // src/data.cpp:1753-1803: phenotype and failure files read together; NA phenotype or failure "-9" drops the individual
@@ -360,7 +392,8 @@ int main(int argc, const char **argv) {
         }
         if (!opt.readFromBedFile && !opt.readFromSparseFiles) throw std::runtime_error("either --bfile or --sparse-dir/--sparse-basename is needed");
 
-        std::vector<double> y, fail;
+        std::vector<double> y, fail, Xcov;
+        uint32_t n_cov = 0;
         std::vector<uint32_t> na;
         const bool bayesW = (opt.bayesType == "bayesWMPI");
         if (!opt.bedToSparse) {
@@ -369,9 +402,14 @@ int main(int argc, const char **argv) {
                 if (opt.failureFile.empty()) throw std::runtime_error("--failure has to be set for bayesWMPI");
                 if (opt.quad_points.empty()) throw std::runtime_error("--quad_points has to be set for bayesWMPI (3,5,7,9,11,13,15,17,25)");
                 read_phen_fail(opt.phenotypeFile, opt.failureFile, Nraw, y, fail, na);
+            } else if (!opt.covariatesFile.empty()) {
+                read_phen_cov(opt.phenotypeFile, opt.covariatesFile, Nraw, y, Xcov, n_cov, na);
+                printf("INFO   : using covariate file: %s (numFixedEffect = %u)\n", opt.covariatesFile.c_str(), n_cov);   // :1550, data.cpp:1664
             } else {
                 read_phen(opt.phenotypeFile, Nraw, y, na);
             }
+            if (bayesW && !opt.covariatesFile.empty())
+                throw std::runtime_error("--covariates with bayesWMPI (gamma_dens, src/BayesW.cpp:119-129, 1366-1413) is not available in this build");
         }
         // groups and mixtures (src/BayesRRm.cpp:981-996)
         std::vector<int32_t> groups;
@@ -595,6 +633,7 @@ int main(int argc, const char **argv) {
             if (!opt.seedSet) memcpy(&seed, id + HB_NCCL_ID_BYTES, 4);
         }
         HB(hb_brr_init(ctx, y.data(), groups.empty() ? nullptr : groups.data(), mSflat.data(), nullptr, seed));  // multi-GPU: also checks that the seed is common
+        if (n_cov) HB(hb_brr_set_covariates(ctx, Xcov.data(), n_cov));   // src/BayesRRm.cpp:1546-1560, 2648-2681
         if (!root || opt.restart) {
             bet.open_rw(out + ".bet", false); acu.open_rw(out + ".acu", false); cpn.open_rw(out + ".cpn", false);
             xb.open_rw(out + ".xbet", false); xc.open_rw(out + ".xcpn", false);
@@ -675,6 +714,13 @@ int main(int argc, const char **argv) {
                     perm.resize((size_t)bl[t_first + t]);
                     HB(hb_brr_get_task_perm(ctx, t, perm.data()));
                     dump_file(out + ".mrk." + std::to_string(t_first + t), it, (uint32_t)bl[t_first + t], perm.data());
+                }
+                if (n_cov) {   // .gam.<rank> / .xiv.<rank>: u32 it; u32 len; f64 / i32 [len] (:2811-2831)
+                    std::vector<double> gam(n_cov);
+                    std::vector<int32_t> xiv(n_cov);
+                    HB(hb_brr_get_gamma(ctx, gam.data(), xiv.data()));
+                    dump_file(out + ".gam." + std::to_string(opt.rank), it, n_cov, gam.data());
+                    dump_file(out + ".xiv." + std::to_string(opt.rank), it, n_cov, xiv.data());
                 }
                 HB(hb_brr_get_state(ctx, beta.data(), comp.data(), nullptr));
                 // u32 Mtot; u32 it; data[Mtot] (:2818-2838)

@@ -176,7 +176,7 @@ class GenotypeStore:
 class BayesRRm:
     """The BayesRRm chain on one GPU (src/BayesRRm.cpp:933-2939, marker loop :1709-2490)."""
 
-    def __init__(self, store: GenotypeStore, y, mS, groups=None, sigmaG0=None, seed=0):
+    def __init__(self, store: GenotypeStore, y, mS, groups=None, sigmaG0=None, seed=0, covariates=None):
         self.store = store
         self._lib = store._lib
         G, K = store.n_groups, store.n_mix
@@ -191,6 +191,12 @@ class BayesRRm:
         s0 = arr(sigmaG0, np.float64)
         check(self._lib.hb_brr_init(store._h, ptr(y), ptr(g), ptr(self.mS), ptr(s0), C.c_uint32(seed & 0xFFFFFFFF)))
         self.iteration_index = 0
+        self.n_cov = 0
+        if covariates is not None:   # hydra's --covariates (src/BayesRRm.cpp:2648-2681): X (n_ind, n_cov), used as given
+            X = arr(covariates, np.float64)
+            assert X.ndim == 2 and X.shape[0] == store.n_ind, X.shape
+            check(self._lib.hb_brr_set_covariates(store._h, ptr(X), C.c_uint32(X.shape[1])))
+            self.n_cov = X.shape[1]
 
     def iteration(self, tape=None):
         """One Gibbs iteration. tape = dict(zmu, perm, u, z[, sigmaG, pi, sigmaE]) for deterministic replay."""
@@ -200,7 +206,7 @@ class BayesRRm:
         if tape is not None:
             t = capi.HbBrrTape()
             for name, dt in (("zmu", np.float64), ("perm", np.int32), ("u", np.float64), ("z", np.float64),
-                             ("sigmaG", np.float64), ("pi", np.float64), ("sigmaE", np.float64)):
+                             ("sigmaG", np.float64), ("pi", np.float64), ("sigmaE", np.float64), ("xI", np.int32), ("zcov", np.float64)):
                 v = tape.get(name)
                 if v is not None:
                     a = arr(np.atleast_1d(v), dt)
@@ -232,6 +238,13 @@ class BayesRRm:
         assert beta.flags.c_contiguous and comp.flags.c_contiguous and acum.flags.c_contiguous and len(beta) == len(comp) == len(acum) == s.m_local
         check(self._lib.hb_brr_get_state(s._h, ptr(beta), ptr(comp), ptr(acum)))
         return beta, comp, acum
+
+    def gamma(self):
+        """Fixed effects and their current order (the reference's .gam / .xiv files)."""
+        g, x = np.zeros(self.n_cov), np.zeros(self.n_cov, np.int32)
+        if self.n_cov:
+            check(self._lib.hb_brr_get_gamma(self.store._h, ptr(g), ptr(x)))
+        return g, x
 
     def set_state(self, beta=None, components=None):
         check(self._lib.hb_brr_set_state(self.store._h, ptr(arr(beta, np.float64)), ptr(arr(components, np.int32))))

@@ -136,6 +136,8 @@ typedef struct hb_brr_tape {
     const double *sigmaG; /* n_groups values AFTER this iteration (:2570), NULL = draw */
     const double *pi;     /* n_groups*n_mix (:2577), NULL = draw */
     const double *sigmaE; /* 1 value (:2690), NULL = draw */
+    const int32_t *xI;    /* n_covariates: order of the fixed effects in this iteration (std::shuffle(xI), :2653), NULL = draw */
+    const double *zcov;   /* n_covariates standard normals for gamma (:2671), NULL = draw */
 } hb_brr_tape;
 
 typedef struct hb_brr_iter_out {
@@ -173,6 +175,16 @@ int hb_brr_load_state(hb_ctx *ctx, const void *buf, size_t n);
 int hb_brr_get_task_epsilon(hb_ctx *ctx, uint32_t task_local, double *eps);
 /* current marker order of local task t (.mrk.<rank>, :2828) */
 int hb_brr_get_task_perm(hb_ctx *ctx, uint32_t task_local, int32_t *perm);
+
+/* Fixed effects, hydra's --covariates (src/BayesRRm.cpp:2648-2681, reader src/data.cpp:1615-1672): X is n_ind x n_cov,
+ * row-major, used as read (the reference neither centres nor scales it; denom = (N-1) + sigmaE/sigmaF assumes standardised
+ * columns, sigmaF = s02F = 1, src/BayesRRm.h:34). Call after hb_brr_init; every hb_brr_iteration then updates gamma and
+ * epsilon between the group hyper-parameters and sigmaE. One gamma per covariate for all tasks, drawn from the
+ * hyper-parameter stream (the reference draws on every rank from the rank's own stream and does not broadcast,
+ * its ranks' residuals diverge; flagged, not reproduced). n_cov == 0 switches the block off. */
+int hb_brr_set_covariates(hb_ctx *ctx, const double *X, uint32_t n_cov);
+/* gamma[n_cov] and the current order xI[n_cov] (either may be NULL); the .gam / .xiv files of :2811-2831 */
+int hb_brr_get_gamma(hb_ctx *ctx, double *gamma, int32_t *xI);
 
 /* ---- BayesW chain (Weibull survival; src/BayesW.cpp:905-1907), single GPU in this version ------------- */
 /* hb_config.model = 1. y: N log-times, fail: N failure indicators (0/1; src/data.cpp:1779), mS as for BayesRRm,

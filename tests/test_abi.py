@@ -39,7 +39,7 @@ def test_abi_version(lib):
 def test_struct_sizes_match_header(lib):
     from hydra_b200 import capi
     assert C.sizeof(capi.HbConfig) == lib.hb_sizeof_config()
-    assert C.sizeof(capi.HbBrrTape) == 7 * 8
+    assert C.sizeof(capi.HbBrrTape) == 9 * 8
     assert C.sizeof(capi.HbBrrIterOut) == lib.hb_sizeof_iter_out()
 
 

@@ -98,8 +98,16 @@ def test_cli_accepts_the_reference_sync_options_and_refuses_unsupported_ones(tmp
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("has no effect here") == 3
-    r = subprocess.run(base_args(d, "o", ["--bfile", os.path.join(d, "t"), "--dry-run", "--covariates", "x.cov"]), capture_output=True, text=True)
+    r = subprocess.run(base_args(d, "o", ["--bfile", os.path.join(d, "t"), "--dry-run", "--check-RAM"]), capture_output=True, text=True)
     assert r.returncode != 0 and "not supported by hydra_b200" in r.stdout + r.stderr
+    # --covariates: phenotype and covariate files are read together, an NA in either drops the individual (src/data.cpp:1615-1672)
+    rng = np.random.default_rng(0)
+    with open(os.path.join(d, "t.cov"), "w") as f:
+        for i in range(600):
+            f.write(f"F{i} I{i} {rng.normal():.6f} {'NA' if i == 11 else f'{rng.normal():.6f}'}\n")
+    r = subprocess.run(base_args(d, "o", ["--bfile", os.path.join(d, "t"), "--dry-run", "--covariates", os.path.join(d, "t.cov")]), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "numFixedEffect = 2" in r.stdout and "(8 NA phenotypes)" in r.stdout    # 7 NA phenotypes + 1 NA covariate
 
 
 def test_cli_reads_the_reference_example_files():
@@ -318,3 +326,36 @@ def test_cli_two_processes_two_gpus_equal_one_process(tmp_path):
     e1 = np.fromfile(os.path.join(d, "one", "run.eps.3"), np.float64, offset=8)
     e2 = np.fromfile(os.path.join(d, "two", "run.eps.3"), np.float64, offset=8)
     np.testing.assert_allclose(e2, e1, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_cli_covariates_run_equals_python_run(tmp_path):
+    """hydra's --covariates through the C++ host: same chain as the Python front-end; .gam / .xiv written at the save points
+    in the reference's layout (u32 it; u32 len; f64 / i32 [len], src/BayesRRm.cpp:2811-2831)."""
+    import hydra_b200
+    d = str(tmp_path)
+    bed, y, na, groups = write_dataset(d)
+    N, M, F = 600, 150, 2
+    rng = np.random.default_rng(4)
+    X = rng.normal(size=(N, F))
+    with open(os.path.join(d, "t.cov"), "w") as f:
+        for i in range(N):
+            f.write(f"F{i} I{i} " + " ".join(repr(float(v)) for v in X[i]) + "\n")
+    r = subprocess.run(base_args(d, "cov", ["--bfile", os.path.join(d, "t"), "--covariates", os.path.join(d, "t.cov")]), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    its, beta = read_bet(os.path.join(d, "cov", "run.bet"), M)
+    keep = np.setdiff1d(np.arange(N), na)
+    with hydra_b200.GenotypeStore(N, M, na_inds=na, tasks=3, sync_rate=5, n_groups=2, n_mix=4, repr_mode="bed") as st:
+        st.load_data_from_bed(bed)
+        st.finalize()
+        brr = hydra_b200.BayesRRm(st, y[keep], [[0.001, 0.01, 0.1]] * 2, groups=groups, seed=1222, covariates=X[keep])
+        for it in range(5):
+            brr.iteration()
+            if it % 2 == 0:
+                assert np.array_equal(brr.state()[0], beta[it // 2]), f"python vs CLI beta at iteration {it}"
+            if it == 4:
+                gam, xiv = brr.gamma()
+    raw = open(os.path.join(d, "cov", "run.gam.0"), "rb").read()
+    assert struct.unpack("<II", raw[:8]) == (4, F) and np.array_equal(np.frombuffer(raw[8:], np.float64), gam)
+    raw = open(os.path.join(d, "cov", "run.xiv.0"), "rb").read()
+    assert struct.unpack("<II", raw[:8]) == (4, F) and np.array_equal(np.frombuffer(raw[8:], np.int32), xiv)

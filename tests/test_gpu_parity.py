@@ -331,3 +331,58 @@ def test_restart_keeps_a_switched_off_group_off():
             h = brr2.hyper()
             assert np.array_equal(brr2.state()[0], straight[k][0]) and np.array_equal(h["cass"], straight[k][1])
             assert np.array_equal(h["sigmaG"], straight[k][2]) and h["sigmaG"][1] == 0.0
+
+
+# ------------------------------------------------------------------------------------ fixed effects (--covariates)
+@pytest.mark.parametrize("replay_hyper", [True, False])
+def test_chain_replay_with_covariates(replay_hyper):
+    """src/BayesRRm.cpp:2648-2681: per iteration, between the group hyper-parameters and sigmaE, every covariate's gamma is
+    drawn and epsilon updated. Replay: the oracle's hyper-parameter values and the covariate order / normals come from the
+    tape; otherwise both sides draw them from the hyper-parameter stream of RNG spec v1 (order: sigmaG, pi per group, the
+    shuffle of the covariates, their normals, sigmaE)."""
+    import hydra_b200
+    N, M, T, SR, G, K, F, n_iter, seed = 1300, 220, 3, 4, 2, 4, 3, 4, 61
+    rng = np.random.default_rng(seed)
+    bed, g = random_bed(rng, M, N, pmiss=0.01)
+    sp = reference_lists(bed, N)
+    X = rng.normal(size=(N, F))
+    X = (X - X.mean(0)) / X.std(0, ddof=1)
+    X[:, 2] += 0.3                                  # one column that is not centred: the residual of (global) task 0 matters
+    y = simulate_y(rng, g, n_causal=12) + X @ np.array([0.8, -0.5, 0.0])
+    groups = (np.arange(M) % G).astype(np.int32)
+    mS = np.tile(np.array([0.0, 0.001, 0.01, 0.1]), (G, 1))
+    sigmaG0 = np.array([0.3, 0.6])
+    tape = oracle.TapeMaker(seed, T, M).make(n_iter)
+    if replay_hyper:
+        tape["xI"] = np.array([rng.permutation(F) for _ in range(n_iter)], np.int32)
+        tape["zcov"] = rng.normal(size=(n_iter, F))
+    hseed = (seed ^ 0x5bd1e995) & 0xFFFFFFFF
+    ref = oracle.brr_chain(N, M, T, K, G, SR, n_iter, sp, y, groups, mS, tape, sigmaG0, hyper_seed=hseed, covariates=X)
+    with hydra_b200.GenotypeStore(N, M, tasks=T, sync_rate=SR, n_groups=G, n_mix=K) as st:
+        st.load_data_from_bed(bed)
+        st.finalize()
+        brr = hydra_b200.BayesRRm(st, y, mS, groups=groups, sigmaG0=sigmaG0, seed=seed, covariates=X)
+        for it in range(n_iter):
+            tp = dict(zmu=tape["zmu"][it], perm=tape["perm"][it], u=tape["u"][it], z=tape["z"][it])
+            if replay_hyper:
+                tp.update(sigmaG=ref["sigmaG"][it], pi=ref["pi"][it], sigmaE=ref["sigmaE"][it:it + 1], xI=tape["xI"][it], zcov=tape["zcov"][it])
+            o = brr.iteration(tp)
+            beta, comp, _ = brr.state()
+            gam, xI = brr.gamma()
+            h = brr.hyper()
+            assert np.array_equal(comp, ref["comp"][it]), f"components differ at iteration {it}"
+            np.testing.assert_allclose(gam, ref["gamma"][it], rtol=RTOL, atol=1e-14, err_msg=f"gamma it {it}")
+            np.testing.assert_allclose(beta, ref["beta"][it], rtol=RTOL, atol=1e-15)
+            np.testing.assert_allclose(o["e_sqn"], ref["esqn"][it], rtol=RTOL)
+            np.testing.assert_allclose(h["sigmaE"], ref["sigmaE"][it], rtol=RTOL)
+            for t in range(T):
+                np.testing.assert_allclose(brr.task_epsilon(t), ref["eps"][it, t], rtol=RTOL, atol=1e-12, err_msg=f"eps it {it} task {t}")
+        assert abs(gam[0]) > 0.2 and abs(gam[1]) > 0.1     # the simulated fixed effects are found
+        # restart keeps the fixed effects
+        blob = brr.save_state()
+        brr.iteration()
+        want = (brr.gamma()[0].copy(), brr.state()[0].copy())
+        brr2 = hydra_b200.BayesRRm(st, y, mS, groups=groups, sigmaG0=sigmaG0, seed=seed, covariates=X)
+        brr2.load_state(blob)
+        brr2.iteration()
+        assert np.array_equal(brr2.gamma()[0], want[0]) and np.array_equal(brr2.state()[0], want[1])

@@ -119,3 +119,21 @@ def test_chain_is_task_layout_invariant_when_sync_every_marker_single_task():
                             usebed=np.ones(M, np.uint8), bed=bed)
     assert np.array_equal(out2["comp"], out["comp"])
     np.testing.assert_allclose(out2["beta"], out["beta"], rtol=1e-9, atol=1e-14)
+
+
+def test_oracle_fixed_effects_recover_simulated_gamma():
+    """--covariates (src/BayesRRm.cpp:2648-2681): with standardised covariates the posterior mean of gamma is the simulated
+    fixed effect on the scale of the standardised phenotype."""
+    rng = np.random.default_rng(1)
+    N, M, T, K = 800, 60, 2, 4
+    bed, g = random_bed(rng, M, N)
+    sp = reference_lists(bed, N)
+    X = rng.normal(size=(N, 3))
+    X = (X - X.mean(0)) / X.std(0, ddof=1)
+    y = simulate_y(rng, g, n_causal=5) + X @ np.array([0.5, -0.3, 0.0])
+    sd = (y - y.mean()).std(ddof=1)
+    tape = oracle.TapeMaker(3, T, M).make(60)
+    ref = oracle.brr_chain(N, M, T, K, 1, 3, 60, sp, y, np.zeros(M, np.int32), np.array([[0, .001, .01, .1]]), tape, np.array([.5]),
+                           hyper_seed=9, covariates=X, want_eps=False)
+    gm = ref["gamma"][20:].mean(0)
+    np.testing.assert_allclose(gm, np.array([0.5, -0.3, 0.0]) / sd, atol=0.06)
