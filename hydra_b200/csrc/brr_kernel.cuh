@@ -213,6 +213,18 @@ __device__ __forceinline__ uint64_t ld_ll(const uint4 *src, uint32_t tag, uint32
     }
     return ((uint64_t)v.z << 32) | v.x;
 }
+// three consecutive units, requested together
+__device__ __forceinline__ void ld_ll3(const uint4 *src, uint32_t tag, uint32_t *err, uint64_t &d0, uint64_t &d1, uint64_t &d2) {
+    uint4 a, b, c;
+    for (uint32_t it = 0;; it++) {
+        asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(src) : "memory");
+        asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(src + 1) : "memory");
+        asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w) : "l"(src + 2) : "memory");
+        if (a.y == tag && a.w == tag && b.y == tag && b.w == tag && c.y == tag && c.w == tag) break;
+        if (it > (1u << 26)) { atomicExch(err, 2u); break; }
+    }
+    d0 = ((uint64_t)a.z << 32) | a.x; d1 = ((uint64_t)b.z << 32) | b.x; d2 = ((uint64_t)c.z << 32) | c.x;
+}
 __device__ __forceinline__ uint32_t ld_ll_u32(const uint4 *rec, uint32_t byte_off, uint32_t tag, uint32_t *err) {
     const uint64_t v = ld_ll(rec + byte_off / 8u, tag, err);
     return (byte_off & 4u) ? (uint32_t)(v >> 32) : (uint32_t)v;
@@ -1239,31 +1251,41 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                     if (blockIdx.x == 0 && tid == 0) atomicExch(P.pc.err, 3u);
                     break;
                 }
-                // ---- 5d. the peers' changed markers, straight from the inboxes (no merge: any order gives the same slice)
-                for (uint32_t hh = 1; hh < NR; hh++) {
-                    const uint32_t h = (me + hh) % NR, n_h = pcnt[h];
-                    const unsigned char *reg = P.pc.inbox_local + ((size_t)par * NR + h) * P.pc.inbox_stride;
-                    for (uint32_t x0 = 0; x0 < n_h; x0 += kChgCap) {
-                        const uint32_t nx = min((uint32_t)kChgCap, n_h - x0);
-                        if (tid < kChgCap) {
-                            Blk bk;
-                            bk.ptr = nullptr; bk.nw = 0; bk.b1 = 0; bk.b2 = 0; bk.n1 = 0; bk.n2 = 0; bk.nm = 0;
-                            double dbs = 0.0, mv = 0.0;
-                            if (tid < nx) {
-                                const uint4 *le = reinterpret_cast<const uint4 *>(reg + 16 + (size_t)(x0 + tid) * kLLEntry);
-                                dbs = __longlong_as_double((long long)ld_ll(le + 1, (uint32_t)seq, P.pc.err));
-                                mv = __longlong_as_double((long long)ld_ll(le + 2, (uint32_t)seq, P.pc.err));
-                                const uint64_t rr = ld_ll(le + 3, (uint32_t)seq, P.pc.err);
-                                bk = decode_block_ll(reinterpret_cast<const uint4 *>(reg + kInboxHeader) + (rr >> 4), (rr & 1ull) != 0,
-                                                     c, S, L, (uint32_t)seq, P.pc.err);
+                // ---- 5d. the peers' changed markers, straight from the inboxes (no merge by position: any order gives the
+                //          same slice). The entries of ALL peers fill common chunks: the fixed cost of a chunk (entry ->
+                //          directory -> words, three dependent reads, plus the staging barriers) is paid once per 64 markers,
+                //          not once per peer.
+                uint32_t n_peers = 0;
+                for (uint32_t hh = 1; hh < NR; hh++) n_peers += pcnt[(me + hh) % NR];
+                for (uint32_t x0 = 0; x0 < n_peers; x0 += kChgCap) {
+                    const uint32_t nx = min((uint32_t)kChgCap, n_peers - x0);
+                    if (tid < kChgCap) {
+                        Blk bk;
+                        bk.ptr = nullptr; bk.nw = 0; bk.b1 = 0; bk.b2 = 0; bk.n1 = 0; bk.n2 = 0; bk.nm = 0;
+                        double dbs = 0.0, mv = 0.0;
+                        if (tid < nx) {
+                            uint32_t x = x0 + tid, h = me;
+                            for (uint32_t hh = 1; hh < NR; hh++) {  // source GPU and index in its list
+                                h = (me + hh) % NR;
+                                const uint32_t n_h = pcnt[h];
+                                if (x < n_h) break;
+                                x -= n_h;
                             }
-                            stage_chunk(chg, stg_scr, nx, bk, dbs, mv, (uint32_t)seq, P.q_scale, tid);
+                            const unsigned char *reg = P.pc.inbox_local + ((size_t)par * NR + h) * P.pc.inbox_stride;
+                            const uint4 *le = reinterpret_cast<const uint4 *>(reg + 16 + (size_t)x * kLLEntry);
+                            uint64_t e1, e2, rr;   // the entry's three data units in one round trip
+                            ld_ll3(le + 1, (uint32_t)seq, P.pc.err, e1, e2, rr);
+                            dbs = __longlong_as_double((long long)e1);
+                            mv = __longlong_as_double((long long)e2);
+                            bk = decode_block_ll(reinterpret_cast<const uint4 *>(reg + kInboxHeader) + (rr >> 4), (rr & 1ull) != 0,
+                                                 c, S, L, (uint32_t)seq, P.pc.err);
                         }
-                        __syncthreads();
-                        any |= chg->any != 0u;
-                        off_q -= chg->qm_sum;
-                        slice_sum_q += apply_chunk(chg, nx, true, Eq, L, (r == 0) ? &cnt_s[8] : nullptr, P.pc.err);
+                        stage_chunk(chg, stg_scr, nx, bk, dbs, mv, (uint32_t)seq, P.q_scale, tid);
                     }
+                    __syncthreads();
+                    any |= chg->any != 0u;
+                    off_q -= chg->qm_sum;
+                    slice_sum_q += apply_chunk(chg, nx, true, Eq, L, (r == 0) ? &cnt_s[8] : nullptr, P.pc.err);
                 }
             }
             if (off_q > (1ll << 61) || off_q < -(1ll << 61)) atomicExch(P.pc.err, 5u);
