@@ -70,7 +70,9 @@ constexpr uint32_t kMaxMerged = 4096;        // changed markers of one window th
 // whether the data of THIS window have arrived -- no fence and no arrival counter at system scope (a
 // red.release.sys per CTA and window cost 4-5 us on NVLink).
 constexpr size_t kLLEntry = 2 * sizeof(ChgEnt);
-constexpr size_t kInboxHeader = 16 + (size_t)kMaxMerged * kLLEntry;
+constexpr size_t kDirBase = 16 + (size_t)kMaxMerged * kLLEntry;      // slice directory entries of a list's first kDirCap markers
+constexpr uint32_t kDirCap = 64, kDirSlices = 148;                    //   [kDirCap][S] x 2 LL units: {first unit of the block | n1 | n2 << 16, nm}
+constexpr size_t kInboxHeader = kDirBase + (size_t)kDirCap * kDirSlices * 32;
 
 // Exchange of the changed markers between the GPUs of one node (replaces MPI_Allreduce of deltaEps,
 // src/BayesRRm.cpp:2051, 2456): every GPU pushes (position, deltaBeta*mstd, mave, genotype record) of its
@@ -225,6 +227,35 @@ __device__ __forceinline__ void ld_ll3(const uint4 *src, uint32_t tag, uint32_t 
     }
     d0 = ((uint64_t)a.z << 32) | a.x; d1 = ((uint64_t)b.z << 32) | b.x; d2 = ((uint64_t)c.z << 32) | c.x;
 }
+// four units at different places, requested together
+__device__ __forceinline__ void ld_ll4(const uint4 *p0, const uint4 *p1, const uint4 *p2, const uint4 *p3, uint32_t tag, uint32_t *err,
+                                       uint64_t &d0, uint64_t &d1, uint64_t &d2, uint64_t &d3) {
+    uint4 a, b, c, d;
+    for (uint32_t it = 0;; it++) {
+        asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(p0) : "memory");
+        asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p1) : "memory");
+        asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w) : "l"(p2) : "memory");
+        asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w) : "l"(p3) : "memory");
+        if (a.y == tag && a.w == tag && b.y == tag && b.w == tag && c.y == tag && c.w == tag && d.y == tag && d.w == tag) break;
+        if (it > (1u << 26)) { atomicExch(err, 2u); break; }
+    }
+    d0 = ((uint64_t)a.z << 32) | a.x; d1 = ((uint64_t)b.z << 32) | b.x; d2 = ((uint64_t)c.z << 32) | c.x; d3 = ((uint64_t)d.z << 32) | d.x;
+}
+// slice block of a record in an inbox from the directory units its sender shipped with the list
+__device__ __forceinline__ Blk block_from_ll_dir(const uint4 *payload, uint64_t da, uint64_t db, uint32_t L) {
+    Blk b;
+    const uint32_t n12 = (uint32_t)(da >> 32);
+    b.ptr = reinterpret_cast<const uint64_t *>(payload + (uint32_t)da);
+    if (n12 == 0xFFFFFFFFu) {
+        b.nw = L / 32; b.b1 = 0xFFFFFFFFu; b.b2 = 0xFFFFFFFFu; b.n1 = 0; b.n2 = 0; b.nm = 0;
+    } else {
+        const uint32_t nm = (uint32_t)db;
+        const uint32_t w1 = ((n12 & 0xFFFFu) + 3) / 4, w2 = ((n12 >> 16) + 3) / 4, wm = (nm + 3) / 4;
+        b.b1 = w1; b.b2 = w1 + w2; b.nw = w1 + w2 + wm;
+        b.n1 = n12 & 0xFFFFu; b.n2 = n12 >> 16; b.nm = nm;
+    }
+    return b;
+}
 __device__ __forceinline__ uint32_t ld_ll_u32(const uint4 *rec, uint32_t byte_off, uint32_t tag, uint32_t *err) {
     const uint64_t v = ld_ll(rec + byte_off / 8u, tag, err);
     return (byte_off & 4u) ? (uint32_t)(v >> 32) : (uint32_t)v;
@@ -238,6 +269,10 @@ __device__ __forceinline__ uint4 ld_nc_v4(const uint4 *p) {  // read-only for th
     return v;
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// bulk form: [p, p + bytes) into L2, both multiples of 16
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 
 // ---- slice block dot product on the fixed-point slice. Integer sums are exact: the lanes', warps' and units' shares can
 //      be added in any order. Two accumulators per marker: a12 = sum_1 + 2 sum_2, am = sum_missing.
@@ -437,13 +472,15 @@ __device__ __forceinline__ void st_slot(uint4 *p, double val, uint32_t tag) {
 // the window tag next to the data, so no fence or arrival counter is needed. Lane kk < K then evaluates
 // mixture component kk; sums over components are taken in component order (same order as the reference).
 __device__ __forceinline__ void draw_marker_warp(const BrrParams &P, const ItemTab *tab, uint32_t k, const HypTabs &H, uint32_t p, uint32_t q,
-                                 uint32_t dbuf, uint32_t buf3, uint32_t tag, uint32_t lane, long long *tp) {
+                                 uint32_t dbuf, uint32_t buf3, uint32_t tag, uint32_t lane, long long *tp, unsigned long long *gs = nullptr) {
     long long t0_ = tp ? clock64() : 0ll;
+#define HB_GS(i) do { if (gs && lane == 0) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); gs[i] = g_; } } while (0)
+    HB_GS(0);
     const uint4 *sl = P.slots + (size_t)p * P.S;
     // A marker with a non-zero effect will change: its place in the window's list of changed markers is reserved now, so
     // that the round trip of the atomic overlaps the wait for the partials and the draw.
     // The same atomic reserves the place of its record in the peers' inboxes (multi-GPU).
-    const unsigned long long resv = 1ull | ((P.pc.nranks > 1) ? ((unsigned long long)(tab->meta[k].rec_bytes >> 3) << 32) : 0ull);  // LL units = 8-byte words
+    const unsigned long long resv = 1ull | ((P.pc.nranks > 1) ? ((unsigned long long)(tab->meta[k].rec_bytes >> 3) << 32) : 0ull);   // (read again below with the rest)  // LL units = 8-byte words
     unsigned long long idx_early = ~0ull;   // (meaningful in lane 0)
     if (lane == 0 && P.mode == MODE_CHAIN && tab->meta[k].beta != 0.0) idx_early = atomicAdd(P.chg_cnt + buf3, resv);
     // The marker's slice directory entries (one per lane) are requested now, for every marker: if it changes, they are
@@ -451,6 +488,9 @@ __device__ __forceinline__ void draw_marker_warp(const BrrParams &P, const ItemT
     uint4 mydir = make_uint4(0u, 0u, 0u, 0u);
     const size_t Qn = (size_t)P.lmax * P.T;
     if (P.mode == MODE_CHAIN && P.dirw && lane < P.S) mydir = ld_nc_v4(P.dirw + (size_t)lane * Qn + q);
+    // everything the draw needs from the table is read before the wait (the poll's memory clobber would hold the loads back)
+    const WinMeta wm = tab->meta[k];
+    const bool g_active = (P.mode == MODE_DOT) ? true : (P.grp_active[wm.grp] != 0);
     double acc = 0.0;
     for (uint32_t c0 = 0; c0 < P.S; c0 += 32) {
         const uint32_t cc = c0 + lane;
@@ -462,19 +502,20 @@ __device__ __forceinline__ void draw_marker_warp(const BrrParams &P, const ItemT
     }
     const double sum = warp_sum(acc);  // xor tree: fixed order
     if (tp && lane == 0) { const long long t_ = clock64(); tp[0] += t_ - t0_; t0_ = t_; }
-    const double mstd = tab->meta[k].mstd;
+    HB_GS(1);
+    const double mstd = wm.mstd;
     (void)dbuf;
     if (P.mode == MODE_DOT) {
         if (lane == 0) P.num_out[q] = __dmul_rn(mstd, sum);
         return;
     }
-    const int32_t m = tab->meta[k].m;
-    const int g = tab->meta[k].grp;
+    const int32_t m = wm.m;
+    const int g = wm.grp;
     const uint32_t K = P.K;
-    const double beta_old = tab->meta[k].beta;
+    const double beta_old = wm.beta;
     double beta_new = 0.0, acum0 = 1.0;
     int comp = -1;
-    if (P.grp_active[g]) {
+    if (g_active) {
         // num = mstd*(...) ; num += beta*(N-1)            (:1809/:316-342, :1855)
         const double num = __dadd_rn(__dmul_rn(mstd, sum), __dmul_rn(beta_old, P.dNm1));
         const uint32_t kk = (lane < K) ? lane : 0;
@@ -484,7 +525,7 @@ __device__ __forceinline__ void draw_marker_warp(const BrrParams &P, const ItemT
             // log(pi) - 0.5*log(...) + muk*num*i_2sigE, evaluated left to right        (:1874-1876)
             logL = __dadd_rn(__dadd_rn(logL, -H.chalf[g * K + kk]), __dmul_rn(__dmul_rn(muk, num), P.i_2sigE));
         }
-        const double prob = tab->meta[k].u;                                               // :1880
+        const double prob = wm.u;                                                         // :1880
         if (K * K <= 32u) {
             // All K terms of the cascade at once: lane j*K + i evaluates exp(logL[i] - logL[j]); term[j] = 1 / sum_i (in
             // component order), or 0 where the reference's 700-test fires (:1884-1890 for j = 0, :1915-1919 for j > 0).
@@ -521,9 +562,10 @@ __device__ __forceinline__ void draw_marker_warp(const BrrParams &P, const ItemT
         }
         }
         const double muc = __shfl_sync(0xffffffffu, muk, comp);
-        if (comp > 0) beta_new = __dadd_rn(muc, __dmul_rn(H.sdk[g * K + comp], tab->meta[k].z));  // :1901
+        if (comp > 0) beta_new = __dadd_rn(muc, __dmul_rn(H.sdk[g * K + comp], wm.z));  // :1901
     }                                                                                // else :1924-1925
     if (tp && lane == 0) { const long long t_ = clock64(); tp[1] += t_ - t0_; t0_ = t_; }
+    HB_GS(2);
     {   // changed marker: the directory entries go next to the list entry (all lanes), then lane 0 writes the entry
         const double dbeta_w = beta_old - beta_new;
         const bool chg_w = (dbeta_w != 0.0 || idx_early != ~0ull);   // lane 0's view decides
@@ -551,7 +593,7 @@ __device__ __forceinline__ void draw_marker_warp(const BrrParams &P, const ItemT
             const uint32_t idx = (uint32_t)got, off_units = (uint32_t)(got >> 32);
             ChgEnt en;
             en.p = (P.pc.nranks > 1) ? (p / P.T) * P.pc.T_total + P.pc.t_first + (p % P.T) : p;
-            en.m = (uint32_t)m; en.dbs = dbs; en.mave = tab->meta[k].mave; en.rec = tab->meta[k].rec;
+            en.m = (uint32_t)m; en.dbs = dbs; en.mave = wm.mave; en.rec = wm.rec;
             P.chg_list[(size_t)buf3 * P.Wmax + idx] = en;
             if (P.pc.nranks > 1) P.chg_off[(size_t)buf3 * P.Wmax + idx] = off_units;  // pushed to the peers after the grid barrier
             if (dbeta != 0.0) atomicAdd(&P.stats[5], 1ull);
@@ -632,10 +674,10 @@ __device__ __forceinline__ void finish_table(ItemTab *tab, uint4 *udesc, const B
                     b.b1 = w1; b.b2 = w1 + w2; b.nw = w1 + w2 + wm;
                 }
                 tab->ptr[k] = b.ptr; tab->nw[k] = b.nw; tab->b1[k] = b.b1; tab->b2[k] = b.b2;
-                if (prefetch) {
-                    const char *pa = reinterpret_cast<const char *>(b.ptr);
-                    const char *pe = pa + (size_t)b.nw * 8;
-                    for (pa = reinterpret_cast<const char *>((uintptr_t)pa & ~(uintptr_t)127); pa < pe; pa += 128) prefetch_l2(pa);
+                if (prefetch && b.nw) {   // one bulk request per block (the copy engine's path, not the load/store unit's queue)
+                    const uintptr_t pa = reinterpret_cast<uintptr_t>(b.ptr) & ~(uintptr_t)15;
+                    const uintptr_t pe = (reinterpret_cast<uintptr_t>(b.ptr) + (size_t)b.nw * 8 + 15) & ~(uintptr_t)15;
+                    prefetch_l2_bulk(reinterpret_cast<const void *>(pa), (uint32_t)(pe - pa));
                 }
             }
         }
@@ -718,7 +760,7 @@ struct ChgTab {  // changed markers of a window, staged for the epsilon update. 
     long long bed_delta;        // same for its BED entries (counted while they are applied)
     long long qm_sum;           // sum of mave*mstd*deltaBeta on the grid 2^-kOffShift: the base term -mave*mstd*deltaBeta of every
                                 // individual (:265-267) is kept as ONE scalar per launch
-    long long pad_;
+    unsigned long long live_mask;   // bit x: entry x is a sparse block with something to apply
 };
 static_assert(sizeof(ChgTab) % 16 == 0, "ChgTab");
 
@@ -745,6 +787,8 @@ __device__ __forceinline__ void store_entry(ChgTab *chg, uint32_t x, const Blk &
 __device__ __forceinline__ void stage_chunk(ChgTab *chg, uint32_t *scr /*[64]*/, uint32_t nx, const Blk &b, double dbs, double mave, uint32_t ll,
                                             double q_scale, uint32_t tid /* < 64 */) {
     const uint32_t lane = tid & 31u, wrp = tid >> 5;
+    const bool two = nx > 32u;   // short chunks (the usual case) are staged by the first warp alone: no exchange, no barrier
+    if (!two && wrp) return;
     const bool valid = tid < nx;
     long long q1 = 0, qm = 0, dl = 0, qo = 0;
     if (valid) entry_deltas(b, dbs, mave, q_scale, q1, qm, dl, qo);
@@ -760,9 +804,18 @@ __device__ __forceinline__ void stage_chunk(ChgTab *chg, uint32_t *scr /*[64]*/,
     const uint32_t tot = __shfl_sync(0xffffffffu, s0, 31);
     dl = (long long)warp_sum_u64((u64)dl);
     qo = (long long)warp_sum_u64((u64)qo);
-    const uint32_t nsp = __popc(__ballot_sync(0xffffffffu, live && !bed)), nbd = __popc(__ballot_sync(0xffffffffu, bed));
+    const uint32_t msp = __ballot_sync(0xffffffffu, live && !bed);
+    const uint32_t nsp = __popc(msp), nbd = __popc(__ballot_sync(0xffffffffu, bed));
+    if (!two) {
+        if (valid) store_entry(chg, tid, b, ll, q1, qm, nwe, s0 - a);
+        if (tid == 0) {
+            *reinterpret_cast<uint4 *>(&chg->total) = make_uint4(tot, nsp, nbd, (nsp + nbd) ? 1u : 0u);
+            chg->delta_sum = dl; chg->qm_sum = qo; chg->bed_delta = 0ll; chg->live_mask = (unsigned long long)msp;
+        }
+        return;
+    }
     if (lane == 0) {   // this warp's totals for the other one
-        scr[wrp * 8 + 0] = tot; scr[wrp * 8 + 1] = nsp; scr[wrp * 8 + 2] = nbd;
+        scr[wrp * 8 + 0] = tot; scr[wrp * 8 + 1] = nsp; scr[wrp * 8 + 2] = nbd; scr[wrp * 8 + 3] = msp;
         *reinterpret_cast<long long *>(scr + wrp * 8 + 4) = dl; *reinterpret_cast<long long *>(scr + wrp * 8 + 6) = qo;
     }
     named_barrier(2, 64);
@@ -773,6 +826,7 @@ __device__ __forceinline__ void stage_chunk(ChgTab *chg, uint32_t *scr /*[64]*/,
         chg->delta_sum = *reinterpret_cast<long long *>(scr + 4) + *reinterpret_cast<long long *>(scr + 12);
         chg->qm_sum = *reinterpret_cast<long long *>(scr + 6) + *reinterpret_cast<long long *>(scr + 14);
         chg->bed_delta = 0ll;
+        chg->live_mask = (unsigned long long)scr[3] | ((unsigned long long)scr[11] << 32);
     }
 }
 // Unit mode (one entry per thread, any thread): the entry, its sums through shared-memory atomics; finish_chunk adds the prefix.
@@ -796,9 +850,13 @@ __device__ __forceinline__ void finish_chunk(ChgTab *chg, uint32_t nx, uint32_t 
     const uint32_t tot0 = __shfl_sync(0xffffffffu, s0, 31), tot1 = __shfl_sync(0xffffffffu, s1, 31);
     if (lane < nx) chg->c[lane].z = s0 - a0;
     if (lane + 32u < nx) chg->c[lane + 32u].z = tot0 + s1 - a1;
-    const uint32_t nsp = __popc(__ballot_sync(0xffffffffu, v0 && !bed0)) + __popc(__ballot_sync(0xffffffffu, v1 && !bed1));
+    const uint32_t m0 = __ballot_sync(0xffffffffu, v0 && !bed0), m1 = __ballot_sync(0xffffffffu, v1 && !bed1);
+    const uint32_t nsp = __popc(m0) + __popc(m1);
     const uint32_t nbd = __popc(__ballot_sync(0xffffffffu, bed0)) + __popc(__ballot_sync(0xffffffffu, bed1));
-    if (lane == 0) { chg->bed_delta = 0ll; chg->total = tot0 + tot1; chg->n_sparse = nsp; chg->n_bed = nbd; chg->any = (nsp + nbd) ? 1u : 0u; }
+    if (lane == 0) {
+        chg->bed_delta = 0ll; chg->total = tot0 + tot1; chg->n_sparse = nsp; chg->n_bed = nbd; chg->any = (nsp + nbd) ? 1u : 0u;
+        chg->live_mask = (unsigned long long)m0 | ((unsigned long long)m1 << 32);
+    }
 }
 // last entry x < nx whose prefix is <= f
 __device__ __forceinline__ uint32_t find_chunk_entry(const ChgTab *chg, uint32_t nx, uint32_t f) {
@@ -852,6 +910,7 @@ __device__ __forceinline__ long long apply_chunk(ChgTab *chg, uint32_t nx, bool 
                                                  unsigned long long *nnz_upd, uint32_t *err) {
     const uint32_t tid = threadIdx.x;
     const uint32_t total = chg->total, nbed = chg->n_bed;
+    const unsigned long long live = chg->live_mask;
     long long added = chg->delta_sum;
     bool synced = true;   // nothing written since the last barrier
     for (uint32_t f0 = 0; f0 < total; f0 += kApplyQ * kThreads) {
@@ -878,8 +937,10 @@ __device__ __forceinline__ long long apply_chunk(ChgTab *chg, uint32_t nx, bool 
         // entries touched by this round: [x_first, x_last]; trailing entries without flattened words are skipped
         const uint32_t fend = min(total, f0 + kApplyQ * kThreads);
         const uint32_t x_first = find_chunk_entry(chg, nx, f0), x_last = find_chunk_entry(chg, nx, fend - 1u);
-        for (uint32_t x = x_first; x <= x_last; x++) {
-            if (chg->b[x].z == 0u || chg->b[x].w == 0xFFFFFFFFu) continue;   // nothing to apply / BED (below)
+        // the sparse entries of [x_first, x_last] that have something to apply (the others, and BED blocks, are skipped)
+        unsigned long long todo = live & (~0ull << x_first) & (~0ull >> (63u - x_last));
+        for (; todo; todo &= todo - 1ull) {
+            const uint32_t x = (uint32_t)__ffsll((long long)todo) - 1u;
             if (!synced) __syncthreads();
             if (x >= xlo && x <= xhi) {
 #pragma unroll
@@ -912,11 +973,7 @@ __device__ __forceinline__ long long apply_chunk(ChgTab *chg, uint32_t nx, bool 
         added += chg->bed_delta;
         synced = false;   // (chg was read after the barrier: one more before it is restaged)
     }
-    if (tid == 0 && nnz_upd)
-        for (uint32_t x = 0; x < nx; x++) {
-            const uint4 eb = chg->b[x];
-            if (eb.w != 0xFFFFFFFFu) *nnz_upd += 4ull * eb.z;
-        }
+    if (tid == 0 && nnz_upd) *nnz_upd += 4ull * total;   // (total = words of the chunk's sparse entries)
     __syncthreads();   // the slice is complete; chg may be restaged
     return added;
 }
@@ -1072,29 +1129,32 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                     if (tab->meta[k].m >= 0) {   // (a padded task step contributes nothing, :2029-2034)
                         // partial of num/mstd: sum_1 + 2 sum_2 + mave*sum_M - mave*sum_slice   (:327-339)
                         u64 s12 = 0, sm = 0;
+#pragma unroll 1
                         for (uint32_t u = tab->ucum[k], u1 = tab->ucum[k + 1]; u < u1; u++) { s12 += upart[2u * u]; sm += upart[2u * u + 1u]; }
                         const double d12 = (double)(long long)s12 * P.q_inv, dm = (double)(long long)(sm - (u64)slice_sum_q) * P.q_inv;
                         st_slot(P.slots + (size_t)p * S + c, fma(tab->meta[k].mave, dm, d12), tag);
                     }
                 }
                 HB_STAMP(11, tid == 0);
-                if (tid < kTabCap) {  // traffic counters (warps 0..3 hold the items): one plain add per warp
-                    uint32_t v = 0, vb = 0;
-                    if (tid < nk && tab->meta[tid].m >= 0) {
-                        if (tab->b1[tid] == 0xFFFFFFFFu) vb = 1u; else v = 4u * tab->nw[tid];
-                    }
-                    v = __reduce_add_sync(0xffffffffu, v);
-                    vb = __reduce_add_sync(0xffffffffu, vb);
-                    if (lane == 0) { cnt_s[2 * warp] += v; cnt_s[2 * warp + 1] += vb; }
-                }
                 // ---- 4. draws: item kk of the group is drawn by slice-CTA kk % S, one warp per item;
                 //         meanwhile the upper warps prepare the next window's table
                 if (warp < kDrawWarps) {
-                    const uint32_t kf = (c + S - (k0 % S)) % S;  // first table entry owned by this CTA
+                    const uint32_t kf = (k0 == 0u) ? c : (c + S - (k0 % S)) % S;  // first table entry owned by this CTA
                     for (uint32_t k = kf + warp * S; k < nk; k += kDrawWarps * S)
-                        if (tab->meta[k].m >= 0) draw_marker_warp(P, tab, k, H, r + R * (k0 + k), base + r + R * (k0 + k), dbuf, win % 3u, tag, lane, (warp == 0) ? &tph[13] : nullptr);
+                        if (tab->meta[k].m >= 0) draw_marker_warp(P, tab, k, H, r + R * (k0 + k), base + r + R * (k0 + k), dbuf, win % 3u, tag, lane, (warp == 0) ? &tph[13] : nullptr,
+                                                                     (P.cta_cycles && win == 10 && warp == 0) ? &gts[12] : nullptr);
                     HB_STAMP(8 + (warp & 1u), lane == 0 && warp < 2);
-                } else if (stage_next) {
+                } else if (tid < kDrawWarps * 32 + kTabCap) {  // traffic counters, by the table warps (off the draws' path)
+                    const uint32_t t = tid - kDrawWarps * 32, w = t >> 5;
+                    uint32_t v = 0, vb = 0;
+                    if (t < nk && tab->meta[t].m >= 0) {
+                        if (tab->b1[t] == 0xFFFFFFFFu) vb = 1u; else v = 4u * tab->nw[t];
+                    }
+                    v = __reduce_add_sync(0xffffffffu, v);
+                    vb = __reduce_add_sync(0xffffffffu, vb);
+                    if (lane == 0) { cnt_s[2 * w] += v; cnt_s[2 * w + 1] += vb; }
+                }
+                if (warp >= kDrawWarps && stage_next) {
                     const uint32_t j1 = j0 + n, n1 = min(SR, P.lmax - j1);
                     finish_table(&tabs[(win + 1u) & 1u], udesc, P, r, c, j1 * P.T, n1 * P.T, 0, kDrawWarps * 32, blockDim.x - kDrawWarps * 32, !(P.flags & 1u));
                     HB_STAMP(10, tid == kDrawWarps * 32);
@@ -1133,11 +1193,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
             ChgEnt spec;
             spec.p = 0xFFFFFFFFu; spec.m = 0; spec.dbs = 0.0; spec.mave = 0.0; spec.rec = 0;
             uint4 sdir = make_uint4(0u, 0u, 0u, 0u);
-            if (tid < kChgCap) { spec = ld_chg_ent(llist + tid); sdir = __ldcg(ldir + (size_t)tid * S + c); }
+            uint32_t soff = 0;                        // multi-GPU: first unit of the marker's record in the peers' inboxes
+            if (tid < kChgCap) {
+                spec = ld_chg_ent(llist + tid); sdir = __ldcg(ldir + (size_t)tid * S + c);
+                if (NR > 1) soff = __ldcg(P.chg_off + (size_t)buf3 * P.Wmax + tid);
+            }
             const unsigned long long cntv = __ldcg(P.chg_cnt + buf3);
             const uint32_t nloc = (uint32_t)cntv;
             if (blockIdx.x == 0 && tid == 0) P.chg_cnt[(win + 2u) % 3u] = 0ull;  // free since the previous grid barrier
-            bool ok = true;
+            bool ok = true, fast_push = false;
+            uint32_t push_f = 0;
+            unsigned long long push_v = 0ull, hv_early = 0ull;
             if (NR > 1) {
                 // ---- 5a. this GPU's changed markers for every peer, over NVLink in the LL form (tagged 16-byte stores on
                 // peer-mapped pointers, no fence, no arrival counter): the count (one 8-byte store, tagged), the list
@@ -1152,7 +1218,53 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                 if (blockIdx.x == 0 && tid < NR && tid != me)
                     *reinterpret_cast<volatile unsigned long long *>(P.pc.inbox_peer[tid] + region) =
                         (unsigned long long)(ok ? nloc : 0xFFFFFFFFu) | (seq << 32);
-                if (ok && nloc > 0) {
+                // the slice directory entries of the list's first kDirCap markers travel with it: the CTA of slice c in replica
+                // group 0 ships those of its slice (no dependent read of the record's directory on the other side)
+                if (ok && r == 0 && tid < min(nloc, kDirCap)) {
+                    uint64_t da, db;
+                    if (spec.rec & 1ull) { da = (uint64_t)(soff + c * (L / 32)) | (0xFFFFFFFFull << 32); db = 0ull; }
+                    else { da = (uint64_t)(soff + dir_bytes(S) / 8u + sdir.x) | ((uint64_t)sdir.y << 32); db = (uint64_t)sdir.z; }
+                    for (uint32_t h = 0; h < NR; h++) {
+                        if (h == me) continue;
+                        uint4 *d = reinterpret_cast<uint4 *>(P.pc.inbox_peer[h] + region + kDirBase) + ((size_t)tid * S + c) * 2;
+                        st_ll(d, da, (uint32_t)seq); st_ll(d + 1, db, (uint32_t)seq);
+                    }
+                }
+                fast_push = ok && nloc > 0 && nloc <= kChgCap && units <= nctas * blockDim.x;
+                if (fast_push) {
+                    // the usual case: everything comes from the registers of the speculative read; every thread moves at
+                    // most one unit, whose load overlaps the staging of the local chunk (stores: see 5b)
+                    uint32_t *sp = psort;
+                    unsigned long long *srec = reinterpret_cast<unsigned long long *>(psort + ((nloc + 2u) & ~1u));
+                    if (tid < nloc) {
+                        sp[tid] = soff; srec[tid] = spec.rec;
+                        if (blockIdx.x == 0) {
+                            const uint64_t e0 = (uint64_t)spec.p | ((uint64_t)(uint32_t)seq << 32);
+                            const uint64_t e3 = (spec.rec & 1ull) | ((unsigned long long)soff << 4);
+                            for (uint32_t h = 0; h < NR; h++) {
+                                if (h == me) continue;
+                                uint4 *d = reinterpret_cast<uint4 *>(P.pc.inbox_peer[h] + region + 16 + (size_t)tid * kLLEntry);
+                                st_ll(d, e0, (uint32_t)seq); st_ll(d + 1, (uint64_t)__double_as_longlong(spec.dbs), (uint32_t)seq);
+                                st_ll(d + 2, (uint64_t)__double_as_longlong(spec.mave), (uint32_t)seq); st_ll(d + 3, e3, (uint32_t)seq);
+                            }
+                        }
+                    }
+                    if (tid == 0) sp[nloc] = units;
+                    __syncthreads();
+                    push_f = blockIdx.x * blockDim.x + tid;
+                    if (push_f < units) {
+                        const uint32_t e = find_entry(sp, nloc, push_f);
+                        push_v = __ldg(reinterpret_cast<const unsigned long long *>(srec[e] & ~15ull) + (push_f - sp[e]));
+                        if (warp >= 2) {   // warps 0 and 1 stage the local chunk first
+                            for (uint32_t h = 0; h < NR; h++)
+                                if (h != me) st_ll(reinterpret_cast<uint4 *>(P.pc.inbox_peer[h] + region + kInboxHeader) + push_f, push_v, (uint32_t)seq);
+                        }
+                    }
+                    // a first look at the peers' counts (answered during the local update)
+                    if (tid < NR && tid != me)
+                        hv_early = *reinterpret_cast<const volatile unsigned long long *>(P.pc.inbox_local + ((size_t)par * NR + tid) * P.pc.inbox_stride);
+                } else
+                if (ok && nloc > 0) {   // long lists / heavy records
                     // scratch: first unit of every entry [nloc + 1], then the record addresses [nloc]; very long lists
                     // are searched in global memory instead
                     constexpr uint32_t kScr = 4 * kUnitCap;
@@ -1195,6 +1307,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                     __syncthreads();  // the scratch is free again
                 }
             }
+            HB_SUB(11);
             // ---- 5b. this GPU's own changed markers (the peers' are still on their way). Warps 0 and 1 stage a chunk (one entry
             //          per thread); the slice directory entry travels with the list entry (written by the drawing warp), and
             //          the first 64 entries were requested together with the count: one L2 round trip up to here.
@@ -1212,6 +1325,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                             dbs = en.dbs; mv = en.mave;
                         }
                         stage_chunk(chg, stg_scr, nx, bk, dbs, mv, 0u, P.q_scale, tid);
+                    }
+                    if (x0 == 0 && fast_push && warp < 2 && push_f < (uint32_t)(cntv >> 32)) {
+                        for (uint32_t h = 0; h < NR; h++)
+                            if (h != me)
+                                st_ll(reinterpret_cast<uint4 *>(P.pc.inbox_peer[h] + ((size_t)par * NR + me) * P.pc.inbox_stride + kInboxHeader) + push_f, push_v,
+                                      (uint32_t)seq_w);
                     }
                     __syncthreads();
                     HB_SUB(9);
@@ -1233,9 +1352,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                         bool late = false;
                         const volatile unsigned long long *hdr =
                             reinterpret_cast<const volatile unsigned long long *>(P.pc.inbox_local + ((size_t)par * NR + tid) * P.pc.inbox_stride);
-                        unsigned long long hv = 0;
+                        unsigned long long hv = hv_early;
                         uint32_t spin = 0;
-                        while (!late && (uint32_t)((hv = *hdr) >> 32) != (uint32_t)seq) {
+                        while (!late && (uint32_t)(hv >> 32) != (uint32_t)seq) {
+                            hv = *hdr;
+                            if ((uint32_t)(hv >> 32) == (uint32_t)seq) break;
                             if (clock64() - t0 > P.pc.timeout_cycles) late = true;
                             if ((++spin & 0xFFu) == 0u && *reinterpret_cast<volatile uint32_t *>(P.pc.err) != 0u) late = true;  // somebody already gave up
                         }
@@ -1245,6 +1366,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                     pcnt[tid] = nh;
                 }
                 __syncthreads();
+                HB_SUB(12);
                 bool bad = false;
                 for (uint32_t h = 0; h < NR; h++) bad |= (pcnt[h] == 0xFFFFFFFFu);
                 if (bad) {  // give up: the host reports the failure after the launch
@@ -1273,12 +1395,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                             }
                             const unsigned char *reg = P.pc.inbox_local + ((size_t)par * NR + h) * P.pc.inbox_stride;
                             const uint4 *le = reinterpret_cast<const uint4 *>(reg + 16 + (size_t)x * kLLEntry);
-                            uint64_t e1, e2, rr;   // the entry's three data units in one round trip
-                            ld_ll3(le + 1, (uint32_t)seq, P.pc.err, e1, e2, rr);
+                            uint64_t e1, e2;
+                            if (x < kDirCap) {   // entry and directory units in one round trip
+                                const uint4 *ld = reinterpret_cast<const uint4 *>(reg + kDirBase) + ((size_t)x * S + c) * 2;
+                                uint64_t da, db;
+                                ld_ll4(le + 1, le + 2, ld, ld + 1, (uint32_t)seq, P.pc.err, e1, e2, da, db);
+                                bk = block_from_ll_dir(reinterpret_cast<const uint4 *>(reg + kInboxHeader), da, db, L);
+                            } else {
+                                uint64_t rr;
+                                ld_ll3(le + 1, (uint32_t)seq, P.pc.err, e1, e2, rr);
+                                bk = decode_block_ll(reinterpret_cast<const uint4 *>(reg + kInboxHeader) + (rr >> 4), (rr & 1ull) != 0,
+                                                     c, S, L, (uint32_t)seq, P.pc.err);
+                            }
                             dbs = __longlong_as_double((long long)e1);
                             mv = __longlong_as_double((long long)e2);
-                            bk = decode_block_ll(reinterpret_cast<const uint4 *>(reg + kInboxHeader) + (rr >> 4), (rr & 1ull) != 0,
-                                                 c, S, L, (uint32_t)seq, P.pc.err);
                         }
                         stage_chunk(chg, stg_scr, nx, bk, dbs, mv, (uint32_t)seq, P.q_scale, tid);
                     }

@@ -1158,7 +1158,11 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
         fprintf(stderr, "[hb] fixed-point grid 2^-%d\n", c->last_sh);
         {
             const double nwin = (double)std::max<unsigned long long>(1, pin_stats[1]);
-            const char *nm8[8] = {"upd:count", "upd:stage", "upd:apply", "-", "-", "draw:poll", "draw:math", "draw:store"};
+            const char *nm8[8] = {"upd:count", "upd:stage", "upd:apply", "xchg:push", "xchg:wait", "draw:poll", "draw:math", "draw:store"};
+            const char *nmp[8] = {"table", "dot", "publish+draw", "barrier", "update(local)", "sums", "-", "update(peers)"};
+            fprintf(stderr, "[hb] CTA 0 thread 0 cycles per window, phases:");
+            for (int i = 0; i < 8; i++) fprintf(stderr, " %s=%.0f", nmp[i], (double)pin_stats[8 + i] / nwin);
+            fprintf(stderr, "\n");
             fprintf(stderr, "[hb] CTA 0 thread 0 cycles per window:");
             for (int i = 0; i < 8; i++) fprintf(stderr, " %s=%.0f", nm8[i], (double)pin_stats[16 + i] / nwin);
             fprintf(stderr, "\n");
@@ -1169,9 +1173,15 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
         // globaltimer stamps (ns) of window 10 at the end of each phase, relative to the earliest "table done"
         unsigned long long t0 = ~0ull;
         for (size_t b = 0; b < nc; b++) t0 = std::min(t0, cy[b * 16 + 0]);
-        const int ord[11] = {0, 1, 11, 8, 9, 10, 2, 3, 4, 7, 5};
-        const char *nm[11] = {"tab", "dot", "publish", "draws of warp 0", "draws of warp 1", "next table", "pub", "bar", "upd0", "updA", "sum"};
-        for (int i = 0; i < 11; i++) {
+        const int ord[14] = {0, 1, 11, 12, 13, 14, 8, 9, 10, 2, 3, 4, 7, 5};
+        const char *nm[14] = {"tab", "dot", "publish", "w0 draw start", "w0 poll", "w0 math", "draws of warp 0", "draws of warp 1", "next table", "pub", "bar", "upd0", "updA", "sum"};
+        if (getenv("HB_DEBUG_CYCLES")[0] == '2')   // one row per CTA (block = r * S + c)
+            for (size_t b = 0; b < nc; b++) {
+                fprintf(stderr, "[hb cta %3zu r %2zu c %2zu]", b, b / c->S, b % c->S);
+                for (int i = 0; i < 14; i++) fprintf(stderr, " %s=%lld", nm[i], (long long)(cy[b * 16 + ord[i]] - t0));
+                fprintf(stderr, "\n");
+            }
+        for (int i = 0; i < 14; i++) {
             double mn = 1e300, mx = 0, sm = 0;
             for (size_t b = 0; b < nc; b++) { const double v = (double)(cy[b * 16 + ord[i]] - t0); mn = std::min(mn, v); mx = std::max(mx, v); sm += v; }
             fprintf(stderr, "[hb window 10, ns since first CTA started its dot] end of %-16s min %8.0f mean %8.0f max %8.0f\n", nm[i], mn, sm / (double)nc, mx);
