@@ -42,7 +42,9 @@ typedef struct hb_ctx hb_ctx;
 /* Genotype representation choice, src/data.cpp:886-1069 (mixed), options.hpp:86 */
 #define HB_REPR_SPARSE 0 /* all markers as index lists      (--sparse-dir/--sparse-basename) */
 #define HB_REPR_BED 1    /* all markers as 2-bit BED bytes  (dotp_lut path)                   */
-#define HB_REPR_MIXED 2  /* BED iff (n1+n2+nm)/N > threshold_fnz (src/data.cpp:931-932)       */
+#define HB_REPR_MIXED 2  /* USEBED iff (n1+n2+nm)/N > threshold_fnz (src/data.cpp:931-932); such a marker is kept as
+                          * 2-bit codes in HBM only where that halves its 16-bit index lists (> 25 % non-zeros):
+                          * the kernel's sums are exact, results do not depend on the stored form */
 
 typedef struct hb_config {
     int32_t device;           /* CUDA device ordinal */
