@@ -1194,16 +1194,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
             spec.p = 0xFFFFFFFFu; spec.m = 0; spec.dbs = 0.0; spec.mave = 0.0; spec.rec = 0;
             uint4 sdir = make_uint4(0u, 0u, 0u, 0u);
             uint32_t soff = 0;                        // multi-GPU: first unit of the marker's record in the peers' inboxes
-            if (tid < kChgCap) {
-                spec = ld_chg_ent(llist + tid); sdir = __ldcg(ldir + (size_t)tid * S + c);
-                if (NR > 1) soff = __ldcg(P.chg_off + (size_t)buf3 * P.Wmax + tid);
+            // (multi-GPU: warps 2 and 3 read the same for the exchange, so that warps 0 and 1 go straight to the local update)
+            const uint32_t ts = (NR > 1 && tid >= kChgCap) ? tid - kChgCap : tid;
+            if (tid < kChgCap || (NR > 1 && tid < 2 * kChgCap)) {
+                spec = ld_chg_ent(llist + ts); sdir = __ldcg(ldir + (size_t)ts * S + c);
+                if (NR > 1) soff = __ldcg(P.chg_off + (size_t)buf3 * P.Wmax + ts);
             }
             const unsigned long long cntv = __ldcg(P.chg_cnt + buf3);
             const uint32_t nloc = (uint32_t)cntv;
             if (blockIdx.x == 0 && tid == 0) P.chg_cnt[(win + 2u) % 3u] = 0ull;  // free since the previous grid barrier
             bool ok = true, fast_push = false;
             uint32_t push_f = 0;
-            unsigned long long push_v = 0ull, hv_early = 0ull;
+            unsigned long long push_v = 0ull;
             if (NR > 1) {
                 // ---- 5a. this GPU's changed markers for every peer, over NVLink in the LL form (tagged 16-byte stores on
                 // peer-mapped pointers, no fence, no arrival counter): the count (one 8-byte store, tagged), the list
@@ -1218,53 +1220,54 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                 if (blockIdx.x == 0 && tid < NR && tid != me)
                     *reinterpret_cast<volatile unsigned long long *>(P.pc.inbox_peer[tid] + region) =
                         (unsigned long long)(ok ? nloc : 0xFFFFFFFFu) | (seq << 32);
-                // the slice directory entries of the list's first kDirCap markers travel with it: the CTA of slice c in replica
-                // group 0 ships those of its slice (no dependent read of the record's directory on the other side)
-                if (ok && r == 0 && tid < min(nloc, kDirCap)) {
-                    uint64_t da, db;
-                    if (spec.rec & 1ull) { da = (uint64_t)(soff + c * (L / 32)) | (0xFFFFFFFFull << 32); db = 0ull; }
-                    else { da = (uint64_t)(soff + dir_bytes(S) / 8u + sdir.x) | ((uint64_t)sdir.y << 32); db = (uint64_t)sdir.z; }
-                    for (uint32_t h = 0; h < NR; h++) {
-                        if (h == me) continue;
-                        uint4 *d = reinterpret_cast<uint4 *>(P.pc.inbox_peer[h] + region + kDirBase) + ((size_t)tid * S + c) * 2;
-                        st_ll(d, da, (uint32_t)seq); st_ll(d + 1, db, (uint32_t)seq);
+                // The slice directory entries of the list's first kDirCap markers travel with it: the CTA of slice c in replica
+                // group 0 ships those of its slice (no dependent read of the record's directory on the other side).
+                auto push_dirs = [&](uint32_t t) {
+                    if (ok && r == 0 && t < min(nloc, kDirCap)) {
+                        uint64_t da, db;
+                        if (spec.rec & 1ull) { da = (uint64_t)(soff + c * (L / 32)) | (0xFFFFFFFFull << 32); db = 0ull; }
+                        else { da = (uint64_t)(soff + dir_bytes(S) / 8u + sdir.x) | ((uint64_t)sdir.y << 32); db = (uint64_t)sdir.z; }
+                        for (uint32_t h = 0; h < NR; h++) {
+                            if (h == me) continue;
+                            uint4 *d = reinterpret_cast<uint4 *>(P.pc.inbox_peer[h] + region + kDirBase) + ((size_t)t * S + c) * 2;
+                            st_ll(d, da, (uint32_t)seq); st_ll(d + 1, db, (uint32_t)seq);
+                        }
                     }
-                }
-                fast_push = ok && nloc > 0 && nloc <= kChgCap && units <= nctas * blockDim.x;
+                };
+                constexpr uint32_t kPushThreads = kThreads - 2 * 32;   // warps 2..15 move the records
+                fast_push = ok && nloc > 0 && nloc <= kChgCap && units <= nctas * kPushThreads;
                 if (fast_push) {
-                    // the usual case: everything comes from the registers of the speculative read; every thread moves at
-                    // most one unit, whose load overlaps the staging of the local chunk (stores: see 5b)
-                    uint32_t *sp = psort;
-                    unsigned long long *srec = reinterpret_cast<unsigned long long *>(psort + ((nloc + 2u) & ~1u));
-                    if (tid < nloc) {
-                        sp[tid] = soff; srec[tid] = spec.rec;
-                        if (blockIdx.x == 0) {
+                    // The usual case: warps 0 and 1 go straight to the local update; warps 2 and 3 (which hold the same
+                    // speculative read) build the scratch, ship entries and directory entries; warps 2..15 move the
+                    // records, at most one unit per thread, whose load is in flight during the staging of the local chunk
+                    // (stores: see 5b).
+                    if (warp >= 2) {
+                        uint32_t *sp = psort;
+                        unsigned long long *srec = reinterpret_cast<unsigned long long *>(psort + ((nloc + 2u) & ~1u));
+                        const uint32_t t2 = tid - 2 * 32;
+                        if (t2 < nloc) { sp[t2] = soff; srec[t2] = spec.rec; }
+                        if (t2 == 0) sp[nloc] = units;
+                        named_barrier(3, kPushThreads);
+                        push_f = blockIdx.x * kPushThreads + t2;
+                        if (push_f < units) {
+                            const uint32_t e = find_entry(sp, nloc, push_f);
+                            push_v = __ldg(reinterpret_cast<const unsigned long long *>(srec[e] & ~15ull) + (push_f - sp[e]));
+                        }
+                        if (blockIdx.x == 0 && t2 < nloc) {
                             const uint64_t e0 = (uint64_t)spec.p | ((uint64_t)(uint32_t)seq << 32);
                             const uint64_t e3 = (spec.rec & 1ull) | ((unsigned long long)soff << 4);
                             for (uint32_t h = 0; h < NR; h++) {
                                 if (h == me) continue;
-                                uint4 *d = reinterpret_cast<uint4 *>(P.pc.inbox_peer[h] + region + 16 + (size_t)tid * kLLEntry);
+                                uint4 *d = reinterpret_cast<uint4 *>(P.pc.inbox_peer[h] + region + 16 + (size_t)t2 * kLLEntry);
                                 st_ll(d, e0, (uint32_t)seq); st_ll(d + 1, (uint64_t)__double_as_longlong(spec.dbs), (uint32_t)seq);
                                 st_ll(d + 2, (uint64_t)__double_as_longlong(spec.mave), (uint32_t)seq); st_ll(d + 3, e3, (uint32_t)seq);
                             }
                         }
+                        if (warp < 4) push_dirs(t2);
                     }
-                    if (tid == 0) sp[nloc] = units;
-                    __syncthreads();
-                    push_f = blockIdx.x * blockDim.x + tid;
-                    if (push_f < units) {
-                        const uint32_t e = find_entry(sp, nloc, push_f);
-                        push_v = __ldg(reinterpret_cast<const unsigned long long *>(srec[e] & ~15ull) + (push_f - sp[e]));
-                        if (warp >= 2) {   // warps 0 and 1 stage the local chunk first
-                            for (uint32_t h = 0; h < NR; h++)
-                                if (h != me) st_ll(reinterpret_cast<uint4 *>(P.pc.inbox_peer[h] + region + kInboxHeader) + push_f, push_v, (uint32_t)seq);
-                        }
-                    }
-                    // a first look at the peers' counts (answered during the local update)
-                    if (tid < NR && tid != me)
-                        hv_early = *reinterpret_cast<const volatile unsigned long long *>(P.pc.inbox_local + ((size_t)par * NR + tid) * P.pc.inbox_stride);
                 } else
-                if (ok && nloc > 0) {   // long lists / heavy records
+                if (ok && nloc > 0) {   // long lists / heavy records: all threads
+                    if (tid < kChgCap) push_dirs(tid);
                     // scratch: first unit of every entry [nloc + 1], then the record addresses [nloc]; very long lists
                     // are searched in global memory instead
                     constexpr uint32_t kScr = 4 * kUnitCap;
@@ -1326,7 +1329,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                         }
                         stage_chunk(chg, stg_scr, nx, bk, dbs, mv, 0u, P.q_scale, tid);
                     }
-                    if (x0 == 0 && fast_push && warp < 2 && push_f < (uint32_t)(cntv >> 32)) {
+                    if (x0 == 0 && fast_push && warp >= 2 && push_f < (uint32_t)(cntv >> 32)) {
                         for (uint32_t h = 0; h < NR; h++)
                             if (h != me)
                                 st_ll(reinterpret_cast<uint4 *>(P.pc.inbox_peer[h] + ((size_t)par * NR + me) * P.pc.inbox_stride + kInboxHeader) + push_f, push_v,
@@ -1352,7 +1355,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                         bool late = false;
                         const volatile unsigned long long *hdr =
                             reinterpret_cast<const volatile unsigned long long *>(P.pc.inbox_local + ((size_t)par * NR + tid) * P.pc.inbox_stride);
-                        unsigned long long hv = hv_early;
+                        unsigned long long hv = 0ull;
                         uint32_t spin = 0;
                         while (!late && (uint32_t)(hv >> 32) != (uint32_t)seq) {
                             hv = *hdr;
