@@ -43,7 +43,7 @@ class HbBrrTape(C.Structure):
 class HbBrrIterOut(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("sigmaE", "e_sqn", "epssum", "loop_ms", "iter_ms")] + [
         (n, C.c_uint64) for n in ("n_sync", "n_windows", "n_launches", "nnz_processed", "nnz_updated", "bed_markers", "markers_changed")
-    ] + [("phase_cycles", C.c_uint64 * 8)]
+    ] + [("phase_cycles", C.c_uint64 * 8), ("windows_ahead", C.c_uint64), ("draws_repeated", C.c_uint64)]
 
 
 class HbBwTape(C.Structure):

@@ -581,10 +581,9 @@ __device__ __forceinline__ void draw_marker_warp(const BrrParams &P, const ItemT
         }
     }
     if (lane == 0) {
-        if (comp >= 0) {
-            atomicAdd(&P.cass[g * K + comp], 1);                                     // :1904
-            P.comp[m] = comp;
-        }
+        // (cass, :1904, is counted from comp[] after the marker loop, k_beta_sqnorm: a draw can be discarded and repeated, see
+        // "windows run ahead" in the kernel)
+        if (comp >= 0) P.comp[m] = comp;
         const double dbeta = beta_old - beta_new;                                    // :1933
         if (dbeta != 0.0 || idx_early != ~0ull) {
             // (a reserved entry of a marker that drew its old value again carries 0 and does not count as a change)
@@ -596,7 +595,6 @@ __device__ __forceinline__ void draw_marker_warp(const BrrParams &P, const ItemT
             en.m = (uint32_t)m; en.dbs = dbs; en.mave = wm.mave; en.rec = wm.rec;
             P.chg_list[(size_t)buf3 * P.Wmax + idx] = en;
             if (P.pc.nranks > 1) P.chg_off[(size_t)buf3 * P.Wmax + idx] = off_units;  // pushed to the peers after the grid barrier
-            if (dbeta != 0.0) atomicAdd(&P.stats[5], 1ull);
         }
         P.beta[m] = beta_new;
         P.acum[m] = acum0;
@@ -761,6 +759,8 @@ struct ChgTab {  // changed markers of a window, staged for the epsilon update. 
     long long qm_sum;           // sum of mave*mstd*deltaBeta on the grid 2^-kOffShift: the base term -mave*mstd*deltaBeta of every
                                 // individual (:265-267) is kept as ONE scalar per launch
     unsigned long long live_mask;   // bit x: entry x is a sparse block with something to apply
+    uint32_t n_changed;             // entries with deltaBeta != 0 (whatever their slice blocks hold): "the window changed something"
+    uint32_t pad0_, pad1_, pad2_;
 };
 static_assert(sizeof(ChgTab) % 16 == 0, "ChgTab");
 
@@ -806,15 +806,18 @@ __device__ __forceinline__ void stage_chunk(ChgTab *chg, uint32_t *scr /*[64]*/,
     qo = (long long)warp_sum_u64((u64)qo);
     const uint32_t msp = __ballot_sync(0xffffffffu, live && !bed);
     const uint32_t nsp = __popc(msp), nbd = __popc(__ballot_sync(0xffffffffu, bed));
+    const uint32_t nch = __popc(__ballot_sync(0xffffffffu, valid && dbs != 0.0));
     if (!two) {
         if (valid) store_entry(chg, tid, b, ll, q1, qm, nwe, s0 - a);
         if (tid == 0) {
-            *reinterpret_cast<uint4 *>(&chg->total) = make_uint4(tot, nsp, nbd, (nsp + nbd) ? 1u : 0u);
+            *reinterpret_cast<uint4 *>(&chg->total) = make_uint4(tot, nsp, nbd, nch ? 1u : 0u);
             chg->delta_sum = dl; chg->qm_sum = qo; chg->bed_delta = 0ll; chg->live_mask = (unsigned long long)msp;
+            chg->n_changed = nch;
         }
         return;
     }
     if (lane == 0) {   // this warp's totals for the other one
+        scr[16 + wrp] = nch;
         scr[wrp * 8 + 0] = tot; scr[wrp * 8 + 1] = nsp; scr[wrp * 8 + 2] = nbd; scr[wrp * 8 + 3] = msp;
         *reinterpret_cast<long long *>(scr + wrp * 8 + 4) = dl; *reinterpret_cast<long long *>(scr + wrp * 8 + 6) = qo;
     }
@@ -822,7 +825,8 @@ __device__ __forceinline__ void stage_chunk(ChgTab *chg, uint32_t *scr /*[64]*/,
     const uint32_t base = wrp ? scr[0] : 0u;
     if (valid) store_entry(chg, tid, b, ll, q1, qm, nwe, base + s0 - a);
     if (tid == 0) {
-        *reinterpret_cast<uint4 *>(&chg->total) = make_uint4(scr[0] + scr[8], scr[1] + scr[9], scr[2] + scr[10], (scr[1] + scr[9] + scr[2] + scr[10]) ? 1u : 0u);
+        *reinterpret_cast<uint4 *>(&chg->total) = make_uint4(scr[0] + scr[8], scr[1] + scr[9], scr[2] + scr[10], (scr[16] + scr[17]) ? 1u : 0u);
+        chg->n_changed = scr[16] + scr[17];
         chg->delta_sum = *reinterpret_cast<long long *>(scr + 4) + *reinterpret_cast<long long *>(scr + 12);
         chg->qm_sum = *reinterpret_cast<long long *>(scr + 6) + *reinterpret_cast<long long *>(scr + 14);
         chg->bed_delta = 0ll;
@@ -855,6 +859,7 @@ __device__ __forceinline__ void finish_chunk(ChgTab *chg, uint32_t nx, uint32_t 
     const uint32_t nbd = __popc(__ballot_sync(0xffffffffu, bed0)) + __popc(__ballot_sync(0xffffffffu, bed1));
     if (lane == 0) {
         chg->bed_delta = 0ll; chg->total = tot0 + tot1; chg->n_sparse = nsp; chg->n_bed = nbd; chg->any = (nsp + nbd) ? 1u : 0u;
+        chg->n_changed = nsp + nbd;
         chg->live_mask = (unsigned long long)m0 | ((unsigned long long)m1 << 32);
     }
 }
@@ -989,12 +994,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
     __shared__ uint4 udesc[kUnitCap];                   // work units of the dot phase
     __shared__ unsigned long long cnt_s[10];             // traffic counters: per warp 0..3 {non-zeros read by the dot, BED blocks}, [8] update
     __shared__ uint32_t chg_n;
+    __shared__ unsigned long long spec_cnt[2];
     __shared__ uint32_t chg_base[33];
     __shared__ __align__(16) uint32_t psort[4 * kUnitCap];   // scratch of the exchange (unit offsets of the entries)
     u64 *upart = reinterpret_cast<u64 *>(psort);        // unit partials of the dot phase: {a12, am} per unit
     __shared__ uint32_t pcnt[kMaxRanks];
     __shared__ uint32_t abort_s;                        // != 0: the exchange failed somewhere, leave the window loop
-    __shared__ __align__(8) uint32_t stg_scr[16];       // the two staging warps' totals
+    __shared__ __align__(8) uint32_t stg_scr[20];       // the two staging warps' totals; [18]: first changed step of a window run ahead
 
     const uint32_t S = P.S, L = P.L, R = P.R;
     const uint32_t c = blockIdx.x % S, r = blockIdx.x / S;
@@ -1044,12 +1050,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
     uint32_t j0 = 0, since = 0, win = 0;
     uint32_t n_sync = 0;
     if (tid < 10) cnt_s[tid] = 0;
+    if (tid < 2) spec_cnt[tid] = 0;
     const uint64_t padw = (uint64_t)L * 0x0001000100010001ull;
     const uint32_t SR = (P.SR == 0) ? 1u : P.SR;
 
     while (j0 < P.lmax) {
+        // Windows run ahead. After `sync_rate` steps without a change the reference synchronises after every single step
+        // (:2044-2050), i.e. until the next change the steps read an epsilon that does not move. Such steps are taken `sync_rate`
+        // at a time here: if none of them changes a marker the result is the same; otherwise the steps up to and including
+        // the first one with a change are exactly what the reference computes -- their changed markers are applied -- and
+        // the later steps are discarded and repeated by the next window (effects, components and Acum are simply written
+        // again; the component counts are taken from comp[] after the loop; the draws are counter-based). One GPU only.
+        const bool spec_win = (P.mode == MODE_CHAIN && P.pc.nranks == 1 && SR > 1u && since >= SR && !(P.flags & 2u));
         const uint32_t n = (P.mode != MODE_CHAIN) ? (P.lmax - j0)
-                                                  : ((since >= SR) ? 1u : min(SR - since, P.lmax - j0));
+                                                  : ((since >= SR) ? (spec_win ? min(SR, P.lmax - j0) : 1u) : min(SR - since, P.lmax - j0));
+        uint32_t s_star = 0xFFFFFFFFu;   // first step of a window run ahead that changed a marker
         const uint32_t W = n * P.T, base = j0 * P.T;
         const uint32_t dbuf = win & 1u;
         const uint32_t n_items = (W > r) ? (W - r + R - 1) / R : 0;
@@ -1315,6 +1330,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
             //          per thread); the slice directory entry travels with the list entry (written by the drawing warp), and
             //          the first 64 entries were requested together with the count: one L2 round trip up to here.
             if (ok) {
+                if (spec_win && nloc > 0) {   // first step with a change (entries of later steps are dropped below)
+                    if (nloc <= kChgCap) {
+                        if (tid < kChgCap) {
+                            uint32_t v = (tid < nloc && spec.dbs != 0.0) ? spec.p / P.T : 0xFFFFFFFFu;
+                            v = __reduce_min_sync(0xffffffffu, v);
+                            if (lane == 0) stg_scr[18 + warp] = v;   // (read by everybody after the staging barrier)
+                            if (nloc > 32u) { named_barrier(2, 64); v = min(stg_scr[18], stg_scr[19]); }
+                            s_star = v;
+                        }
+                    } else {
+                        uint32_t v = 0xFFFFFFFFu;
+                        for (uint32_t i = tid; i < nloc; i += blockDim.x) {
+                            const ChgEnt en = ld_chg_ent(llist + i);
+                            if (en.dbs != 0.0) v = min(v, en.p / P.T);
+                        }
+                        v = __reduce_min_sync(0xffffffffu, v);
+                        if (lane == 0) chg_base[warp] = v;
+                        __syncthreads();
+                        v = 0xFFFFFFFFu;
+                        for (uint32_t w = 0; w < (blockDim.x >> 5); w++) v = min(v, chg_base[w]);
+                        __syncthreads();
+                        s_star = v;
+                    }
+                }
                 for (uint32_t x0 = 0; x0 < nloc; x0 += kChgCap) {
                     const uint32_t nx = min((uint32_t)kChgCap, nloc - x0);
                     if (tid < kChgCap) {
@@ -1326,6 +1365,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                             const uint4 dv = (x0 == 0) ? sdir : __ldcg(ldir + (size_t)(x0 + tid) * S + c);
                             bk = block_from_dir(en.rec, dv, c, S, L);
                             dbs = en.dbs; mv = en.mave;
+                            if (spec_win && en.p / P.T != s_star) dbs = 0.0;   // a later step of a window run ahead: repeated
                         }
                         stage_chunk(chg, stg_scr, nx, bk, dbs, mv, 0u, P.q_scale, tid);
                     }
@@ -1338,10 +1378,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                     __syncthreads();
                     HB_SUB(9);
                     any |= chg->any != 0u;
+                    if (blockIdx.x == 0 && tid == 0) cnt_s[9] += chg->n_changed;
                     off_q -= chg->qm_sum;
                     slice_sum_q += apply_chunk(chg, nx, false, Eq, L, (r == 0) ? &cnt_s[8] : nullptr, P.pc.err);
                     HB_SUB(10);
                 }
+                if (spec_win && nloc > 0 && nloc <= kChgCap) s_star = min(stg_scr[18], stg_scr[19]);
             }
             HB_PHASE(4);
             if (NR > 1) {
@@ -1464,13 +1506,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
             if (off_q > (1ll << 61) || off_q < -(1ll << 61)) atomicExch(P.pc.err, 5u);
             HB_PHASE(4);
         }
+        uint32_t n_done = n;
+        if (spec_win) {
+            if (s_star != 0xFFFFFFFFu) n_done = s_star + 1u;   // (then `any` is set)
+            if (blockIdx.x == 0 && tid == 0) { spec_cnt[0]++; spec_cnt[1] += (unsigned long long)(n - n_done) * P.T; }
+        }
         if (any) {
             since = 0;
             n_sync++;
         } else {
-            since += n;
+            since += n_done;
         }
-        j0 += n;
+        j0 += n_done;
         win++;
         HB_PHASE(5);
     }
@@ -1509,7 +1556,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
         if (nd) atomicAdd(&P.stats[2], nd);
         if (nb && c == 0) atomicAdd(&P.stats[4], nb);
         if (r == 0 && cnt_s[8]) atomicAdd(&P.stats[3], cnt_s[8]);
-        if (blockIdx.x == 0) P.stats[6] = cnt_s[9];   // arbitration rounds of the update (CTA 0)
+        if (blockIdx.x == 0) { atomicAdd(&P.stats[5], cnt_s[9]); P.stats[6] = spec_cnt[0]; P.stats[7] = spec_cnt[1]; }   // changed markers; windows run ahead, draws repeated
     }
 }
 
@@ -1607,17 +1654,27 @@ __global__ void __launch_bounds__(256) k_window_order(const int32_t *__restrict_
 // inside chunk b, a second small kernel adds the chunk sums in chunk order (fixed order: bit-reproducible)
 constexpr uint32_t kSqChunks = 148;
 __global__ void __launch_bounds__(256) k_beta_sqnorm(const double *__restrict__ beta, const int32_t *__restrict__ grp,
-                                                     uint32_t M, double *__restrict__ part) {
+                                                     uint32_t M, double *__restrict__ part, const int32_t *__restrict__ comp,
+                                                     const uint8_t *__restrict__ grp_active, uint32_t K, int32_t *__restrict__ cass) {
     __shared__ double red[32];
+    __shared__ int32_t hist[32];
     const int g = blockIdx.y;
     const uint32_t per = (M + gridDim.x - 1) / gridDim.x, m0 = blockIdx.x * per, m1 = min(M, m0 + per);
+    // component counts of the group (cass, :1904): taken from comp[] once the marker loop is over, every marker once
+    const bool count = (cass != nullptr) && grp_active[g] && K <= 32u;
+    if (threadIdx.x < 32) hist[threadIdx.x] = 0;
+    __syncthreads();
     double v = 0.0;
     for (uint32_t m = m0 + threadIdx.x; m < m1; m += blockDim.x) {
         const double b = beta[m];
-        if (grp[m] == g) v += b * b;
+        if (grp[m] == g) {
+            v += b * b;
+            if (count) atomicAdd(&hist[comp[m]], 1);
+        }
     }
     const double s = block_sum(v, red);
     if (threadIdx.x == 0) part[(size_t)g * gridDim.x + blockIdx.x] = s;
+    if (count && threadIdx.x < K && hist[threadIdx.x]) atomicAdd(&cass[(size_t)g * K + threadIdx.x], hist[threadIdx.x]);
 }
 __global__ void k_beta_sqnorm_fin(const double *__restrict__ part, uint32_t nchunks, uint32_t G, double *__restrict__ out) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;

@@ -1149,7 +1149,7 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
     // ---- group statistics (:2496-2521)
     double *d_bsq = c->d_small.p + 1 + 2 * c->S;
     HB_TRY(c->d_bsq_part.ensure((size_t)G * kSqChunks));
-    k_beta_sqnorm<<<dim3(kSqChunks, G), 256, 0, st>>>(c->d_beta.p, c->d_grp.p, M, c->d_bsq_part.p);
+    k_beta_sqnorm<<<dim3(kSqChunks, G), 256, 0, st>>>(c->d_beta.p, c->d_grp.p, M, c->d_bsq_part.p, c->d_comp.p, c->d_active.p, K, c->d_cass.p);
     k_beta_sqnorm_fin<<<(G + 127) / 128, 128, 0, st>>>(c->d_bsq_part.p, kSqChunks, G, d_bsq);
     HB_CUDA(cudaGetLastError());
     const size_t nsmall = 1 + 4 * (size_t)c->S + G;
@@ -1310,6 +1310,7 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
         out->nnz_processed = pin_stats[2]; out->nnz_updated = pin_stats[3];
         out->bed_markers = pin_stats[4]; out->markers_changed = changed_all;
         for (int i = 0; i < 8; i++) out->phase_cycles[i] = pin_stats[8 + i];
+        out->windows_ahead = pin_stats[6]; out->draws_repeated = pin_stats[7];
     }
     return HB_OK;
 }

@@ -156,6 +156,8 @@ typedef struct hb_brr_iter_out {
     uint64_t bed_markers;     /* markers processed through the BED path */
     uint64_t markers_changed; /* markers with deltaBeta != 0 */
     uint64_t phase_cycles[8]; /* CTA 0 SM cycles: table, dot, publish+draw, grid barrier, update set-up, slice sum, update loads, update apply */
+    uint64_t windows_ahead;   /* windows of sync_rate steps taken where the reference synchronises after every step (no change expected) */
+    uint64_t draws_repeated;  /* marker draws of such windows that were discarded and repeated after an earlier step changed a marker */
 } hb_brr_iter_out;
 
 /* One Gibbs iteration: mu, marker loop (sync windows), group statistics, hyper-parameters.

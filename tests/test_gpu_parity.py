@@ -127,7 +127,7 @@ def test_dot_and_scaadd(repr_mode, N, M, n_slices):
 
 # ------------------------------------------------------------------------------------ chain replay
 def _run_chain_case(N, M, T, SR, G, K, repr_mode, n_iter, seed, n_na=0, n_slices=0, replay_hyper=True, max_ctas=0,
-                    threshold_fnz=0.35):
+                    threshold_fnz=0.35, n_causal=None):
     import hydra_b200
     rng = np.random.default_rng(seed)
     bed, g = random_bed(rng, M, N, pmiss=0.01)
@@ -135,7 +135,7 @@ def _run_chain_case(N, M, T, SR, G, K, repr_mode, n_iter, seed, n_na=0, n_slices
     sp = reference_lists(bed, N, na)
     Nc = N - n_na
     keep = np.setdiff1d(np.arange(N), na)
-    y = simulate_y(rng, g[:, keep], n_causal=max(3, M // 10))
+    y = simulate_y(rng, g[:, keep], n_causal=max(3, M // 10) if n_causal is None else n_causal)
     groups = (np.arange(M) % G).astype(np.int32)
     mS = np.tile(np.array([0.0] + [10.0 ** (-(K - 1 - k)) for k in range(1, K)]), (G, 1))
     mS[:, 1:] *= (1.0 + 0.5 * np.arange(G))[:, None]
@@ -156,6 +156,7 @@ def _run_chain_case(N, M, T, SR, G, K, repr_mode, n_iter, seed, n_na=0, n_slices
         st.finalize()
         assert np.array_equal(st.marker_is_bed(), usebed)
         brr = hydra_b200.BayesRRm(st, y, mS, groups=groups, sigmaG0=sigmaG0, seed=seed)
+        totals = {}
         for it in range(n_iter):
             tp = dict(zmu=tape["zmu"][it], perm=tape["perm"][it], u=tape["u"][it], z=tape["z"][it])
             if replay_hyper:
@@ -171,11 +172,23 @@ def _run_chain_case(N, M, T, SR, G, K, repr_mode, n_iter, seed, n_na=0, n_slices
             np.testing.assert_allclose(h["bsq"], ref["bsq"][it], rtol=RTOL)
             np.testing.assert_allclose(o["e_sqn"], ref["esqn"][it], rtol=RTOL)
             assert o["n_sync"] == ref["nsync"][it]
+            for k in ("windows_ahead", "draws_repeated", "n_windows", "markers_changed"):
+                totals[k] = totals.get(k, 0) + o[k]
             for t in range(T):
                 np.testing.assert_allclose(brr.task_epsilon(t), ref["eps"][it, t], rtol=RTOL, atol=1e-12, err_msg=f"eps it {it} task {t}")
             np.testing.assert_allclose(h["sigmaE"], ref["sigmaE"][it], rtol=RTOL)
             np.testing.assert_allclose(h["sigmaG"], ref["sigmaG"][it], rtol=RTOL)
             np.testing.assert_allclose(h["pi"], ref["pi"][it], rtol=RTOL)
+    return totals
+
+
+def test_chain_replay_windows_run_ahead():
+    # Few causal markers: after a few iterations most steps change nothing, the reference synchronises after every step
+    # (:2044-2050) and the kernel takes sync_rate such steps at a time, discarding and repeating the steps behind the first
+    # change. Same per-iteration parity as every other case, and both outcomes of a window run ahead must have occurred.
+    for repr_mode, seed in (("sparse", 11), ("mixed", 12)):
+        t = _run_chain_case(N=1800, M=1536, T=4, SR=5, G=2, K=3, repr_mode=repr_mode, n_iter=6, seed=seed, n_causal=4, n_slices=3)
+        assert t["windows_ahead"] > 20 and t["draws_repeated"] > 0, t
 
 
 def test_chain_replay_config1_single_task_bed():
