@@ -739,6 +739,7 @@ __device__ __forceinline__ uint32_t find_entry(const uint32_t *cum, uint32_t n, 
 constexpr uint32_t kApplyQ = 4;          // 64-bit words staged in registers per thread and round
 constexpr uint32_t kHypSmem = 64;        // G*K up to this: hyper-parameter tables live in shared memory
 constexpr uint32_t kWarps = kThreads / 32;
+constexpr uint32_t kSpecMax = 64;        // windows run ahead: up to this many steps
 constexpr uint32_t kDrawWarps = 8;       // warps that collect partials and draw; the others prebuild the next table
 
 // clock read that cannot be scheduled before `dep` is available (developer timing of phases that end with loads in flight)
@@ -995,6 +996,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
     __shared__ unsigned long long cnt_s[10];             // traffic counters: per warp 0..3 {non-zeros read by the dot, BED blocks}, [8] update
     __shared__ uint32_t chg_n;
     __shared__ unsigned long long spec_cnt[2];
+    __shared__ uint32_t cnt_step[2 * kSpecMax];         // windows run ahead: non-zeros read / BED blocks by step of the window
     __shared__ uint32_t chg_base[33];
     __shared__ __align__(16) uint32_t psort[4 * kUnitCap];   // scratch of the exchange (unit offsets of the entries)
     u64 *upart = reinterpret_cast<u64 *>(psort);        // unit partials of the dot phase: {a12, am} per unit
@@ -1051,6 +1053,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
     uint32_t n_sync = 0;
     if (tid < 10) cnt_s[tid] = 0;
     if (tid < 2) spec_cnt[tid] = 0;
+    if (tid < 2 * kSpecMax) cnt_step[tid] = 0;
     const uint64_t padw = (uint64_t)L * 0x0001000100010001ull;
     const uint32_t SR = (P.SR == 0) ? 1u : P.SR;
 
@@ -1060,8 +1063,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
         // at a time here: if none of them changes a marker the result is the same; otherwise the steps up to and including
         // the first one with a change are exactly what the reference computes -- their changed markers are applied -- and
         // the later steps are discarded and repeated by the next window (effects, components and Acum are simply written
-        // again; the component counts are taken from comp[] after the loop; the draws are counter-based). One GPU only.
-        const bool spec_win = (P.mode == MODE_CHAIN && P.pc.nranks == 1 && SR > 1u && since >= SR && !(P.flags & 2u));
+        // again; the component counts are taken from comp[] after the loop; the draws are counter-based). With several GPUs
+        // the first changed step is taken over the lists of all GPUs (every GPU sees every list), before anything is applied.
+        const bool spec_win = (P.mode == MODE_CHAIN && SR > 1u && SR <= kSpecMax && since >= SR && !(P.flags & 2u));
+        const uint32_t Tdiv = (P.pc.nranks > 1) ? P.pc.T_total : P.T;   // list entries carry the global window position
         const uint32_t n = (P.mode != MODE_CHAIN) ? (P.lmax - j0)
                                                   : ((since >= SR) ? (spec_win ? min(SR, P.lmax - j0) : 1u) : min(SR - since, P.lmax - j0));
         uint32_t s_star = 0xFFFFFFFFu;   // first step of a window run ahead that changed a marker
@@ -1165,9 +1170,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                     if (t < nk && tab->meta[t].m >= 0) {
                         if (tab->b1[t] == 0xFFFFFFFFu) vb = 1u; else v = 4u * tab->nw[t];
                     }
-                    v = __reduce_add_sync(0xffffffffu, v);
-                    vb = __reduce_add_sync(0xffffffffu, vb);
-                    if (lane == 0) { cnt_s[2 * w] += v; cnt_s[2 * w + 1] += vb; }
+                    if (spec_win) {   // by step: only the steps that are kept count (window end)
+                        const uint32_t st = (r + R * (k0 + t)) / P.T;
+                        if (v) atomicAdd(&cnt_step[st], v);
+                        if (vb) atomicAdd(&cnt_step[kSpecMax + st], vb);
+                    } else {
+                        v = __reduce_add_sync(0xffffffffu, v);
+                        vb = __reduce_add_sync(0xffffffffu, vb);
+                        if (lane == 0) { cnt_s[2 * w] += v; cnt_s[2 * w + 1] += vb; }
+                    }
                 }
                 if (warp >= kDrawWarps && stage_next) {
                     const uint32_t j1 = j0 + n, n1 = min(SR, P.lmax - j1);
@@ -1325,71 +1336,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                     __syncthreads();  // the scratch is free again
                 }
             }
-            HB_SUB(11);
-            // ---- 5b. this GPU's own changed markers (the peers' are still on their way). Warps 0 and 1 stage a chunk (one entry
-            //          per thread); the slice directory entry travels with the list entry (written by the drawing warp), and
-            //          the first 64 entries were requested together with the count: one L2 round trip up to here.
-            if (ok) {
-                if (spec_win && nloc > 0) {   // first step with a change (entries of later steps are dropped below)
-                    if (nloc <= kChgCap) {
-                        if (tid < kChgCap) {
-                            uint32_t v = (tid < nloc && spec.dbs != 0.0) ? spec.p / P.T : 0xFFFFFFFFu;
-                            v = __reduce_min_sync(0xffffffffu, v);
-                            if (lane == 0) stg_scr[18 + warp] = v;   // (read by everybody after the staging barrier)
-                            if (nloc > 32u) { named_barrier(2, 64); v = min(stg_scr[18], stg_scr[19]); }
-                            s_star = v;
-                        }
-                    } else {
-                        uint32_t v = 0xFFFFFFFFu;
-                        for (uint32_t i = tid; i < nloc; i += blockDim.x) {
-                            const ChgEnt en = ld_chg_ent(llist + i);
-                            if (en.dbs != 0.0) v = min(v, en.p / P.T);
-                        }
-                        v = __reduce_min_sync(0xffffffffu, v);
-                        if (lane == 0) chg_base[warp] = v;
-                        __syncthreads();
-                        v = 0xFFFFFFFFu;
-                        for (uint32_t w = 0; w < (blockDim.x >> 5); w++) v = min(v, chg_base[w]);
-                        __syncthreads();
-                        s_star = v;
-                    }
-                }
-                for (uint32_t x0 = 0; x0 < nloc; x0 += kChgCap) {
-                    const uint32_t nx = min((uint32_t)kChgCap, nloc - x0);
-                    if (tid < kChgCap) {
-                        Blk bk;
-                        bk.ptr = nullptr; bk.nw = 0; bk.b1 = 0; bk.b2 = 0; bk.n1 = 0; bk.n2 = 0; bk.nm = 0;
-                        double dbs = 0.0, mv = 0.0;
-                        if (tid < nx) {
-                            const ChgEnt en = (x0 == 0) ? spec : ld_chg_ent(llist + x0 + tid);
-                            const uint4 dv = (x0 == 0) ? sdir : __ldcg(ldir + (size_t)(x0 + tid) * S + c);
-                            bk = block_from_dir(en.rec, dv, c, S, L);
-                            dbs = en.dbs; mv = en.mave;
-                            if (spec_win && en.p / P.T != s_star) dbs = 0.0;   // a later step of a window run ahead: repeated
-                        }
-                        stage_chunk(chg, stg_scr, nx, bk, dbs, mv, 0u, P.q_scale, tid);
-                    }
-                    if (x0 == 0 && fast_push && warp >= 2 && push_f < (uint32_t)(cntv >> 32)) {
-                        for (uint32_t h = 0; h < NR; h++)
-                            if (h != me)
-                                st_ll(reinterpret_cast<uint4 *>(P.pc.inbox_peer[h] + ((size_t)par * NR + me) * P.pc.inbox_stride + kInboxHeader) + push_f, push_v,
-                                      (uint32_t)seq_w);
-                    }
-                    __syncthreads();
-                    HB_SUB(9);
-                    any |= chg->any != 0u;
-                    if (blockIdx.x == 0 && tid == 0) cnt_s[9] += chg->n_changed;
-                    off_q -= chg->qm_sum;
-                    slice_sum_q += apply_chunk(chg, nx, false, Eq, L, (r == 0) ? &cnt_s[8] : nullptr, P.pc.err);
-                    HB_SUB(10);
-                }
-                if (spec_win && nloc > 0 && nloc <= kChgCap) s_star = min(stg_scr[18], stg_scr[19]);
-            }
-            HB_PHASE(4);
-            if (NR > 1) {
+            // 5c as a function: it runs before the local update in a window run ahead, after it otherwise
+            const unsigned long long seq = seq_w;
+            auto wait_counts = [&]() -> bool {
                 // ---- 5c. wait for every peer's count of this window (it follows the peer's own grid barrier); entries and
                 //          records are validated unit by unit when they are read
-                const unsigned long long seq = seq_w;
                 if (tid < NR) {
                     uint32_t nh = ok ? nloc : 0xFFFFFFFFu;
                     if (tid != me) {
@@ -1414,10 +1365,105 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                 HB_SUB(12);
                 bool bad = false;
                 for (uint32_t h = 0; h < NR; h++) bad |= (pcnt[h] == 0xFFFFFFFFu);
-                if (bad) {  // give up: the host reports the failure after the launch
-                    if (blockIdx.x == 0 && tid == 0) atomicExch(P.pc.err, 3u);
-                    break;
+                if (bad && blockIdx.x == 0 && tid == 0) atomicExch(P.pc.err, 3u);  // give up: the host reports the failure after the launch
+                return bad;
+            };
+            bool counts_done = false;
+            if (spec_win && NR > 1) {
+                // window run ahead, several GPUs: the first step with a change over ALL lists, before anything is applied
+                if (wait_counts()) break;
+                counts_done = true;
+                uint32_t v = 0xFFFFFFFFu;
+                for (uint32_t i = tid; i < nloc; i += blockDim.x) {
+                    const ChgEnt en = ld_chg_ent(llist + i);
+                    if (en.dbs != 0.0) v = min(v, en.p / Tdiv);
                 }
+                uint32_t n_peers = 0;
+                for (uint32_t hh = 1; hh < NR; hh++) n_peers += pcnt[(me + hh) % NR];
+                for (uint32_t y = tid; y < n_peers; y += blockDim.x) {
+                    uint32_t x = y, h = me;
+                    for (uint32_t hh = 1; hh < NR; hh++) {
+                        h = (me + hh) % NR;
+                        const uint32_t n_h = pcnt[h];
+                        if (x < n_h) break;
+                        x -= n_h;
+                    }
+                    const uint4 *le = reinterpret_cast<const uint4 *>(P.pc.inbox_local + ((size_t)par * NR + h) * P.pc.inbox_stride + 16 + (size_t)x * kLLEntry);
+                    const uint64_t e0 = ld_ll(le, (uint32_t)seq, P.pc.err), e1 = ld_ll(le + 1, (uint32_t)seq, P.pc.err);
+                    if (__longlong_as_double((long long)e1) != 0.0) v = min(v, (uint32_t)e0 / Tdiv);
+                }
+                v = __reduce_min_sync(0xffffffffu, v);
+                if (lane == 0) chg_base[warp] = v;
+                __syncthreads();
+                v = 0xFFFFFFFFu;
+                for (uint32_t w = 0; w < (blockDim.x >> 5); w++) v = min(v, chg_base[w]);
+                __syncthreads();
+                s_star = v;
+            }
+            HB_SUB(11);
+            // ---- 5b. this GPU's own changed markers (the peers' are still on their way). Warps 0 and 1 stage a chunk (one entry
+            //          per thread); the slice directory entry travels with the list entry (written by the drawing warp), and
+            //          the first 64 entries were requested together with the count: one L2 round trip up to here.
+            if (ok) {
+                if (spec_win && NR == 1 && nloc > 0) {   // first step with a change (entries of later steps are dropped below)
+                    if (nloc <= kChgCap) {
+                        if (tid < kChgCap) {
+                            uint32_t v = (tid < nloc && spec.dbs != 0.0) ? spec.p / Tdiv : 0xFFFFFFFFu;
+                            v = __reduce_min_sync(0xffffffffu, v);
+                            if (lane == 0) stg_scr[18 + warp] = v;   // (read by everybody after the staging barrier)
+                            if (nloc > 32u) { named_barrier(2, 64); v = min(stg_scr[18], stg_scr[19]); }
+                            s_star = v;
+                        }
+                    } else {
+                        uint32_t v = 0xFFFFFFFFu;
+                        for (uint32_t i = tid; i < nloc; i += blockDim.x) {
+                            const ChgEnt en = ld_chg_ent(llist + i);
+                            if (en.dbs != 0.0) v = min(v, en.p / Tdiv);
+                        }
+                        v = __reduce_min_sync(0xffffffffu, v);
+                        if (lane == 0) chg_base[warp] = v;
+                        __syncthreads();
+                        v = 0xFFFFFFFFu;
+                        for (uint32_t w = 0; w < (blockDim.x >> 5); w++) v = min(v, chg_base[w]);
+                        __syncthreads();
+                        s_star = v;
+                    }
+                }
+                for (uint32_t x0 = 0; x0 < nloc; x0 += kChgCap) {
+                    const uint32_t nx = min((uint32_t)kChgCap, nloc - x0);
+                    if (tid < kChgCap) {
+                        Blk bk;
+                        bk.ptr = nullptr; bk.nw = 0; bk.b1 = 0; bk.b2 = 0; bk.n1 = 0; bk.n2 = 0; bk.nm = 0;
+                        double dbs = 0.0, mv = 0.0;
+                        if (tid < nx) {
+                            const ChgEnt en = (x0 == 0) ? spec : ld_chg_ent(llist + x0 + tid);
+                            const uint4 dv = (x0 == 0) ? sdir : __ldcg(ldir + (size_t)(x0 + tid) * S + c);
+                            bk = block_from_dir(en.rec, dv, c, S, L);
+                            dbs = en.dbs; mv = en.mave;
+                            if (spec_win && en.p / Tdiv != s_star) dbs = 0.0;   // a later step of a window run ahead: repeated
+                        }
+                        stage_chunk(chg, stg_scr, nx, bk, dbs, mv, 0u, P.q_scale, tid);
+                    }
+                    if (x0 == 0 && fast_push && warp >= 2 && push_f < (uint32_t)(cntv >> 32)) {
+                        for (uint32_t h = 0; h < NR; h++)
+                            if (h != me)
+                                st_ll(reinterpret_cast<uint4 *>(P.pc.inbox_peer[h] + ((size_t)par * NR + me) * P.pc.inbox_stride + kInboxHeader) + push_f, push_v,
+                                      (uint32_t)seq_w);
+                    }
+                    __syncthreads();
+                    HB_SUB(9);
+                    any |= chg->any != 0u;
+                    if (blockIdx.x == 0 && tid == 0) cnt_s[9] += chg->n_changed;
+                    off_q -= chg->qm_sum;
+                    slice_sum_q += apply_chunk(chg, nx, false, Eq, L, (r == 0) ? &cnt_s[8] : nullptr, P.pc.err);
+                    HB_SUB(10);
+                }
+                if (spec_win && NR == 1 && nloc > 0 && nloc <= kChgCap) s_star = min(stg_scr[18], stg_scr[19]);
+            }
+            HB_PHASE(4);
+            if (NR > 1) {
+                // ---- 5c. the peers' counts (unless the window ran ahead: done above)
+                if (!counts_done && wait_counts()) break;
                 // ---- 5d. the peers' changed markers, straight from the inboxes (no merge by position: any order gives the
                 //          same slice). The entries of ALL peers fill common chunks: the fixed cost of a chunk (entry ->
                 //          directory -> words, three dependent reads, plus the staging barriers) is paid once per 64 markers,
@@ -1454,6 +1500,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                             }
                             dbs = __longlong_as_double((long long)e1);
                             mv = __longlong_as_double((long long)e2);
+                            if (spec_win && (uint32_t)ld_ll(le, (uint32_t)seq, P.pc.err) / Tdiv != s_star) dbs = 0.0;   // repeated step
                         }
                         stage_chunk(chg, stg_scr, nx, bk, dbs, mv, (uint32_t)seq, P.q_scale, tid);
                     }
@@ -1510,6 +1557,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
         if (spec_win) {
             if (s_star != 0xFFFFFFFFu) n_done = s_star + 1u;   // (then `any` is set)
             if (blockIdx.x == 0 && tid == 0) { spec_cnt[0]++; spec_cnt[1] += (unsigned long long)(n - n_done) * P.T; }
+            if (tid == 0) {   // traffic counters: the steps that are kept (a barrier of the update lies behind the last add)
+                unsigned long long a = 0, b = 0;
+                for (uint32_t st = 0; st < n; st++) {
+                    if (st < n_done) { a += cnt_step[st]; b += cnt_step[kSpecMax + st]; }
+                    cnt_step[st] = 0; cnt_step[kSpecMax + st] = 0;
+                }
+                cnt_s[0] += a; cnt_s[1] += b;
+            }
         }
         if (any) {
             since = 0;

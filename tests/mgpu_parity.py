@@ -26,12 +26,15 @@ def main():
         # dense trait, 64 tasks per GPU x sync rate 10: most of the 640 markers per GPU and window change, i.e. more than
         # 1024 changed markers per window from 2 GPUs on (the old merge gave up there with error 4)
         (600, 4096, 64, 10, 1, 4, "sparse", 3, 31),
+        # few causal markers: most steps change nothing, the windows run ahead (sync_rate steps at a time where the reference
+        # synchronises after every step) and the first changed step is taken over the lists of all GPUs
+        (1800, 1536, 2, 5, 2, 3, "sparse", 6, 11),
     ]):
         T = TL * world
         rng = np.random.default_rng(seed)
         bed, g = random_bed(rng, M, N, pmiss=0.01)
         sp = reference_lists(bed, N)
-        y = simulate_y(rng, g, n_causal=M if case == 3 else max(3, M // 10), h2=0.9 if case == 3 else 0.5)
+        y = simulate_y(rng, g, n_causal=M if case == 3 else (4 if case == 4 else max(3, M // 10)), h2=0.9 if case == 3 else 0.5)
         groups = (np.arange(M) % G).astype(np.int32)
         mS = np.tile(np.array([0.0] + [10.0 ** (-(K - 1 - k)) for k in range(1, K)]), (G, 1))
         if case == 3:
@@ -48,6 +51,7 @@ def main():
         st.finalize()
         st.comm_init(dist)
         brr = hydra_b200.BayesRRm(st, y, mS, groups=groups, sigmaG0=sigmaG0, seed=seed)
+        ahead = repeated = 0
         for it in range(n_iter):
             tp = dict(zmu=tape["zmu"][it][rank * TL:(rank + 1) * TL], perm=tape["perm"][it][ms:ms + ml], u=tape["u"][it][ms:ms + ml],
                       z=tape["z"][it][ms:ms + ml], sigmaG=ref["sigmaG"][it], pi=ref["pi"][it], sigmaE=ref["sigmaE"][it:it + 1])
@@ -60,12 +64,15 @@ def main():
             np.testing.assert_allclose(h["bsq"], ref["bsq"][it], rtol=1e-10)
             np.testing.assert_allclose(o["e_sqn"], ref["esqn"][it], rtol=1e-10)
             assert o["n_sync"] == ref["nsync"][it]
+            ahead += o["windows_ahead"]; repeated += o["draws_repeated"]
             if case == 3 and it == n_iter - 1 and rank == 0:
                 per_window = o["markers_changed"] / max(1, o["n_windows"])
                 print(f"case 3: {per_window:.0f} changed markers per window over all GPUs", flush=True)
                 assert per_window > 0.4 * 640 * world, per_window   # > 1024 from 4 GPUs on
             for t in range(TL):
                 np.testing.assert_allclose(brr.task_epsilon(t), ref["eps"][it, rank * TL + t], rtol=1e-10, atol=1e-12)
+        if case == 4:
+            assert ahead > 20 and repeated > 0, (ahead, repeated)
         st.close()
         dist.barrier()
         if rank == 0:

@@ -22,4 +22,4 @@ def test_multi_gpu_replay_matches_oracle(world):
            "--master-port", str(29500 + world), os.path.join(ROOT, "tests", "mgpu_parity.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "HB_PEER_TIMEOUT_S": "20"})
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "case 3 ok" in r.stdout
+    assert "case 4 ok" in r.stdout
