@@ -213,7 +213,7 @@ def bayesw_line(a, local_rank, with_cpu=True):
     from hydra_b200 import synth
     M = a.m_per_gpu
     store = hydra_b200.GenotypeStore(a.n, M, tasks=a.tasks_per_gpu, sync_rate=a.sync_rate, n_groups=1, n_mix=4, repr_mode="sparse",
-                                     device=local_rank, model="bayesW")
+                                     device=local_rank, model="bayesW", n_slices=a.n_slices)
     t0 = time.time()
     synth.stage_synthetic(store, a.spectrum)
     stage_s = time.time() - t0
