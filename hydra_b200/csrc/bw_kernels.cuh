@@ -375,6 +375,26 @@ __global__ void __launch_bounds__(512) k_bw_reduce(const double *__restrict__ E,
 }
 
 // unit-level entry points for parity tests: one thread evaluates the scalar functions on the device
+// Fixed effects (src/BayesW.cpp:119-129, 1366-1413): sum_i exp(a*eps_i + b*x_i + c0) with x = one covariate column on the
+// slice layout (gamma_dens evaluated at gamma: a = alpha, b = alpha*(gamma_old - gamma), c0 = -EuMasc), slice partials.
+__global__ void __launch_bounds__(512) k_bw_reduce_cov(const double *__restrict__ E, const double *__restrict__ x, uint32_t N, uint32_t L,
+                                                       double shift, double a, double b, double c0, double *__restrict__ part) {
+    __shared__ double red[16];
+    const uint32_t c = blockIdx.x;
+    double v = 0.0;
+    for (uint32_t i = threadIdx.x; i < L; i += blockDim.x) {
+        const size_t gi = (size_t)c * L + i;
+        if (gi < N) v += exp(a * (E[gi] + shift) + b * x[gi] + c0);
+    }
+    const double s = bw_block_sum(v, red);
+    if (threadIdx.x == 0) part[c] = s;
+}
+// eps += d * x (the residual after a fixed effect moved from gamma_old to gamma_old - d, :1408-1410)
+__global__ void k_bw_axpy_cov(double *__restrict__ E, const double *__restrict__ x, size_t n, double d) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) E[i] += d * x[i];
+}
+
 __global__ void k_bw_unit_marginal(BwMarker m, int rule, const double *prior, const double *cVa, int km1, double *post) {
     bw_marginal_likelihoods(rule, prior, cVa, km1, m, post);
 }

@@ -141,6 +141,7 @@ struct hb_ctx {
     bool bw_ready = false;
     int bw_rule = -1;
     double bw_alpha = 0.0, bw_mu = 0.0, bw_d = 0.0, bw_sumSigmaG = 0.0;
+    std::vector<double> bw_fail_h, bw_sff;   // failure indicators (host copy) and sum_failure_fix of the fixed effects (src/BayesW.cpp:1235-1237)
     uint64_t bw_evals = 0;
     DevBuf<double> d_sd, d_sumfail, d_fail, d_bwsc, d_bw_vi;
     std::vector<double> sd_h, sumfail_h;
@@ -1572,7 +1573,7 @@ int hb_brr_load_state(hb_ctx *c, const void *buf, size_t n) {
         HB_CHECK(r.ok && F == c->F, HB_ERR_ARG, "hb_brr_load_state: the state has %u fixed effects, this chain %u (call hb_brr_set_covariates first)", F, c->F);
         r.get(c->gamma.data(), F); r.get(c->xI.data(), F);
         HB_CHECK(r.ok, HB_ERR_ARG, "hb_brr_load_state: truncated state");
-        if (F) HB_CUDA(cudaMemcpy(c->d_gamma.p, c->gamma.data(), sizeof(double) * F, cudaMemcpyHostToDevice));
+        if (F && !c->bw_ready) HB_CUDA(cudaMemcpy(c->d_gamma.p, c->gamma.data(), sizeof(double) * F, cudaMemcpyHostToDevice));   // (BayesW keeps gamma on the host)
     }
     c->eps_set = true;
     return HB_OK;

@@ -209,6 +209,40 @@ void read_phen_cov(const std::string &phen, const std::string &covf, uint32_t n_
     if (line != n_ind) throw std::runtime_error("phenotype file [" + phen + "] has " + std::to_string(line) + " lines, --number-individuals is " + std::to_string(n_ind));
 }
 
+// src/data.cpp:1679-1752: phenotype, covariate and failure files read together; an NA phenotype, an NA in any covariate or a
+// failure of "-9" drops the individual; X is kept as read (row-major, individuals x covariates)
+void read_phen_fail_cov(const std::string &phen, const std::string &covf, const std::string &failf, uint32_t n_ind, std::vector<double> &y,
+                        std::vector<double> &fail, std::vector<double> &X, uint32_t &n_cov, std::vector<uint32_t> &na) {
+    std::ifstream inp(phen), inc(covf), inf(failf);
+    if (!inp) throw std::runtime_error("Error: can not open the phenotype file [" + phen + "] to read.");
+    if (!inc) throw std::runtime_error("Error: can not open the covariates file [" + covf + "] to read.");
+    if (!inf) throw std::runtime_error("Error: can not open the failure file [" + failf + "] to read.");
+    std::string lp, lc, lf;
+    uint32_t line = 0;
+    n_cov = 0;
+    while (std::getline(inp, lp)) {
+        auto tp = split(lp, " \t\r");
+        if (tp.empty()) continue;
+        if (!std::getline(inc, lc)) throw std::runtime_error("covariates file [" + covf + "] is shorter than the phenotype file");
+        if (!std::getline(inf, lf)) throw std::runtime_error("failure file [" + failf + "] is shorter than the phenotype file");
+        auto tc = split(lc, " \t\r"), tf = split(lf, " \t\r");
+        if (tp.size() < 3 || tc.size() < 3 || tf.empty()) throw std::runtime_error("phenotype / covariates / failure files: malformed line " + std::to_string(line + 1));
+        bool naC = false;
+        for (size_t i = 2; i < tc.size(); i++) naC |= (tc[i] == "NA");
+        if (tp[2] != "NA" && !naC && tf[0] != "-9") {
+            if (n_cov == 0) n_cov = (uint32_t)tc.size() - 2;
+            if (tc.size() - 2 != n_cov) throw std::runtime_error("covariates file [" + covf + "]: line " + std::to_string(line + 1) + " has a different number of columns");
+            y.push_back(atof(tp[2].c_str()));
+            fail.push_back(atof(tf[0].c_str()));
+            for (size_t i = 2; i < tc.size(); i++) X.push_back(std::stod(tc[i]));
+        } else {
+            na.push_back(line);
+        }
+        line++;
+    }
+    if (line != n_ind) throw std::runtime_error("phenotype file [" + phen + "] has " + std::to_string(line) + " lines, --number-individuals is " + std::to_string(n_ind));
+}
+
 // src/data.cpp:1753-1803: phenotype and failure files read together; NA phenotype or failure "-9" drops the individual
 void read_phen_fail(const std::string &phen, const std::string &failf, uint32_t n_ind, std::vector<double> &y, std::vector<double> &fail,
                     std::vector<uint32_t> &na) {
@@ -401,15 +435,18 @@ int main(int argc, const char **argv) {
             if (bayesW) {
                 if (opt.failureFile.empty()) throw std::runtime_error("--failure has to be set for bayesWMPI");
                 if (opt.quad_points.empty()) throw std::runtime_error("--quad_points has to be set for bayesWMPI (3,5,7,9,11,13,15,17,25)");
-                read_phen_fail(opt.phenotypeFile, opt.failureFile, Nraw, y, fail, na);
+                if (!opt.covariatesFile.empty()) {
+                    read_phen_fail_cov(opt.phenotypeFile, opt.covariatesFile, opt.failureFile, Nraw, y, fail, Xcov, n_cov, na);
+                    printf("INFO   : using covariate file: %s (numFixedEffect = %u)\n", opt.covariatesFile.c_str(), n_cov);
+                } else {
+                    read_phen_fail(opt.phenotypeFile, opt.failureFile, Nraw, y, fail, na);
+                }
             } else if (!opt.covariatesFile.empty()) {
                 read_phen_cov(opt.phenotypeFile, opt.covariatesFile, Nraw, y, Xcov, n_cov, na);
                 printf("INFO   : using covariate file: %s (numFixedEffect = %u)\n", opt.covariatesFile.c_str(), n_cov);   // :1550, data.cpp:1664
             } else {
                 read_phen(opt.phenotypeFile, Nraw, y, na);
             }
-            if (bayesW && !opt.covariatesFile.empty())
-                throw std::runtime_error("--covariates with bayesWMPI (gamma_dens, src/BayesW.cpp:119-129, 1366-1413) is not available in this build");
         }
         // groups and mixtures (src/BayesRRm.cpp:981-996)
         std::vector<int32_t> groups;
@@ -527,11 +564,12 @@ int main(int argc, const char **argv) {
         uint32_t seed = opt.seedSet ? opt.seed : (uint32_t)time(nullptr);  // multi-GPU: rank 0's value is shipped with the NCCL id (below)
         if (bayesW) {
             HB(hb_bw_init(ctx, y.data(), fail.data(), groups.empty() ? nullptr : groups.data(), mSflat.data(), (uint32_t)atoi(opt.quad_points.c_str()), seed));
+            if (n_cov) HB(hb_bw_set_covariates(ctx, Xcov.data(), n_cov));   // fixed effects by ARMS, src/BayesW.cpp:1366-1413
             struct stat sbw;
             if (stat(opt.mcmcOutDir.c_str(), &sbw) != 0 && system(("mkdir -p " + opt.mcmcOutDir).c_str()) != 0)
                 throw std::runtime_error("could not create output directory --mcmc-out-dir " + opt.mcmcOutDir);
             const std::string out = opt.mcmcOut();
-            OutFile csv, bet, cpn;
+            OutFile csv, bet, cpn, gam;
             uint32_t it_first = 0, n_saved = 0;
             if (opt.restart) {  // as for BayesRRm: state file of the last --save point, outputs cut back to it
                 uint32_t it_saved = 0;
@@ -542,11 +580,15 @@ int main(int argc, const char **argv) {
                     truncate((out + ".cpn").c_str(), 4 + (off_t)n_saved * (4 + (off_t)Mtot * 4)) != 0)
                     fatal("--restart: cannot cut the .bet/.cpn files back to the restart point");
                 csv.open_append(out + ".csv"); bet.open_append(out + ".bet"); cpn.open_append(out + ".cpn");
+                if (n_cov) { truncate_csv(out + ".gam", it_saved); gam.open_append(out + ".gam"); }
                 printf("INFO   : restarting after iteration %u (%u records in .bet/.cpn)\n", it_saved, n_saved);
             } else {
                 csv.open(out + ".csv"); bet.open(out + ".bet"); cpn.open(out + ".cpn");
+                if (n_cov) gam.open(out + ".gam");
                 bet.put(&Mtot, 1); cpn.put(&Mtot, 1);
             }
+            std::vector<double> gamv(n_cov);
+            std::vector<int32_t> xiv(n_cov);
             std::vector<double> beta(Mtot), sigmaG(G), pi((size_t)G * K), bsq(G), eps(N);
             std::vector<int32_t> comp(Mtot), cass((size_t)G * K), m0(G);
             double tot_ms = 0.0;
@@ -571,9 +613,18 @@ int main(int argc, const char **argv) {
                     bet.put(&it, 1); bet.put(beta.data(), Mtot);
                     cpn.put(&it, 1); cpn.put(comp.data(), Mtot);
                     fflush(csv.f); fflush(bet.f); fflush(cpn.f);
+                    if (n_cov) {   // "%5d, %20.17f, ..." (:1970-1980)
+                        HB(hb_bw_get_gamma(ctx, gamv.data(), xiv.data()));
+                        int ng = snprintf(buff, sizeof(buff), "%5d", (int)it);
+                        for (uint32_t f = 0; f < n_cov; f++) ng += snprintf(buff + ng, sizeof(buff) - ng, ", %20.17f", gamv[f]);
+                        ng += snprintf(buff + ng, sizeof(buff) - ng, "\n");
+                        gam.put(buff, (size_t)ng);
+                        fflush(gam.f);
+                    }
                     n_saved++;
                 }
                 if (it > 0 && it % opt.save == 0) {
+                    if (n_cov) { HB(hb_bw_get_gamma(ctx, gamv.data(), xiv.data())); dump_file(out + ".xiv", it, n_cov, xiv.data()); }   // :1982-1990
                     HB(hb_get_epsilon(ctx, eps.data()));
                     dump_file(out + ".eps.0", it, N, eps.data());
                     write_restart_file(out + ".rst.0", ctx, it, n_saved);

@@ -276,8 +276,9 @@ class BayesRRm:
 class BayesW:
     """The BayesW (Weibull survival) chain on one GPU (src/BayesW.cpp:905-1907). `store` must be created with model="bayesW"."""
 
-    def __init__(self, store: GenotypeStore, y, failure, mS, groups=None, quad_points=25, seed=0):
+    def __init__(self, store: GenotypeStore, y, failure, mS, groups=None, quad_points=25, seed=0, covariates=None):
         self.store = store
+        self.n_cov = 0
         self._lib = store._lib
         G, K = store.n_groups, store.n_mix
         mS = np.asarray(mS, dtype=np.float64).reshape(G, -1)
@@ -290,6 +291,15 @@ class BayesW:
         assert y.shape == (store.n_ind,) and f.shape == (store.n_ind,)
         g = arr(groups, np.int32)
         check(self._lib.hb_bw_init(store._h, ptr(y), ptr(f), ptr(g), ptr(self.mS), C.c_uint32(quad_points), C.c_uint32(seed & 0xFFFFFFFF)))
+        if covariates is not None:   # fixed effects, N x F as read from the covariate file (src/BayesW.cpp:1366-1413)
+            X = np.ascontiguousarray(np.asarray(covariates, np.float64).reshape(store.n_ind, -1))
+            self.n_cov = X.shape[1]
+            check(self._lib.hb_bw_set_covariates(store._h, ptr(X), C.c_uint32(self.n_cov)))
+
+    def gamma(self):
+        g, xI = np.zeros(self.n_cov), np.zeros(self.n_cov, np.int32)
+        check(self._lib.hb_bw_get_gamma(self.store._h, ptr(g), ptr(xI)))
+        return g, xI
 
     def iteration(self, tape=None):
         out = capi.HbBwIterOut()
@@ -297,7 +307,7 @@ class BayesW:
         tp = None
         if tape is not None:
             t = capi.HbBwTape()
-            for name, dt in (("perm", np.int32), ("p", np.float64), ("sigmaG", np.float64), ("pi", np.float64)):
+            for name, dt in (("perm", np.int32), ("p", np.float64), ("sigmaG", np.float64), ("pi", np.float64), ("xI", np.int32)):
                 v = tape.get(name)
                 if v is not None:
                     a = arr(np.atleast_1d(v), dt)

@@ -201,6 +201,7 @@ typedef struct hb_bw_tape {
     const double *p;      /* m_local: U(0,1) of the marker processed at step j of each task (:1528) */
     const double *sigmaG; /* n_groups values AFTER this iteration (:1893), NULL = draw */
     const double *pi;     /* n_groups*n_mix (:1899-1903), NULL = draw */
+    const int32_t *xI;    /* n_cov: order of the fixed effects in this iteration (:1369), NULL = shuffled from the hyper-parameter stream */
 } hb_bw_tape;
 
 typedef struct hb_bw_iter_out {
@@ -213,6 +214,12 @@ typedef struct hb_bw_iter_out {
 /* One Gibbs iteration: ARMS for mu and alpha (N-sums of exp on the device), marker loop, sigmaG / pi_L draws.
  * ARMS uniforms: RNG spec v1 (Philox, 31-bit integers in the form of src/BayesW_arms.cpp:913-918). */
 int hb_bw_iteration(hb_ctx *ctx, const hb_bw_tape *tape, hb_bw_iter_out *out);
+/* Fixed effects of BayesW (--covariates with bayesWMPI; src/BayesW.cpp:1366-1413, gamma_dens :119-129): X is N x n_cov, row-major,
+ * as read from the covariate file. Call after hb_bw_init; every hb_bw_iteration then draws each gamma by ARMS on gamma +- 0.075
+ * (between mu and alpha, in the iteration's order; the density's N-sum runs on the device, uniforms: Philox stream 'ARMG') and
+ * moves the residual. n_cov == 0 switches the block off. hb_bw_get_gamma: gamma[n_cov] and the last order xI[n_cov]. */
+int hb_bw_set_covariates(hb_ctx *ctx, const double *X, uint32_t n_cov);
+int hb_bw_get_gamma(hb_ctx *ctx, double *gamma, int32_t *xI);
 int hb_bw_get_hyper(hb_ctx *ctx, double *sigmaG, double *pi, double *mu, double *alpha, double *bsq, int32_t *cass, int32_t *m0);
 /* marker statistics of BayesW: mstd is the SD (not its inverse), sum_failure (:1211-1232); m_local each */
 int hb_bw_marker_stats(hb_ctx *ctx, double *sd, double *sum_failure);

@@ -396,11 +396,14 @@ class _BwArgs(C.Structure):
                                              "tape_perm", "tape_p", "tape_sigmaG", "tape_pi")]
                 + [("seed", C.c_uint32), ("hyper_seed", C.c_uint32), ("arms", C.c_void_p)]
                 + [(n, C.c_void_p) for n in ("out_beta", "out_comp", "out_eps", "out_mu", "out_alpha", "out_sigmaG", "out_pi", "out_bsq",
-                                             "out_cass", "out_nsync", "out_err")])
+                                             "out_cass", "out_nsync", "out_err")]
+                + [("X", C.c_void_p), ("F", C.c_int32), ("tape_xI", C.c_void_p), ("out_gamma", C.c_void_p)])
 
 
-def bw_chain(N, Mtot, T, K, G, sync_rate, n_iter, quad_points, sp: SparseLists, y, fail, groups, mS, tape, seed, hyper=None, hyper_seed=0):
-    """BayesW oracle chain; tape = dict(perm, p); hyper = dict(sigmaG, pi) to replay values, else drawn with mt19937(hyper_seed)."""
+def bw_chain(N, Mtot, T, K, G, sync_rate, n_iter, quad_points, sp: SparseLists, y, fail, groups, mS, tape, seed, hyper=None, hyper_seed=0,
+             covariates=None):
+    """BayesW oracle chain; tape = dict(perm, p[, xI]); hyper = dict(sigmaG, pi) to replay values, else drawn with mt19937(hyper_seed);
+    covariates = N x F matrix of fixed effects (src/BayesW.cpp:1366-1413), tape["xI"] = their order per iteration (n_iter x F)."""
     keep = []
 
     def k(a, dt):
@@ -423,6 +426,13 @@ def bw_chain(N, Mtot, T, K, G, sync_rate, n_iter, quad_points, sp: SparseLists, 
     if hyper is not None:
         a.tape_sigmaG, a.tape_pi = k(hyper["sigmaG"], np.float64), k(hyper["pi"], np.float64)
     a.seed, a.hyper_seed = seed & 0xFFFFFFFF, hyper_seed & 0xFFFFFFFF
+    if covariates is not None:
+        Xc = np.asarray(covariates, np.float64).reshape(N, -1)
+        a.F = Xc.shape[1]
+        a.X = k(np.asfortranarray(Xc).T.copy(), np.float64)      # column-major: F contiguous columns of N
+        a.tape_xI = k(tape.get("xI"), np.int32)
+        out["gamma"] = np.zeros((n_iter, a.F))
+        a.out_gamma = out["gamma"].ctypes.data
     a.arms = C.cast(arms_ref().ho_ref_arms, C.c_void_p)
     for name in ("beta", "comp", "eps", "mu", "alpha", "sigmaG", "pi", "bsq", "cass", "nsync", "err"):
         setattr(a, "out_" + name, out[name].ctypes.data)

@@ -359,3 +359,57 @@ def test_cli_covariates_run_equals_python_run(tmp_path):
     assert struct.unpack("<II", raw[:8]) == (4, F) and np.array_equal(np.frombuffer(raw[8:], np.float64), gam)
     raw = open(os.path.join(d, "cov", "run.xiv.0"), "rb").read()
     assert struct.unpack("<II", raw[:8]) == (4, F) and np.array_equal(np.frombuffer(raw[8:], np.int32), xiv)
+
+
+@pytest.mark.gpu
+def test_cli_bayesw_covariates_run_equals_python_run(tmp_path):
+    """--covariates with bayesWMPI (src/BayesW.cpp:1366-1413): phenotype, covariate and failure files read together
+    (src/data.cpp:1679-1752: an NA in any of them drops the individual); .gam as text lines "%5d, %20.17f, ..." per thinned
+    iteration (:1970-1980), .xiv at the save points; --restart continues byte for byte."""
+    import hydra_b200
+    d = str(tmp_path)
+    N, M, F = 600, 80, 2
+    rng = np.random.default_rng(22)
+    bed, g = random_bed(rng, M, N, pmiss=0.01)
+    with open(os.path.join(d, "w.bed"), "wb") as f:
+        f.write(bytes([0x6C, 0x1B, 0x01]) + bed.tobytes())
+    open(os.path.join(d, "w.bim"), "w").write("".join(f"1\trs{j}\t0\t{j + 1}\tA\tC\n" for j in range(M)))
+    open(os.path.join(d, "w.fam"), "w").write("".join(f"F{i} I{i} 0 0 1 -9\n" for i in range(N)))
+    X = np.column_stack([rng.integers(0, 2, N).astype(np.float64), rng.normal(size=N)])
+    y = 4.1 + X @ np.array([0.04, -0.02]) + 0.1 * np.log(rng.exponential(size=N))
+    fail = (rng.random(N) > 0.1).astype(int)
+    na_p, na_f, na_c = {5, 17}, {40}, {77}
+    open(os.path.join(d, "w.phen"), "w").write("".join(f"F{i} I{i} {'NA' if i in na_p else repr(float(y[i]))}\n" for i in range(N)))
+    open(os.path.join(d, "w.fail"), "w").write("".join(f"{-9 if i in na_f else fail[i]}\n" for i in range(N)))
+    open(os.path.join(d, "w.cov"), "w").write("".join(f"F{i} I{i} {'NA' if i in na_c else repr(float(X[i, 0]))} {repr(float(X[i, 1]))}\n" for i in range(N)))
+    base = [_exe(), "--mpibayes", "bayesWMPI", "--bfile", os.path.join(d, "w"), "--pheno", os.path.join(d, "w.phen"),
+            "--failure", os.path.join(d, "w.fail"), "--covariates", os.path.join(d, "w.cov"), "--quad_points", "11",
+            "--number-individuals", str(N), "--number-markers", str(M), "--S", "0.001,0.01,0.1", "--thin", "1", "--save", "2",
+            "--seed", "9", "--sync-rate", "3", "--tasks", "2", "--mcmc-out-name", "w"]
+    r = subprocess.run(base + ["--chain-length", "4", "--mcmc-out-dir", os.path.join(d, "o")], capture_output=True, text=True)
+    assert r.returncode == 0 and "numFixedEffect = 2" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    its, beta = read_bet(os.path.join(d, "o", "w.bet"), M)
+    na = np.array(sorted(na_p | na_f | na_c), np.uint32)
+    keep = np.setdiff1d(np.arange(N), na)
+    gam_lines = open(os.path.join(d, "o", "w.gam")).read().strip().split("\n")
+    assert len(gam_lines) == 4
+    with hydra_b200.GenotypeStore(N, M, na_inds=na, tasks=2, sync_rate=3, n_groups=1, n_mix=4, repr_mode="bed", model="bayesW") as st:
+        st.load_data_from_bed(bed)
+        st.finalize()
+        bw = hydra_b200.BayesW(st, y[keep], fail[keep].astype(float), [[0.001, 0.01, 0.1]], quad_points=11, seed=9, covariates=X[keep])
+        for it in range(4):
+            bw.iteration()
+            assert np.array_equal(bw.state()[0], beta[it])
+            gam, xiv = bw.gamma()
+            f = gam_lines[it].split(",")
+            assert int(f[0]) == it and np.allclose([float(v) for v in f[1:]], gam, rtol=0, atol=1e-16)
+            if it == 2:
+                raw = open(os.path.join(d, "o", "w.xiv"), "rb").read()
+                assert struct.unpack("<II", raw[:8]) == (2, F) and np.array_equal(np.frombuffer(raw[8:], np.int32), xiv)
+    assert np.abs(gam).max() > 1e-3
+    r = subprocess.run(base + ["--chain-length", "3", "--mcmc-out-dir", os.path.join(d, "p")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    r = subprocess.run(base + ["--chain-length", "4", "--mcmc-out-dir", os.path.join(d, "p"), "--restart"], capture_output=True, text=True)
+    assert r.returncode == 0 and "restarting after iteration 2" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    for ext in ("csv", "bet", "cpn", "gam", "eps.0"):
+        assert open(os.path.join(d, "o", "w." + ext), "rb").read() == open(os.path.join(d, "p", "w." + ext), "rb").read(), ext

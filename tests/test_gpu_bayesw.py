@@ -149,3 +149,45 @@ def test_bayesw_chain_replay(T, SR, G, repr_mode, replay_hyper):
             np.testing.assert_allclose(bw.epsilon(), ref["eps"][it], rtol=1e-10, atol=1e-12, err_msg=f"eps it {it}")
             np.testing.assert_allclose(h["sigmaG"], ref["sigmaG"][it], rtol=1e-10)
             np.testing.assert_allclose(h["pi"], ref["pi"][it], rtol=1e-10)
+
+
+def test_bayesw_chain_replay_with_covariates():
+    """Fixed effects of BayesW (src/BayesW.cpp:1366-1413, gamma_dens :119-129): each gamma by ARMS between mu and alpha, the
+    density's N-sum on the device; order of the covariates from the tape, ARMS uniforms from the Philox stream 'ARMG'."""
+    if oracle.arms_ref() is None:
+        pytest.skip("oracle/_ref/libarms_ref.so not built")
+    import hydra_b200
+    N, M, K, G, T, SR, F, n_iter, seed, quad = 900, 90, 4, 1, 2, 3, 3, 4, 23, 25
+    rng = np.random.default_rng(5)
+    bed, g = random_bed(rng, M, N, pmiss=0.01)
+    sp = reference_lists(bed, N)
+    X = np.column_stack([rng.integers(0, 2, N).astype(np.float64), rng.normal(size=N), rng.normal(size=N) * 0.5])
+    y, fail = _weibull_data(rng, g)
+    y = y + X @ np.array([0.03, -0.02, 0.01])
+    groups = np.zeros(M, np.int32)
+    mS = np.array([[0.0, 0.001, 0.01, 0.1]])
+    tm = oracle.TapeMaker(seed, T, M).make(n_iter)
+    xI = np.stack([rng.permutation(F) for _ in range(n_iter)]).astype(np.int32)
+    tape = dict(perm=tm["perm"], p=tm["u"], xI=xI)
+    ref = oracle.bw_chain(N, M, T, K, G, SR, n_iter, quad, sp, y, fail, groups, mS, tape, seed, hyper_seed=(seed ^ 0x5bd1e995) & 0xFFFFFFFF,
+                          covariates=X)
+    assert np.abs(ref["gamma"][-1]).max() > 1e-3          # the fixed effects moved
+    with _store(N, M, tasks=T, sync_rate=SR, n_groups=G, n_mix=K, repr_mode="sparse") as st:
+        st.load_data_from_bed(bed)
+        st.finalize()
+        bw = hydra_b200.BayesW(st, y, fail, mS, groups=groups, quad_points=quad, seed=seed, covariates=X)
+        for it in range(n_iter):
+            o = bw.iteration(dict(perm=tape["perm"][it], p=tape["p"][it], xI=xI[it], sigmaG=ref["sigmaG"][it], pi=ref["pi"][it]))
+            gam, order = bw.gamma()
+            assert np.array_equal(order, xI[it])
+            # a gamma is a point of [gamma_old - 0.075, gamma_old + 0.075] found by inverting the ARMS envelope: its error scales with
+            # that range (measured 3.4e-12 absolute), not with its own size (values of 1e-3 here)
+            np.testing.assert_allclose(gam, ref["gamma"][it], rtol=1e-10, atol=2e-11, err_msg=f"gamma it {it}")
+            np.testing.assert_allclose(o["mu"], ref["mu"][it], rtol=1e-11, err_msg=f"mu it {it}")
+            np.testing.assert_allclose(o["alpha"], ref["alpha"][it], rtol=1e-11, err_msg=f"alpha it {it}")
+            beta, comp = bw.state()
+            assert np.array_equal(comp, ref["comp"][it]), f"components differ at iteration {it}"
+            # gamma's absolute error enters epsilon as x * d(gamma) (|x| up to 3) and from there the ARMS draws of the effects
+            np.testing.assert_allclose(beta, ref["beta"][it], rtol=1e-10, atol=1e-11, err_msg=f"beta it {it}")
+            assert o["n_sync"] == ref["nsync"][it]
+            np.testing.assert_allclose(bw.epsilon(), ref["eps"][it], rtol=1e-10, atol=5e-11, err_msg=f"eps it {it}")
