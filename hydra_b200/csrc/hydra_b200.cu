@@ -1348,6 +1348,54 @@ int hb_brr_set_state(hb_ctx *c, const double *beta, const int32_t *components) {
     return HB_OK;
 }
 
+// The reference's own restart (src/BayesRRm.cpp:842-928): the chain state is read back from the OUTPUT files of the last save
+// point -- .csv (sigmaG, sigmaE, pi), .xbet / .xcpn (effects, components), .mus.<task>, .eps.<task>, .mrk.<task> -- which this
+// library's host writes in the reference's layouts. Everything those files hold is put back; the random streams are not in
+// them (the reference's .rng files hold Boost engines), so they are re-seeded from (seed, iteration): the chain continues from the
+// saved state with fresh draws, not bit-for-bit (hb_brr_load_state does that).
+int hb_brr_restore_outputs(hb_ctx *c, uint32_t iterations_done, const double *sigmaG, const double *pi, double sigmaE,
+                           const double *mu_tasks_local, const double *beta, const int32_t *components, const double *eps_task0,
+                           const int32_t *perm_local) {
+    HB_CHECK(c && c->brr_ready && !c->bw_ready, HB_ERR_STATE, "hb_brr_restore_outputs: call hb_brr_init first");
+    HB_CHECK(sigmaG && pi && mu_tasks_local && beta && components && eps_task0, HB_ERR_ARG, "hb_brr_restore_outputs: null argument");
+    HB_CUDA(cudaSetDevice(c->dev));
+    if (c->prefetch.joinable()) c->prefetch.join();
+    c->have_next = false;
+    c->iteration = iterations_done;
+    for (uint32_t g = 0; g < c->G; g++) {
+        c->sigmaG[g] = sigmaG[g];
+        if (g < c->active.size()) c->active[g] = (sigmaG[g] != 0.0) ? 1 : 0;   // adaV follows sigmaG (:1592-1597)
+        double ps = 0.0;
+        for (uint32_t k = 0; k < c->K; k++) { c->pi[g * c->K + k] = pi[g * c->K + k]; ps += pi[g * c->K + k]; }
+        HB_CHECK(fabs(ps - 1.0) < 1e-6, HB_ERR_ARG, "hb_brr_restore_outputs: pi of group %u sums to %.9g", g, ps);
+    }
+    HB_CHECK(sigmaE > 0.0, HB_ERR_ARG, "hb_brr_restore_outputs: sigmaE = %g", sigmaE);
+    c->sigmaE = sigmaE;
+    for (uint32_t t = 0; t < c->T; t++) c->mu[t] = mu_tasks_local[t];
+    HB_TRY(hb_set_epsilon(c, eps_task0));                    // residual of local task 0; the other tasks differ by mu (hb_brr_get_task_epsilon)
+    for (uint32_t s0 = 0, sl = 0; sl < c->S; s0 += c->L, sl++) {
+        double v = 0.0;
+        for (uint32_t i = s0; i < std::min(c->N, s0 + c->L); i++) v += eps_task0[i];
+        c->slice_sum_h[sl] = v;
+    }
+    HB_TRY(hb_brr_set_state(c, beta, components));
+    HB_CUDA(cudaMemset(c->d_acum.p, 0, sizeof(double) * c->M));
+    if (perm_local) {
+        size_t o = 0;
+        for (uint32_t t = 0; t < c->T; t++) {
+            const int32_t len = c->blkL[c->t_first + t];
+            for (int32_t j = 0; j < len; j++, o++) {
+                HB_CHECK(perm_local[o] >= 0 && perm_local[o] < len, HB_ERR_ARG, "hb_brr_restore_outputs: marker order of task %u: %d out of range", t, perm_local[o]);
+                c->perm[o] = perm_local[o];
+            }
+        }
+    }
+    const uint32_t mix = iterations_done * 0x9E3779B9u;
+    for (uint32_t t = 0; t < c->T; t++) c->task_rng[t].seed((c->seed + 1000u * (c->t_first + t)) ^ mix);
+    c->hyper_rng.seed((c->seed ^ 0x5bd1e995u) ^ mix);
+    return HB_OK;
+}
+
 int hb_brr_get_task_epsilon(hb_ctx *c, uint32_t task_local, double *eps) {
     HB_CHECK(c && c->brr_ready && eps, HB_ERR_STATE, "hb_brr_get_task_epsilon: call hb_brr_init first");
     HB_CHECK(task_local < c->T, HB_ERR_ARG, "task %u out of range", task_local);

@@ -384,6 +384,65 @@ void read_restart_file(const std::string &path, hb_ctx *ctx, uint32_t &it, uint3
     HB(hb_brr_load_state(ctx, blob.data(), blob.size()));
     it = head[1]; n_saved = head[2];
 }
+// src/BayesRRm.cpp:842-928 / data.cpp read_mcmc_output_*: the state of the last save point from the OUTPUT files (reference layouts):
+//   .csv     "it, G, sigmaG[G], sigmaE, h2, m0, G, K, pi[G*K]" per thinned iteration -> the last line of a save point (it > 0, it % save == 0)
+//   .xbet / .xcpn   u32 Mtot; u32 it; f64 / i32 [Mtot]          .mus.<task>  {u32 it; f64 mu} per thinned iteration
+//   .eps.<task>     u32 it; u32 N; f64[N]                        .mrk.<task>  u32 it; u32 len; i32[len]
+template <class T>
+static void read_at(const std::string &path, size_t off, T *dst, size_t n) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) fatal("--restart: cannot open " + path);
+    if (fseek(f, (long)off, SEEK_SET) != 0 || fread(dst, sizeof(T), n, f) != n) { fclose(f); fatal("--restart: " + path + " is too short"); }
+    fclose(f);
+}
+void restart_from_outputs(const std::string &out, hb_ctx *ctx, uint32_t Mtot, uint32_t N, uint32_t G, uint32_t K, uint32_t t_first, uint32_t TL,
+                          uint32_t m_start, uint32_t m_local, const std::vector<int32_t> &blkL, uint32_t save, uint32_t &it_saved, uint32_t &n_saved) {
+    std::ifstream in(out + ".csv");
+    if (!in) fatal("--restart: neither " + out + ".rst.<rank> nor " + out + ".csv exists");
+    std::string line, best;
+    uint32_t n_lines = 0, best_lines = 0;
+    while (std::getline(in, line)) {
+        if (line.empty()) continue;
+        n_lines++;
+        const uint32_t it = (uint32_t)atoi(line.c_str());
+        if (it > 0 && it % save == 0) { best = line; best_lines = n_lines; }
+    }
+    if (best.empty()) fatal("There is no point in restarting a chain from iteration 0 (not saved anyway) => restart your analysis from scratch");  // :869-874
+    std::vector<double> v;
+    for (auto &tok : split(best, ", ")) v.push_back(atof(tok.c_str()));
+    if (v.size() != 2 + G + 5 + (size_t)G * K || (uint32_t)v[1] != G) fatal("--restart: " + out + ".csv does not belong to a run with these groups / mixtures");
+    it_saved = (uint32_t)v[0]; n_saved = best_lines;
+    std::vector<double> sigmaG(v.begin() + 2, v.begin() + 2 + G), pi(v.begin() + 2 + G + 5, v.end());
+    const double sigmaE = v[2 + G];
+    uint32_t head[2];
+    std::vector<double> beta(m_local), mu(TL), eps(N);
+    std::vector<int32_t> comp(m_local), perm(m_local);
+    read_at(out + ".xbet", 0, head, 2);
+    if (head[0] != Mtot || head[1] != it_saved) fatal("--restart: " + out + ".xbet holds iteration " + std::to_string(head[1]) + ", the .csv file's last save point is " + std::to_string(it_saved));
+    read_at(out + ".xbet", 8 + (size_t)m_start * 8, beta.data(), m_local);
+    read_at(out + ".xcpn", 0, head, 2);
+    if (head[0] != Mtot || head[1] != it_saved) fatal("--restart: " + out + ".xcpn does not hold iteration " + std::to_string(it_saved));
+    read_at(out + ".xcpn", 8 + (size_t)m_start * 4, comp.data(), m_local);
+    size_t po = 0;
+    for (uint32_t t = 0; t < TL; t++) {
+        const std::string ts = std::to_string(t_first + t);
+        struct __attribute__((packed)) { uint32_t it; double mu; } rec;
+        read_at(out + ".mus." + ts, (size_t)(n_saved - 1) * 12, reinterpret_cast<unsigned char *>(&rec), 12);
+        if (rec.it != it_saved) fatal("--restart: " + out + ".mus." + ts + " does not hold iteration " + std::to_string(it_saved) + " at record " + std::to_string(n_saved - 1));
+        mu[t] = rec.mu;
+        read_at(out + ".mrk." + ts, 0, head, 2);
+        if (head[0] != it_saved || head[1] != (uint32_t)blkL[t_first + t]) fatal("--restart: " + out + ".mrk." + ts + " does not hold iteration " + std::to_string(it_saved));
+        read_at(out + ".mrk." + ts, 8, perm.data() + po, (size_t)blkL[t_first + t]);
+        po += (size_t)blkL[t_first + t];
+    }
+    read_at(out + ".eps." + std::to_string(t_first), 0, head, 2);
+    if (head[0] != it_saved || head[1] != N) fatal("--restart: " + out + ".eps." + std::to_string(t_first) + " does not hold iteration " + std::to_string(it_saved));
+    read_at(out + ".eps." + std::to_string(t_first), 8, eps.data(), N);
+    HB(hb_brr_restore_outputs(ctx, it_saved + 1, sigmaG.data(), pi.data(), sigmaE, mu.data(), beta.data(), comp.data(), eps.data(), perm.data()));
+    printf("RESTART: from files: %s.* files (no %s.rst.<rank>: state of the output files, fresh random streams)\n", out.c_str(), out.c_str());  // :849
+    printf("RESTART: iteration_to_restart_from = %u\n", it_saved);
+}
+
 // keep the .csv lines of the iterations up to `it` (first field of every line)
 void truncate_csv(const std::string &path, uint32_t it) {
     std::ifstream in(path);
@@ -696,7 +755,15 @@ int main(int argc, const char **argv) {
             // continue the chain after the last --save point of the interrupted run: state back into the library, output
             // files cut back to that iteration (the reference does the same from its own files, :842-928)
             uint32_t it_saved = 0;
-            read_restart_file(out + ".rst." + std::to_string(opt.rank), ctx, it_saved, n_saved);
+            struct stat srst;
+            if (stat((out + ".rst." + std::to_string(opt.rank)).c_str(), &srst) == 0) {
+                read_restart_file(out + ".rst." + std::to_string(opt.rank), ctx, it_saved, n_saved);
+            } else {   // the reference's own way: from the output files of the last save point
+                if (n_cov) fatal("--restart from the output files with --covariates: only the .rst.<rank> state files carry the fixed effects");
+                std::vector<int32_t> bs(opt.tasks), bl(opt.tasks);
+                HB(hb_get_task_blocks(ctx, bs.data(), bl.data()));
+                restart_from_outputs(out, ctx, Mtot, N, G, K, opt.rank * TL, TL, m_start, m_local, bl, opt.save, it_saved, n_saved);
+            }
             {   // the per-process state files are written independently: all must stem from the same --save point
                 const uint64_t v[2] = {it_saved, n_saved};
                 HB(hb_comm_check_equal(ctx, v, 2, "--restart: the restart point (iteration, records) of the <out>.rst.<rank> files"));

@@ -219,6 +219,16 @@ class BayesRRm:
         d["phase_cycles"] = list(out.phase_cycles)
         return d
 
+    def restore_outputs(self, iterations_done, sigmaG, pi, sigmaE, mu_tasks, beta, components, eps_task0, perm=None):
+        """The reference's restart from its output files (src/BayesRRm.cpp:842-928): see hb_brr_restore_outputs."""
+        s = self.store
+        a = [arr(sigmaG, np.float64), arr(pi, np.float64), arr(np.atleast_1d(mu_tasks), np.float64), arr(beta, np.float64),
+             arr(components, np.int32), arr(eps_task0, np.float64)]
+        p = arr(perm, np.int32) if perm is not None else None
+        check(self._lib.hb_brr_restore_outputs(s._h, C.c_uint32(iterations_done), ptr(a[0]), ptr(a[1]), C.c_double(float(sigmaE)), ptr(a[2]),
+                                               ptr(a[3]), ptr(a[4]), ptr(a[5]), ptr(p) if p is not None else None))
+        self.iteration_index = iterations_done
+
     def hyper(self):
         s = self.store
         G, K = s.n_groups, s.n_mix

@@ -169,6 +169,13 @@ int hb_brr_get_hyper(hb_ctx *ctx, double *sigmaG, double *pi, double *sigmaE, do
 /* Beta, components, Acum of the local markers (the slices written to .bet/.cpn/.acu, :2779-2785) */
 int hb_brr_get_state(hb_ctx *ctx, double *beta, int32_t *components, double *acum);
 int hb_brr_set_state(hb_ctx *ctx, const double *beta, const int32_t *components); /* --restart */
+/* The reference's restart from its OUTPUT files (src/BayesRRm.cpp:842-928, data.cpp read_mcmc_output_*): what .csv, .xbet, .xcpn,
+ * .mus.<task>, .eps.<task>, .mrk.<task> of the last save point hold is put back (arrays of the local markers / tasks, eps of local
+ * task 0, perm_local may be NULL); the next hb_brr_iteration is iteration `iterations_done`. The random streams are not in those
+ * files: they are re-seeded from (seed, iterations_done) -- a continuation with fresh draws; hb_brr_load_state continues bit for bit. */
+int hb_brr_restore_outputs(hb_ctx *ctx, uint32_t iterations_done, const double *sigmaG, const double *pi, double sigmaE,
+                           const double *mu_tasks_local, const double *beta, const int32_t *components, const double *eps_task0,
+                           const int32_t *perm_local);
 /* --restart (src/BayesRRm.cpp:842-928: the reference reads .csv .bet .cpn .eps .mrk .mus .rng back). The complete chain
  * state of this GPU as one opaque blob: hyper-parameters, per-task mu, residual, effects / components / Acum and the host
  * random streams. `buf == NULL`: only *need is set. After hb_brr_init (or hb_bw_init: the pair serves both models) with the

@@ -407,3 +407,54 @@ def test_cli_bayesw_covariates_run_equals_python_run(tmp_path):
     assert r.returncode == 0 and "restarting after iteration 2" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     for ext in ("csv", "bet", "cpn", "gam", "eps.0"):
         assert open(os.path.join(d, "o", "w." + ext), "rb").read() == open(os.path.join(d, "p", "w." + ext), "rb").read(), ext
+
+
+@pytest.mark.gpu
+def test_cli_restart_from_the_output_files(tmp_path):
+    """The reference's own restart (src/BayesRRm.cpp:842-928): without a .rst state file the chain state is read back from the
+    output files of the last save point (.csv, .xbet, .xcpn, .mus, .eps, .mrk -- reference layouts). The random streams are
+    re-seeded, so the continuation is checked against the Python front-end restored from the same files."""
+    import glob
+    import hydra_b200
+    d = str(tmp_path)
+    bed, y, na, groups = write_dataset(d)
+    N, M, T = 600, 150, 3
+    def args(n):
+        a = base_args(d, "o", ["--bfile", os.path.join(d, "t")])
+        a[a.index("--chain-length") + 1] = str(n)
+        a[a.index("--thin") + 1] = "1"
+        return a
+    r = subprocess.run(args(5), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    o = os.path.join(d, "o", "run")
+    for f in glob.glob(o + ".rst.*"):
+        os.remove(f)
+    its0, beta0 = read_bet(o + ".bet", M)
+    assert its0.tolist() == [0, 1, 2, 3, 4]
+    # what the files of the save point (iteration 4) hold
+    line = [float(v) for v in open(o + ".csv").read().strip().split("\n")[4].split(",")]
+    G, K = 2, 4
+    assert int(line[0]) == 4 and int(line[1]) == G
+    sigmaG, sigmaE, pi = np.array(line[2:2 + G]), line[2 + G], np.array(line[2 + G + 5:]).reshape(G, K)
+    xb = open(o + ".xbet", "rb").read(); xc = open(o + ".xcpn", "rb").read()
+    assert struct.unpack("<II", xb[:8]) == (M, 4)
+    beta4, comp4 = np.frombuffer(xb[8:], np.float64), np.frombuffer(xc[8:], np.int32)
+    assert np.array_equal(beta4, beta0[4])
+    mu = np.array([np.frombuffer(open(f"{o}.mus.{t}", "rb").read(), np.dtype([("it", "<u4"), ("mu", "<f8")]))["mu"][4] for t in range(T)])
+    eps0 = np.frombuffer(open(o + ".eps.0", "rb").read()[8:], np.float64)
+    perm = np.concatenate([np.frombuffer(open(f"{o}.mrk.{t}", "rb").read()[8:], np.int32) for t in range(T)])
+    r = subprocess.run(args(8) + ["--restart"], capture_output=True, text=True)
+    assert r.returncode == 0 and "iteration_to_restart_from = 4" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    its, beta = read_bet(o + ".bet", M)
+    assert its.tolist() == list(range(8)) and np.array_equal(beta[:5], beta0)          # the old records stay, three are appended
+    assert len(open(o + ".csv").read().strip().split("\n")) == 8
+    keep = np.setdiff1d(np.arange(N), na)
+    with hydra_b200.GenotypeStore(N, M, na_inds=na, tasks=T, sync_rate=5, n_groups=G, n_mix=K, repr_mode="bed") as st:
+        st.load_data_from_bed(bed)
+        st.finalize()
+        brr = hydra_b200.BayesRRm(st, y[keep], [[0.001, 0.01, 0.1]] * G, groups=groups, seed=1222)
+        brr.restore_outputs(5, sigmaG, pi, sigmaE, mu, beta4, comp4, eps0, perm)
+        for it in range(5, 8):
+            brr.iteration()
+            assert np.array_equal(brr.state()[0], beta[it]), f"python (restored from the files) vs CLI --restart at iteration {it}"
+    assert not np.array_equal(beta[5], beta[4])
