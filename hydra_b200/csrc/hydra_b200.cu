@@ -429,6 +429,8 @@ int hb_create(const hb_config *cfg, hb_ctx **out) {
         for (uint32_t S = smin; S <= std::min(max_ctas, smin + smin / 4); S++)
             if (S * (max_ctas / S) > best * (max_ctas / best)) best = S;
         c->S = best;
+        // BayesW keeps the residual in global memory (one CTA per slice in k_bw_update): twice the slices measured +6 % (150 -> 142 us per window)
+        if (cfg->model == 1 && 2 * best <= max_ctas) c->S = 2 * best;
     }
     c->L = slice_len(c->S);
     HB_CHECK(c->S <= max_ctas, HB_ERR_ARG, "hb_create: %u slices > %u CTAs", c->S, max_ctas);
