@@ -440,15 +440,22 @@ def main():
 
     # ---- end-to-end leg through the host API: per step H2D of the marker order (+hyper tables), D2H of beta/components/acum
     # the results land in pinned host buffers (what a writer of .bet/.cpn/.acu files would hand to the library)
-    pinned = (torch.empty(store.m_local, dtype=torch.float64, pin_memory=True).numpy(),
-              torch.empty(store.m_local, dtype=torch.int32, pin_memory=True).numpy(),
-              torch.empty(store.m_local, dtype=torch.float64, pin_memory=True).numpy())
+    # (two sets: the read-back of step i runs on a copy stream while step i+1 computes, the way a thin-every-iteration writer
+    # uses hb_brr_get_state_async; every step's results are complete in host memory before the buffers are reused and before
+    # the clock stops)
+    pinned = [(torch.empty(store.m_local, dtype=torch.float64, pin_memory=True).numpy(),
+               torch.empty(store.m_local, dtype=torch.int32, pin_memory=True).numpy(),
+               torch.empty(store.m_local, dtype=torch.float64, pin_memory=True).numpy()) for _ in range(2)]
+    brr.state_async(pinned[1])                 # untimed: creates the copy stream and the device snapshot buffers
+    brr.state_wait()
     sync_all()
     t_e2e = time.perf_counter()
-    for _ in range(a.steps):
+    for i in range(a.steps):
         brr.iteration()
-        brr.state(out=pinned)
+        brr.state_wait()                       # step i-1 is in host memory (its buffer set is free again at step i+1)
+        brr.state_async(pinned[i & 1])
         brr.hyper()
+    brr.state_wait()
     sync_all()
     e2e_ms = (time.perf_counter() - t_e2e) * 1e3
     t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
@@ -502,7 +509,7 @@ def main():
                             "markers_changed_last_step": outs[-1]["markers_changed"], "us_per_window": loop_ms * 1e3 / sum(o["n_windows"] for o in outs)},
             "e2e": {"value": M_total * a.steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(4 * store.m_local + 8 * 4 * 4 + 1), "d2h_bytes_per_step": int(20 * store.m_local + 8 * (3 + 2 * store.n_slices) + 16 + 128),
-                    "ms_per_step": e2e_ms / a.steps, "what": "BayesRRm.iteration() + state() + hyper() through the C ABI: marker order H2D, beta/components/acum D2H every step (thin=1)"},
+                    "ms_per_step": e2e_ms / a.steps, "what": "BayesRRm.iteration() + state_async()/state_wait() + hyper() through the C ABI: marker order H2D, beta/components/acum D2H into pinned host memory every step (thin=1), the read-back of a step overlapping the next step's marker loop"},
             "gpu_launches": int(sum(o["n_launches"] for o in outs)),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "dram": roof_dram, "smem": roof_smem,

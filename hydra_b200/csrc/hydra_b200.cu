@@ -116,6 +116,12 @@ struct hb_ctx {
 
     // marker state
     DevBuf<double> d_beta, d_acum;
+    // hb_brr_get_state_async: snapshot + copy stream, so that the read-back of iteration i overlaps the marker loop of i+1
+    DevBuf<double> d_snap_beta, d_snap_acum;
+    DevBuf<int32_t> d_snap_comp;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_snap = nullptr, ev_copy = nullptr;
+    bool copy_pending = false;
     DevBuf<int32_t> d_comp, d_cass;
     // per-iteration inputs
     DevBuf<int32_t> d_order, d_perm, d_task_len, d_task_off;
@@ -194,6 +200,9 @@ struct hb_ctx {
         if (pin) cudaFreeHost(pin);
         for (auto &e : ev)
             if (e) cudaEventDestroy(e);
+        if (ev_snap) cudaEventDestroy(ev_snap);
+        if (ev_copy) cudaEventDestroy(ev_copy);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -1338,6 +1347,41 @@ int hb_brr_get_state(hb_ctx *c, double *beta, int32_t *components, double *acum)
     if (components) HB_CUDA(cudaMemcpyAsync(components, c->d_comp.p, sizeof(int32_t) * c->M, cudaMemcpyDeviceToHost, c->stream));
     if (acum) HB_CUDA(cudaMemcpyAsync(acum, c->d_acum.p, sizeof(double) * c->M, cudaMemcpyDeviceToHost, c->stream));
     HB_CUDA(cudaStreamSynchronize(c->stream));
+    return HB_OK;
+}
+
+// Asynchronous form for writers that thin every iteration (.bet/.cpn/.acu, :2768-2785): the three arrays are snapshotted on the
+// device (3 x M, ~10 us) and copied to the caller's (pinned) buffers on a second stream while the next hb_brr_iteration runs.
+// The buffers belong to the library until hb_brr_state_wait returns; a second call waits for the first copy itself.
+int hb_brr_get_state_async(hb_ctx *c, double *beta, int32_t *components, double *acum) {
+    HB_CHECK(c && c->brr_ready, HB_ERR_STATE, "hb_brr_get_state_async: call hb_brr_init first");
+    HB_CUDA(cudaSetDevice(c->dev));
+    if (!c->copy_stream) {
+        HB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        HB_CUDA(cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming));
+        HB_CUDA(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+        HB_TRY(c->d_snap_beta.alloc(c->M)); HB_TRY(c->d_snap_acum.alloc(c->M)); HB_TRY(c->d_snap_comp.alloc(c->M));
+    }
+    if (c->copy_pending) HB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));   // the previous copy still reads the snapshot
+    if (beta) HB_CUDA(cudaMemcpyAsync(c->d_snap_beta.p, c->d_beta.p, sizeof(double) * c->M, cudaMemcpyDeviceToDevice, c->stream));
+    if (components) HB_CUDA(cudaMemcpyAsync(c->d_snap_comp.p, c->d_comp.p, sizeof(int32_t) * c->M, cudaMemcpyDeviceToDevice, c->stream));
+    if (acum) HB_CUDA(cudaMemcpyAsync(c->d_snap_acum.p, c->d_acum.p, sizeof(double) * c->M, cudaMemcpyDeviceToDevice, c->stream));
+    HB_CUDA(cudaEventRecord(c->ev_snap, c->stream));
+    HB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_snap, 0));
+    if (beta) HB_CUDA(cudaMemcpyAsync(beta, c->d_snap_beta.p, sizeof(double) * c->M, cudaMemcpyDeviceToHost, c->copy_stream));
+    if (components) HB_CUDA(cudaMemcpyAsync(components, c->d_snap_comp.p, sizeof(int32_t) * c->M, cudaMemcpyDeviceToHost, c->copy_stream));
+    if (acum) HB_CUDA(cudaMemcpyAsync(acum, c->d_snap_acum.p, sizeof(double) * c->M, cudaMemcpyDeviceToHost, c->copy_stream));
+    HB_CUDA(cudaEventRecord(c->ev_copy, c->copy_stream));
+    c->copy_pending = true;
+    return HB_OK;
+}
+
+int hb_brr_state_wait(hb_ctx *c) {
+    HB_CHECK(c && c->brr_ready, HB_ERR_STATE, "hb_brr_state_wait: call hb_brr_init first");
+    if (!c->copy_pending) return HB_OK;
+    HB_CUDA(cudaSetDevice(c->dev));
+    HB_CUDA(cudaEventSynchronize(c->ev_copy));
+    c->copy_pending = false;
     return HB_OK;
 }
 

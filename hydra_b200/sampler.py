@@ -249,6 +249,21 @@ class BayesRRm:
         check(self._lib.hb_brr_get_state(s._h, ptr(beta), ptr(comp), ptr(acum)))
         return beta, comp, acum
 
+    def state_async(self, out):
+        """As state(out=...), but returns at once: the copies run on a second stream while the next iteration() computes. `out`
+        (page-locked arrays for a true DMA) must not be touched until state_wait() has returned."""
+        s = self.store
+        beta, comp, acum = out
+        assert beta.dtype == np.float64 and comp.dtype == np.int32 and acum.dtype == np.float64
+        assert beta.flags.c_contiguous and comp.flags.c_contiguous and acum.flags.c_contiguous and len(beta) == len(comp) == len(acum) == s.m_local
+        self._async_keep = out
+        check(self._lib.hb_brr_get_state_async(s._h, ptr(beta), ptr(comp), ptr(acum)))
+
+    def state_wait(self):
+        check(self._lib.hb_brr_state_wait(self.store._h))
+        out, self._async_keep = getattr(self, "_async_keep", None), None
+        return out
+
     def gamma(self):
         """Fixed effects and their current order (the reference's .gam / .xiv files)."""
         g, x = np.zeros(self.n_cov), np.zeros(self.n_cov, np.int32)

@@ -168,6 +168,11 @@ int hb_brr_get_hyper(hb_ctx *ctx, double *sigmaG, double *pi, double *sigmaE, do
                      double *bsq, int32_t *cass, int32_t *m0);
 /* Beta, components, Acum of the local markers (the slices written to .bet/.cpn/.acu, :2779-2785) */
 int hb_brr_get_state(hb_ctx *ctx, double *beta, int32_t *components, double *acum);
+/* The same for a writer that thins every iteration: returns at once, the copies (into the caller's buffers, page-locked for a
+ * true DMA) run on a second stream while the next hb_brr_iteration computes; the buffers are the library's until
+ * hb_brr_state_wait returns. */
+int hb_brr_get_state_async(hb_ctx *ctx, double *beta, int32_t *components, double *acum);
+int hb_brr_state_wait(hb_ctx *ctx);
 int hb_brr_set_state(hb_ctx *ctx, const double *beta, const int32_t *components); /* --restart */
 /* The reference's restart from its OUTPUT files (src/BayesRRm.cpp:842-928, data.cpp read_mcmc_output_*): what .csv, .xbet, .xcpn,
  * .mus.<task>, .eps.<task>, .mrk.<task> of the last save point hold is put back (arrays of the local markers / tasks, eps of local

@@ -399,3 +399,37 @@ def test_chain_replay_with_covariates(replay_hyper):
         brr2.load_state(blob)
         brr2.iteration()
         assert np.array_equal(brr2.gamma()[0], want[0]) and np.array_equal(brr2.state()[0], want[1])
+
+
+def test_async_state_readback_equals_synchronous():
+    """hb_brr_get_state_async / hb_brr_state_wait: the read-back of iteration i overlaps iteration i+1 and still returns the
+    state of iteration i."""
+    import hydra_b200
+    rng = np.random.default_rng(8)
+    N, M = 1500, 600
+    bed, g = random_bed(rng, M, N, pmiss=0.01)
+    y = simulate_y(rng, g, n_causal=30)
+    def run(asynchronous):
+        res = []
+        with hydra_b200.GenotypeStore(N, M, tasks=4, sync_rate=5, n_groups=1, n_mix=4, repr_mode="sparse") as st:
+            st.load_data_from_bed(bed)
+            st.finalize()
+            brr = hydra_b200.BayesRRm(st, y, [[0.001, 0.01, 0.1]], seed=5)
+            bufs = [(np.zeros(M), np.zeros(M, np.int32), np.zeros(M)) for _ in range(2)]
+            for it in range(4):
+                brr.iteration()
+                if asynchronous:
+                    done = brr.state_wait()
+                    if done is not None:
+                        res.append(tuple(a.copy() for a in done))
+                    brr.state_async(bufs[it & 1])
+                else:
+                    res.append(tuple(a.copy() for a in brr.state()))
+            if asynchronous:
+                res.append(tuple(a.copy() for a in brr.state_wait()))
+        return res
+    a, b = run(True), run(False)
+    assert len(a) == len(b) == 4
+    for it in range(4):
+        for x, yv in zip(a[it], b[it]):
+            assert np.array_equal(x, yv), it
