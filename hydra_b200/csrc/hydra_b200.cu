@@ -174,6 +174,7 @@ struct hb_ctx {
     std::vector<double> zmu_next;
     std::thread prefetch;
     bool have_next = false;
+    bool order_ready = false;   // the next iteration's window order (k_window_order) is already on the device
     double *pin = nullptr;      // pinned host scratch
     size_t pin_n = 0;
 
@@ -1040,6 +1041,7 @@ int hb_brr_init(hb_ctx *c, const double *y, const int32_t *groups, const double 
     HB_TRY(ensure_scratch(c, c->SR * c->T));
     HB_TRY(ensure_pin(c, std::max<size_t>(4 * (size_t)G * K, 8 + 4 * (size_t)c->S + G + (size_t)G * K + 32)));  // hyp tables (4*G*K) and the per-iteration read-back share it
     c->iteration = 0;
+    c->order_ready = false;
     c->brr_ready = true;
     c->F = 0; c->gamma.clear(); c->xI.clear();   // fixed effects are attached after the init (hb_brr_set_covariates)
     { const uint64_t sv = seed; HB_TRY(check_equal_over_ranks(c, &sv, 1, "the seed (give every process the same --seed)")); }
@@ -1060,6 +1062,7 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
     // next iteration's draws are produced on a worker thread while the GPU runs the marker loop.
     if (c->prefetch.joinable()) c->prefetch.join();
     std::vector<double> zmu(T, 0.0);
+    bool drew_ahead = false;   // this iteration uses the order that was drawn (and possibly laid out on the device) ahead
     if (!tape) {
         if (!c->have_next) {  // first iteration (or after a taped one): draw now
             for (uint32_t t = 0; t < T; t++) {
@@ -1073,6 +1076,7 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
         } else {
             zmu = c->zmu_next;
             c->perm.swap(c->perm_next);
+            drew_ahead = true;
         }
         c->have_next = false;
     }
@@ -1098,18 +1102,24 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
             }
         }
     }
-    HB_CUDA(cudaMemcpyAsync(c->d_perm.p, c->perm.data(), sizeof(int32_t) * M, cudaMemcpyHostToDevice, st));
     const uint32_t Q = c->lmax * T;
-    if (tape) {
-        HB_CUDA(cudaMemcpyAsync(c->d_ut.p, tape->u, sizeof(double) * M, cudaMemcpyHostToDevice, st));
-        HB_CUDA(cudaMemcpyAsync(c->d_zt.p, tape->z, sizeof(double) * M, cudaMemcpyHostToDevice, st));
+    // (the order of this iteration may already be on the device: launched at the end of the previous call, while the host drew
+    // the hyper-parameters)
+    const bool reuse_order = c->order_ready && !tape && drew_ahead;
+    c->order_ready = false;
+    if (!reuse_order) {
+        HB_CUDA(cudaMemcpyAsync(c->d_perm.p, c->perm.data(), sizeof(int32_t) * M, cudaMemcpyHostToDevice, st));
+        if (tape) {
+            HB_CUDA(cudaMemcpyAsync(c->d_ut.p, tape->u, sizeof(double) * M, cudaMemcpyHostToDevice, st));
+            HB_CUDA(cudaMemcpyAsync(c->d_zt.p, tape->z, sizeof(double) * M, cudaMemcpyHostToDevice, st));
+        }
+        k_window_order<<<c->lmax, std::min(256u, (T + 31u) & ~31u), 0, st>>>(c->d_perm.p, tape ? c->d_ut.p : nullptr, tape ? c->d_zt.p : nullptr,
+                                                         c->d_task_len.p, c->d_task_off.p, T, c->lmax, c->seed, c->iteration,
+                                                         c->t_first, c->d_order.p, c->d_u.p, c->d_z.p,
+                                                         c->d_rec.p, c->d_mave.p, c->d_mstd.p, c->d_beta.p, c->d_grp.p, c->d_rec_bytes.p,
+                                                         c->balance ? c->d_wts.p : nullptr, c->S, c->d_wmeta.p, c->d_dirw.p);
+        HB_CUDA(cudaGetLastError());
     }
-    k_window_order<<<c->lmax, std::min(256u, (T + 31u) & ~31u), 0, st>>>(c->d_perm.p, tape ? c->d_ut.p : nullptr, tape ? c->d_zt.p : nullptr,
-                                                     c->d_task_len.p, c->d_task_off.p, T, c->lmax, c->seed, c->iteration,
-                                                     c->t_first, c->d_order.p, c->d_u.p, c->d_z.p,
-                                                     c->d_rec.p, c->d_mave.p, c->d_mstd.p, c->d_beta.p, c->d_grp.p, c->d_rec_bytes.p,
-                                                     c->balance ? c->d_wts.p : nullptr, c->S, c->d_wmeta.p, c->d_dirw.p);
-    HB_CUDA(cudaGetLastError());
 
     // ---- hyper-parameter tables (:1721-1723, 1750, 1863-1876, 1901)
     const size_t gk = (size_t)G * K;
@@ -1172,7 +1182,20 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
     HB_CUDA(cudaMemcpyAsync(pin_cass, c->d_cass.p, sizeof(int32_t) * gk, cudaMemcpyDeviceToHost, st));
     HB_CUDA(cudaMemcpyAsync(pin_stats, c->d_stats.p, sizeof(unsigned long long) * 32, cudaMemcpyDeviceToHost, st));
     HB_CUDA(cudaEventRecord(c->ev[3], st));
-    HB_CUDA(cudaStreamSynchronize(st));
+    // The next iteration's order is known (worker thread above) and nothing it needs changes any more (effects, records): its
+    // window layout runs on the device now, while the host waits for the statistics and draws the hyper-parameters.
+    bool order_ahead = false;
+    if (!tape && c->have_next && !c->debug_cycles && !getenv("HB_NO_ORDER_AHEAD")) {
+        if (c->prefetch.joinable()) c->prefetch.join();
+        HB_CUDA(cudaMemcpyAsync(c->d_perm.p, c->perm_next.data(), sizeof(int32_t) * M, cudaMemcpyHostToDevice, st));
+        k_window_order<<<c->lmax, std::min(256u, (T + 31u) & ~31u), 0, st>>>(c->d_perm.p, nullptr, nullptr, c->d_task_len.p, c->d_task_off.p, T, c->lmax,
+                                                         c->seed, c->iteration + 1, c->t_first, c->d_order.p, c->d_u.p, c->d_z.p,
+                                                         c->d_rec.p, c->d_mave.p, c->d_mstd.p, c->d_beta.p, c->d_grp.p, c->d_rec_bytes.p,
+                                                         c->balance ? c->d_wts.p : nullptr, c->S, c->d_wmeta.p, c->d_dirw.p);
+        HB_CUDA(cudaGetLastError());
+        order_ahead = true;
+    }
+    HB_CUDA(cudaEventSynchronize(c->ev[3]));
 
     if (c->debug_cycles) {  // developer aid: spread of the per-CTA phase cycles
         fprintf(stderr, "[hb] fixed-point grid 2^-%d\n", c->last_sh);
@@ -1310,6 +1333,7 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
     if (tape && tape->sigmaE) c->sigmaE = tape->sigmaE[0];
     else c->sigmaE = c->hyper_rng.inv_scaled_chisq(v0E + dN, (e_sqn_g + v0E * s02E) / (v0E + dN));  // :2690
     c->iteration++;
+    c->order_ready = order_ahead;
 
     if (out) {
         memset(out, 0, sizeof(*out));
@@ -1387,6 +1411,7 @@ int hb_brr_state_wait(hb_ctx *c) {
 
 int hb_brr_set_state(hb_ctx *c, const double *beta, const int32_t *components) {
     HB_CHECK(c && c->brr_ready, HB_ERR_STATE, "hb_brr_set_state: call hb_brr_init first");
+    c->order_ready = false;   // the window layout carries the effects
     HB_CUDA(cudaSetDevice(c->dev));
     if (beta) HB_CUDA(cudaMemcpyAsync(c->d_beta.p, beta, sizeof(double) * c->M, cudaMemcpyHostToDevice, c->stream));
     if (components) HB_CUDA(cudaMemcpyAsync(c->d_comp.p, components, sizeof(int32_t) * c->M, cudaMemcpyHostToDevice, c->stream));
@@ -1407,6 +1432,7 @@ int hb_brr_restore_outputs(hb_ctx *c, uint32_t iterations_done, const double *si
     HB_CUDA(cudaSetDevice(c->dev));
     if (c->prefetch.joinable()) c->prefetch.join();
     c->have_next = false;
+    c->order_ready = false;
     c->iteration = iterations_done;
     for (uint32_t g = 0; g < c->G; g++) {
         c->sigmaG[g] = sigmaG[g];
@@ -1635,6 +1661,7 @@ int hb_brr_load_state(hb_ctx *c, const void *buf, size_t n) {
              head[2], head[3], head[4], head[5], head[6], head[7], head[8], c->N, c->M, c->T, c->G, c->K, c->S, c->L);
     const size_t nE = (size_t)c->S * c->L;
     c->seed = head[9]; c->iteration = head[10]; c->have_next = head[11] != 0;
+    c->order_ready = false;
     c->shift = r.one<double>(); c->sigmaE = r.one<double>(); c->seq_base = r.one<unsigned long long>();
     double bwv[4] = {0, 0, 0, 0};
     r.get(bwv, 4);
