@@ -139,6 +139,7 @@ struct BrrParams {
     double *num_out;       // MODE_DOT: [W]
     PeerComm pc;
     uint32_t flags;        // bit 0: no L2 prefetch of the next window (developer knob)
+    uint32_t n_ahead;      // steps of a window run ahead (>= sync_rate, <= kSpecMax; 0 = sync_rate)
     unsigned long long *cta_cycles;  // optional [gridDim*8] per-CTA phase cycles (HB_DEBUG_CYCLES=1)
 };
 
@@ -1056,6 +1057,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
     if (tid < 2 * kSpecMax) cnt_step[tid] = 0;
     const uint64_t padw = (uint64_t)L * 0x0001000100010001ull;
     const uint32_t SR = (P.SR == 0) ? 1u : P.SR;
+    // A window run ahead takes NA steps: sync_rate of them, or more where a step holds few markers (one task with sync rate 1:
+    // every marker is a step of its own, and a window of one marker pays the whole latency chain)
+    const uint32_t NA = (SR > kSpecMax) ? 1u : min(kSpecMax, max(SR, P.n_ahead));
 
     while (j0 < P.lmax) {
         // Windows run ahead. After `sync_rate` steps without a change the reference synchronises after every single step
@@ -1065,10 +1069,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
         // the later steps are discarded and repeated by the next window (effects, components and Acum are simply written
         // again; the component counts are taken from comp[] after the loop; the draws are counter-based). With several GPUs
         // the first changed step is taken over the lists of all GPUs (every GPU sees every list), before anything is applied.
-        const bool spec_win = (P.mode == MODE_CHAIN && SR > 1u && SR <= kSpecMax && since >= SR && !(P.flags & 2u));
+        const bool spec_win = (P.mode == MODE_CHAIN && NA > 1u && since >= SR && !(P.flags & 2u));
         const uint32_t Tdiv = (P.pc.nranks > 1) ? P.pc.T_total : P.T;   // list entries carry the global window position
         const uint32_t n = (P.mode != MODE_CHAIN) ? (P.lmax - j0)
-                                                  : ((since >= SR) ? (spec_win ? min(SR, P.lmax - j0) : 1u) : min(SR - since, P.lmax - j0));
+                                                  : ((since >= SR) ? (spec_win ? min(NA, P.lmax - j0) : 1u) : min(SR - since, P.lmax - j0));
         uint32_t s_star = 0xFFFFFFFFu;   // first step of a window run ahead that changed a marker
         const uint32_t W = n * P.T, base = j0 * P.T;
         const uint32_t dbuf = win & 1u;
@@ -1091,7 +1095,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                 // the next window's marker data start their way into the other table now (speculating that this window
                 // ends with a synchronisation: next window = SR steps); they land during the dot phase
                 const bool stage_next = (P.mode == MODE_CHAIN && k0 + kTabCap >= n_items && j0 + n < P.lmax);
-                if (stage_next) stage_items(&tabs[(win + 1u) & 1u], P, r, c, (j0 + n) * P.T, min(SR, P.lmax - (j0 + n)) * P.T, 0, tid, blockDim.x);
+                const uint32_t n_next = min(spec_win ? NA : SR, P.lmax - (j0 + n));   // the likely next window: no change -> the regime stays
+                if (stage_next) stage_items(&tabs[(win + 1u) & 1u], P, r, c, (j0 + n) * P.T, n_next * P.T, 0, tid, blockDim.x);
                 // ---- 2. dot: warp w takes the units w, w + 16, ... two at a time (their gathers and the two warp reductions
                 //         interleave: twice the independent work per warp), while the words of the next two units are in flight
                 //         (four register sets in rotation, no copies)
@@ -1181,7 +1186,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_brr_iteration(const BrrParams P
                     }
                 }
                 if (warp >= kDrawWarps && stage_next) {
-                    const uint32_t j1 = j0 + n, n1 = min(SR, P.lmax - j1);
+                    const uint32_t j1 = j0 + n, n1 = n_next;
                     finish_table(&tabs[(win + 1u) & 1u], udesc, P, r, c, j1 * P.T, n1 * P.T, 0, kDrawWarps * 32, blockDim.x - kDrawWarps * 32, !(P.flags & 1u));
                     HB_STAMP(10, tid == kDrawWarps * 32);
                 }

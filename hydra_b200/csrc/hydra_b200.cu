@@ -174,6 +174,7 @@ struct hb_ctx {
     std::vector<double> zmu_next;
     std::thread prefetch;
     bool have_next = false;
+    uint32_t n_ahead = 0;       // steps of a window run ahead
     bool order_ready = false;   // the next iteration's window order (k_window_order) is already on the device
     double *pin = nullptr;      // pinned host scratch
     size_t pin_n = 0;
@@ -264,7 +265,7 @@ static void fill_params(hb_ctx *c, BrrParams &P) {
     P.slice_max_out = c->d_small.p + 1 + 3 * c->S + c->G;
     P.beta = c->d_beta.p; P.comp = c->d_comp.p; P.acum = c->d_acum.p; P.cass = c->d_cass.p;
     P.order = c->d_order.p; P.u = c->d_u.p; P.z = c->d_z.p;
-    P.T = 1; P.SR = 1; P.lmax = 0; P.K = c->K; P.G = c->G;
+    P.T = 1; P.SR = 1; P.lmax = 0; P.K = c->K; P.G = c->G; P.n_ahead = 0;
     const size_t gk = (size_t)c->G * c->K;
     P.logPi = c->d_hyp.p; P.chalf = c->d_hyp.p + gk; P.denom = c->d_hyp.p + 2 * gk; P.sdk = c->d_hyp.p + 3 * gk;
     P.grp_active = c->d_active.p;
@@ -325,7 +326,7 @@ static int launch_window_kernel(hb_ctx *c, BrrParams &P) {
     HB_CUDA(cudaMemsetAsync(c->d_bar.p, 0, sizeof(uint32_t), c->stream));
     HB_CUDA(cudaMemsetAsync(c->d_chg_cnt.p, 0, 16 * sizeof(uint32_t), c->stream));
     // the slots carry window tags starting at 1: clear what this launch can touch
-    const size_t wuse = std::min<size_t>(c->Wmax, (P.mode == MODE_CHAIN) ? (size_t)std::max(1u, P.SR) * P.T : (size_t)P.lmax * P.T);
+    const size_t wuse = std::min<size_t>(c->Wmax, (P.mode == MODE_CHAIN) ? (size_t)std::max(std::max(1u, P.SR), P.n_ahead) * P.T : (size_t)P.lmax * P.T);
     HB_CUDA(cudaMemsetAsync(c->d_slots.p, 0, wuse * c->S * sizeof(uint4), c->stream));
     void *args[] = {(void *)&P};
     dim3 grid(c->S * c->R), block(kThreads);
@@ -1038,7 +1039,10 @@ int hb_brr_init(hb_ctx *c, const double *y, const int32_t *groups, const double 
         HB_CUDA(cudaMemcpy(c->d_wts.p, w.data(), sizeof(uint32_t) * c->M, cudaMemcpyHostToDevice));
     }
     HB_TRY(c->d_perm.ensure(c->M)); HB_TRY(c->d_ut.ensure(c->M)); HB_TRY(c->d_zt.ensure(c->M));
-    HB_TRY(ensure_scratch(c, c->SR * c->T));
+    // windows run ahead (brr_kernel.cuh): sync_rate steps, or enough steps for ~32 window positions where the tasks are few
+    c->n_ahead = std::min<uint32_t>(kSpecMax, std::max<uint32_t>(c->SR, (32u + c->T - 1) / c->T));
+    if (getenv("HB_N_AHEAD")) c->n_ahead = std::min<uint32_t>(kSpecMax, std::max<uint32_t>(c->SR, (uint32_t)atoi(getenv("HB_N_AHEAD"))));
+    HB_TRY(ensure_scratch(c, std::max(c->SR, c->n_ahead) * c->T));
     HB_TRY(ensure_pin(c, std::max<size_t>(4 * (size_t)G * K, 8 + 4 * (size_t)c->S + G + (size_t)G * K + 32)));  // hyp tables (4*G*K) and the per-iteration read-back share it
     c->iteration = 0;
     c->order_ready = false;
@@ -1144,7 +1148,7 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
     // ---- marker loop
     BrrParams P;
     fill_params(c, P);
-    P.mode = MODE_CHAIN; P.T = T; P.SR = c->SR; P.lmax = c->lmax;
+    P.mode = MODE_CHAIN; P.T = T; P.SR = c->SR; P.lmax = c->lmax; P.n_ahead = c->n_ahead;
     P.meta = c->d_wmeta.p; P.dirw = c->d_dirw.p;
     P.shift_in = c->shift;  // fold the accumulated constant into the stored residual
     P.i_2sigE = 1.0 / (2.0 * c->sigmaE);
