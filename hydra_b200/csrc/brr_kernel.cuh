@@ -140,6 +140,7 @@ struct BrrParams {
     PeerComm pc;
     uint32_t flags;        // bit 0: no L2 prefetch of the next window (developer knob)
     uint32_t n_ahead;      // steps of a window run ahead (>= sync_rate, <= kSpecMax; 0 = sync_rate)
+    const double *fh;      // bayesFHMPI: [3*M] per-marker denom, 0.5*log(..), sd of this iteration (k_fh_prepare), else NULL
     unsigned long long *cta_cycles;  // optional [gridDim*8] per-CTA phase cycles (HB_DEBUG_CYCLES=1)
 };
 
@@ -492,6 +493,9 @@ __device__ __forceinline__ void draw_marker_warp(const BrrParams &P, const ItemT
     // everything the draw needs from the table is read before the wait (the poll's memory clobber would hold the loads back)
     const WinMeta wm = tab->meta[k];
     const bool g_active = (P.mode == MODE_DOT) ? true : (P.grp_active[wm.grp] != 0);
+    // bayesFHMPI: the marker's own prior (src/BayesRRm.cpp:1730, 1748, 1871) replaces the per-(group, component) tables
+    double fh_den = 0.0, fh_ch = 0.0, fh_sd = 0.0;
+    if (P.fh) { const double *f = P.fh + 3 * (size_t)wm.m; fh_den = __ldg(f); fh_ch = __ldg(f + 1); fh_sd = __ldg(f + 2); }
     double acc = 0.0;
     for (uint32_t c0 = 0; c0 < P.S; c0 += 32) {
         const uint32_t cc = c0 + lane;
@@ -522,9 +526,9 @@ __device__ __forceinline__ void draw_marker_warp(const BrrParams &P, const ItemT
         const uint32_t kk = (lane < K) ? lane : 0;
         double muk = 0.0, logL = H.logPi[g * K + kk];
         if (kk > 0) {
-            muk = num / H.denom[g * K + kk];                                          // :1859
-            // log(pi) - 0.5*log(...) + muk*num*i_2sigE, evaluated left to right        (:1874-1876)
-            logL = __dadd_rn(__dadd_rn(logL, -H.chalf[g * K + kk]), __dmul_rn(__dmul_rn(muk, num), P.i_2sigE));
+            muk = num / (P.fh ? fh_den : H.denom[g * K + kk]);                        // :1859
+            // log(pi) - 0.5*log(...) + muk*num*i_2sigE, evaluated left to right        (:1874-1876; FH :1869-1872)
+            logL = __dadd_rn(__dadd_rn(logL, -(P.fh ? fh_ch : H.chalf[g * K + kk])), __dmul_rn(__dmul_rn(muk, num), P.i_2sigE));
         }
         const double prob = wm.u;                                                         // :1880
         if (K * K <= 32u) {
@@ -563,7 +567,7 @@ __device__ __forceinline__ void draw_marker_warp(const BrrParams &P, const ItemT
         }
         }
         const double muc = __shfl_sync(0xffffffffu, muk, comp);
-        if (comp > 0) beta_new = __dadd_rn(muc, __dmul_rn(H.sdk[g * K + comp], wm.z));  // :1901
+        if (comp > 0) beta_new = __dadd_rn(muc, __dmul_rn(P.fh ? fh_sd : H.sdk[g * K + comp], wm.z));  // :1901
     }                                                                                // else :1924-1925
     if (tp && lane == 0) { const long long t_ = clock64(); tp[1] += t_ - t0_; t0_ = t_; }
     HB_GS(2);

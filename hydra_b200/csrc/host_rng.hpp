@@ -43,6 +43,8 @@ struct HostRng {
     // src/distributions_boost.cpp:92-94, 112-114
     double inv_gamma(double shape, double scale) { return 1.0 / (gamma(shape) * (1.0 / scale)); }
     double inv_scaled_chisq(double dof, double scale) { return inv_gamma(0.5 * dof, 0.5 * dof * scale); }
+    // src/distributions_boost.cpp:97-103
+    double inv_gamma_rate(double shape, double rate) { return 1.0 / (gamma(shape) * (1.0 / rate)); }
     template <class T>
     void shuffle(T *a, int n) {  // Fisher-Yates
         for (int i = n - 1; i >= 1; i--) {

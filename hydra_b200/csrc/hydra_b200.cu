@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "convert.cuh"
 #include "cov_kernel.cuh"
+#include "fh_kernels.cuh"
 #include "host_rng.hpp"
 
 #include <nccl.h>
@@ -168,6 +169,14 @@ struct hb_ctx {
     DevBuf<uint32_t> d_covbar;
     std::vector<double> gamma;
     std::vector<int32_t> xI;
+    // per-group priors (--groupPriorsFile: v0G, s02G; --dPriorsFile: Dirichlet parameters); empty = the built-in constants
+    std::vector<double> grp_priors, dirichlet;
+    // bayesFHMPI (src/BayesRRm.cpp:1125-1163 ...): global scale tau and its hyper-parameter, slab variance per group, local scales
+    bool fh_on = false;
+    hb_fh_config fh_cfg{};
+    double fh_hypTau = 0.0, fh_tau = 0.0, fh_sbsqn = 0.0;
+    std::vector<double> fh_c;
+    DevBuf<double> d_fh_lambda, d_fh_nu, d_fh_par, d_fh_c, d_fh_part, d_fh_g;
     std::vector<int32_t> perm;  // M: task-local order per local task block
     std::vector<int32_t> perm_next;   // the next iteration's order, shuffled on a worker thread during the marker loop
     void *pinned_perm[2] = {nullptr, nullptr};  // both buffers are page-locked (cudaHostRegister): the per-iteration H2D copy is a DMA
@@ -265,7 +274,7 @@ static void fill_params(hb_ctx *c, BrrParams &P) {
     P.slice_max_out = c->d_small.p + 1 + 3 * c->S + c->G;
     P.beta = c->d_beta.p; P.comp = c->d_comp.p; P.acum = c->d_acum.p; P.cass = c->d_cass.p;
     P.order = c->d_order.p; P.u = c->d_u.p; P.z = c->d_z.p;
-    P.T = 1; P.SR = 1; P.lmax = 0; P.K = c->K; P.G = c->G; P.n_ahead = 0;
+    P.T = 1; P.SR = 1; P.lmax = 0; P.K = c->K; P.G = c->G; P.n_ahead = 0; P.fh = nullptr;
     const size_t gk = (size_t)c->G * c->K;
     P.logPi = c->d_hyp.p; P.chalf = c->d_hyp.p + gk; P.denom = c->d_hyp.p + 2 * gk; P.sdk = c->d_hyp.p + 3 * gk;
     P.grp_active = c->d_active.p;
@@ -356,6 +365,7 @@ extern "C" {
 int hb_abi_version(void) { return HB_ABI_VERSION; }
 int hb_sizeof_config(void) { return (int)sizeof(hb_config); }
 int hb_sizeof_iter_out(void) { return (int)sizeof(hb_brr_iter_out); }
+int hb_sizeof_brr_tape(void) { return (int)sizeof(hb_brr_tape); }
 const char *hb_last_error(void) { return g_err; }
 
 int hb_create(const hb_config *cfg, hb_ctx **out) {
@@ -1043,11 +1053,12 @@ int hb_brr_init(hb_ctx *c, const double *y, const int32_t *groups, const double 
     c->n_ahead = std::min<uint32_t>(kSpecMax, std::max<uint32_t>(c->SR, (32u + c->T - 1) / c->T));
     if (getenv("HB_N_AHEAD")) c->n_ahead = std::min<uint32_t>(kSpecMax, std::max<uint32_t>(c->SR, (uint32_t)atoi(getenv("HB_N_AHEAD"))));
     HB_TRY(ensure_scratch(c, std::max(c->SR, c->n_ahead) * c->T));
-    HB_TRY(ensure_pin(c, std::max<size_t>(4 * (size_t)G * K, 8 + 4 * (size_t)c->S + G + (size_t)G * K + 32)));  // hyp tables (4*G*K) and the per-iteration read-back share it
+    HB_TRY(ensure_pin(c, std::max<size_t>(4 * (size_t)G * K, 16 + 4 * (size_t)c->S + G + (size_t)G * K + 32)));  // hyp tables (4*G*K) and the per-iteration read-back share it
     c->iteration = 0;
     c->order_ready = false;
     c->brr_ready = true;
     c->F = 0; c->gamma.clear(); c->xI.clear();   // fixed effects are attached after the init (hb_brr_set_covariates)
+    c->fh_on = false; c->grp_priors.clear(); c->dirichlet.clear();   // so are the prior files and bayesFH (hb_brr_set_group_priors / hb_brr_set_fh)
     { const uint64_t sv = seed; HB_TRY(check_equal_over_ranks(c, &sv, 1, "the seed (give every process the same --seed)")); }
     return HB_OK;
 }
@@ -1058,7 +1069,8 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
     if (tape) HB_CHECK(tape->zmu && tape->perm && tape->u && tape->z, HB_ERR_ARG, "hb_brr_iteration: tape needs zmu, perm, u and z");
     const uint32_t N = c->N, K = c->K, G = c->G, T = c->T, M = c->M;
     const double dN = (double)N, dNm1 = (double)(N - 1);
-    const double v0E = 0.0001, s02E = 0.0001, v0G = 0.0001, s02G = 0.0001;  // src/BayesRRm.h:30-33
+    const double v0E = 0.0001, s02E = 0.0001;  // src/BayesRRm.h:30-33
+    double v0G = 0.0001, s02G = 0.0001;        // overwritten group by group where a priors file was given (:2545-2548)
     cudaStream_t st = c->stream;
     HB_CUDA(cudaEventRecord(c->ev[0], st));
 
@@ -1132,7 +1144,7 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
         const double sigE_G = c->sigmaE / c->sigmaG[g], sigG_E = c->sigmaG[g] / c->sigmaE;
         for (uint32_t k = 0; k < K; k++) {
             hyp[g * K + k] = log(c->pi[g * K + k]);
-            if (k == 0 || !c->active[g]) continue;
+            if (k == 0 || !c->active[g] || c->fh_on) continue;   // (FH: per-marker values from k_fh_prepare)
             hyp[gk + g * K + k] = 0.5 * log(sigG_E * dNm1 * c->cVa[g * K + k] + 1.0);
             const double den = dNm1 + sigE_G * c->cVaI[g * K + k];
             hyp[2 * gk + g * K + k] = den;
@@ -1145,10 +1157,31 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
     HB_CUDA(cudaMemsetAsync(c->d_cass.p, 0, sizeof(int32_t) * gk, st));  // :1697
     HB_CUDA(cudaMemsetAsync(c->d_stats.p, 0, sizeof(unsigned long long) * 32, st));
 
+    // ---- bayesFHMPI: nu_var and the marker's own prior variance (:1727-1731), for all markers at once
+    FhParams FQ{};
+    int fh_launches = 0;
+    if (c->fh_on) {
+        if (tape) HB_CHECK(tape->gnu && tape->glam, HB_ERR_ARG, "hb_brr_iteration: a tape for bayesFH needs gnu and glam");
+        FQ.M = M; FQ.m_start = c->m_start; FQ.seed = c->seed; FQ.iteration = c->iteration;
+        FQ.shape = 0.5 + 0.5 * c->fh_cfg.v0L; FQ.v0L = c->fh_cfg.v0L; FQ.tau = c->fh_tau; FQ.sigmaE = c->sigmaE; FQ.dNm1 = dNm1;
+        FQ.c_slab = c->d_fh_c.p; FQ.grp = c->d_grp.p; FQ.beta = c->d_beta.p;
+        FQ.lambda = c->d_fh_lambda.p; FQ.nu = c->d_fh_nu.p; FQ.par = c->d_fh_par.p; FQ.part = c->d_fh_part.p;
+        HB_CUDA(cudaMemcpyAsync(c->d_fh_c.p, c->fh_c.data(), sizeof(double) * G, cudaMemcpyHostToDevice, st));
+        if (tape) {
+            HB_CUDA(cudaMemcpyAsync(c->d_fh_g.p, tape->gnu, sizeof(double) * M, cudaMemcpyHostToDevice, st));
+            HB_CUDA(cudaMemcpyAsync(c->d_fh_g.p + M, tape->glam, sizeof(double) * M, cudaMemcpyHostToDevice, st));
+        }
+        FQ.g_tape = tape ? c->d_fh_g.p : nullptr;
+        k_fh_prepare<<<std::max(1u, std::min(4u * 148u, (M + 255u) / 256u)), 256, 0, st>>>(FQ);
+        HB_CUDA(cudaGetLastError());
+        fh_launches = 1;
+    }
+
     // ---- marker loop
     BrrParams P;
     fill_params(c, P);
     P.mode = MODE_CHAIN; P.T = T; P.SR = c->SR; P.lmax = c->lmax; P.n_ahead = c->n_ahead;
+    if (c->fh_on) P.fh = c->d_fh_par.p;
     P.meta = c->d_wmeta.p; P.dirw = c->d_dirw.p;
     P.shift_in = c->shift;  // fold the accumulated constant into the stored residual
     P.i_2sigE = 1.0 / (2.0 * c->sigmaE);
@@ -1182,6 +1215,15 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
     double *pin_small = c->pin;
     int32_t *pin_cass = reinterpret_cast<int32_t *>(c->pin + nsmall);
     unsigned long long *pin_stats = reinterpret_cast<unsigned long long *>(c->pin + nsmall + (gk + 1) / 2 + 1);
+    double *pin_fh = c->pin + nsmall + (gk + 1) / 2 + 1 + 32;
+    if (c->fh_on) {   // lambda_var from the final effects (:1952) and the scaled sum of squares (:2506-2509)
+        FQ.g_tape = tape ? c->d_fh_g.p + M : nullptr;
+        k_fh_finish<<<kSqChunks, 256, 0, st>>>(FQ);
+        k_beta_sqnorm_fin<<<1, 32, 0, st>>>(c->d_fh_part.p, kSqChunks, 1, c->d_fh_part.p + kSqChunks);
+        HB_CUDA(cudaGetLastError());
+        HB_CUDA(cudaMemcpyAsync(pin_fh, c->d_fh_part.p + kSqChunks, sizeof(double), cudaMemcpyDeviceToHost, st));
+        fh_launches += 2;
+    }
     HB_CUDA(cudaMemcpyAsync(pin_small, c->d_small.p, sizeof(double) * nsmall, cudaMemcpyDeviceToHost, st));
     HB_CUDA(cudaMemcpyAsync(pin_cass, c->d_cass.p, sizeof(int32_t) * gk, cudaMemcpyDeviceToHost, st));
     HB_CUDA(cudaMemcpyAsync(pin_stats, c->d_stats.p, sizeof(unsigned long long) * 32, cudaMemcpyDeviceToHost, st));
@@ -1249,6 +1291,7 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
     const double e_sqn = s2 + 2.0 * off * s1 + dN * off * off;
     for (uint32_t g = 0; g < G; g++) c->bsq[g] = pin_small[1 + 2 * c->S + g];
     for (size_t x = 0; x < gk; x++) c->cass[x] = pin_cass[x];
+    if (c->fh_on) c->fh_sbsqn = pin_fh[0];
     double e_sqn_g = e_sqn;
     double mu_g0 = c->mu[0];
     unsigned long long changed_all = pin_stats[5];
@@ -1285,15 +1328,30 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
             c->sigmaG[g] = 0.0;
             continue;
         }
+        if (!c->grp_priors.empty()) { v0G = c->grp_priors[2 * g]; s02G = c->grp_priors[2 * g + 1]; }   // :2545-2548
+        const double m0 = (double)c->m0[g];
+        if (c->fh_on) {   // :2557-2565 (hypTau and tau are drawn again in every group's pass, as the reference does)
+            if (tape && tape->fh_hyper) {
+                c->fh_hypTau = tape->fh_hyper[3 * g]; c->fh_tau = tape->fh_hyper[3 * g + 1]; c->fh_c[g] = tape->fh_hyper[3 * g + 2];
+            } else {
+                const hb_fh_config &f = c->fh_cfg;
+                c->fh_hypTau = c->hyper_rng.inv_gamma_rate(0.5 + 0.5 * f.v0t, 1.0 / (f.tau0 * f.tau0) + 1.0 / c->fh_tau);
+                c->fh_tau = c->hyper_rng.inv_gamma_rate(0.5 * (m0 + f.v0t), f.v0t / c->fh_hypTau + (0.5 * c->fh_sbsqn));
+                c->fh_c[g] = c->hyper_rng.inv_scaled_chisq(f.v0c + m0, (c->bsq[g] * m0 + f.v0c * f.s02c) / (f.v0c + m0));
+            }
+            c->sigmaG[g] = c->bsq[g];
+        }
         if (tape && tape->sigmaG && tape->pi) {
-            c->sigmaG[g] = tape->sigmaG[g];
+            if (!c->fh_on) c->sigmaG[g] = tape->sigmaG[g];
             for (uint32_t k = 0; k < K; k++) c->pi[g * K + k] = tape->pi[g * K + k];
         } else {
-            const double m0 = (double)c->m0[g];
-            c->sigmaG[g] = c->hyper_rng.inv_scaled_chisq(v0G + m0, (c->bsq[g] * m0 + v0G * s02G) / (v0G + m0));  // :2570
+            if (!c->fh_on) c->sigmaG[g] = c->hyper_rng.inv_scaled_chisq(v0G + m0, (c->bsq[g] * m0 + v0G * s02G) / (v0G + m0));  // :2570
             double s = 0.0;
-            for (uint32_t k = 0; k < K; k++) { c->pi[g * K + k] = c->hyper_rng.gamma((double)c->cass[g * K + k] + 1.0); s += c->pi[g * K + k]; }
-            for (uint32_t k = 0; k < K; k++) c->pi[g * K + k] /= s;  // dirichlet(cass+1), :2577
+            for (uint32_t k = 0; k < K; k++) {   // dirichlet(cass + dirc), dirc = 1 unless --dPriorsFile (:1184-1185, :2551-2554, :2576-2577)
+                const double dk = c->dirichlet.empty() ? 1.0 : c->dirichlet[g * K + k];
+                c->pi[g * K + k] = c->hyper_rng.gamma((double)c->cass[g * K + k] + dk); s += c->pi[g * K + k];
+            }
+            for (uint32_t k = 0; k < K; k++) c->pi[g * K + k] /= s;
         }
     }
     // ---- fixed effects (:2648-2681): gamma and epsilon, then the residual's statistics again
@@ -1346,7 +1404,7 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
         cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); out->loop_ms = ms;
         cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); out->iter_ms = ms;
         out->n_sync = pin_stats[0]; out->n_windows = pin_stats[1];
-        out->n_launches = 4 + (uint64_t)cov_launches;
+        out->n_launches = 4 + (uint64_t)cov_launches + (uint64_t)fh_launches;
         out->nnz_processed = pin_stats[2]; out->nnz_updated = pin_stats[3];
         out->bed_markers = pin_stats[4]; out->markers_changed = changed_all;
         for (int i = 0; i < 8; i++) out->phase_cycles[i] = pin_stats[8 + i];
@@ -1520,6 +1578,68 @@ int hb_brr_get_gamma(hb_ctx *c, double *gamma, int32_t *xI) {
     return HB_OK;
 }
 
+int hb_brr_set_group_priors(hb_ctx *c, const double *v0G_s02G, const double *dirichlet) {
+    HB_CHECK(c && c->brr_ready, HB_ERR_STATE, "hb_brr_set_group_priors: call hb_brr_init first");
+    HB_CHECK(c->cfg.model == 0, HB_ERR_ARG, "hb_brr_set_group_priors: BayesRRm / BayesFH only");
+    c->grp_priors.clear(); c->dirichlet.clear();
+    if (v0G_s02G) {
+        for (uint32_t g = 0; g < c->G; g++)
+            HB_CHECK(v0G_s02G[2 * g] > 0.0 && v0G_s02G[2 * g + 1] > 0.0, HB_ERR_ARG, "hb_brr_set_group_priors: v0G and s02G of group %u must be positive", g);
+        c->grp_priors.assign(v0G_s02G, v0G_s02G + 2 * (size_t)c->G);
+    }
+    if (dirichlet) {
+        for (size_t x = 0; x < (size_t)c->G * c->K; x++)
+            HB_CHECK(dirichlet[x] > 0.0, HB_ERR_ARG, "hb_brr_set_group_priors: Dirichlet parameter %zu must be positive", x);
+        c->dirichlet.assign(dirichlet, dirichlet + (size_t)c->G * c->K);
+    }
+    return HB_OK;
+}
+
+int hb_brr_set_fh(hb_ctx *c, const hb_fh_config *cfg, const double *state0) {
+    HB_CHECK(c && c->brr_ready, HB_ERR_STATE, "hb_brr_set_fh: call hb_brr_init first");
+    HB_CHECK(c->cfg.model == 0, HB_ERR_ARG, "hb_brr_set_fh: bayesFH is a variant of BayesRRm");
+    HB_CUDA(cudaSetDevice(c->dev));
+    if (!cfg) { c->fh_on = false; return HB_OK; }
+    // The reference neither reduces the scaled sum of squares over its ranks nor broadcasts tau / c_slab (src/BayesRRm.cpp:2503-2510,
+    // 2557-2565): with several ranks every rank follows its own FH parameters. One GPU (any number of tasks) only.
+    HB_CHECK(c->nranks == 1, HB_ERR_STATE, "hb_brr_set_fh: bayesFH runs on one GPU");
+    HB_CHECK(cfg->v0L > 0.0 && cfg->v0t > 0.0 && cfg->v0c > 0.0 && cfg->s02c > 0.0 && cfg->tau0 > 0.0, HB_ERR_ARG,
+             "hb_brr_set_fh: v0L, v0t, v0c, s02c and tau0 must be positive");
+    const uint32_t G = c->G, M = c->M;
+    c->fh_cfg = *cfg;
+    c->fh_c.assign(G, 0.0);
+    if (state0) {
+        c->fh_hypTau = state0[0]; c->fh_tau = state0[1];
+        for (uint32_t g = 0; g < G; g++) c->fh_c[g] = state0[2 + g];
+        HB_CHECK(c->fh_tau > 0.0, HB_ERR_ARG, "hb_brr_set_fh: tau must be positive");
+    } else {   // :1147-1154, from the hyper-parameter stream
+        c->fh_hypTau = c->hyper_rng.inv_gamma_rate(0.5, 1.0 / (cfg->tau0 * cfg->tau0));
+        c->fh_tau = c->hyper_rng.inv_gamma_rate(0.5 * cfg->v0t, cfg->v0t / c->fh_hypTau);
+        for (uint32_t g = 0; g < G; g++) c->fh_c[g] = c->hyper_rng.inv_scaled_chisq(cfg->v0c, cfg->s02c);
+    }
+    double cs = 0.0;
+    for (uint32_t g = 0; g < G; g++) cs += c->fh_c[g];
+    HB_TRY(c->d_fh_lambda.alloc(M)); HB_TRY(c->d_fh_nu.alloc(M)); HB_TRY(c->d_fh_par.alloc(3 * (size_t)M));
+    HB_TRY(c->d_fh_c.alloc(G)); HB_TRY(c->d_fh_part.alloc(kSqChunks + 1)); HB_TRY(c->d_fh_g.alloc(2 * (size_t)M));
+    std::vector<double> lam(M, cs / (double)c->Mtot);                                    // :1161
+    HB_CUDA(cudaMemcpy(c->d_fh_lambda.p, lam.data(), sizeof(double) * M, cudaMemcpyHostToDevice));
+    HB_CUDA(cudaMemset(c->d_fh_nu.p, 0, sizeof(double) * M));
+    c->fh_sbsqn = 0.0;
+    c->fh_on = true;
+    return HB_OK;
+}
+
+int hb_brr_get_fh(hb_ctx *c, double *scalars3, double *c_slab, double *lambda_var, double *nu_var) {
+    HB_CHECK(c && c->brr_ready && c->fh_on, HB_ERR_STATE, "hb_brr_get_fh: call hb_brr_set_fh first");
+    HB_CUDA(cudaSetDevice(c->dev));
+    if (scalars3) { scalars3[0] = c->fh_hypTau; scalars3[1] = c->fh_tau; scalars3[2] = c->fh_sbsqn; }
+    if (c_slab) std::copy(c->fh_c.begin(), c->fh_c.end(), c_slab);
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    if (lambda_var) HB_CUDA(cudaMemcpy(lambda_var, c->d_fh_lambda.p, sizeof(double) * c->M, cudaMemcpyDeviceToHost));
+    if (nu_var) HB_CUDA(cudaMemcpy(nu_var, c->d_fh_nu.p, sizeof(double) * c->M, cudaMemcpyDeviceToHost));
+    return HB_OK;
+}
+
 int hb_comm_get_unique_id(uint8_t id[HB_NCCL_ID_BYTES]) {
     HB_CHECK(id, HB_ERR_ARG, "null argument");
     static_assert(sizeof(ncclUniqueId) <= HB_NCCL_ID_BYTES, "ncclUniqueId larger than HB_NCCL_ID_BYTES");
@@ -1537,6 +1657,7 @@ int hb_comm_init(hb_ctx *c, const uint8_t id[HB_NCCL_ID_BYTES], int rank, int nr
     HB_CHECK(c && id, HB_ERR_ARG, "null argument");
     HB_CHECK(nranks >= 1 && nranks <= (int)kMaxRanks && rank >= 0 && rank < nranks, HB_ERR_ARG, "hb_comm_init: rank %d of %d (max %u GPUs)", rank, nranks, kMaxRanks);
     HB_CHECK(!c->nccl, HB_ERR_STATE, "hb_comm_init: already initialised");
+    HB_CHECK(!(c->fh_on && nranks > 1), HB_ERR_STATE, "hb_comm_init: bayesFH runs on one GPU");
     HB_CUDA(cudaSetDevice(c->dev));
     if (nranks == 1) return HB_OK;
     ncclUniqueId u;
@@ -1645,6 +1766,16 @@ int hb_brr_save_state(hb_ctx *c, void *buf, size_t cap, size_t *need) {
     HB_CUDA(cudaMemcpy(hd.data(), c->d_acum.p, sizeof(double) * c->M, cudaMemcpyDeviceToHost)); w.put(hd.data(), c->M);
     HB_CUDA(cudaMemcpy(hi.data(), c->d_comp.p, sizeof(int32_t) * c->M, cudaMemcpyDeviceToHost)); w.put(hi.data(), c->M);
     { const uint32_t F = c->F; w.one(F); w.put(c->gamma.data(), F); w.put(c->xI.data(), F); }   // fixed effects (.gam / .xiv of the reference)
+    {   // bayesFH: global / slab scales and the local scales
+        const uint32_t fh = c->fh_on ? 1u : 0u;
+        w.one(fh);
+        if (fh) {
+            const double sc[3] = {c->fh_hypTau, c->fh_tau, c->fh_sbsqn};
+            w.put(sc, 3); w.put(c->fh_c.data(), c->G);
+            HB_CUDA(cudaMemcpy(hd.data(), c->d_fh_lambda.p, sizeof(double) * c->M, cudaMemcpyDeviceToHost)); w.put(hd.data(), c->M);
+            HB_CUDA(cudaMemcpy(hd.data(), c->d_fh_nu.p, sizeof(double) * c->M, cudaMemcpyDeviceToHost)); w.put(hd.data(), c->M);
+        }
+    }
     *need = w.b.size();
     if (!buf) return HB_OK;
     HB_CHECK(cap >= w.b.size(), HB_ERR_ARG, "hb_brr_save_state: buffer of %zu bytes, %zu needed", cap, w.b.size());
@@ -1699,6 +1830,20 @@ int hb_brr_load_state(hb_ctx *c, const void *buf, size_t n) {
         r.get(c->gamma.data(), F); r.get(c->xI.data(), F);
         HB_CHECK(r.ok, HB_ERR_ARG, "hb_brr_load_state: truncated state");
         if (F && !c->bw_ready) HB_CUDA(cudaMemcpy(c->d_gamma.p, c->gamma.data(), sizeof(double) * F, cudaMemcpyHostToDevice));   // (BayesW keeps gamma on the host)
+    }
+    {
+        const uint32_t fh = r.one<uint32_t>();
+        HB_CHECK(r.ok && (fh != 0) == c->fh_on, HB_ERR_ARG, "hb_brr_load_state: the state %s a bayesFH chain, this chain %s (call hb_brr_set_fh first)",
+                 fh ? "is" : "is not", c->fh_on ? "is" : "is not");
+        if (fh) {
+            double sc[3] = {0, 0, 0};
+            r.get(sc, 3); r.get(c->fh_c.data(), c->G);
+            c->fh_hypTau = sc[0]; c->fh_tau = sc[1]; c->fh_sbsqn = sc[2];
+            r.get(hd.data(), c->M); HB_CHECK(r.ok, HB_ERR_ARG, "hb_brr_load_state: truncated state");
+            HB_CUDA(cudaMemcpy(c->d_fh_lambda.p, hd.data(), sizeof(double) * c->M, cudaMemcpyHostToDevice));
+            r.get(hd.data(), c->M); HB_CHECK(r.ok, HB_ERR_ARG, "hb_brr_load_state: truncated state");
+            HB_CUDA(cudaMemcpy(c->d_fh_nu.p, hd.data(), sizeof(double) * c->M, cudaMemcpyHostToDevice));
+        }
     }
     c->eps_set = true;
     return HB_OK;

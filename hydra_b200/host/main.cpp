@@ -15,6 +15,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <iterator>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -29,7 +30,8 @@ namespace {
 
 struct Options {  // names follow the reference's Options class (src/options.hpp:20-138)
     std::string bayesType, bedFile, phenotypeFile, failureFile, quad_points, groupIndexFile, groupMixtureFile, mcmcOutDir, mcmcOutNam, sparseDir, sparseBsn,
-        markerBlocksFile, covariatesFile;
+        markerBlocksFile, covariatesFile, priorsFile, dPriorsFile;
+    double tau0 = 1.0, s02c = 1.0, v0c = 3, v0L = 3, v0t = 3;   // bayesFHMPI, src/options.hpp:91-96
     bool bedToSparse = false, dryRun = false, readFromBedFile = false, readFromSparseFiles = false, restart = false;
     uint32_t numberMarkers = 0, numberIndividuals = 0, chainLength = 10000, burnin = 5000, thin = 5, save = 10, syncRate = 1,
              shuffleMarkers = 1, tasks = 1, device = 0, blocksPerRank = 1, rank = 0, world = 1;
@@ -61,6 +63,24 @@ std::vector<std::string> split(const std::string &s, const char *seps) {
         if (j == std::string::npos) j = s.size();
         if (j > i) out.push_back(s.substr(i, j - i));
         i = j + 1;
+    }
+    return out;
+}
+
+// The two prior files (src/data.cpp:2034-2061 read_group_priors, :2069-2096 read_dirichlet_priors): groups separated by ';',
+// values by ','; one row per group. --groupPriorsFile: v0G, s02G; --dPriorsFile: one Dirichlet parameter per mixture component.
+std::vector<double> read_prior_matrix(const std::string &file, uint32_t rows, uint32_t cols, const char *what) {
+    std::ifstream in(file);
+    if (!in) throw std::runtime_error(std::string("Error: can not open the ") + what + " file [" + file + "] to read.");
+    const std::string text{std::istreambuf_iterator<char>(in), std::istreambuf_iterator<char>()};
+    std::vector<std::string> grp;
+    for (const std::string &g : split(text, ";")) if (g.find_first_not_of(" \t\r\n") != std::string::npos) grp.push_back(g);
+    if (grp.size() != rows) throw std::runtime_error(std::string(what) + " [" + file + "]: " + std::to_string(grp.size()) + " groups, the run has " + std::to_string(rows));
+    std::vector<double> out;
+    for (uint32_t g = 0; g < rows; g++) {
+        const std::vector<std::string> v = split(grp[g], ", \t\r\n");
+        if (v.size() < cols) throw std::runtime_error(std::string(what) + " [" + file + "]: group " + std::to_string(g) + " has " + std::to_string(v.size()) + " values, " + std::to_string(cols) + " needed");
+        for (uint32_t k = 0; k < cols; k++) out.push_back(std::stod(v[k]));
     }
     return out;
 }
@@ -114,7 +134,14 @@ Options parse(int argc, const char **argv) {
         // no-ops; --ignore-xfiles concerns the reference's restart files, which this host does not read (state file instead).
         else if (a == "--sparse-sync" || a == "--bed-sync" || a == "--ignore-xfiles") o.ignored.push_back(a);
         else if (a == "--covariates") o.covariatesFile = need(i);   // src/options.cpp:286-290
-        else if (a == "--check-RAM" || a == "--groupPriorsFile" || a == "--dPriorsFile")
+        else if (a == "--groupPriorsFile") o.priorsFile = need(i);   // src/options.cpp:278-285
+        else if (a == "--dPriorsFile") o.dPriorsFile = need(i);
+        else if (a == "--tau0") o.tau0 = atof(need(i));               // src/options.cpp:116-135
+        else if (a == "--v0c") o.v0c = atof(need(i));
+        else if (a == "--s02c") o.s02c = atof(need(i));
+        else if (a == "--v0L") o.v0L = atof(need(i));
+        else if (a == "--v0t") o.v0t = atof(need(i));
+        else if (a == "--check-RAM")
             throw std::runtime_error("option \"" + a + "\" of hydra is not supported by hydra_b200 yet (see DESIGN.md, out of scope)");
         else
             throw std::runtime_error("\nError: invalid option \"" + a + "\".\n");  // src/options.cpp:292-296
@@ -530,8 +557,12 @@ int main(int argc, const char **argv) {
             printf("INFO   : dry run: options and input files parsed, nothing computed\n");
             return 0;
         }
-        if (!opt.bedToSparse && opt.bayesType != "bayesMPI" && !bayesW)
-            throw std::runtime_error("--mpibayes " + opt.bayesType + ": bayesMPI (BayesRRm) and bayesWMPI (BayesW) are available in this build");
+        const bool bayesFH = (opt.bayesType == "bayesFHMPI");
+        if (!opt.bedToSparse && opt.bayesType != "bayesMPI" && !bayesW && !bayesFH)
+            throw std::runtime_error("--mpibayes " + opt.bayesType + ": bayesMPI (BayesRRm), bayesFHMPI (BayesFH) and bayesWMPI (BayesW) are available in this build");
+        if (bayesFH && opt.world > 1) throw std::runtime_error("--mpibayes bayesFHMPI runs on one GPU (any number of --tasks)");
+        if (bayesW && (!opt.priorsFile.empty() || !opt.dPriorsFile.empty()))
+            throw std::runtime_error("--groupPriorsFile / --dPriorsFile are read by bayesMPI and bayesFHMPI (src/BayesRRm.cpp:2545-2554), not by bayesWMPI");
         if (bayesW && repr == HB_REPR_MIXED) throw std::runtime_error("bayesWMPI reads bed or sparse input, not both (src/BayesW.cpp:1149-1192)");
 
         // ---- device context
@@ -744,6 +775,19 @@ int main(int argc, const char **argv) {
         }
         HB(hb_brr_init(ctx, y.data(), groups.empty() ? nullptr : groups.data(), mSflat.data(), nullptr, seed));  // multi-GPU: also checks that the seed is common
         if (n_cov) HB(hb_brr_set_covariates(ctx, Xcov.data(), n_cov));   // src/BayesRRm.cpp:1546-1560, 2648-2681
+        if (!opt.priorsFile.empty() || !opt.dPriorsFile.empty()) {          // src/main.cpp:151-157
+            std::vector<double> gp, dp;
+            if (!opt.priorsFile.empty()) gp = read_prior_matrix(opt.priorsFile, G, 2, "--groupPriorsFile");
+            if (!opt.dPriorsFile.empty()) dp = read_prior_matrix(opt.dPriorsFile, G, K, "--dPriorsFile");
+            HB(hb_brr_set_group_priors(ctx, gp.empty() ? nullptr : gp.data(), dp.empty() ? nullptr : dp.data()));
+        }
+        if (bayesFH) {                                                       // src/BayesRRm.cpp:1125-1163
+            hb_fh_config fc{opt.v0L, opt.v0t, opt.v0c, opt.s02c, opt.tau0};
+            HB(hb_brr_set_fh(ctx, &fc, nullptr));
+            double sc[3];
+            HB(hb_brr_get_fh(ctx, sc, nullptr, nullptr, nullptr));
+            if (root) printf("INFO   : bayesFH: tau0 %g v0t %g v0c %g s02c %g v0L %g; initial hypTau %.6g tau %.6g\n", opt.tau0, opt.v0t, opt.v0c, opt.s02c, opt.v0L, sc[0], sc[1]);
+        }
         if (!root || opt.restart) {
             bet.open_rw(out + ".bet", false); acu.open_rw(out + ".acu", false); cpn.open_rw(out + ".cpn", false);
             xb.open_rw(out + ".xbet", false); xc.open_rw(out + ".xcpn", false);

@@ -173,10 +173,16 @@ class GenotypeStore:
         check(self._lib.hb_scaadd_markers(self._h, ptr(m), ptr(d), C.c_uint32(len(m))))
 
 
+FH_DEFAULTS = dict(v0L=3.0, v0t=3.0, v0c=3.0, s02c=1.0, tau0=1.0)   # src/options.hpp:91-96
+
+
 class BayesRRm:
     """The BayesRRm chain on one GPU (src/BayesRRm.cpp:933-2939, marker loop :1709-2490)."""
 
-    def __init__(self, store: GenotypeStore, y, mS, groups=None, sigmaG0=None, seed=0, covariates=None):
+    def __init__(self, store: GenotypeStore, y, mS, groups=None, sigmaG0=None, seed=0, covariates=None, group_priors=None,
+                 dirichlet_priors=None, fh=None):
+        """`group_priors` (n_groups, 2) = hydra's --groupPriorsFile, `dirichlet_priors` (n_groups, n_mix) = --dPriorsFile;
+        `fh` = dict(v0L, v0t, v0c, s02c, tau0[, state0]) (missing keys: src/options.hpp:91-96) runs --bayesType bayesFHMPI."""
         self.store = store
         self._lib = store._lib
         G, K = store.n_groups, store.n_mix
@@ -197,16 +203,34 @@ class BayesRRm:
             assert X.ndim == 2 and X.shape[0] == store.n_ind, X.shape
             check(self._lib.hb_brr_set_covariates(store._h, ptr(X), C.c_uint32(X.shape[1])))
             self.n_cov = X.shape[1]
+        if group_priors is not None or dirichlet_priors is not None:
+            gp = None if group_priors is None else arr(np.asarray(group_priors, np.float64).reshape(G, 2), np.float64)
+            dp = None if dirichlet_priors is None else arr(np.asarray(dirichlet_priors, np.float64).reshape(G, K), np.float64)
+            check(self._lib.hb_brr_set_group_priors(store._h, ptr(gp), ptr(dp)))
+        self.fh = None
+        if fh is not None:
+            self.fh = dict(FH_DEFAULTS, **{k: float(fh[k]) for k in FH_DEFAULTS if k in fh})
+            cfg = capi.HbFhConfig(**self.fh)
+            s0 = None if fh.get("state0") is None else arr(np.asarray(fh["state0"], np.float64).reshape(2 + G), np.float64)
+            check(self._lib.hb_brr_set_fh(store._h, C.byref(cfg), ptr(s0)))
+
+    def fh_state(self):
+        """bayesFH: dict(hypTau, tau, scaledBSQN, c_slab, lambda_var, nu_var) after the last iteration."""
+        s = self.store
+        sc, cs, lam, nu = np.zeros(3), np.zeros(s.n_groups), np.zeros(s.m_local), np.zeros(s.m_local)
+        check(self._lib.hb_brr_get_fh(s._h, ptr(sc), ptr(cs), ptr(lam), ptr(nu)))
+        return dict(hypTau=sc[0], tau=sc[1], scaledBSQN=sc[2], c_slab=cs, lambda_var=lam, nu_var=nu)
 
     def iteration(self, tape=None):
-        """One Gibbs iteration. tape = dict(zmu, perm, u, z[, sigmaG, pi, sigmaE]) for deterministic replay."""
+        """One Gibbs iteration. tape = dict(zmu, perm, u, z[, sigmaG, pi, sigmaE][, gnu, glam, fh_hyper]) for deterministic replay."""
         out = capi.HbBrrIterOut()
         keep = []
         tp = None
         if tape is not None:
             t = capi.HbBrrTape()
             for name, dt in (("zmu", np.float64), ("perm", np.int32), ("u", np.float64), ("z", np.float64),
-                             ("sigmaG", np.float64), ("pi", np.float64), ("sigmaE", np.float64), ("xI", np.int32), ("zcov", np.float64)):
+                             ("sigmaG", np.float64), ("pi", np.float64), ("sigmaE", np.float64), ("xI", np.int32), ("zcov", np.float64),
+                             ("gnu", np.float64), ("glam", np.float64), ("fh_hyper", np.float64)):
                 v = tape.get(name)
                 if v is not None:
                     a = arr(np.atleast_1d(v), dt)

@@ -35,7 +35,7 @@ extern "C" {
 #define HB_ERR_NCCL -4
 #define HB_ERR_NOMEM -5
 
-#define HB_ABI_VERSION 1
+#define HB_ABI_VERSION 2
 
 typedef struct hb_ctx hb_ctx;
 
@@ -72,6 +72,7 @@ typedef struct hb_config {
 int hb_abi_version(void);
 int hb_sizeof_config(void);   /* sizeof(hb_config): lets a foreign-language binding check its struct layout */
 int hb_sizeof_iter_out(void); /* sizeof(hb_brr_iter_out) */
+int hb_sizeof_brr_tape(void);
 const char *hb_last_error(void);
 int hb_create(const hb_config *cfg, hb_ctx **out);
 void hb_destroy(hb_ctx *ctx);
@@ -140,6 +141,10 @@ typedef struct hb_brr_tape {
     const double *sigmaE; /* 1 value (:2690), NULL = draw */
     const int32_t *xI;    /* n_covariates: order of the fixed effects in this iteration (std::shuffle(xI), :2653), NULL = draw */
     const double *zcov;   /* n_covariates standard normals for gamma (:2671), NULL = draw */
+    /* bayesFH (hb_brr_set_fh); all three ignored otherwise */
+    const double *gnu;    /* m_local standard Gamma(0.5 + 0.5*v0L, 1) variates behind the nu_var draws (:1729), by local marker */
+    const double *glam;   /* m_local, the lambda_var draws (:1952) */
+    const double *fh_hyper; /* n_groups*3: hypTau, tau, c_slab[g] as drawn in group g's pass (:2559-2562), NULL = draw */
 } hb_brr_tape;
 
 typedef struct hb_brr_iter_out {
@@ -201,6 +206,27 @@ int hb_brr_get_task_perm(hb_ctx *ctx, uint32_t task_local, int32_t *perm);
 int hb_brr_set_covariates(hb_ctx *ctx, const double *X, uint32_t n_cov);
 /* gamma[n_cov] and the current order xI[n_cov] (either may be NULL); the .gam / .xiv files of :2811-2831 */
 int hb_brr_get_gamma(hb_ctx *ctx, double *gamma, int32_t *xI);
+
+/* Per-group priors, hydra's --groupPriorsFile (v0G, s02G of the sigmaG draw per group, src/BayesRRm.cpp:2545-2548, reader
+ * src/data.cpp:2034-2061) and --dPriorsFile (Dirichlet parameters of the pi draw per group, :2551-2554, 2576-2577, reader
+ * src/data.cpp:2069-2096): v0G_s02G is n_groups x 2, dirichlet n_groups x n_mix, row-major; NULL = the built-in constants
+ * (0.0001, 0.0001 and 1.0). Call after hb_brr_init. */
+int hb_brr_set_group_priors(hb_ctx *ctx, const double *v0G_s02G, const double *dirichlet);
+
+/* bayesFHMPI (hydra --bayesType bayesFHMPI; src/BayesRRm.cpp:1125-1163 initialisation, :1727-1731 nu_var and the marker's own
+ * prior variance, :1747-1748 / :1869-1872 its use in the mixture draw, :1942-1952 lambda_var, :2503-2510 scaled sum of squares,
+ * :2557-2565 hypTau / tau / c_slab; defaults src/options.hpp:91-96). Call after hb_brr_init (cfg == NULL switches it off);
+ * state0 = { hypTau, tau, c_slab[n_groups] } or NULL = drawn from the hyper-parameter stream in the reference's order. The two
+ * per-marker draws leave the marker loop (they depend on the marker's own previous state only): one kernel before it, one after.
+ * One GPU: the reference neither reduces the scaled sum of squares nor broadcasts tau / c_slab, its ranks' parameters diverge
+ * (flagged, not reproduced; with several tasks on one GPU the sum runs over all markers, as in a one-rank run). */
+typedef struct hb_fh_config {
+    double v0L, v0t, v0c, s02c, tau0;
+} hb_fh_config;
+int hb_brr_set_fh(hb_ctx *ctx, const hb_fh_config *cfg, const double *state0);
+/* scalars3 = { hypTau, tau, scaledBSQN of the last iteration }, c_slab[n_groups], lambda_var / nu_var of the local markers
+ * (any may be NULL) */
+int hb_brr_get_fh(hb_ctx *ctx, double *scalars3, double *c_slab, double *lambda_var, double *nu_var);
 
 /* ---- BayesW chain (Weibull survival; src/BayesW.cpp:905-1907), single GPU in this version ------------- */
 /* hb_config.model = 1. y: N log-times, fail: N failure indicators (0/1; src/data.cpp:1779), mS as for BayesRRm,

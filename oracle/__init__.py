@@ -271,14 +271,32 @@ class _BrrArgs(C.Structure):
         + [(n, C.c_void_p) for n in ("out_beta", "out_comp", "out_acum", "out_mu", "out_eps", "out_sigmaG", "out_sigmaE",
                                      "out_pi", "out_bsq", "out_cass", "out_esqn", "out_epssum", "out_nsync", "out_loop_seconds")]
         + [("X", C.c_void_p), ("F", C.c_int32), ("tape_xI", C.c_void_p), ("tape_zcov", C.c_void_p), ("out_gamma", C.c_void_p)]
+        + [("group_priors", C.c_void_p), ("dirichlet", C.c_void_p), ("fh", C.c_int32)]
+        + [(n, C.c_double) for n in ("fh_v0L", "fh_v0t", "fh_v0c", "fh_s02c", "fh_tau0")]
+        + [(n, C.c_void_p) for n in ("fh_state0", "tape_gnu", "tape_glam", "tape_fh_hyper")]
+        + [("fh_seed", C.c_uint32)]
+        + [(n, C.c_void_p) for n in ("out_fh", "out_lambda", "out_nu")]
     )
 
 
+FH_DEFAULTS = dict(v0L=3.0, v0t=3.0, v0c=3.0, s02c=1.0, tau0=1.0)   # src/options.hpp:91-96
+
+
+def fh_gamma(seed, marker, iteration, which, a):
+    """Standard Gamma(a, 1) variate behind the nu_var (which=0) / lambda_var (which=1) draw of a marker (RNG spec v1)."""
+    f = lib().ho_fh_gamma
+    f.restype = C.c_double
+    return f(C.c_uint32(seed), C.c_uint32(marker), C.c_uint32(iteration), C.c_int(which), C.c_double(a))
+
+
 def brr_chain(N, Mtot, T, K, G, sync_rate, n_iter, sp: SparseLists, y_raw, groups, mS, tape, sigmaG0,
-              usebed=None, bed=None, hyper=None, hyper_seed=0, want_eps=True, fast=False, want_marker_out=True, covariates=None):
+              usebed=None, bed=None, hyper=None, hyper_seed=0, want_eps=True, fast=False, want_marker_out=True, covariates=None,
+              fh=None, group_priors=None, dirichlet=None):
     """Run the BayesRRm oracle chain. `tape` = dict(zmu, perm, u, z); `hyper` =
     dict(sigmaG, sigmaE, pi) to replay hyper-parameter VALUES, or None to draw
-    them with mt19937(hyper_seed) (RNG spec v1).  Returns dict of per-iteration outputs."""
+    them with mt19937(hyper_seed) (RNG spec v1).  Returns dict of per-iteration outputs.
+    `fh` = dict(v0L, v0t, v0c, s02c, tau0[, state0 (2+G), seed]) switches bayesFHMPI on; the tape may then carry gnu / glam
+    (n_iter, Mtot) and fh_hyper (n_iter, G, 3). `group_priors` (G, 2) and `dirichlet` (G, K) are the two prior files."""
     keep = []
 
     def k(a, dt):
@@ -320,6 +338,18 @@ def brr_chain(N, Mtot, T, K, G, sync_rate, n_iter, sp: SparseLists, y_raw, group
         a.tape_xI, a.tape_zcov = k(tape.get("xI"), np.int32), k(tape.get("zcov"), np.float64)
         out["gamma"] = np.zeros((n_iter, Xc.shape[1]))
         a.out_gamma = out["gamma"].ctypes.data
+    a.group_priors, a.dirichlet = k(group_priors, np.float64), k(dirichlet, np.float64)
+    if fh is not None:
+        p = dict(FH_DEFAULTS, **{q: fh[q] for q in FH_DEFAULTS if q in fh})
+        a.fh = 1
+        a.fh_v0L, a.fh_v0t, a.fh_v0c, a.fh_s02c, a.fh_tau0 = p["v0L"], p["v0t"], p["v0c"], p["s02c"], p["tau0"]
+        a.fh_state0 = k(fh.get("state0"), np.float64)
+        a.fh_seed = int(fh.get("seed", 0)) & 0xFFFFFFFF
+        a.tape_gnu, a.tape_glam, a.tape_fh_hyper = k(tape.get("gnu"), np.float64), k(tape.get("glam"), np.float64), k(tape.get("fh_hyper"), np.float64)
+        out["fh"] = np.zeros((n_iter, 3 + G))
+        out["lambda"] = np.zeros((n_iter, Mtot))
+        out["nu"] = np.zeros((n_iter, Mtot))
+        a.out_fh, a.out_lambda, a.out_nu = out["fh"].ctypes.data, out["lambda"].ctypes.data, out["nu"].ctypes.data
     for name in ("beta", "comp", "acum", "mu", "eps", "sigmaG", "sigmaE", "pi", "bsq", "cass", "esqn", "epssum", "nsync", "loop_seconds"):
         v = out[name]
         setattr(a, "out_" + name, None if v is None else v.ctypes.data)

@@ -438,6 +438,40 @@ HO_API void ho_marker_draws(uint32_t seed, uint32_t task, uint32_t iteration, ui
     *z = sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925 * u2);
 }
 
+/* BayesFH per-marker standard Gamma(a, 1) variates of spec v1 (the reference draws them from the rank's Boost stream inside
+ * inv_gamma_rate_rng, src/BayesRRm.cpp:1729 and :1952; src/distributions_boost.cpp:57-61, 97-103): Marsaglia-Tsang, one Philox
+ * block per attempt, keyed by (seed, global marker), counter (attempt, iteration, tag); `which` 0 = nu_var, 1 = lambda_var. */
+#define HO_TAG_FHNU 0x46484E55u /* 'FHNU' */
+#define HO_TAG_FHLA 0x46484C41u /* 'FHLA' */
+HO_API double ho_fh_gamma(uint32_t seed, uint32_t marker, uint32_t iteration, int which, double a) {
+    const uint32_t tag = which ? HO_TAG_FHLA : HO_TAG_FHNU;
+    const double a1 = (a < 1.0) ? a + 1.0 : a;
+    const double d = a1 - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    double g = d;
+    for (uint32_t attempt = 0; attempt < 4096u; attempt++) {
+        uint32_t ctr[4] = {attempt, iteration, tag, 0}, key[2] = {seed, marker}, w[4];
+        ho_philox4x32(ctr, key, w);
+        const double u1 = ((double)w[0] + 0.5) * (1.0 / 4294967296.0);
+        const double u2 = ((double)w[1] + 0.5) * (1.0 / 4294967296.0);
+        const double x = sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925 * u2);
+        double v = 1.0 + c * x;
+        if (v <= 0.0) continue;
+        v = v * v * v;
+        const double u = 1.0 - ((double)(w[2] >> 5) * 67108864.0 + (double)(w[3] >> 6)) * (1.0 / 9007199254740992.0);
+        g = d * v;
+        if (u < 1.0 - 0.0331 * (x * x) * (x * x)) break;
+        if (log(u) < 0.5 * x * x + d * (1.0 - v + log(v))) break;
+    }
+    if (a < 1.0) {
+        uint32_t ctr[4] = {0xFFFFFFFFu, iteration, tag, 0}, key[2] = {seed, marker}, w[4];
+        ho_philox4x32(ctr, key, w);
+        g *= pow(((double)w[0] + 0.5) * (1.0 / 4294967296.0), 1.0 / a);
+    }
+    return g;
+}
+/* src/distributions_boost.cpp:97-103: inv_gamma_rate_rng(shape, rate) = 1 / rgamma(shape, 1/rate), g the standard variate */
+static double ho_inv_gamma_rate_from(double g, double rate) { return 1.0 / (g * (1.0 / rate)); }
+
 /* ------------------------------------------------------------------------- */
 /* Synthetic genotypes; counter-based, integer thresholds     */
 /* cell (i,j): word k=i%4 of philox(ctr=(i/4, j, attempt, 'GENO'), key=seed)    */
@@ -523,6 +557,21 @@ typedef struct {
     const int32_t *tape_xI;   /* n_iter*F: order of the covariates per iteration, or NULL -> Fisher-Yates of the running order with mt_hyper */
     const double *tape_zcov;  /* n_iter*F: standard normals, or NULL -> mt_hyper */
     double *out_gamma;        /* n_iter*F */
+    /* per-group priors: --groupPriorsFile (v0G, s02G per group, :2545-2548) and --dPriorsFile (Dirichlet parameters, :2551-2554) */
+    const double *group_priors; /* G*2 or NULL -> v0G = s02G = 0.0001 */
+    const double *dirichlet;    /* G*K or NULL -> 1.0 (:1184-1185) */
+    /* bayesFHMPI (horseshoe-type local scales; src/BayesRRm.cpp:1125-1163, 1727-1731, 1747-1748, 1869-1872, 1942-1952, 2503-2510,
+     * 2557-2565); fh == 0: off */
+    int32_t fh;
+    double fh_v0L, fh_v0t, fh_v0c, fh_s02c, fh_tau0;   /* src/options.hpp:91-96 */
+    const double *fh_state0;    /* 2+G: hypTau, tau, c_slab[G] after :1147-1154, or NULL -> drawn with mt_hyper in that order */
+    const double *tape_gnu;     /* n_iter*Mtot standard Gamma(0.5+0.5*v0L) variates of the nu_var draws (:1729) by GLOBAL marker, NULL -> ho_fh_gamma */
+    const double *tape_glam;    /* n_iter*Mtot, the lambda_var draws (:1952) */
+    const double *tape_fh_hyper;/* n_iter*G*3: hypTau, tau, c_slab[g] as drawn in group g's pass (:2559-2562), NULL -> mt_hyper */
+    uint32_t fh_seed;           /* seed of ho_fh_gamma */
+    double *out_fh;             /* n_iter*(3+G): hypTau, tau, scaledBSQN, c_slab[G] */
+    double *out_lambda;         /* n_iter*Mtot */
+    double *out_nu;             /* n_iter*Mtot */
 } ho_brr_args;
 
 static double now_s(void) {
@@ -538,7 +587,8 @@ HO_API int ho_brr_chain(const ho_brr_args *a) {
     const int N = a->N, Mtot = a->Mtot, T = a->T, K = a->K, G = a->G;
     const int km1 = K - 1;
     const double dN = (double)N, dNm1 = (double)(N - 1);
-    const double v0E = 0.0001, s02E = 0.0001, v0G = 0.0001, s02G = 0.0001; /* src/BayesRRm.h:30-33 */
+    const double v0E = 0.0001, s02E = 0.0001; /* src/BayesRRm.h:30-33 */
+    double v0G = 0.0001, s02G = 0.0001;       /* overwritten group by group where a priors file was given (:2545-2548) */
 
     int *MrankS = (int *)malloc(sizeof(int) * T), *MrankL = (int *)malloc(sizeof(int) * T);
     ho_define_blocks_of_markers(Mtot, MrankS, MrankL, (uint)T);
@@ -563,6 +613,28 @@ HO_API int ho_brr_chain(const ho_brr_args *a) {
     for (int g = 0; g < G; g++) if (MtotGrp[g] == 0) sigmaG[g] = 0.0; /* :1239-1240 */
 
     ho_mt mt_hyper; ho_mt_seed(&mt_hyper, a->hyper_seed);
+    /* :1125-1163 FH initialisation */
+    const int fh = a->fh;
+    const double v0L = a->fh_v0L, v0t = a->fh_v0t, v0c = a->fh_v0c, s02c = a->fh_s02c, tau0 = a->fh_tau0;
+    double hypTau = 0.0, tau = 0.0, scaledBSQN = 0.0;
+    double *c_slab = (double *)calloc((size_t)G, sizeof(double));
+    double *lambda_var = (double *)calloc((size_t)(Mtot > 0 ? Mtot : 1), sizeof(double));
+    double *nu_var = (double *)calloc((size_t)(Mtot > 0 ? Mtot : 1), sizeof(double));
+    double *gnu = (double *)calloc((size_t)(Mtot > 0 ? Mtot : 1), sizeof(double));
+    double *glam = (double *)calloc((size_t)(Mtot > 0 ? Mtot : 1), sizeof(double));
+    if (fh) {
+        if (a->fh_state0) {
+            hypTau = a->fh_state0[0]; tau = a->fh_state0[1];
+            for (int g = 0; g < G; g++) c_slab[g] = a->fh_state0[2 + g];
+        } else {
+            hypTau = ho_inv_gamma_rate_from(ho_mt_gamma(&mt_hyper, 0.5), 1.0 / (tau0 * tau0));        /* :1147 */
+            tau = ho_inv_gamma_rate_from(ho_mt_gamma(&mt_hyper, 0.5 * v0t), v0t / hypTau);            /* :1150 */
+            for (int g = 0; g < G; g++) c_slab[g] = ho_inv_scaled_chisq(&mt_hyper, v0c, s02c);        /* :1153-1154 */
+        }
+        double cs = 0.0;
+        for (int g = 0; g < G; g++) cs += c_slab[g];
+        for (int m = 0; m < Mtot; m++) lambda_var[m] = cs / (double)Mtot;                             /* :1161 */
+    }
     int *xI = (int *)malloc(sizeof(int) * (size_t)(a->F > 0 ? a->F : 1));
     double *gam = (double *)calloc((size_t)(a->F > 0 ? a->F : 1), sizeof(double));   /* gamma.setZero() :1092 */
     for (int i = 0; i < a->F; i++) xI[i] = i;                                         /* :1113-1117 */
@@ -621,6 +693,13 @@ HO_API int ho_brr_chain(const ho_brr_args *a) {
             tsad[r] = 0.0;
         }
         memset(cass, 0, sizeof(int) * (size_t)T * G * K);       /* :1697 */
+        if (fh) {   /* the standard gamma variates behind this iteration's nu_var / lambda_var draws */
+            const double sh = 0.5 + 0.5 * v0L;
+            for (int m = 0; m < Mtot; m++) {
+                gnu[m] = a->tape_gnu ? a->tape_gnu[(size_t)itx * Mtot + m] : ho_fh_gamma(a->fh_seed, (uint32_t)m, (uint32_t)(a->iter0 + itx), 0, sh);
+                glam[m] = a->tape_glam ? a->tape_glam[(size_t)itx * Mtot + m] : ho_fh_gamma(a->fh_seed, (uint32_t)m, (uint32_t)(a->iter0 + itx), 1, sh);
+            }
+        }
         int sinceLastSync = 0;
         int64_t nsync = 0;
         double t_loop = now_s();
@@ -644,8 +723,16 @@ HO_API int ho_brr_chain(const ho_brr_args *a) {
                     const double sigE_G = sigmaE / sigmaG[grp]; /* :1721-1723 */
                     const double sigG_E = sigmaG[grp] / sigmaE;
                     const double i_2sigE = 1.0 / (2.0 * sigmaE);
+                    double lambda_tilde = 0.0;
+                    if (fh) {                                   /* :1727-1731 */
+                        nu_var[gm] = ho_inv_gamma_rate_from(gnu[gm], v0L / lambda_var[gm] + 1);
+                        lambda_tilde = tau * c_slab[grp] / (tau + c_slab[grp] * lambda_var[gm]);
+                    }
                     if (adaV[gm]) {
-                        for (int i = 1; i <= km1; ++i) denom[i - 1] = dNm1 + sigE_G * cVaI[grp * K + i]; /* :1750 */
+                        for (int i = 1; i <= km1; ++i) {
+                            if (fh) denom[i - 1] = dNm1 + sigmaE / lambda_tilde;                 /* :1747-1748 */
+                            else denom[i - 1] = dNm1 + sigE_G * cVaI[grp * K + i];               /* :1750 */
+                        }
                         double num;
                         if (a->usebed && a->usebed[gm]) {
                             num = ho_lut_dotprod(a->bed + (size_t)gm * a->snpLenByt, eps[r], N, mave[gm], mstd[gm]);
@@ -657,8 +744,10 @@ HO_API int ho_brr_chain(const ho_brr_args *a) {
                         for (int i = 1; i <= km1; i++) muk[i] = num / denom[i - 1]; /* :1859 */
                         muk[0] = 0.0;
                         for (int i = 0; i < K; i++) logL[i] = log(estPi[grp * K + i]); /* :1863-1864 */
-                        for (int i = 1; i < 1 + km1; i++)       /* :1874-1876 */
-                            logL[i] = logL[i] - 0.5 * log(sigG_E * dNm1 * cVa[grp * K + i] + 1.0) + muk[i] * num * i_2sigE;
+                        for (int i = 1; i < 1 + km1; i++) {
+                            if (fh) logL[i] = logL[i] - 0.5 * log((lambda_tilde / sigmaE) * dNm1 + 1.0) + muk[i] * num * i_2sigE;  /* :1869-1872 */
+                            else logL[i] = logL[i] - 0.5 * log(sigG_E * dNm1 * cVa[grp * K + i] + 1.0) + muk[i] * num * i_2sigE;   /* :1874-1876 */
+                        }
                         double prob = tu[MrankS[r] + j];        /* :1880 */
                         double acum;
                         int any = 0;
@@ -685,6 +774,8 @@ HO_API int ho_brr_chain(const ho_brr_args *a) {
                     double betaOld = beta;
                     beta = Beta[gm];
                     deltaBeta = betaOld - beta;                 /* :1933 */
+                    if (fh)                                     /* :1942-1952 */
+                        lambda_var[gm] = ho_inv_gamma_rate_from(glam[gm], 0.5 * beta * beta / tau + v0L / nu_var[gm]);
                     if (deltaBeta != 0.0) {                     /* :1965 */
                         if (a->usebed && a->usebed[gm])
                             ho_lut_scaadd(deltaEps, a->bed + (size_t)gm * a->snpLenByt, deltaBeta, mave[gm], mstd[gm], N);
@@ -731,6 +822,11 @@ HO_API int ho_brr_chain(const ho_brr_args *a) {
             free(loc);
         }
         for (int x = 0; x < G * K; x++) { int s = 0; for (int r = 0; r < T; r++) s += cass[(size_t)r * G * K + x]; sum_cass[x] = s; }
+        /* :2503-2510 scaled sum of squares. The reference sums over the rank's own markers and does not reduce it (nor does it
+         * broadcast tau / c_slab: its ranks' FH parameters diverge); here, as for the other hyper-parameters, ONE value: the sum
+         * over all markers, which is what a one-rank run of the reference computes. */
+        scaledBSQN = 0.0;
+        if (fh) for (int i = 0; i < Mtot; i++) scaledBSQN += Beta[i] * Beta[i] / lambda_var[i];
 
         /* :2525-2578 */
         for (int g = 0; g < G; g++) {
@@ -743,14 +839,29 @@ HO_API int ho_brr_chain(const ho_brr_args *a) {
                 sigmaG[g] = 0.0;
                 continue;
             }
+            if (a->group_priors) { v0G = a->group_priors[g * 2 + 0]; s02G = a->group_priors[g * 2 + 1]; }   /* :2545-2548 */
+            if (fh) {                                           /* :2557-2565 */
+                if (a->tape_fh_hyper) {
+                    const double *h = a->tape_fh_hyper + ((size_t)itx * G + g) * 3;
+                    hypTau = h[0]; tau = h[1]; c_slab[g] = h[2];
+                } else {
+                    hypTau = ho_inv_gamma_rate_from(ho_mt_gamma(&mt_hyper, 0.5 + 0.5 * v0t), 1.0 / (tau0 * tau0) + 1.0 / tau);
+                    tau = ho_inv_gamma_rate_from(ho_mt_gamma(&mt_hyper, 0.5 * (m0[g] + v0t)), v0t / hypTau + (0.5 * scaledBSQN));
+                    c_slab[g] = ho_inv_scaled_chisq(&mt_hyper, v0c + (double)m0[g], (bsq[g] * (double)m0[g] + v0c * s02c) / (v0c + (double)m0[g]));
+                }
+                sigmaG[g] = bsq[g];                             /* :2565 */
+            }
             if (a->tape_sigmaG) {
-                sigmaG[g] = a->tape_sigmaG[(size_t)itx * G + g];
+                if (!fh) sigmaG[g] = a->tape_sigmaG[(size_t)itx * G + g];
                 for (int k = 0; k < K; k++) estPi[g * K + k] = a->tape_pi[((size_t)itx * G + g) * K + k];
             } else {
-                sigmaG[g] = ho_inv_scaled_chisq(&mt_hyper, v0G + (double)m0[g],
-                                                (bsq[g] * (double)m0[g] + v0G * s02G) / (v0G + (double)m0[g])); /* :2570 */
-                double s = 0.0;                                 /* :2576-2577 dirichlet(cass+1) */
-                for (int k = 0; k < K; k++) { estPi[g * K + k] = ho_mt_gamma(&mt_hyper, (double)sum_cass[g * K + k] + 1.0); s += estPi[g * K + k]; }
+                if (!fh) sigmaG[g] = ho_inv_scaled_chisq(&mt_hyper, v0G + (double)m0[g],
+                                                         (bsq[g] * (double)m0[g] + v0G * s02G) / (v0G + (double)m0[g])); /* :2570 */
+                double s = 0.0;                                 /* :2576-2577 dirichlet(cass + dirc), dirc = 1 unless --dPriorsFile */
+                for (int k = 0; k < K; k++) {
+                    const double dk = a->dirichlet ? a->dirichlet[g * K + k] : 1.0;
+                    estPi[g * K + k] = ho_mt_gamma(&mt_hyper, (double)sum_cass[g * K + k] + dk); s += estPi[g * K + k];
+                }
                 for (int k = 0; k < K; k++) estPi[g * K + k] /= s;
             }
         }
@@ -793,6 +904,13 @@ HO_API int ho_brr_chain(const ho_brr_args *a) {
         if (a->out_bsq) memcpy(a->out_bsq + (size_t)itx * G, bsq, sizeof(double) * G);
         if (a->out_cass) memcpy(a->out_cass + (size_t)itx * G * K, sum_cass, sizeof(int) * G * K);
         if (a->out_esqn) a->out_esqn[itx] = e_sqn;
+        if (fh && a->out_fh) {
+            double *o = a->out_fh + (size_t)itx * (3 + G);
+            o[0] = hypTau; o[1] = tau; o[2] = scaledBSQN;
+            for (int g = 0; g < G; g++) o[3 + g] = c_slab[g];
+        }
+        if (fh && a->out_lambda) memcpy(a->out_lambda + (size_t)itx * Mtot, lambda_var, sizeof(double) * Mtot);
+        if (fh && a->out_nu) memcpy(a->out_nu + (size_t)itx * Mtot, nu_var, sizeof(double) * Mtot);
     }
 
     for (int r = 0; r < T; r++) { free(eps[r]); free(tmpEps[r]); free(dEpsSum[r]); free(deltaEpsT[r]); }
@@ -801,6 +919,7 @@ HO_API int ho_brr_chain(const ho_brr_args *a) {
     free(bsq); free(m0); free(tsad);
     free(mave); free(mstd); free(sigmaG); free(MtotGrp); free(cVa); free(cVaI); free(estPi);
     free(MrankS); free(MrankL); free(xI); free(gam);
+    free(c_slab); free(lambda_var); free(nu_var); free(gnu); free(glam);
     return 0;
 }
 

@@ -33,13 +33,14 @@ def test_header_symbols_all_exported(lib):
 
 
 def test_abi_version(lib):
-    assert lib.hb_abi_version() == 1
+    assert lib.hb_abi_version() == 2
 
 
 def test_struct_sizes_match_header(lib):
     from hydra_b200 import capi
     assert C.sizeof(capi.HbConfig) == lib.hb_sizeof_config()
-    assert C.sizeof(capi.HbBrrTape) == 9 * 8
+    assert C.sizeof(capi.HbBrrTape) == lib.hb_sizeof_brr_tape() == 12 * 8
+    assert C.sizeof(capi.HbFhConfig) == 5 * 8
     assert C.sizeof(capi.HbBrrIterOut) == lib.hb_sizeof_iter_out()
 
 

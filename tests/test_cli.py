@@ -458,3 +458,57 @@ def test_cli_restart_from_the_output_files(tmp_path):
             brr.iteration()
             assert np.array_equal(brr.state()[0], beta[it]), f"python (restored from the files) vs CLI --restart at iteration {it}"
     assert not np.array_equal(beta[5], beta[4])
+
+
+@pytest.mark.gpu
+def test_cli_bayesfh_and_prior_files_equal_python_run(tmp_path):
+    """--mpibayes bayesFHMPI with --tau0/--v0t/--v0c/--s02c/--v0L (src/options.cpp:116-135) and the two prior files
+    (--groupPriorsFile "v0,s02; v0,s02", --dPriorsFile "a,b,c,d; ...", src/data.cpp:2034-2096) through the C++ host: same chain as
+    the Python front-end, and --restart (state file) continues it byte for byte."""
+    import hydra_b200
+    d = str(tmp_path)
+    bed, y, na, groups = write_dataset(d)
+    N, M = 600, 150
+    open(os.path.join(d, "t.gp"), "w").write("4.0,0.2; 2.5,0.05\n")
+    open(os.path.join(d, "t.dp"), "w").write("5,1,1,1; 1,2,2,0.5\n")
+    fhargs = ["--bfile", os.path.join(d, "t"), "--dPriorsFile", os.path.join(d, "t.dp"), "--tau0", "0.5", "--v0t", "4", "--v0L", "2.5"]
+
+    def args(out, extra):
+        a = base_args(d, out, fhargs + extra)
+        a[a.index("bayesMPI")] = "bayesFHMPI"
+        return a
+    r = subprocess.run(args("fh", []), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "bayesFH: tau0 0.5 v0t 4 v0c 3 s02c 1 v0L 2.5" in r.stdout
+    its, beta = read_bet(os.path.join(d, "fh", "run.bet"), M)
+    keep = np.setdiff1d(np.arange(N), na)
+    with hydra_b200.GenotypeStore(N, M, na_inds=na, tasks=3, sync_rate=5, n_groups=2, n_mix=4, repr_mode="bed") as st:
+        st.load_data_from_bed(bed)
+        st.finalize()
+        brr = hydra_b200.BayesRRm(st, y[keep], [[0.001, 0.01, 0.1]] * 2, groups=groups, seed=1222, fh=dict(tau0=0.5, v0t=4.0, v0L=2.5),
+                                  dirichlet_priors=[[5, 1, 1, 1], [1, 2, 2, 0.5]])
+        for it in range(5):
+            brr.iteration()
+            if it % 2 == 0:
+                assert np.array_equal(brr.state()[0], beta[it // 2]), f"python vs CLI beta at iteration {it}"
+        assert (beta[-1] != 0).any()
+    # restart from the state file of the save point (iteration 4): a run of 10 equals a run of 6 continued to 10
+    a10 = args("fh10", [])
+    a10[a10.index("--chain-length") + 1] = "10"
+    assert subprocess.run(a10, capture_output=True, text=True).returncode == 0
+    ar = args("fh", ["--restart"])
+    ar[ar.index("--chain-length") + 1] = "10"
+    r = subprocess.run(ar, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    for ext in (".bet", ".cpn", ".csv"):
+        assert open(os.path.join(d, "fh", "run" + ext), "rb").read() == open(os.path.join(d, "fh10", "run" + ext), "rb").read(), ext
+    # --groupPriorsFile with bayesMPI: the sigmaG column of the .csv differs from the run with the built-in priors, pi does too
+    r1 = subprocess.run(base_args(d, "gp", ["--bfile", os.path.join(d, "t"), "--groupPriorsFile", os.path.join(d, "t.gp")]), capture_output=True, text=True)
+    r0 = subprocess.run(base_args(d, "gp0", ["--bfile", os.path.join(d, "t")]), capture_output=True, text=True)
+    assert r1.returncode == 0 and r0.returncode == 0, r1.stdout[-1500:] + r1.stderr[-1500:]
+    c1, c0 = open(os.path.join(d, "gp", "run.csv")).read(), open(os.path.join(d, "gp0", "run.csv")).read()
+    assert c1 != c0 and c1.split("\n")[0].split(",")[0] == c0.split("\n")[0].split(",")[0]
+    # malformed prior file: loud
+    open(os.path.join(d, "bad.gp"), "w").write("4.0,0.2\n")
+    r = subprocess.run(base_args(d, "bad", ["--bfile", os.path.join(d, "t"), "--groupPriorsFile", os.path.join(d, "bad.gp")]), capture_output=True, text=True)
+    assert r.returncode != 0 and "1 groups, the run has 2" in r.stdout + r.stderr
