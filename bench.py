@@ -355,6 +355,30 @@ def latency_floor(a, local_rank):
             "config": f"N={a.n}, {M} markers of spectrum {a.spectrum}, 1 task x sync_rate 1 (one marker per synchronisation window)"}
 
 
+def bayesfh_sub(a, local_rank):
+    """bayesFHMPI (horseshoe-type local scales, src/BayesRRm.cpp:1125-1163 ...) on the headline layout: the same marker kernel with
+    per-marker prior operands plus k_fh_prepare / k_fh_finish either side of it. A driver-visible number, not the headline."""
+    import hydra_b200
+    from hydra_b200 import synth
+    M = 262_144
+    st = hydra_b200.GenotypeStore(a.n, M, tasks=a.tasks_per_gpu, sync_rate=a.sync_rate, n_groups=1, n_mix=4, repr_mode="sparse", device=local_rank,
+                                  n_slices=a.n_slices)
+    synth.stage_synthetic(st, a.spectrum)
+    y, _, _ = synth.simulate_phenotype(st, n_causal=1250)
+    brr = hydra_b200.BayesRRm(st, y, [[0.0001, 0.001, 0.01]], seed=1222, fh={})
+    for _ in range(3):
+        brr.iteration()
+    outs = [brr.iteration() for _ in range(4)]
+    f = brr.fh_state()
+    st.close()
+    it_ms = float(sum(o["iter_ms"] for o in outs)) / len(outs)
+    return {"value": M / (it_ms * 1e-3), "unit": UNIT, "ms_per_step": it_ms, "marker_loop_ms": float(sum(o["loop_ms"] for o in outs)) / len(outs),
+            "us_per_window": float(sum(o["loop_ms"] for o in outs)) * 1e3 / sum(o["n_windows"] for o in outs),
+            "gpu_launches": int(sum(o["n_launches"] for o in outs)), "tau": float(f["tau"]), "markers_changed_last_step": int(outs[-1]["markers_changed"]),
+            "workload": f"bayesFHMPI sparse, synthetic N={a.n} M={M} (spectrum {a.spectrum}), {a.tasks_per_gpu} tasks x sync_rate {a.sync_rate}, "
+                        "device time of whole iterations (iter_ms)"}
+
+
 # ----------------------------------------------------------------------------- main
 def main():
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep NCCL's version banner off stdout (one JSON line only)
@@ -531,6 +555,10 @@ def main():
                 res["latency_floor"] = latency_floor(a, local_rank)
             except Exception as e:
                 res["latency_floor"] = {"error": repr(e)}
+            try:
+                res["bayesfh"] = bayesfh_sub(a, local_rank)
+            except Exception as e:
+                res["bayesfh"] = {"error": repr(e)}
             try:  # BayesW (BASELINE config 3 at scale): a driver-visible number next to the headline
                 import copy
                 b = copy.copy(a)

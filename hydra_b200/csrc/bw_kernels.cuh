@@ -44,6 +44,9 @@ struct BwParams {
     int mode;
     const double *beta_in;     // BW_VISUMS: beta_old per position (unit mode)
     double *out;               // unit modes: [W*4]
+    double *delta;             // several GPUs: [S*L + 2] this GPU's epsilon change of the window (zeroed), then { its constant term, its
+                               // number of changed markers }: summed over the GPUs (the reference's MPI_Allreduce of deltaEps,
+                               // src/BayesW.cpp:1799-1835) and applied by k_bw_apply_delta; NULL on one GPU
 };
 
 __device__ __forceinline__ double bw_block_sum(double v, double *red) {
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(512) k_bw_update(const BwParams P) {
     const uint32_t n = *P.chg_cnt;
     const double shift_old = *P.shift_in;
     double off = 0.0;
-    double *E = P.E + (size_t)c * L;
+    double *E = (P.delta ? P.delta : P.E) + (size_t)c * L;
     if (n > kMaxMerged) {
         if (c == 0 && tid == 0) atomicExch(P.err, 4u);
         return;
@@ -341,6 +344,10 @@ __global__ void __launch_bounds__(512) k_bw_update(const BwParams P) {
             }
         }
     }
+    if (P.delta) {   // several GPUs: the change itself is the result; k_bw_apply_delta adds the sum over the GPUs to epsilon
+        if (c == 0 && tid == 0) { P.delta[(size_t)P.S * L] = off; P.delta[(size_t)P.S * L + 1] = (double)n; }
+        return;
+    }
     const double shift_new = shift_old + off;
     if (c == 0 && tid == 0) *P.shift_out = shift_new;
     // refresh the slice's sum of vi (:1832-1834)
@@ -350,6 +357,30 @@ __global__ void __launch_bounds__(512) k_bw_update(const BwParams P) {
         if ((size_t)c * L + i < P.N) {
             const double x = exp(P.alpha * __ldcg(E + i) + bconst);
             P.vi[(size_t)c * L + i] = x;  // gathered by k_bw_window until the next synchronisation
+            v += x;
+        }
+    }
+    const double s = bw_block_sum(v, red);
+    if (tid == 0) P.Vpart[c] = s;
+}
+
+// Several GPUs: epsilon += the epsilon changes of all GPUs (P.delta after the all-reduce), then the slice's vi and their sum as
+// in k_bw_update. Every GPU adds the same numbers to the same epsilon: the replicas stay bit-identical.
+__global__ void __launch_bounds__(512) k_bw_apply_delta(const BwParams P) {
+    __shared__ double red[16];
+    const uint32_t c = blockIdx.x, tid = threadIdx.x, L = P.L;
+    double *E = P.E + (size_t)c * L;
+    const double *D = P.delta + (size_t)c * L;
+    const double shift_new = *P.shift_in + P.delta[(size_t)P.S * L];
+    if (c == 0 && tid == 0) *P.shift_out = shift_new;
+    double v = 0.0;
+    const double bconst = P.alpha * shift_new - kBwEuMasc;
+    for (uint32_t i = tid; i < L; i += blockDim.x) {
+        const double e = __ldcg(E + i) + D[i];
+        __stcg(E + i, e);
+        if ((size_t)c * L + i < P.N) {
+            const double x = exp(P.alpha * e + bconst);
+            P.vi[(size_t)c * L + i] = x;
             v += x;
         }
     }

@@ -150,7 +150,7 @@ struct hb_ctx {
     double bw_alpha = 0.0, bw_mu = 0.0, bw_d = 0.0, bw_sumSigmaG = 0.0;
     std::vector<double> bw_fail_h, bw_sff;   // failure indicators (host copy) and sum_failure_fix of the fixed effects (src/BayesW.cpp:1235-1237)
     uint64_t bw_evals = 0;
-    DevBuf<double> d_sd, d_sumfail, d_fail, d_bwsc, d_bw_vi;
+    DevBuf<double> d_sd, d_sumfail, d_fail, d_bwsc, d_bw_vi, d_bw_delta;
     std::vector<double> sd_h, sumfail_h;
 
     // chain (host)
