@@ -207,29 +207,48 @@ def bayesw_cpu_run(a, n_markers, m_total, n_iter=2):
             "compile": "gcc -O2 (oracle) + the reference's src/BayesW_arms.cpp object code"}
 
 
-def bayesw_line(a, local_rank, with_cpu=True):
+def bayesw_line(a, local_rank, with_cpu=True, dist=None):
+    """One GPU, or (dist = torch.distributed, one process per GPU) weak scaling: m_per_gpu markers and tasks_per_gpu tasks per GPU,
+    epsilon replicated, the window's epsilon changes summed with ncclAllReduce (src/BayesW.cpp:1799-1835)."""
     import torch
     import hydra_b200
     from hydra_b200 import synth
-    M = a.m_per_gpu
-    store = hydra_b200.GenotypeStore(a.n, M, tasks=a.tasks_per_gpu, sync_rate=a.sync_rate, n_groups=1, n_mix=4, repr_mode="sparse",
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    M = a.m_per_gpu * world
+    store = hydra_b200.GenotypeStore(a.n, M, tasks=a.tasks_per_gpu * world, task_first=rank * a.tasks_per_gpu, tasks_local=a.tasks_per_gpu,
+                                     sync_rate=a.sync_rate, n_groups=1, n_mix=4, repr_mode="sparse",
                                      device=local_rank, model="bayesW", n_slices=a.n_slices)
     t0 = time.time()
     synth.stage_synthetic(store, a.spectrum)
     stage_s = time.time() - t0
-    g, _, _ = synth.simulate_phenotype(store, n_causal=max(10, M // 200))
+    if dist is not None:
+        store.comm_init(dist)
+    g, _, _ = synth.simulate_phenotype(store, n_causal=max(10, M // 200), dist=dist)
     y, fail = weibull_phenotype(a.n, g)
     bw = hydra_b200.BayesW(store, y, fail, [[0.001, 0.01, 0.1]], quad_points=25, seed=5)
     n1, n2, nm = store.marker_counts()
     nnz_total = int((n1.astype(np.int64) + n2 + nm).sum())
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(*v):
+        t = torch.tensor(v, dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.cpu()]
     for _ in range(a.warmup):
         bw.iteration()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    torch.cuda.synchronize()
+    sync_all()
     t_wall = time.perf_counter()
     outs = [bw.iteration() for _ in range(a.steps)]
-    torch.cuda.synchronize()
+    sync_all()
     wall_ms = (time.perf_counter() - t_wall) * 1e3
     loop_ms = float(sum(o["loop_ms"] for o in outs))
     t_e2e = time.perf_counter()
@@ -237,25 +256,26 @@ def bayesw_line(a, local_rank, with_cpu=True):
         bw.iteration()
         bw.state()
         bw.hyper()
-    torch.cuda.synchronize()
+    sync_all()
     e2e_ms = (time.perf_counter() - t_e2e) * 1e3
+    wall_ms, loop_ms, e2e_ms = max_over_ranks(wall_ms, loop_ms, e2e_ms)
     clocks = sampler.stop()
     # algorithmic bytes: 12 B per stored non-zero visited (index + vi), per synchronisation 16*N (epsilon read, vi written)
     alg = [12.0 * nnz_total + 16.0 * store.n_ind * o["n_sync"] for o in outs]
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
     peak = float(peaks["hbm_gbs"]) if peaks else 6650.0
     achieved = float(np.sum(alg)) / (loop_ms * 1e-3) / 1e9
-    cfg = workload_config(a, 1)
+    cfg = workload_config(a, world)
     cfg["workload"] = (f"BayesW (Weibull, 25 quadrature points) sparse, synthetic N={a.n} M={M} (spectrum {a.spectrum}), 1 group, "
-                       f"S=0.001,0.01,0.1, {a.tasks_per_gpu} tasks x sync_rate {a.sync_rate}, 10 % censored")
+                       f"S=0.001,0.01,0.1, {a.tasks_per_gpu * world} tasks x sync_rate {a.sync_rate}, 10 % censored")
     cfg["m_markers"] = M
-    res = {"metric": METRIC, "model": "bayesW", "value": M * a.steps / (wall_ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": a.steps,
+    res = {"metric": METRIC, "model": "bayesW", "value": M * a.steps / (wall_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
            "warmup": a.warmup, "ms_per_step": wall_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic (device-generated genotypes, simulated Weibull phenotype)", "config": cfg,
            "marker_loop": {"ms_per_step": loop_ms / a.steps, "marker_updates_per_sec": M * a.steps / (loop_ms * 1e-3),
                            "windows_per_step": outs[-1]["n_windows"], "us_per_window": loop_ms * 1e3 / sum(o["n_windows"] for o in outs),
                            "markers_changed_last_step": outs[-1]["markers_changed"]},
-           "e2e": {"value": M * a.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(4 * M), "d2h_bytes_per_step": int(12 * M + 256),
+           "e2e": {"value": M * a.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(4 * store.m_local), "d2h_bytes_per_step": int(12 * store.m_local + 256),
                    "ms_per_step": e2e_ms / a.steps, "what": "BayesW.iteration() + state() + hyper() through the C ABI"},
            "gpu_launches": int(sum(o["n_launches"] for o in outs)),
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
@@ -264,9 +284,11 @@ def bayesw_line(a, local_rank, with_cpu=True):
                         "algorithmic_bytes_per_launch": float(np.mean(alg)),
                         "note": "latency-bound: the window waits for the serial ARMS draws of its few changing markers (DESIGN.md 6)"},
            "clocks": clocks,
-           "layout": {"slices": store.n_slices, "genotype_bytes_per_gpu": store.genotype_bytes, "mean_nnz_per_marker": nnz_total / M,
+           "layout": {"slices": store.n_slices, "genotype_bytes_per_gpu": store.genotype_bytes, "mean_nnz_per_marker": nnz_total / store.m_local,
                       "stage_seconds": stage_s}}
-    if with_cpu and not a.no_cpu_baseline:
+    if world > 1:
+        res["exchange"] = "per window: ncclAllReduce of the dense epsilon change (N + 2 doubles) over NVLink / NVSwitch"
+    if with_cpu and not a.no_cpu_baseline and world == 1:
         try:
             res["cpu_baseline"] = bayesw_cpu_run(a, min(2048, M), M)
         except Exception as e:
@@ -275,8 +297,18 @@ def bayesw_line(a, local_rank, with_cpu=True):
     return res
 
 
-def bayesw_main(a, local_rank):
-    print(json.dumps(bayesw_line(a, local_rank)), flush=True)
+def bayesw_main(a, local_rank, world=1):
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    res = bayesw_line(a, local_rank, dist=dist)
+    if dist is None or dist.get_rank() == 0:
+        print(json.dumps(res), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
     return 0
 
 
@@ -394,9 +426,7 @@ def main():
             return 0
         return reference_arm(a, world)
     if a.model == "bayesw":
-        if world > 1:
-            raise SystemExit("bench.py --model bayesw: BayesW runs on one GPU in this version")
-        return bayesw_main(a, local_rank)
+        return bayesw_main(a, local_rank, world)
 
     import torch
     import hydra_b200

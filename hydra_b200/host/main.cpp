@@ -572,7 +572,7 @@ int main(int argc, const char **argv) {
         cfg.n_ind_raw = Nraw; cfg.n_na = (uint32_t)na.size(); cfg.na_inds = na.data();
         const uint32_t TL = opt.tasks / opt.world;
         cfg.m_total = Mtot; cfg.n_tasks_total = opt.tasks; cfg.task_first = opt.rank * TL; cfg.n_tasks_local = TL;
-        if (opt.world > 1 && (bayesW || opt.bedToSparse)) throw std::runtime_error("bayesWMPI and --bed-to-sparse run on one GPU (one process) in this version");
+        if (opt.world > 1 && opt.bedToSparse) throw std::runtime_error("--bed-to-sparse runs on one GPU (one process)");
         cfg.sync_rate = opt.syncRate; cfg.n_groups = G; cfg.n_mix = K;
         cfg.repr_mode = opt.bedToSparse ? HB_REPR_SPARSE : repr;
         cfg.threshold_fnz = opt.thresholdFnz;
@@ -652,35 +652,85 @@ int main(int argc, const char **argv) {
         for (uint32_t g = 0; g < G; g++)
             for (uint32_t k = 1; k < K; k++) mSflat[g * K + k] = mS[g][k - 1];
         uint32_t seed = opt.seedSet ? opt.seed : (uint32_t)time(nullptr);  // multi-GPU: rank 0's value is shipped with the NCCL id (below)
+        // one process per GPU: NCCL unique id (and rank 0's seed) through a file next to the outputs, then hb_comm_init (a barrier)
+        const bool root = (opt.rank == 0);
+        auto comm_setup = [&](const std::string &out) {
+            if (opt.world > 1) {
+                // NCCL unique id through a file next to the outputs (rank 0 writes, the others wait for it)
+                const char *job = getenv("TORCHELASTIC_RUN_ID") ? getenv("TORCHELASTIC_RUN_ID") : (getenv("SLURM_JOB_ID") ? getenv("SLURM_JOB_ID") : (getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "0"));
+                const std::string idf = out + ".ncclid." + job;
+                // the file carries the NCCL id and rank 0's seed: without --seed every process would otherwise take its own
+                // time(0), and the hyper-parameter streams (drawn on every GPU instead of MPI_Bcast, :2585, 2705, 2731) would differ
+                uint8_t id[HB_NCCL_ID_BYTES + 4];
+                const time_t t_start = time(nullptr);
+                if (root) {
+                    unlink(idf.c_str());  // a file left by a crashed run must not be picked up by the other ranks
+                    HB(hb_comm_get_unique_id(id));
+                    memcpy(id + HB_NCCL_ID_BYTES, &seed, 4);
+                    FILE *f = fopen((idf + ".tmp").c_str(), "wb");
+                    if (!f || fwrite(id, 1, sizeof(id), f) != sizeof(id)) throw std::runtime_error("cannot write " + idf);
+                    fclose(f);
+                    if (rename((idf + ".tmp").c_str(), idf.c_str()) != 0) throw std::runtime_error("cannot publish " + idf);
+                } else {
+                    bool ok = false;
+                    for (int tries = 0; tries < 1200 && !ok; tries++) {
+                        struct stat st;
+                        if (stat(idf.c_str(), &st) == 0 && st.st_size == (off_t)sizeof(id) && st.st_mtime >= t_start - 30) {  // the launcher starts the ranks together
+                            FILE *f = fopen(idf.c_str(), "rb");
+                            ok = f && fread(id, 1, sizeof(id), f) == sizeof(id);
+                            if (f) fclose(f);
+                        }
+                        if (!ok) usleep(100000);
+                    }
+                    if (!ok) throw std::runtime_error("timed out waiting for the NCCL id file " + idf);
+                }
+                HB(hb_comm_init(ctx, id, (int)opt.rank, (int)opt.world));
+                if (root) unlink(idf.c_str());
+                if (!opt.seedSet) memcpy(&seed, id + HB_NCCL_ID_BYTES, 4);
+            }
+        };
         if (bayesW) {
-            HB(hb_bw_init(ctx, y.data(), fail.data(), groups.empty() ? nullptr : groups.data(), mSflat.data(), (uint32_t)atoi(opt.quad_points.c_str()), seed));
-            if (n_cov) HB(hb_bw_set_covariates(ctx, Xcov.data(), n_cov));   // fixed effects by ARMS, src/BayesW.cpp:1366-1413
+            // Several GPUs (one process each, src/BayesW.cpp:1645, 1799-1835): every process samples its marker range, rank 0 writes
+            // the .csv and the replicated residual, every process its slice of .bet / .cpn at the reference's offsets.
             struct stat sbw;
             if (stat(opt.mcmcOutDir.c_str(), &sbw) != 0 && system(("mkdir -p " + opt.mcmcOutDir).c_str()) != 0)
                 throw std::runtime_error("could not create output directory --mcmc-out-dir " + opt.mcmcOutDir);
             const std::string out = opt.mcmcOut();
-            OutFile csv, bet, cpn, gam;
+            const std::string rstf = out + ".rst." + std::to_string(opt.rank);
+            OutFile csv, gam;
+            SharedFile bet, cpn;
+            if (root && !opt.restart) {
+                bet.open_rw(out + ".bet", true); cpn.open_rw(out + ".cpn", true);
+                bet.write_at(&Mtot, 4, 0); cpn.write_at(&Mtot, 4, 0);
+            }
+            comm_setup(out);
+            HB(hb_bw_init(ctx, y.data(), fail.data(), groups.empty() ? nullptr : groups.data(), mSflat.data(), (uint32_t)atoi(opt.quad_points.c_str()), seed));
+            if (n_cov) HB(hb_bw_set_covariates(ctx, Xcov.data(), n_cov));   // fixed effects by ARMS, src/BayesW.cpp:1366-1413
             uint32_t it_first = 0, n_saved = 0;
             if (opt.restart) {  // as for BayesRRm: state file of the last --save point, outputs cut back to it
                 uint32_t it_saved = 0;
-                read_restart_file(out + ".rst.0", ctx, it_saved, n_saved);
+                read_restart_file(rstf, ctx, it_saved, n_saved);
                 it_first = it_saved + 1;
-                truncate_csv(out + ".csv", it_saved);
-                if (truncate((out + ".bet").c_str(), 4 + (off_t)n_saved * (4 + (off_t)Mtot * 8)) != 0 ||
-                    truncate((out + ".cpn").c_str(), 4 + (off_t)n_saved * (4 + (off_t)Mtot * 4)) != 0)
-                    fatal("--restart: cannot cut the .bet/.cpn files back to the restart point");
-                csv.open_append(out + ".csv"); bet.open_append(out + ".bet"); cpn.open_append(out + ".cpn");
-                if (n_cov) { truncate_csv(out + ".gam", it_saved); gam.open_append(out + ".gam"); }
-                printf("INFO   : restarting after iteration %u (%u records in .bet/.cpn)\n", it_saved, n_saved);
-            } else {
-                csv.open(out + ".csv"); bet.open(out + ".bet"); cpn.open(out + ".cpn");
+                if (root) {
+                    truncate_csv(out + ".csv", it_saved);
+                    if (truncate((out + ".bet").c_str(), 4 + (off_t)n_saved * (4 + (off_t)Mtot * 8)) != 0 ||
+                        truncate((out + ".cpn").c_str(), 4 + (off_t)n_saved * (4 + (off_t)Mtot * 4)) != 0)
+                        fatal("--restart: cannot cut the .bet/.cpn files back to the restart point");
+                    csv.open_append(out + ".csv");
+                    if (n_cov) { truncate_csv(out + ".gam", it_saved); gam.open_append(out + ".gam"); }
+                    printf("INFO   : restarting after iteration %u (%u records in .bet/.cpn)\n", it_saved, n_saved);
+                }
+                const uint64_t v[2] = {it_saved, n_saved};   // also the barrier between rank 0's truncation and the other ranks' writes
+                HB(hb_comm_check_equal(ctx, v, 2, "--restart: the restart point (iteration, records) of the <out>.rst.<rank> files"));
+            } else if (root) {
+                csv.open(out + ".csv");
                 if (n_cov) gam.open(out + ".gam");
-                bet.put(&Mtot, 1); cpn.put(&Mtot, 1);
             }
+            if (!root || opt.restart) { bet.open_rw(out + ".bet", false); cpn.open_rw(out + ".cpn", false); }
             std::vector<double> gamv(n_cov);
             std::vector<int32_t> xiv(n_cov);
-            std::vector<double> beta(Mtot), sigmaG(G), pi((size_t)G * K), bsq(G), eps(N);
-            std::vector<int32_t> comp(Mtot), cass((size_t)G * K), m0(G);
+            std::vector<double> beta(m_local), sigmaG(G), pi((size_t)G * K), bsq(G), eps(N);
+            std::vector<int32_t> comp(m_local), cass((size_t)G * K), m0(G);
             double tot_ms = 0.0;
             for (uint32_t it = it_first; it < opt.chainLength; it++) {
                 hb_bw_iter_out io;
@@ -690,20 +740,24 @@ int main(int argc, const char **argv) {
                 HB(hb_bw_get_hyper(ctx, sigmaG.data(), pi.data(), &mu, &alpha, bsq.data(), cass.data(), m0.data()));
                 double sG = 0.0; int m0s = 0;
                 for (uint32_t g = 0; g < G; g++) { sG += sigmaG[g]; m0s += m0[g]; }
-                printf("%u. %d; %.7g; %.7g; %.7g\n", it, m0s, mu, alpha, sG);  // src/BayesW.cpp:1909-1911
+                if (root) printf("%u. %d; %.7g; %.7g; %.7g\n", it, m0s, mu, alpha, sG);  // src/BayesW.cpp:1909-1911
                 if (it % opt.thin == 0) {
                     char buff[65536];
-                    int n = snprintf(buff, sizeof(buff), "%5d, %20.15f, %20.15f, %20.15f, %20.15f, %7d, %7d, %2d", (int)it, mu, sG, alpha,
-                                     sG / (sG + 9.86960440109 / (6 * alpha * alpha)), m0s, (int)G, (int)K);  // :1942
-                    for (uint32_t g = 0; g < G; g++) n += snprintf(buff + n, sizeof(buff) - n, ", %20.15f", sigmaG[g]);
-                    for (size_t x = 0; x < (size_t)G * K; x++) n += snprintf(buff + n, sizeof(buff) - n, ", %20.15f", pi[x]);
-                    n += snprintf(buff + n, sizeof(buff) - n, "\n");
-                    csv.put(buff, (size_t)n);
+                    if (root) {
+                        int n = snprintf(buff, sizeof(buff), "%5d, %20.15f, %20.15f, %20.15f, %20.15f, %7d, %7d, %2d", (int)it, mu, sG, alpha,
+                                         sG / (sG + 9.86960440109 / (6 * alpha * alpha)), m0s, (int)G, (int)K);  // :1942
+                        for (uint32_t g = 0; g < G; g++) n += snprintf(buff + n, sizeof(buff) - n, ", %20.15f", sigmaG[g]);
+                        for (size_t x = 0; x < (size_t)G * K; x++) n += snprintf(buff + n, sizeof(buff) - n, ", %20.15f", pi[x]);
+                        n += snprintf(buff + n, sizeof(buff) - n, "\n");
+                        csv.put(buff, (size_t)n);
+                        fflush(csv.f);
+                    }
                     HB(hb_brr_get_state(ctx, beta.data(), comp.data(), nullptr));
-                    bet.put(&it, 1); bet.put(beta.data(), Mtot);
-                    cpn.put(&it, 1); cpn.put(comp.data(), Mtot);
-                    fflush(csv.f); fflush(bet.f); fflush(cpn.f);
-                    if (n_cov) {   // "%5d, %20.17f, ..." (:1970-1980)
+                    const size_t ob = 4 + (size_t)n_saved * (4 + (size_t)Mtot * 8), oc = 4 + (size_t)n_saved * (4 + (size_t)Mtot * 4);
+                    if (root) { bet.write_at(&it, 4, ob); cpn.write_at(&it, 4, oc); }                 // :1950-1951
+                    bet.write_at(beta.data(), (size_t)m_local * 8, ob + 4 + (size_t)m_start * 8);      // :1955-1957
+                    cpn.write_at(comp.data(), (size_t)m_local * 4, oc + 4 + (size_t)m_start * 4);
+                    if (n_cov && root) {   // "%5d, %20.17f, ..." (:1970-1980)
                         HB(hb_bw_get_gamma(ctx, gamv.data(), xiv.data()));
                         int ng = snprintf(buff, sizeof(buff), "%5d", (int)it);
                         for (uint32_t f = 0; f < n_cov; f++) ng += snprintf(buff + ng, sizeof(buff) - ng, ", %20.17f", gamv[f]);
@@ -714,13 +768,15 @@ int main(int argc, const char **argv) {
                     n_saved++;
                 }
                 if (it > 0 && it % opt.save == 0) {
-                    if (n_cov) { HB(hb_bw_get_gamma(ctx, gamv.data(), xiv.data())); dump_file(out + ".xiv", it, n_cov, xiv.data()); }   // :1982-1990
-                    HB(hb_get_epsilon(ctx, eps.data()));
-                    dump_file(out + ".eps.0", it, N, eps.data());
-                    write_restart_file(out + ".rst.0", ctx, it, n_saved);
+                    if (root) {
+                        if (n_cov) { HB(hb_bw_get_gamma(ctx, gamv.data(), xiv.data())); dump_file(out + ".xiv", it, n_cov, xiv.data()); }   // :1982-1990
+                        HB(hb_get_epsilon(ctx, eps.data()));
+                        dump_file(out + ".eps.0", it, N, eps.data());
+                    }
+                    write_restart_file(rstf, ctx, it, n_saved);
                 }
             }
-            printf("INFO   : time to process the data: %.3f sec\n", tot_ms * 1e-3);
+            if (root) printf("INFO   : time to process the data: %.3f sec\n", tot_ms * 1e-3);
             hb_destroy(ctx);
             return 0;
         }
@@ -728,7 +784,6 @@ int main(int argc, const char **argv) {
         if (stat(opt.mcmcOutDir.c_str(), &sb) != 0 && system(("mkdir -p " + opt.mcmcOutDir).c_str()) != 0)
             throw std::runtime_error("could not create output directory --mcmc-out-dir " + opt.mcmcOutDir);
         const std::string out = opt.mcmcOut();
-        const bool root = (opt.rank == 0);
         // rank 0 creates the shared files (old ones are replaced, :1269-1309) before the communicator exists; hb_comm_init
         // is a barrier, after which the other processes open them
         SharedFile bet, acu, cpn, xb, xc;
@@ -740,39 +795,7 @@ int main(int argc, const char **argv) {
             bet.write_at(&Mtot, 4, 0); acu.write_at(&Mtot, 4, 0); cpn.write_at(&Mtot, 4, 0);  // :1304-1308
             xb.write_at(&Mtot, 4, 0); xc.write_at(&Mtot, 4, 0);
         }
-        if (opt.world > 1) {
-            // NCCL unique id through a file next to the outputs (rank 0 writes, the others wait for it)
-            const char *job = getenv("TORCHELASTIC_RUN_ID") ? getenv("TORCHELASTIC_RUN_ID") : (getenv("SLURM_JOB_ID") ? getenv("SLURM_JOB_ID") : (getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "0"));
-            const std::string idf = out + ".ncclid." + job;
-            // the file carries the NCCL id and rank 0's seed: without --seed every process would otherwise take its own
-            // time(0), and the hyper-parameter streams (drawn on every GPU instead of MPI_Bcast, :2585, 2705, 2731) would differ
-            uint8_t id[HB_NCCL_ID_BYTES + 4];
-            const time_t t_start = time(nullptr);
-            if (root) {
-                unlink(idf.c_str());  // a file left by a crashed run must not be picked up by the other ranks
-                HB(hb_comm_get_unique_id(id));
-                memcpy(id + HB_NCCL_ID_BYTES, &seed, 4);
-                FILE *f = fopen((idf + ".tmp").c_str(), "wb");
-                if (!f || fwrite(id, 1, sizeof(id), f) != sizeof(id)) throw std::runtime_error("cannot write " + idf);
-                fclose(f);
-                if (rename((idf + ".tmp").c_str(), idf.c_str()) != 0) throw std::runtime_error("cannot publish " + idf);
-            } else {
-                bool ok = false;
-                for (int tries = 0; tries < 1200 && !ok; tries++) {
-                    struct stat st;
-                    if (stat(idf.c_str(), &st) == 0 && st.st_size == (off_t)sizeof(id) && st.st_mtime >= t_start - 30) {  // the launcher starts the ranks together
-                        FILE *f = fopen(idf.c_str(), "rb");
-                        ok = f && fread(id, 1, sizeof(id), f) == sizeof(id);
-                        if (f) fclose(f);
-                    }
-                    if (!ok) usleep(100000);
-                }
-                if (!ok) throw std::runtime_error("timed out waiting for the NCCL id file " + idf);
-            }
-            HB(hb_comm_init(ctx, id, (int)opt.rank, (int)opt.world));
-            if (root) unlink(idf.c_str());
-            if (!opt.seedSet) memcpy(&seed, id + HB_NCCL_ID_BYTES, 4);
-        }
+        comm_setup(out);
         HB(hb_brr_init(ctx, y.data(), groups.empty() ? nullptr : groups.data(), mSflat.data(), nullptr, seed));  // multi-GPU: also checks that the seed is common
         if (n_cov) HB(hb_brr_set_covariates(ctx, Xcov.data(), n_cov));   // src/BayesRRm.cpp:1546-1560, 2648-2681
         if (!opt.priorsFile.empty() || !opt.dPriorsFile.empty()) {          // src/main.cpp:151-157

@@ -228,7 +228,12 @@ int hb_brr_set_fh(hb_ctx *ctx, const hb_fh_config *cfg, const double *state0);
  * (any may be NULL) */
 int hb_brr_get_fh(hb_ctx *ctx, double *scalars3, double *c_slab, double *lambda_var, double *nu_var);
 
-/* ---- BayesW chain (Weibull survival; src/BayesW.cpp:905-1907), single GPU in this version ------------- */
+/* ---- BayesW chain (Weibull survival; src/BayesW.cpp:905-1907) ------------------------------------------
+ * Several GPUs (hb_comm_init before hb_bw_init, one process per GPU): markers and tasks are split as for BayesRRm, epsilon is
+ * replicated; per synchronisation window every GPU's epsilon change is summed with ncclAllReduce over NVLink / NVSwitch (the
+ * reference's MPI_Allreduce of deltaEps, :1799-1835) and added on every GPU, so the replicas stay bit-identical; beta_squaredNorm
+ * and cass are all-reduced per iteration (:1866-1867); mu, alpha and the fixed effects are drawn on every GPU from the same
+ * streams on the same residual. */
 /* hb_config.model = 1. y: N log-times, fail: N failure indicators (0/1; src/data.cpp:1779), mS as for BayesRRm,
  * quad_points in {3,5,7,9,11,13,15,17,25} (--quad_points, :706-709). Initial values as BayesW::init (:728-853). */
 int hb_bw_init(hb_ctx *ctx, const double *y, const double *fail, const int32_t *groups, const double *mS,

@@ -512,3 +512,59 @@ def test_cli_bayesfh_and_prior_files_equal_python_run(tmp_path):
     open(os.path.join(d, "bad.gp"), "w").write("4.0,0.2\n")
     r = subprocess.run(base_args(d, "bad", ["--bfile", os.path.join(d, "t"), "--groupPriorsFile", os.path.join(d, "bad.gp")]), capture_output=True, text=True)
     assert r.returncode != 0 and "1 groups, the run has 2" in r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_bayesw_two_processes_two_gpus_equal_one_process(tmp_path):
+    """bayesWMPI with one process per GPU (mpirun -np 2 hydra --mpibayes bayesWMPI): the two processes' .bet / .cpn slices, rank 0's
+    .csv and residual equal the one-process run with the same 4 tasks (1e-9: the sum of the epsilon changes is taken in another
+    order); --restart from the two .rst.<rank> files continues byte for byte."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    d = str(tmp_path)
+    N, M = 600, 80
+    rng = np.random.default_rng(21)
+    bed, g = random_bed(rng, M, N, pmiss=0.01)
+    with open(os.path.join(d, "w.bed"), "wb") as f:
+        f.write(bytes([0x6C, 0x1B, 0x01]) + bed.tobytes())
+    open(os.path.join(d, "w.bim"), "w").write("".join(f"1\trs{j}\t0\t{j + 1}\tA\tC\n" for j in range(M)))
+    open(os.path.join(d, "w.fam"), "w").write("".join(f"F{i} I{i} 0 0 1 -9\n" for i in range(N)))
+    x = np.where(g < 0, 0, g).astype(np.float64)
+    y = 4.1 + 0.02 * (x[3] - x[3].mean()) - 0.03 * (x[50] - x[50].mean()) + 0.1 * np.log(rng.exponential(size=N))
+    fail = (rng.random(N) > 0.1).astype(int)
+    open(os.path.join(d, "w.phen"), "w").write("".join(f"F{i} I{i} {'NA' if i in (5, 17) else repr(float(y[i]))}\n" for i in range(N)))
+    open(os.path.join(d, "w.fail"), "w").write("".join(f"{fail[i]}\n" for i in range(N)))
+
+    def args(out, extra):
+        return [_exe(), "--mpibayes", "bayesWMPI", "--bfile", os.path.join(d, "w"), "--pheno", os.path.join(d, "w.phen"),
+                "--failure", os.path.join(d, "w.fail"), "--quad_points", "11", "--number-individuals", str(N), "--number-markers", str(M),
+                "--S", "0.001,0.01,0.1", "--thin", "1", "--save", "2", "--seed", "9", "--sync-rate", "3", "--tasks", "4",
+                "--mcmc-out-dir", os.path.join(d, out), "--mcmc-out-name", "w", *extra]
+
+    def run2(out, extra, port):
+        procs = [subprocess.Popen(args(out, extra + ["--rank", str(r), "--world", "2"]), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                                  env={**os.environ, "MASTER_PORT": port}) for r in range(2)]
+        outs = [p.communicate(timeout=300)[0] for p in procs]
+        assert all(p.returncode == 0 for p in procs), outs[0][-1500:] + outs[1][-1500:]
+        return outs
+    r = subprocess.run(args("one", ["--chain-length", "5"]), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    run2("two", ["--chain-length", "5"], "31997")
+    i1, b1 = read_bet(os.path.join(d, "one", "w.bet"), M)
+    i2, b2 = read_bet(os.path.join(d, "two", "w.bet"), M)
+    assert i1.tolist() == i2.tolist() == [0, 1, 2, 3, 4] and (b1 != 0).any()
+    np.testing.assert_allclose(b2, b1, rtol=1e-8, atol=1e-13)
+    assert open(os.path.join(d, "one", "w.cpn"), "rb").read() == open(os.path.join(d, "two", "w.cpn"), "rb").read()
+    e1 = np.fromfile(os.path.join(d, "one", "w.eps.0"), np.float64, offset=8)
+    e2 = np.fromfile(os.path.join(d, "two", "w.eps.0"), np.float64, offset=8)
+    np.testing.assert_allclose(e2, e1, rtol=1e-9, atol=1e-11)
+    c1 = [float(v) for v in open(os.path.join(d, "one", "w.csv")).read().split("\n")[4].split(",")]
+    c2 = [float(v) for v in open(os.path.join(d, "two", "w.csv")).read().split("\n")[4].split(",")]
+    np.testing.assert_allclose(c2, c1, rtol=1e-9)
+    # restart on two GPUs: 3 iterations (save point at 2), then continued to 5 = the uninterrupted two-GPU run, byte for byte
+    run2("twor", ["--chain-length", "3"], "31996")
+    outs = run2("twor", ["--chain-length", "5", "--restart"], "31995")
+    assert "restarting after iteration 2" in outs[0]
+    for ext in ("csv", "bet", "cpn", "eps.0"):
+        assert open(os.path.join(d, "two", "w." + ext), "rb").read() == open(os.path.join(d, "twor", "w." + ext), "rb").read(), ext
