@@ -95,7 +95,7 @@ EXPORTS = [
     "hb_stage_sparse", "hb_stage_synth", "hb_stage_finalize", "hb_marker_counts", "hb_marker_stats", "hb_marker_is_bed",
     "hb_genotype_bytes", "hb_export_sparse", "hb_export_bed", "hb_set_epsilon", "hb_get_epsilon", "hb_dot_markers",
     "hb_scaadd_markers", "hb_brr_init", "hb_brr_iteration", "hb_brr_get_hyper", "hb_brr_get_state", "hb_brr_get_state_async", "hb_brr_state_wait", "hb_brr_set_state", "hb_brr_restore_outputs", "hb_brr_save_state", "hb_brr_load_state",
-    "hb_brr_get_task_epsilon", "hb_brr_get_task_perm", "hb_brr_set_covariates", "hb_brr_get_gamma", "hb_brr_set_group_priors", "hb_brr_set_fh", "hb_brr_get_fh", "hb_comm_get_unique_id", "hb_comm_init", "hb_comm_check_equal",
+    "hb_brr_get_task_epsilon", "hb_brr_get_task_perm", "hb_brr_get_task_rng", "hb_brr_set_covariates", "hb_brr_get_gamma", "hb_brr_set_group_priors", "hb_brr_set_fh", "hb_brr_get_fh", "hb_comm_get_unique_id", "hb_comm_init", "hb_comm_check_equal",
     "hb_bw_init", "hb_bw_iteration", "hb_bw_set_covariates", "hb_bw_get_gamma", "hb_bw_get_hyper", "hb_bw_marker_stats", "hb_bw_vi_sums", "hb_bw_sum_exp",
     "hb_bw_marginal_likelihoods", "hb_bw_arms_beta",
 ]

@@ -1741,6 +1741,20 @@ constexpr uint32_t kRestartMagic = 0x32524248u;  // "HBR2"
 
 extern "C" {
 
+// .rng.<task> of the reference (src/distributions_boost.cpp:38-44: `file << rng`, the text form of a boost::mt19937). Here the
+// text form of the task's std::mt19937 (the same generator, libstdc++'s operator<<: 624 state words and the position).
+int hb_brr_get_task_rng(hb_ctx *c, uint32_t task_local, char *buf, size_t cap, size_t *need) {
+    HB_CHECK(c && c->brr_ready && need, HB_ERR_STATE, "hb_brr_get_task_rng: call hb_brr_init first");
+    HB_CHECK(task_local < c->T, HB_ERR_ARG, "hb_brr_get_task_rng: task %u of %u", task_local, c->T);
+    if (c->prefetch.joinable()) c->prefetch.join();  // the worker thread owns the task streams while it runs
+    const std::string t = rng_text(c->task_rng[task_local]);
+    *need = t.size() + 1;
+    if (!buf) return HB_OK;
+    HB_CHECK(cap >= t.size() + 1, HB_ERR_ARG, "hb_brr_get_task_rng: buffer of %zu bytes, %zu needed", cap, t.size() + 1);
+    memcpy(buf, t.c_str(), t.size() + 1);
+    return HB_OK;
+}
+
 int hb_brr_save_state(hb_ctx *c, void *buf, size_t cap, size_t *need) {
     HB_CHECK(c && c->brr_ready && need, HB_ERR_STATE, "hb_brr_save_state: call hb_brr_init first");
     HB_CUDA(cudaSetDevice(c->dev));

@@ -815,6 +815,12 @@ int main(int argc, const char **argv) {
             bet.open_rw(out + ".bet", false); acu.open_rw(out + ".acu", false); cpn.open_rw(out + ".cpn", false);
             xb.open_rw(out + ".xbet", false); xc.open_rw(out + ".xcpn", false);
         }
+        if (root) {   // list of the files of a dump (:1244-1262), one set of per-task files per reference rank = task
+            std::ofstream lst(out + ".lst");
+            lst << out + ".csv" << "\n" << out + ".xbet" << "\n" << out + ".xcpn" << "\n" << out + ".acu" << "\n";
+            for (uint32_t i = 0; i < opt.tasks; i++)
+                for (const char *e : {".rng.", ".mrk.", ".xiv.", ".eps.", ".gam.", ".mus."}) lst << out + e + std::to_string(i) << "\n";
+        }
         const uint32_t t_first = opt.rank * TL;
         std::vector<OutFile> mus(TL);
         uint32_t it_first = 0, n_saved = 0;
@@ -899,6 +905,12 @@ int main(int argc, const char **argv) {
                     perm.resize((size_t)bl[t_first + t]);
                     HB(hb_brr_get_task_perm(ctx, t, perm.data()));
                     dump_file(out + ".mrk." + std::to_string(t_first + t), it, (uint32_t)bl[t_first + t], perm.data());
+                    size_t need = 0;                                        // .rng.<task>: the task's stream as text (:2805)
+                    HB(hb_brr_get_task_rng(ctx, t, nullptr, 0, &need));
+                    std::string rs(need, '\0');
+                    HB(hb_brr_get_task_rng(ctx, t, &rs[0], need, &need));
+                    std::ofstream rf(out + ".rng." + std::to_string(t_first + t), std::ios::out | std::ios::trunc | std::ios::binary);
+                    rf << rs.c_str();
                 }
                 if (n_cov) {   // .gam.<rank> / .xiv.<rank>: u32 it; u32 len; f64 / i32 [len] (:2811-2831)
                     std::vector<double> gam(n_cov);
@@ -913,6 +925,23 @@ int main(int argc, const char **argv) {
                 xb.write_at(beta.data(), (size_t)m_local * 8, 8 + (size_t)m_start * 8);
                 xc.write_at(comp.data(), (size_t)m_local * 4, 8 + (size_t)m_start * 4);
                 write_restart_file(out + ".rst." + std::to_string(opt.rank), ctx, it, n_saved);
+                // tarball of the dump (:2851-2875): `tar -cf <dir>/tarballs/dump_<name>_<it>__<date>.tar -T <out>.lst` by rank 0 once all
+                // processes have written; the reference runs tar whether or not <dir>/tarballs exists, here only where it does
+                {
+                    const uint64_t v[1] = {it};
+                    HB(hb_comm_check_equal(ctx, v, 1, "the save point"));   // barrier (no-op on one GPU)
+                    struct stat stb;
+                    if (root && stat((opt.mcmcOutDir + "/tarballs").c_str(), &stb) == 0 && S_ISDIR(stb.st_mode)) {
+                        const time_t now = time(nullptr);
+                        const tm *ltm = localtime(&now);
+                        char tar[1024];
+                        snprintf(tar, sizeof(tar), "dump_%s_%05d__%4d-%02d-%02d_%02d-%02d-%02d.tar", opt.mcmcOutNam.c_str(), (int)it, 1900 + ltm->tm_year,
+                                 1 + ltm->tm_mon, ltm->tm_mday, ltm->tm_hour, ltm->tm_min, ltm->tm_sec);
+                        printf("INFO   : will create tarball %s in %s with file listed in %s.\n", tar, opt.mcmcOutDir.c_str(), (out + ".lst").c_str());
+                        const std::string cmd = "tar -cf " + opt.mcmcOutDir + "/tarballs/" + tar + " -T " + out + ".lst 2>/dev/null";
+                        if (system(cmd.c_str()) != 0) printf("WARNING: tar reported missing files (optional outputs such as .gam / .xiv are listed unconditionally, as in the reference)\n");
+                    }
+                }
             }
         }
         if (root)

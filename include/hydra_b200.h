@@ -194,6 +194,9 @@ int hb_brr_save_state(hb_ctx *ctx, void *buf, size_t cap, size_t *need);
 int hb_brr_load_state(hb_ctx *ctx, const void *buf, size_t n);
 /* epsilon of local task t as the reference dumps it to .eps.<rank> (:2827) */
 int hb_brr_get_task_epsilon(hb_ctx *ctx, uint32_t task_local, double *eps);
+/* random stream of local task t as text (.rng.<rank>, :2805, src/distributions_boost.cpp:38-44: the reference dumps its
+ * boost::mt19937 with operator<<; this is the std::mt19937 of RNG spec v1 in libstdc++'s text form). buf == NULL: only *need. */
+int hb_brr_get_task_rng(hb_ctx *ctx, uint32_t task_local, char *buf, size_t cap, size_t *need);
 /* current marker order of local task t (.mrk.<rank>, :2828) */
 int hb_brr_get_task_perm(hb_ctx *ctx, uint32_t task_local, int32_t *perm);
 

@@ -568,3 +568,27 @@ def test_cli_bayesw_two_processes_two_gpus_equal_one_process(tmp_path):
     assert "restarting after iteration 2" in outs[0]
     for ext in ("csv", "bet", "cpn", "eps.0"):
         assert open(os.path.join(d, "two", "w." + ext), "rb").read() == open(os.path.join(d, "twor", "w." + ext), "rb").read(), ext
+
+
+@pytest.mark.gpu
+def test_cli_dump_list_rng_files_and_tarball(tmp_path):
+    """The reference's dump at the save points (src/BayesRRm.cpp:1244-1262 the .lst file, :2805 .rng.<rank> = `file << rng`,
+    :2851-2875 `tar -cf <dir>/tarballs/dump_<name>_<it>__<date>.tar -T <out>.lst`)."""
+    import tarfile
+    d = str(tmp_path)
+    write_dataset(d)
+    os.makedirs(os.path.join(d, "o", "tarballs"))
+    r = subprocess.run(base_args(d, "o", ["--bfile", os.path.join(d, "t")]), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = os.path.join(d, "o", "run")
+    lst = open(out + ".lst").read().split("\n")
+    assert lst[:4] == [out + ".csv", out + ".xbet", out + ".xcpn", out + ".acu"] and out + ".rng.2" in lst and out + ".mus.0" in lst
+    for t in range(3):   # one stream per task: 624 state words and the position, as text
+        w = open(out + f".rng.{t}").read().split()
+        assert len(w) == 625 and all(x.isdigit() for x in w)
+    assert open(out + ".rng.0").read() != open(out + ".rng.1").read()
+    tars = os.listdir(os.path.join(d, "o", "tarballs"))
+    assert len(tars) == 1 and tars[0].startswith("dump_run_00004__") and tars[0].endswith(".tar")
+    names = tarfile.open(os.path.join(d, "o", "tarballs", tars[0])).getnames()
+    for ext in (".csv", ".xbet", ".xcpn", ".acu", ".rng.0", ".mrk.2", ".eps.1", ".mus.0"):
+        assert any(n.endswith("run" + ext) for n in names), (ext, names)
