@@ -282,31 +282,37 @@ __device__ __forceinline__ u64 gather4(uint64_t x, const u64 *__restrict__ Eq) {
     return (Eq[x & 0xFFFFu] + Eq[(x >> 16) & 0xFFFFu]) + (Eq[(x >> 32) & 0xFFFFu] + Eq[x >> 48]);
 }
 // BED word: the lane owns 32 consecutive individuals (word w of the slice block).
+// Shared-memory banks: individual k of ANY word sits in 8-byte bank k mod 16, so lanes that walk their words from the same end
+// hit the same bank (16-way conflicts on a dense marker). Every lane therefore walks its word from its own starting point:
+// the masks are rotated by 2*(lane & 15) bits, find-first-set runs on the rotated masks, and the position is rotated back.
+// The sums are integer: the order of the additions does not matter.
+__constant__ uint32_t g_bed_norot;   // developer knob (HB_NO_BED_ROT=1): walk every word from bit 0
+__device__ __forceinline__ uint32_t rotr32(uint32_t x, uint32_t r) { return __funnelshift_r(x, x, r); }
 __device__ __forceinline__ void dot_bed_word(uint64_t bits, uint32_t w, const u64 *__restrict__ Eq, u64 &a12, u64 &am) {
     // PLINK codes (b1 b0): 00 -> 2, 10 -> 1, 11 -> 0, 01 -> missing. Only the non-zero genotypes are
     // visited: A = individuals with b0 == 0 (genotype 1 or 2), of which those with b1 == 0 as well count twice; the
     // missing ones (b0 == 1, b1 == 0) are rare. The trip count is the lane's number of non-zeros, not 32.
     if (bits == ~0ull) return;  // 32 x genotype 0
     const u64 *e = Eq + 32u * w;
+    const uint32_t r2 = g_bed_norot ? 0u : (threadIdx.x & 15u) * 2u;
 #pragma unroll
     for (uint32_t h = 0; h < 2; h++) {  // 16 individuals per 32-bit half
         const uint32_t v = (uint32_t)(bits >> (32u * h));
         const uint32_t b0 = v & 0x55555555u, b1 = (v >> 1) & 0x55555555u;
-        uint32_t a = ~b0 & 0x55555555u;          // genotype 1 or 2
-        const uint32_t two = a & ~b1;            // genotype 2
-        uint32_t miss = b0 & ~b1;
+        uint32_t a = rotr32(~b0 & 0x55555555u, r2);      // genotype 1 or 2
+        const uint32_t two = rotr32(~b0 & ~b1 & 0x55555555u, r2);   // genotype 2
+        uint32_t miss = rotr32(b0 & ~b1, r2);
         const u64 *eh = e + 16u * h;
         while (a) {
-            const uint32_t pos = __ffs((int)a) - 1u;  // even bit position = 2 x individual
+            const uint32_t pos = __ffs((int)a) - 1u;  // even bit position = 2 x individual (rotated)
             a &= a - 1u;
-            const u64 x = eh[pos >> 1];
-            a12 += x;
-            if ((two >> pos) & 1u) a12 += x;
+            const u64 x = eh[((pos + r2) & 31u) >> 1];
+            a12 += x << ((two >> pos) & 1u);          // genotype 2 counts twice
         }
         while (miss) {
             const uint32_t pos = __ffs((int)miss) - 1u;
             miss &= miss - 1u;
-            am += eh[pos >> 1];
+            am += eh[((pos + r2) & 31u) >> 1];
         }
     }
 }
@@ -358,7 +364,18 @@ __device__ __forceinline__ void dot_unit(const uint4 d, const uint64_t (&x)[4], 
 #pragma unroll
         for (uint32_t t = 0; t < 4; t++)  // load_unit has fetched up to four words per lane
             if (lane + 32u * t < nwords) dot_bed_word(x[t], b2 + lane + 32u * t, Eq, a12, am);
-        for (uint32_t w = lane + 128u; w < nwords; w += 32u) dot_bed_word(ld_stream_u64(ptr + w), b2 + w, Eq, a12, am);
+        // the rest of a long unit: four words per lane requested together (one L2 / HBM round trip per 128 words, not per 32)
+        for (uint32_t w0 = 128u; w0 < nwords; w0 += 128u) {
+            uint64_t y[4];
+#pragma unroll
+            for (uint32_t t = 0; t < 4; t++) {
+                const uint32_t w = w0 + lane + 32u * t;
+                y[t] = ~0ull;                              // 32 x genotype 0: skipped
+                if (w < nwords) y[t] = ld_stream_u64(ptr + w);
+            }
+#pragma unroll
+            for (uint32_t t = 0; t < 4; t++) dot_bed_word(y[t], b2 + w0 + lane + 32u * t, Eq, a12, am);
+        }
         return;
     }
     dot_words(x, 0u, nwords, b1, b2, Eq, lane, a12, am);
@@ -892,18 +909,19 @@ __device__ __forceinline__ void apply_word(uint64_t x, long long q, u64 *__restr
 __device__ __forceinline__ long long apply_bed_word(uint64_t bits, uint32_t w, long long q1, long long q2, long long qm, u64 *__restrict__ Eq) {
     long long added = 0;
     if (bits == ~0ull) return added;
+    const uint32_t r2 = g_bed_norot ? 0u : (threadIdx.x & 15u) * 2u;   // every lane starts at its own bank (see dot_bed_word)
 #pragma unroll
     for (uint32_t h = 0; h < 2; h++) {  // only the non-zero genotypes are visited (codes as in dot_bed_word)
         const uint32_t v = (uint32_t)(bits >> (32u * h));
         const uint32_t b0 = v & 0x55555555u, b1 = (v >> 1) & 0x55555555u;
-        uint32_t a = (~b0 & 0x55555555u) | (b0 & ~b1);  // genotype 1, 2 or missing
-        const uint32_t two = ~b0 & ~b1 & 0x55555555u, miss = b0 & ~b1;
+        uint32_t a = rotr32((~b0 & 0x55555555u) | (b0 & ~b1), r2);  // genotype 1, 2 or missing
+        const uint32_t two = rotr32(~b0 & ~b1 & 0x55555555u, r2), miss = rotr32(b0 & ~b1, r2);
         u64 *eh = Eq + 32u * w + 16u * h;
         while (a) {
             const uint32_t pos = __ffs((int)a) - 1u;
             a &= a - 1u;
             const long long d = ((miss >> pos) & 1u) ? qm : (((two >> pos) & 1u) ? q2 : q1);
-            eh[pos >> 1] += (u64)d;
+            eh[((pos + r2) & 31u) >> 1] += (u64)d;
             added += d;
         }
     }

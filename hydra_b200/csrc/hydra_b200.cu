@@ -397,6 +397,7 @@ int hb_create(const hb_config *cfg, hb_ctx **out) {
     HB_CUDA(cudaGetDeviceProperties(&prop, c->dev));
     HB_CHECK(prop.major >= 10, HB_ERR_CUDA, "hb_create: device %d is sm_%d%d; this library is built for sm_100a only", c->dev, prop.major, prop.minor);
     HB_CHECK(prop.cooperativeLaunch, HB_ERR_CUDA, "hb_create: device lacks cooperative launch");
+    { const uint32_t norot = getenv("HB_NO_BED_ROT") ? 1u : 0u; HB_CUDA(cudaMemcpyToSymbol(g_bed_norot, &norot, sizeof(norot))); }   // developer knob
     c->n_sms = prop.multiProcessorCount;
     c->Nraw = cfg->n_ind_raw;
     c->N = cfg->n_ind_raw - cfg->n_na;
