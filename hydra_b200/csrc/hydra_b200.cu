@@ -1299,13 +1299,14 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
     if (c->nranks > 1) {
         // group statistics summed over the GPUs (MPI_Allreduce of beta_squaredNorm and cass, :2517-2518); e_sqn is that
         // of global task 0, whose sigmaE draw the reference broadcasts (:2705)
-        const size_t nr = G + gk + 3;
+        const size_t nr = G + gk + 4;
         std::vector<double> red(nr, 0.0);
         for (uint32_t g = 0; g < G; g++) red[g] = c->bsq[g];
         for (size_t x = 0; x < gk; x++) red[G + x] = (double)c->cass[x];
         red[G + gk] = (c->t_first == 0) ? e_sqn : 0.0;
         red[G + gk + 1] = (double)pin_stats[5];
         red[G + gk + 2] = (c->t_first == 0) ? c->mu[0] : 0.0;   // mu of global task 0 (the fixed effects use its residual)
+        red[G + gk + 3] = c->fh_on ? c->fh_sbsqn : 0.0;         // bayesFH: scaled sum of squares over all markers (see hb_brr_set_fh)
         HB_CUDA(cudaMemcpyAsync(c->d_red.p, red.data(), sizeof(double) * nr, cudaMemcpyHostToDevice, st));
         HB_NCCL(ncclAllReduce(c->d_red.p, c->d_red.p + nr, nr, ncclDouble, ncclSum, c->nccl, st));
         HB_CUDA(cudaMemcpyAsync(red.data(), c->d_red.p + nr, sizeof(double) * nr, cudaMemcpyDeviceToHost, st));
@@ -1315,6 +1316,7 @@ int hb_brr_iteration(hb_ctx *c, const hb_brr_tape *tape, hb_brr_iter_out *out) {
         e_sqn_g = red[G + gk];
         changed_all = (unsigned long long)llround(red[G + gk + 1]);
         mu_g0 = red[G + gk + 2];
+        if (c->fh_on) c->fh_sbsqn = red[G + gk + 3];
     }
 
     // ---- hyper-parameters (:2525-2578, 2685-2731)
@@ -1602,8 +1604,9 @@ int hb_brr_set_fh(hb_ctx *c, const hb_fh_config *cfg, const double *state0) {
     HB_CUDA(cudaSetDevice(c->dev));
     if (!cfg) { c->fh_on = false; return HB_OK; }
     // The reference neither reduces the scaled sum of squares over its ranks nor broadcasts tau / c_slab (src/BayesRRm.cpp:2503-2510,
-    // 2557-2565): with several ranks every rank follows its own FH parameters. One GPU (any number of tasks) only.
-    HB_CHECK(c->nranks == 1, HB_ERR_STATE, "hb_brr_set_fh: bayesFH runs on one GPU");
+    // 2557-2565): with several ranks every rank follows its own FH parameters (flagged, not reproduced). Here ONE set of parameters:
+    // the sum runs over all markers of all tasks and GPUs (all-reduced with the group statistics), and tau / hypTau / c_slab are
+    // drawn on every GPU from the common hyper-parameter stream.
     HB_CHECK(cfg->v0L > 0.0 && cfg->v0t > 0.0 && cfg->v0c > 0.0 && cfg->s02c > 0.0 && cfg->tau0 > 0.0, HB_ERR_ARG,
              "hb_brr_set_fh: v0L, v0t, v0c, s02c and tau0 must be positive");
     const uint32_t G = c->G, M = c->M;
@@ -1658,7 +1661,6 @@ int hb_comm_init(hb_ctx *c, const uint8_t id[HB_NCCL_ID_BYTES], int rank, int nr
     HB_CHECK(c && id, HB_ERR_ARG, "null argument");
     HB_CHECK(nranks >= 1 && nranks <= (int)kMaxRanks && rank >= 0 && rank < nranks, HB_ERR_ARG, "hb_comm_init: rank %d of %d (max %u GPUs)", rank, nranks, kMaxRanks);
     HB_CHECK(!c->nccl, HB_ERR_STATE, "hb_comm_init: already initialised");
-    HB_CHECK(!(c->fh_on && nranks > 1), HB_ERR_STATE, "hb_comm_init: bayesFH runs on one GPU");
     HB_CUDA(cudaSetDevice(c->dev));
     if (nranks == 1) return HB_OK;
     ncclUniqueId u;

@@ -560,7 +560,6 @@ int main(int argc, const char **argv) {
         const bool bayesFH = (opt.bayesType == "bayesFHMPI");
         if (!opt.bedToSparse && opt.bayesType != "bayesMPI" && !bayesW && !bayesFH)
             throw std::runtime_error("--mpibayes " + opt.bayesType + ": bayesMPI (BayesRRm), bayesFHMPI (BayesFH) and bayesWMPI (BayesW) are available in this build");
-        if (bayesFH && opt.world > 1) throw std::runtime_error("--mpibayes bayesFHMPI runs on one GPU (any number of --tasks)");
         if (bayesW && (!opt.priorsFile.empty() || !opt.dPriorsFile.empty()))
             throw std::runtime_error("--groupPriorsFile / --dPriorsFile are read by bayesMPI and bayesFHMPI (src/BayesRRm.cpp:2545-2554), not by bayesWMPI");
         if (bayesW && repr == HB_REPR_MIXED) throw std::runtime_error("bayesWMPI reads bed or sparse input, not both (src/BayesW.cpp:1149-1192)");

@@ -221,8 +221,9 @@ int hb_brr_set_group_priors(hb_ctx *ctx, const double *v0G_s02G, const double *d
  * :2557-2565 hypTau / tau / c_slab; defaults src/options.hpp:91-96). Call after hb_brr_init (cfg == NULL switches it off);
  * state0 = { hypTau, tau, c_slab[n_groups] } or NULL = drawn from the hyper-parameter stream in the reference's order. The two
  * per-marker draws leave the marker loop (they depend on the marker's own previous state only): one kernel before it, one after.
- * One GPU: the reference neither reduces the scaled sum of squares nor broadcasts tau / c_slab, its ranks' parameters diverge
- * (flagged, not reproduced; with several tasks on one GPU the sum runs over all markers, as in a one-rank run). */
+ * The reference neither reduces the scaled sum of squares over its ranks nor broadcasts tau / c_slab: its ranks' FH parameters
+ * diverge (flagged, not reproduced). Here one set of parameters, as in a one-rank run of the reference: the sum runs over all
+ * markers of all tasks and GPUs, tau / hypTau / c_slab are drawn on every GPU from the common hyper-parameter stream. */
 typedef struct hb_fh_config {
     double v0L, v0t, v0c, s02c, tau0;
 } hb_fh_config;

@@ -81,12 +81,76 @@ def bayesw_cases(rank, world, lr):
             print(f"BayesW multi-GPU parity case {case} ok on {world} GPUs", flush=True)
 
 
+def fh_cases(rank, world, lr):
+    """bayesFHMPI on several GPUs: per-marker scales stay with the marker's GPU, the scaled sum of squares is all-reduced with the
+    group statistics, tau / hypTau / c_slab are drawn on every GPU from the common stream. Against the oracle with T_total tasks."""
+    for case, (N, M, TL, SR, G, K, repr_mode, n_iter, seed, replay) in enumerate([
+        (1500, 600, 2, 5, 2, 4, "sparse", 4, 41, True),
+        (1200, 403, 3, 4, 1, 3, "mixed", 4, 42, False),
+    ]):
+        T = TL * world
+        rng = np.random.default_rng(seed)
+        bed, g = random_bed(rng, M, N, pmiss=0.01)
+        sp = reference_lists(bed, N)
+        y = simulate_y(rng, g, n_causal=max(3, M // 20))
+        groups = (np.arange(M) % G).astype(np.int32)
+        mS = np.tile(np.array([0.0] + [10.0 ** (-(K - 1 - k)) for k in range(1, K)]), (G, 1))
+        sigmaG0 = rng.uniform(0.2, 0.8, size=G)
+        tape = oracle.TapeMaker(seed, T, M).make(n_iter)
+        fh = dict(oracle.FH_DEFAULTS)
+        state0 = None
+        if replay:
+            tape["gnu"] = rng.gamma(2.0, size=(n_iter, M))
+            tape["glam"] = rng.gamma(2.0, size=(n_iter, M))
+            tape["fh_hyper"] = np.stack([rng.uniform(0.5, 3.0, (n_iter, G)), rng.uniform(0.005, 0.05, (n_iter, G)), rng.uniform(0.1, 1.0, (n_iter, G))], axis=2)
+            state0 = np.concatenate([[1.7, 0.02], rng.uniform(0.2, 0.9, G)])
+        fnz = (sp.N1L + sp.N2L + sp.NML).astype(np.float64) / N
+        usebed = {"sparse": np.zeros(M, np.uint8), "mixed": (fnz > 0.35).astype(np.uint8)}[repr_mode]
+        ref = oracle.brr_chain(N, M, T, K, G, SR, n_iter, sp, y, groups, mS, tape, sigmaG0, usebed=usebed, bed=bed_from_lists(sp, N),
+                               hyper_seed=(seed ^ 0x5bd1e995) & 0xFFFFFFFF, fh=dict(fh, state0=state0, seed=seed))
+        st = hydra_b200.GenotypeStore(N, M, tasks=T, task_first=rank * TL, tasks_local=TL, sync_rate=SR, n_groups=G, n_mix=K,
+                                      repr_mode=repr_mode, threshold_fnz=0.35, device=lr)
+        ms, ml = st.m_start, st.m_local
+        st.load_data_from_bed(bed[ms:ms + ml])
+        st.finalize()
+        st.comm_init(dist)
+        brr = hydra_b200.BayesRRm(st, y, mS, groups=groups, sigmaG0=sigmaG0, seed=seed, fh=dict(fh, state0=state0))
+        for it in range(n_iter):
+            tp = None
+            if replay:
+                tp = dict(zmu=tape["zmu"][it][rank * TL:(rank + 1) * TL], perm=tape["perm"][it][ms:ms + ml], u=tape["u"][it][ms:ms + ml],
+                          z=tape["z"][it][ms:ms + ml], gnu=tape["gnu"][it][ms:ms + ml], glam=tape["glam"][it][ms:ms + ml], fh_hyper=tape["fh_hyper"][it],
+                          sigmaG=ref["sigmaG"][it], pi=ref["pi"][it], sigmaE=ref["sigmaE"][it:it + 1])
+            o = brr.iteration(tp)
+            beta, comp, _ = brr.state()
+            h, f = brr.hyper(), brr.fh_state()
+            assert np.array_equal(comp, ref["comp"][it][ms:ms + ml]), f"FH case {case} rank {rank}: components differ at iteration {it}"
+            np.testing.assert_allclose(beta, ref["beta"][it][ms:ms + ml], rtol=1e-10, atol=1e-15)
+            np.testing.assert_allclose(f["lambda_var"], ref["lambda"][it][ms:ms + ml], rtol=1e-10)
+            np.testing.assert_allclose(f["nu_var"], ref["nu"][it][ms:ms + ml], rtol=1e-10)
+            np.testing.assert_allclose([f["hypTau"], f["tau"], f["scaledBSQN"]], ref["fh"][it, :3], rtol=1e-10)
+            np.testing.assert_allclose(f["c_slab"], ref["fh"][it, 3:], rtol=1e-10)
+            assert np.array_equal(h["cass"], ref["cass"][it])
+            np.testing.assert_allclose(h["sigmaG"], ref["sigmaG"][it], rtol=1e-10)
+            np.testing.assert_allclose(h["sigmaE"], ref["sigmaE"][it], rtol=1e-10)
+            assert o["n_sync"] == ref["nsync"][it]
+            for t in range(TL):
+                np.testing.assert_allclose(brr.task_epsilon(t), ref["eps"][it, rank * TL + t], rtol=1e-10, atol=1e-12)
+        st.close()
+        dist.barrier()
+        if rank == 0:
+            print(f"bayesFH multi-GPU parity case {case} ok on {world} GPUs", flush=True)
+
+
 def main():
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-    if "bayesw" in sys.argv[1:]:
-        bayesw_cases(rank, world, lr)
+    if "bayesw" in sys.argv[1:] or "fh" in sys.argv[1:]:
+        if "bayesw" in sys.argv[1:]:
+            bayesw_cases(rank, world, lr)
+        if "fh" in sys.argv[1:]:
+            fh_cases(rank, world, lr)
         dist.destroy_process_group()
         return
     for case, (N, M, TL, SR, G, K, repr_mode, n_iter, seed) in enumerate([

@@ -25,12 +25,13 @@ def test_multi_gpu_replay_matches_oracle(world):
     assert "case 4 ok" in r.stdout
 
 
-def test_multi_gpu_bayesw_replay_matches_oracle():
+def test_multi_gpu_bayesw_and_bayesfh_replay_match_oracle():
     """BayesW over 2 GPUs (the window's epsilon changes summed with ncclAllReduce, src/BayesW.cpp:1799-1835) against the oracle."""
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29511", os.path.join(ROOT, "tests", "mgpu_parity.py"), "bayesw"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+           "--master-port", "29511", os.path.join(ROOT, "tests", "mgpu_parity.py"), "bayesw", "fh"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "HB_PEER_TIMEOUT_S": "20"})
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "BayesW multi-GPU parity case 2 ok" in r.stdout or "skipped" in r.stdout
+    assert "bayesFH multi-GPU parity case 1 ok" in r.stdout   # bayesFHMPI over 2 GPUs (same launch: one torchrun start-up)
