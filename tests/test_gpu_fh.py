@@ -15,16 +15,24 @@ RTOL = 1e-10
 
 
 def _case(N, M, T, SR, G, K, repr_mode, n_iter, seed, replay, n_slices=0, n_causal=None, fhp=None, dirichlet=None, group_priors=None,
-          restart=False):
+          restart=False, n_cov=0):
     import hydra_b200
     rng = np.random.default_rng(seed)
     bed, g = random_bed(rng, M, N, pmiss=0.01)
     sp = reference_lists(bed, N)
     y = simulate_y(rng, g, n_causal=max(3, M // 10) if n_causal is None else n_causal)
+    X = None
+    if n_cov:   # fixed effects next to the FH prior: the covariate block runs between the FH hyper-parameters and sigmaE (:2648-2681)
+        X = rng.normal(size=(N, n_cov))
+        X = (X - X.mean(0)) / X.std(0, ddof=1)
+        y = y + X @ rng.normal(0, 0.4, n_cov)
     groups = (np.arange(M) % G).astype(np.int32)
     mS = np.tile(np.array([0.0] + [10.0 ** (-(K - 1 - k)) for k in range(1, K)]), (G, 1))
     sigmaG0 = rng.uniform(0.2, 0.8, size=G)
     tape = oracle.TapeMaker(seed, T, M).make(n_iter)
+    if n_cov and replay:
+        tape["xI"] = np.array([rng.permutation(n_cov) for _ in range(n_iter)], np.int32)
+        tape["zcov"] = rng.normal(size=(n_iter, n_cov))
     fh = dict(oracle.FH_DEFAULTS, **(fhp or {}))
     fnz = (sp.N1L + sp.N2L + sp.NML).astype(np.float64) / N
     usebed = {"sparse": np.zeros(M, np.uint8), "bed": np.ones(M, np.uint8), "mixed": (fnz > 0.35).astype(np.uint8)}[repr_mode]
@@ -37,14 +45,14 @@ def _case(N, M, T, SR, G, K, repr_mode, n_iter, seed, replay, n_slices=0, n_caus
         tape["fh_hyper"] = np.stack([rng.uniform(0.5, 3.0, (n_iter, G)), rng.uniform(0.005, 0.05, (n_iter, G)), rng.uniform(0.1, 1.0, (n_iter, G))], axis=2)
         state0 = np.concatenate([[1.7, 0.02], rng.uniform(0.2, 0.9, G)])
     ref = oracle.brr_chain(N, M, T, K, G, SR, n_iter, sp, y, groups, mS, tape, sigmaG0, usebed=usebed, bed=bed_from_lists(sp, N),
-                           hyper_seed=hseed, fh=dict(fh, state0=state0, seed=seed), dirichlet=dirichlet, group_priors=group_priors)
+                           hyper_seed=hseed, fh=dict(fh, state0=state0, seed=seed), dirichlet=dirichlet, group_priors=group_priors, covariates=X)
     totals = {}
     with hydra_b200.GenotypeStore(N, M, tasks=T, sync_rate=SR, n_groups=G, n_mix=K, repr_mode=repr_mode, n_slices=n_slices,
                                   threshold_fnz=0.35) as st:
         st.load_data_from_bed(bed)
         st.finalize()
         mk = lambda: hydra_b200.BayesRRm(st, y, mS, groups=groups, sigmaG0=sigmaG0, seed=seed, fh=dict(fh, state0=state0),
-                                         dirichlet_priors=dirichlet, group_priors=group_priors)
+                                         dirichlet_priors=dirichlet, group_priors=group_priors, covariates=X)
         brr = mk()
         blob = None
         for it in range(n_iter):
@@ -54,7 +62,11 @@ def _case(N, M, T, SR, G, K, repr_mode, n_iter, seed, replay, n_slices=0, n_caus
             if replay:
                 tp = dict(zmu=tape["zmu"][it], perm=tape["perm"][it], u=tape["u"][it], z=tape["z"][it], gnu=tape["gnu"][it], glam=tape["glam"][it],
                           fh_hyper=tape["fh_hyper"][it], sigmaG=ref["sigmaG"][it], pi=ref["pi"][it], sigmaE=ref["sigmaE"][it:it + 1])
+                if n_cov:
+                    tp.update(xI=tape["xI"][it], zcov=tape["zcov"][it])
             o = brr.iteration(tp)
+            if n_cov:
+                np.testing.assert_allclose(brr.gamma()[0], ref["gamma"][it], rtol=RTOL, atol=1e-14, err_msg=f"gamma it {it}")
             beta, comp, acum = brr.state()
             h, f = brr.hyper(), brr.fh_state()
             assert np.array_equal(comp, ref["comp"][it]), f"components differ at iteration {it}"
@@ -100,6 +112,14 @@ def test_fh_rng_spec_v1_device_gammas_and_host_hyper_draws():
     """tape = None: the per-marker gammas come from the device's Philox Marsaglia-Tsang, hypTau / tau / c_slab (and their initial
     values, :1147-1154) from the hyper-parameter stream; the oracle draws the same spec on the CPU."""
     _case(N=1000, M=400, T=2, SR=3, G=2, K=3, repr_mode="sparse", n_iter=4, seed=2025, replay=False, restart=True)
+
+
+@pytest.mark.parametrize("replay", [True, False])
+def test_fh_with_covariates_and_group_priors(replay):
+    """bayesFHMPI together with --covariates, --groupPriorsFile and --dPriorsFile: draw order of the hyper-parameter stream per
+    iteration = per group {hypTau, tau, c_slab, pi}, then the covariates' shuffle and normals, then sigmaE."""
+    _case(N=1300, M=300, T=3, SR=4, G=2, K=4, repr_mode="sparse", n_iter=4, seed=77, replay=replay, n_cov=3, restart=True,
+          group_priors=np.array([[4.0, 0.2], [2.5, 0.05]]), dirichlet=np.array([[5.0, 1.0, 1.0, 1.0], [1.0, 2.0, 2.0, 0.5]]))
 
 
 def test_fh_rng_spec_shape_below_one():
