@@ -553,15 +553,30 @@ int main(int argc, const char **argv) {
                repr == HB_REPR_MIXED ? "mixed" : (repr == HB_REPR_BED ? "bed" : "sparse"));
         for (auto &ig : opt.ignored)
             printf("INFO   : option %s has no effect here (the GPUs always exchange the changed markers themselves; restart uses <out>.rst.<rank>)\n", ig.c_str());
-        if (opt.dryRun) {
-            printf("INFO   : dry run: options and input files parsed, nothing computed\n");
-            return 0;
-        }
         const bool bayesFH = (opt.bayesType == "bayesFHMPI");
         if (!opt.bedToSparse && opt.bayesType != "bayesMPI" && !bayesW && !bayesFH)
             throw std::runtime_error("--mpibayes " + opt.bayesType + ": bayesMPI (BayesRRm), bayesFHMPI (BayesFH) and bayesWMPI (BayesW) are available in this build");
         if (bayesW && (!opt.priorsFile.empty() || !opt.dPriorsFile.empty()))
             throw std::runtime_error("--groupPriorsFile / --dPriorsFile are read by bayesMPI and bayesFHMPI (src/BayesRRm.cpp:2545-2554), not by bayesWMPI");
+        // per-group priors (src/main.cpp:151-157): read with the other inputs, so that a malformed file stops a dry run too
+        std::vector<double> group_priors, dirichlet_priors;
+        if (!opt.priorsFile.empty()) {
+            group_priors = read_prior_matrix(opt.priorsFile, G, 2, "--groupPriorsFile");
+            printf("INFO   : group priors (v0G, s02G) of %u group(s) read from %s\n", G, opt.priorsFile.c_str());
+        }
+        if (!opt.dPriorsFile.empty()) {
+            dirichlet_priors = read_prior_matrix(opt.dPriorsFile, G, K, "--dPriorsFile");
+            printf("INFO   : Dirichlet parameters of %u group(s) x %u components read from %s\n", G, K, opt.dPriorsFile.c_str());
+        }
+        if (bayesFH) {
+            if (!(opt.tau0 > 0 && opt.v0t > 0 && opt.v0c > 0 && opt.s02c > 0 && opt.v0L > 0))
+                throw std::runtime_error("bayesFHMPI: --tau0, --v0t, --v0c, --s02c and --v0L must be positive");
+            printf("INFO   : bayesFH hyper-parameters: tau0 %g v0t %g v0c %g s02c %g v0L %g\n", opt.tau0, opt.v0t, opt.v0c, opt.s02c, opt.v0L);
+        }
+        if (opt.dryRun) {
+            printf("INFO   : dry run: options and input files parsed, nothing computed\n");
+            return 0;
+        }
         if (bayesW && repr == HB_REPR_MIXED) throw std::runtime_error("bayesWMPI reads bed or sparse input, not both (src/BayesW.cpp:1149-1192)");
 
         // ---- device context
@@ -797,12 +812,8 @@ int main(int argc, const char **argv) {
         comm_setup(out);
         HB(hb_brr_init(ctx, y.data(), groups.empty() ? nullptr : groups.data(), mSflat.data(), nullptr, seed));  // multi-GPU: also checks that the seed is common
         if (n_cov) HB(hb_brr_set_covariates(ctx, Xcov.data(), n_cov));   // src/BayesRRm.cpp:1546-1560, 2648-2681
-        if (!opt.priorsFile.empty() || !opt.dPriorsFile.empty()) {          // src/main.cpp:151-157
-            std::vector<double> gp, dp;
-            if (!opt.priorsFile.empty()) gp = read_prior_matrix(opt.priorsFile, G, 2, "--groupPriorsFile");
-            if (!opt.dPriorsFile.empty()) dp = read_prior_matrix(opt.dPriorsFile, G, K, "--dPriorsFile");
-            HB(hb_brr_set_group_priors(ctx, gp.empty() ? nullptr : gp.data(), dp.empty() ? nullptr : dp.data()));
-        }
+        if (!group_priors.empty() || !dirichlet_priors.empty())              // :2545-2554
+            HB(hb_brr_set_group_priors(ctx, group_priors.empty() ? nullptr : group_priors.data(), dirichlet_priors.empty() ? nullptr : dirichlet_priors.data()));
         if (bayesFH) {                                                       // src/BayesRRm.cpp:1125-1163
             hb_fh_config fc{opt.v0L, opt.v0t, opt.v0c, opt.s02c, opt.tau0};
             HB(hb_brr_set_fh(ctx, &fc, nullptr));

@@ -110,6 +110,33 @@ def test_cli_accepts_the_reference_sync_options_and_refuses_unsupported_ones(tmp
     assert "numFixedEffect = 2" in r.stdout and "(8 NA phenotypes)" in r.stdout    # 7 NA phenotypes + 1 NA covariate
 
 
+def test_cli_dry_run_bayesfh_options_and_prior_files(tmp_path):
+    """--mpibayes bayesFHMPI with its five options (src/options.cpp:116-135) and the two prior files in the reference's ';' / ','
+    text format (src/data.cpp:2034-2096) are parsed and validated without a GPU."""
+    d = str(tmp_path)
+    write_dataset(d)
+    open(os.path.join(d, "t.gp"), "w").write("4.0,0.2; 2.5,0.05\n")
+    open(os.path.join(d, "t.dp"), "w").write("5,1,1,1;\n 1,2,2,0.5\n")
+
+    def run(extra, typ="bayesFHMPI"):
+        a = base_args(d, "o", ["--bfile", os.path.join(d, "t"), "--dry-run"] + extra)
+        a[a.index("bayesMPI")] = typ
+        return subprocess.run(a, capture_output=True, text=True)
+    r = run(["--groupPriorsFile", os.path.join(d, "t.gp"), "--dPriorsFile", os.path.join(d, "t.dp"), "--tau0", "0.5", "--v0t", "4", "--v0L", "2.5"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "bayesFH hyper-parameters: tau0 0.5 v0t 4 v0c 3 s02c 1 v0L 2.5" in r.stdout
+    assert "group priors (v0G, s02G) of 2 group(s)" in r.stdout and "Dirichlet parameters of 2 group(s) x 4 components" in r.stdout
+    r = run(["--tau0", "-1"])
+    assert r.returncode != 0 and "must be positive" in r.stdout + r.stderr
+    open(os.path.join(d, "bad.dp"), "w").write("5,1,1; 1,2,2\n")          # one value short per group
+    r = run(["--dPriorsFile", os.path.join(d, "bad.dp")], typ="bayesMPI")
+    assert r.returncode != 0 and "3 values, 4 needed" in r.stdout + r.stderr
+    r = run(["--groupPriorsFile", os.path.join(d, "nofile.gp")], typ="bayesMPI")
+    assert r.returncode != 0 and "can not open the --groupPriorsFile file" in r.stdout + r.stderr
+    r = run([], typ="bayesXYZ")
+    assert r.returncode != 0 and "bayesFHMPI (BayesFH)" in r.stdout + r.stderr
+
+
 def test_cli_reads_the_reference_example_files():
     # parser fixtures shipped with the reference (SURVEY 8c iv): copied line counts only, no reference file is read at GPU time
     ex = "/root/reference/example"
