@@ -1808,6 +1808,8 @@ int hb_brr_load_state(hb_ctx *c, const void *buf, size_t n) {
     uint32_t head[12] = {0};
     r.get(head, 12);
     HB_CHECK(r.ok && head[0] == kRestartMagic, HB_ERR_ARG, "hb_brr_load_state: not a hydra_b200 restart state");
+    HB_CHECK(head[1] == (uint32_t)HB_ABI_VERSION, HB_ERR_ARG, "hb_brr_load_state: the state was written by ABI version %u of the library, this is version %d "
+             "(restart from the output files instead: remove the .rst.<rank> files)", head[1], HB_ABI_VERSION);
     HB_CHECK(head[2] == c->N && head[3] == c->M && head[4] == c->T && head[5] == c->G && head[6] == c->K && head[7] == c->S && head[8] == c->L,
              HB_ERR_ARG, "hb_brr_load_state: the state belongs to another problem (N %u M %u tasks %u groups %u mixtures %u slices %u x %u; here %u %u %u %u %u %u x %u)",
              head[2], head[3], head[4], head[5], head[6], head[7], head[8], c->N, c->M, c->T, c->G, c->K, c->S, c->L);
