@@ -44,6 +44,13 @@ struct BwParams {
     int mode;
     const double *beta_in;     // BW_VISUMS: beta_old per position (unit mode)
     double *out;               // unit modes: [W*4]
+    // Window sequence on the device (src/BayesW.cpp:1633-1660: synchronise after sync_rate steps, or after every step while nothing
+    // changes): ctl = { j0, since, n, n_sync, n_changed, n_windows }. The kernels of window w read ctl_in and the last one writes
+    // ctl_out (two blocks in turn), so the host enqueues several windows without waiting for any of them; a window past the end of
+    // the marker loop (j0 >= lmax) does nothing. NULL: base / W / j0 as given (unit modes).
+    const uint32_t *ctl_in;
+    uint32_t *ctl_out;
+    uint32_t lmax, SR;
     double *delta;             // several GPUs: [S*L + 2] this GPU's epsilon change of the window (zeroed), then { its constant term, its
                                // number of changed markers }: summed over the GPUs (the reference's MPI_Allreduce of deltaEps,
                                // src/BayesW.cpp:1799-1835) and applied by k_bw_apply_delta; NULL on one GPU
@@ -136,7 +143,13 @@ __global__ void __launch_bounds__(256) k_bw_window(const BwParams P) {
     __shared__ uint32_t s_cum[kBwMaxS + 1], s_st[kBwMaxS], s_w1[kBwMaxS], s_w12[kBwMaxS];
     __shared__ BwArmsShared s_arms;
     const uint32_t p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int32_t m = P.order[P.base + p];
+    uint32_t w_base = P.base, w_j0 = P.j0;
+    if (P.ctl_in) {   // the window as the device left it
+        w_j0 = P.ctl_in[0];
+        if (w_j0 >= P.lmax || p >= P.ctl_in[2] * P.T) return;
+        w_base = w_j0 * P.T;
+    }
+    const int32_t m = P.order[w_base + p];
     if (m < 0) return;
     const uint64_t rr = P.rec[m];
     const double shift = *P.shift_in;
@@ -243,7 +256,7 @@ __global__ void __launch_bounds__(256) k_bw_window(const BwParams P) {
     }
     double MLsum = 0.0;
     for (uint32_t k = 0; k < K; k++) MLsum += ML[k];
-    const double prob = P.unif[P.base + p];                                       // :1528
+    const double prob = P.unif[w_base + p];                                       // :1528
     double acum = ML[0] / MLsum;                                                  // :1536
     int comp = -1;
     for (uint32_t k = 0; k < K; k++) {
@@ -255,7 +268,7 @@ __global__ void __launch_bounds__(256) k_bw_window(const BwParams P) {
     double beta_new = beta_old;  // the cascade can fall through without a draw (as in the reference)
     if (comp == 0) beta_new = 0.0;
     else if (comp > 0) {
-        BwArmsRand ur{P.seed, P.t_first + (p % P.T), P.iteration, P.j0 + p / P.T, 0u};
+        BwArmsRand ur{P.seed, P.t_first + (p % P.T), P.iteration, w_j0 + p / P.T, 0u};
         const int rc = bw_sample_beta(bm, P.cVa[g * km1 + comp - 1], P.sumSigmaG, beta_old, ur, &beta_new, s_arms.env, BwCoopCumulate{&s_arms});
         if (rc != ARMS_OK) { atomicExch(P.err, (uint32_t)rc); bw_arms_release(s_arms); return; }
     }
@@ -275,6 +288,27 @@ __global__ void __launch_bounds__(256) k_bw_window(const BwParams P) {
 }
 
 // one CTA per slice; entries are applied in window order (global memory epsilon, L2 coherent accesses)
+// one thread: the window sequence after a window with `cnt` changed markers (the host loop of round 1, src/BayesW.cpp:1633-1660)
+__device__ __forceinline__ void bw_ctl_advance(const BwParams &P, uint32_t cnt) {
+    uint32_t j0 = P.ctl_in[0], since = P.ctl_in[1];
+    const uint32_t n = P.ctl_in[2];
+    uint32_t nsync = P.ctl_in[3], nchg = P.ctl_in[4];
+    if (cnt > 0) { since = 0; nsync++; nchg += cnt; } else { since += n; }
+    j0 += n;
+    P.ctl_out[0] = j0; P.ctl_out[1] = since;
+    P.ctl_out[2] = (j0 >= P.lmax) ? 0u : ((since >= P.SR) ? 1u : min(P.SR - since, P.lmax - j0));
+    P.ctl_out[3] = nsync; P.ctl_out[4] = nchg; P.ctl_out[5] = P.ctl_in[5] + 1u;
+}
+// a window past the end: the control block and the shift are handed on unchanged
+__device__ __forceinline__ bool bw_ctl_noop(const BwParams &P, bool hand_on) {
+    if (!P.ctl_in || P.ctl_in[0] < P.lmax) return false;
+    if (hand_on && blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int i = 0; i < 6; i++) P.ctl_out[i] = P.ctl_in[i];
+        *P.shift_out = *P.shift_in;
+    }
+    return true;
+}
+
 __global__ void __launch_bounds__(512) k_bw_update(const BwParams P) {
     __shared__ uint32_t ps[kMaxMerged];
     __shared__ double red[16];
@@ -282,6 +316,7 @@ __global__ void __launch_bounds__(512) k_bw_update(const BwParams P) {
     __shared__ uint32_t s_nw[64], s_b1[64], s_b2[64];
     __shared__ double s_dbs[64], s_mave[64];
     const uint32_t c = blockIdx.x, tid = threadIdx.x, L = P.L;
+    if (bw_ctl_noop(P, P.delta == nullptr)) return;   // (several GPUs: k_bw_apply_delta hands the control block on)
     const uint32_t n = *P.chg_cnt;
     const double shift_old = *P.shift_in;
     double off = 0.0;
@@ -349,7 +384,7 @@ __global__ void __launch_bounds__(512) k_bw_update(const BwParams P) {
         return;
     }
     const double shift_new = shift_old + off;
-    if (c == 0 && tid == 0) *P.shift_out = shift_new;
+    if (c == 0 && tid == 0) { *P.shift_out = shift_new; if (P.ctl_in) bw_ctl_advance(P, n); }
     // refresh the slice's sum of vi (:1832-1834)
     double v = 0.0;
     const double bconst = P.alpha * shift_new - kBwEuMasc;
@@ -369,10 +404,14 @@ __global__ void __launch_bounds__(512) k_bw_update(const BwParams P) {
 __global__ void __launch_bounds__(512) k_bw_apply_delta(const BwParams P) {
     __shared__ double red[16];
     const uint32_t c = blockIdx.x, tid = threadIdx.x, L = P.L;
+    if (bw_ctl_noop(P, true)) return;
     double *E = P.E + (size_t)c * L;
     const double *D = P.delta + (size_t)c * L;
     const double shift_new = *P.shift_in + P.delta[(size_t)P.S * L];
-    if (c == 0 && tid == 0) *P.shift_out = shift_new;
+    if (c == 0 && tid == 0) {
+        *P.shift_out = shift_new;
+        if (P.ctl_in) bw_ctl_advance(P, (uint32_t)llrint(P.delta[(size_t)P.S * L + 1]));   // changed markers over all GPUs
+    }
     double v = 0.0;
     const double bconst = P.alpha * shift_new - kBwEuMasc;
     for (uint32_t i = tid; i < L; i += blockDim.x) {

@@ -151,6 +151,7 @@ struct hb_ctx {
     std::vector<double> bw_fail_h, bw_sff;   // failure indicators (host copy) and sum_failure_fix of the fixed effects (src/BayesW.cpp:1235-1237)
     uint64_t bw_evals = 0;
     DevBuf<double> d_sd, d_sumfail, d_fail, d_bwsc, d_bw_vi, d_bw_delta;
+    DevBuf<uint32_t> d_bw_ctl;   // window sequence of the BayesW marker loop, two blocks of 8 (bw_kernels.cuh)
     std::vector<double> sd_h, sumfail_h;
 
     // chain (host)
